@@ -1,0 +1,151 @@
+/* lakeside_b200.h -- C ABI of liblakeside_b200.so
+ *
+ * B200-native (sm_100a) implementation of cardinalhq/lakeside's per-segment DataExpr evaluation path.
+ * The library replaces, behind the reference's own seam, what the reference delegates to DuckDB over JDBC:
+ *   - Commons.toGlobResultSet       core/src/main/scala/com/cardinal/utils/Commons.scala:200-254
+ *       (DESCRIBE + BaseExpr.generateSql + statement.executeQuery over read_parquet([...], union_by_name=True))
+ *   - the ResultSet reads of Commons.resultSetToSource / toDataPoint   Commons.scala:280-341, 399-462
+ *   - the K-way mergeSorted chains   Commons.scala:391-392, WorkerApi.scala:173, QueryEngineV2.scala:76-97
+ *   - the map-sketch merge of TimeGroupedSketchAggregator   core/.../eval/TimeGroupedSketchAggregator.scala:63-93
+ *
+ * Convention follows the reference's existing FFI (JNA over a C shared object, C strings in, plain data out:
+ * query-api/src/main/resources/lib-trigram.h:77-78, core/.../queries/NLPUtils.scala:30-52): plain C types only,
+ * no C++ / torch types in any signature.  All functions return LK_OK (0) or an LK_ERR_* code; the message is
+ * available from lk_last_error() (thread-local).  There is NO CPU fallback: without a CUDA device every compute
+ * entry point returns LK_ERR_CUDA.
+ *
+ * Threading: every lk_query owns its CUDA stream and buffers; distinct queries may run concurrently from
+ * different threads (the reference evaluates all globs of a request at once, Commons.scala:368-392).
+ */
+#ifndef LAKESIDE_B200_H
+#define LAKESIDE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LK_OK 0
+#define LK_ERR_INVALID 1     /* malformed request JSON / bad argument */
+#define LK_ERR_UNSUPPORTED 2 /* query or file shape outside the GPU path (extract/compute, percentile, compressed pages ...) */
+#define LK_ERR_IO 3          /* file could not be read / not a Parquet file */
+#define LK_ERR_CUDA 4        /* no device / CUDA failure */
+#define LK_ERR_QUERY 5       /* the reference's SQL would fail to bind in DuckDB (e.g. value column absent): stream nothing */
+#define LK_ERR_NOMEM 6
+
+typedef struct lk_query lk_query;   /* one glob evaluation: request + segments + device state */
+typedef struct lk_result lk_result; /* host-resident result rows, sorted by timestamp ascending */
+typedef struct lk_merge lk_merge;   /* K-way merge job */
+
+/* ---- library ------------------------------------------------------------------------------------------ */
+/* options_json (may be NULL): {"device": 0, "max_hash_slots": 134217728, "dense_max_cells": 33554432,
+ *                              "tile_rows": 2048, "host_threads": 8} */
+int lk_init(const char* options_json);
+void lk_shutdown(void);
+const char* lk_last_error(void);
+const char* lk_version(void);
+int lk_device_count(void); /* 0 when no CUDA device is visible; never fails */
+
+/* Pinned host memory for segment bytes handed to lk_query_add_segment_buffer (fast H2D). */
+void* lk_host_alloc(size_t bytes);
+void lk_host_free(void* p);
+
+/* ---- one-shot evaluation: drop-in for Commons.toGlobResultSet (Commons.scala:200-254) ------------------- */
+/* pushdown_request_json: the PushDownRequest JSON the worker receives (model/SegmentRequest.scala:30-60) whose
+ * segmentRequests are exactly the glob's segments; parquet_paths[i] is toParquetFilePath(segmentRequests[i])
+ * (Commons.scala:256-278), already resolved by the caller. */
+int lk_eval(const char* pushdown_request_json, const char* const* parquet_paths, int n_paths, lk_result** out);
+
+/* ---- staged evaluation (resident segments, fused multi-aggregate pass, sharding) ------------------------ */
+/* options_json (may be NULL):
+ *   {"aggregates": [{"aggregation":"sum","rollup":"sum"}, ...]   fused pass: several (aggregation, rollup) pairs sharing
+ *                                                              filter and grouping (QueryEngineV2.scala:280-296 issues them
+ *                                                              as separate requests); default = the request's own chart
+ *    "path": "auto"|"dense"|"hash",                             aggregate table layout
+ *    "exact_sums": false}                                       fixed-order (row order) bit-exact double sums */
+int lk_query_create(const char* pushdown_request_json, const char* options_json, lk_query** out);
+int lk_query_add_segment_file(lk_query* q, const char* path);
+/* The buffer is borrowed and must stay valid until lk_query_prepare returns. */
+int lk_query_add_segment_buffer(lk_query* q, const void* data, size_t len);
+/* Parses footers, page headers and dictionaries, builds the page/run/tile index, compiles the predicate to
+ * dictionary-code tables, uploads the touched column chunks to HBM.  After this the query is device-resident. */
+int lk_query_prepare(lk_query* q);
+/* Sharded evaluation: every rank exports the dictionaries of its group-by columns, the host unions them
+ * (any order-insensitive union, e.g. sorted) and imports the same blob on every rank so that all ranks index one
+ * dense (group x bucket) space.  Blob format: see INTEGRATION.md.  Call between prepare and execute. */
+int lk_query_export_dictionaries(lk_query* q, const void** blob, size_t* len);
+int lk_query_import_dictionaries(lk_query* q, const void* blob, size_t len);
+/* Launches the fused decode+filter+aggregate kernels on the query's stream (asynchronous).  May be called
+ * repeatedly: each call first clears the partial aggregate table. */
+int lk_query_execute(lk_query* q);
+int lk_query_sync(lk_query* q);
+/* Device-resident partial aggregates after execute (dense path), for an NCCL reduce by the host:
+ *   plane 0            : uint64 row counts per cell (presence)
+ *   plane 1 + a        : aggregate a; sum -> float64, count -> uint64, min/max -> order-preserving uint64 keys
+ * Layout: cell = bucket * n_groups + group.  op[a]: 0 sum(f64 add) 1 count(u64 add) 2 min(u64 min) 3 max(u64 max). */
+int lk_query_partial_dense(lk_query* q, int64_t* n_cells, int* n_planes, void** plane_ptrs /*[8]*/, int* plane_ops /*[8]*/);
+/* Hash path: compacts the occupied entries into a device list of n entries of `stride` bytes
+ * {uint64 key; uint64 acc[..]} and merges entries gathered from other ranks. */
+int lk_query_partial_sparse(lk_query* q, void** entries, int64_t* n, int* stride_bytes);
+int lk_query_merge_sparse(lk_query* q, const void* device_entries, int64_t n);
+/* Compacts the non-empty cells into result rows sorted by timestamp, still in HBM (asynchronous apart from one
+ * scalar read-back).  Idempotent until the next execute.  The hash path also returns its table to the clean state. */
+int lk_query_finalize_device(lk_query* q);
+/* lk_query_finalize_device + copy of the rows to (pinned) host memory. */
+int lk_query_finalize(lk_query* q, lk_result** out);
+/* Rows that satisfied the WHERE clause and the [startTs, endTs) range in the last execute (-1 on error). */
+int64_t lk_query_survivors(lk_query* q);
+/* Timings of the last execute/finalize in milliseconds (CUDA events on the query's stream):
+ * [0] H2D upload, [1] scan kernel(s), [2] finalize kernels, [3] D2H, [4] host planning. */
+int lk_query_timings(lk_query* q, double* ms /*[8]*/);
+/* Algorithmic bytes: sum of total_compressed_size of the touched column chunks. */
+int64_t lk_query_touched_bytes(lk_query* q);
+int64_t lk_query_total_rows(lk_query* q);
+int lk_query_stream(lk_query* q, void** cuda_stream);
+int lk_query_info_json(lk_query* q, const char** json); /* plan description (path, tiles, groups, buckets ...) */
+void lk_query_destroy(lk_query* q);
+
+/* ---- result: what Commons.toDataPoint reads from the JDBC ResultSet (Commons.scala:399-462) ------------- */
+int64_t lk_result_num_rows(const lk_result* r);
+int lk_result_num_values(const lk_result* r); /* 1 unless a fused multi-aggregate pass */
+int lk_result_num_tags(const lk_result* r);   /* "name" + existing group-by columns */
+/* JDBC column names in order: col 0 = "_cardinalhq.timestamp" (metrics) or "step_ts" (events); then the value
+ * column(s); then "name"; then the group-by columns that exist (BaseExpr.scala:338-346, 391-403). */
+int lk_result_num_cols(const lk_result* r);
+const char* lk_result_col_name(const lk_result* r, int col);
+const int64_t* lk_result_ts(const lk_result* r);
+const double* lk_result_value(const lk_result* r, int a);       /* SQL NULL reads as 0.0, like ResultSet.getDouble */
+const uint8_t* lk_result_value_null(const lk_result* r, int a); /* 1 where the aggregate is SQL NULL */
+const int32_t* lk_result_tag_codes(const lk_result* r, int t);  /* -1 = SQL NULL */
+int lk_result_tag_dict(const lk_result* r, int t, int32_t* n, const char* const** strings);
+/* Row-at-a-time accessors for a java.sql.ResultSet shim (1-based column index like JDBC). */
+int64_t lk_result_get_long(const lk_result* r, int64_t row, int col);
+double lk_result_get_double(const lk_result* r, int64_t row, int col);
+const char* lk_result_get_string(const lk_result* r, int64_t row, int col); /* NULL for SQL NULL */
+void lk_result_free(lk_result* r);
+
+/* ---- K-way merge of sorted per-segment streams (mergeSorted chains) ------------------ */
+/* Streams are SoA (ts int64, gid int32, value f64), each sorted by ts (ascending, or descending if reverse).
+ * Output order = the left-deep ``s1.mergeSorted(s2)`` fold: by ts, ties by stream index DESCENDING, then original
+ * position.  Host pointers; out_* must hold sum(lens) elements; out_src (optional) receives the source stream. */
+int lk_merge_streams(int k, const int64_t* const* ts, const int32_t* const* gid, const double* const* val,
+                     const int64_t* lens, int reverse, int64_t* out_ts, int32_t* out_gid, double* out_val,
+                     int32_t* out_src);
+/* Resident variant for kernel timing: create uploads, run launches the merge-path kernels, download copies back. */
+int lk_merge_create(int k, const int64_t* const* ts, const int32_t* const* gid, const double* const* val,
+                    const int64_t* lens, int reverse, lk_merge** out);
+int lk_merge_run(lk_merge* m);  /* asynchronous on the job's stream */
+int lk_merge_sync(lk_merge* m);
+int lk_merge_timings(lk_merge* m, double* ms /*[4]*/);
+int lk_merge_download(lk_merge* m, int64_t* out_ts, int32_t* out_gid, double* out_val, int32_t* out_src);
+/* TimeGroupedSketchAggregator map-sketch merge over the merged stream: combines equal (ts, gid) with
+ * op (0 sum/count add, 2 min, 3 max) in merged order; outputs one element per (ts, gid), sorted by ts. */
+int lk_merge_reduce(lk_merge* m, int op, int64_t* n_out, int64_t* out_ts, int32_t* out_gid, double* out_val);
+void lk_merge_destroy(lk_merge* m);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAKESIDE_B200_H */

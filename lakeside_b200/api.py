@@ -1,0 +1,297 @@
+"""Host-side mirror of the reference's segment-evaluator interface, over the C ABI.
+
+Names follow the reference: ``PushDownRequest`` / ``SegmentRequest`` (core/.../model/SegmentRequest.scala:62-98),
+``evaluate_push_down_request`` = ``Commons.evaluatePushDownRequest`` (core/.../utils/Commons.scala:343-397),
+``DataPoint`` (model/DataPoint.scala:19), the map-sketch ``SketchInput`` (PushDownAggregatorStage.scala:95-106).
+Python is only the caller here (the reference's host is Scala; no JVM exists in this image): every row-level
+operation happens inside liblakeside_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+from dataclasses import dataclass
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib
+from ._lib import LakesideError, LakesideQueryError, LakesideUnsupported  # noqa: F401
+
+
+def init(**options) -> None:
+    _lib.check(_lib.load().lk_init(json.dumps(options).encode() if options else None))
+
+
+def device_count() -> int:
+    return int(_lib.load().lk_device_count())
+
+
+@dataclass
+class DataPoint:
+    timestamp: int
+    value: float
+    tags: Dict[str, str]
+
+
+@dataclass
+class SketchInput:
+    timestamp: int
+    tags: Dict[str, str]
+    sketch: Dict[str, float]
+    sketchType: str = "map"
+
+
+class GlobResult:
+    """Column view of an ``lk_result`` (what ``Commons.toDataPoint`` reads from the JDBC ResultSet)."""
+
+    def __init__(self, handle: int):
+        lib = _lib.load()
+        self._h = ctypes.c_void_p(handle)
+        n = self.num_rows = int(lib.lk_result_num_rows(self._h))
+        self.num_values = int(lib.lk_result_num_values(self._h))
+        self.num_tags = int(lib.lk_result_num_tags(self._h))
+        self.columns = [lib.lk_result_col_name(self._h, i).decode() for i in range(lib.lk_result_num_cols(self._h))]
+
+        def arr(ptr, dtype):
+            return np.ctypeslib.as_array(ptr, (n,)).view(dtype).copy() if n else np.zeros(0, dtype)
+
+        self.ts = arr(lib.lk_result_ts(self._h), np.int64)
+        self.values = [arr(lib.lk_result_value(self._h, a), np.float64) for a in range(self.num_values)]
+        self.value_nulls = [arr(lib.lk_result_value_null(self._h, a), np.uint8) for a in range(self.num_values)]
+        self.tag_codes = [arr(lib.lk_result_tag_codes(self._h, t), np.int32) for t in range(self.num_tags)]
+        self.tag_dicts: List[List[str]] = []
+        for t in range(self.num_tags):
+            cnt = ctypes.c_int32()
+            strs = ctypes.POINTER(ctypes.c_char_p)()
+            _lib.check(lib.lk_result_tag_dict(self._h, t, ctypes.byref(cnt), ctypes.byref(strs)))
+            self.tag_dicts.append([strs[i].decode("utf-8", "replace") for i in range(cnt.value)])
+
+    # JDBC-style row access (1-based columns), used by the ResultSet shim test
+    def get_long(self, row: int, col: int) -> int:
+        return int(_lib.load().lk_result_get_long(self._h, row, col))
+
+    def get_double(self, row: int, col: int) -> float:
+        return float(_lib.load().lk_result_get_double(self._h, row, col))
+
+    def get_string(self, row: int, col: int) -> Optional[str]:
+        s = _lib.load().lk_result_get_string(self._h, row, col)
+        return None if s is None else s.decode("utf-8", "replace")
+
+    def close(self):
+        if self._h:
+            _lib.load().lk_result_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def to_data_points(self, query_tags: Optional[Dict[str, Any]] = None, value_index: int = 0) -> List[DataPoint]:
+        """``Commons.toDataPoint`` aggregate branch (Commons.scala:424-461): null / "" / "null" tags are dropped and
+        an empty tag map falls back to the segment's queryTags."""
+        names = self.columns[1 + self.num_values:]
+        tagcols = []
+        for t in range(self.num_tags):
+            d = np.array(self.tag_dicts[t] + [None], dtype=object)
+            tagcols.append(d[np.where(self.tag_codes[t] < 0, len(self.tag_dicts[t]), self.tag_codes[t])])
+        out = []
+        vals = self.values[value_index]
+        for i in range(self.num_rows):
+            tags = {}
+            for nme, col in zip(names, tagcols):
+                v = col[i]
+                if v is not None and v != "null" and v != "":
+                    tags[nme] = v
+            if not tags and query_tags:
+                tags.update(query_tags)
+            out.append(DataPoint(int(self.ts[i]), float(vals[i]), tags))
+        return out
+
+
+class Query:
+    """Staged evaluation of one glob: create -> add segments -> prepare (HBM resident) -> execute -> finalize."""
+
+    def __init__(self, push_down_request_json: str, aggregates: Optional[Sequence[Tuple[str, str]]] = None,
+                 path: str = "auto"):
+        lib = _lib.load()
+        opts: Dict[str, Any] = {"path": path}
+        if aggregates:
+            opts["aggregates"] = [{"aggregation": a, "rollup": r} for a, r in aggregates]
+        self._h = ctypes.c_void_p()
+        self._keep: list = []
+        _lib.check(lib.lk_query_create(push_down_request_json.encode(), json.dumps(opts).encode(), ctypes.byref(self._h)))
+
+    def add_segment_file(self, path: str):
+        _lib.check(_lib.load().lk_query_add_segment_file(self._h, path.encode()))
+
+    def add_segment_buffer(self, ptr: int, length: int, keepalive=None):
+        if keepalive is not None:
+            self._keep.append(keepalive)
+        _lib.check(_lib.load().lk_query_add_segment_buffer(self._h, ctypes.c_void_p(ptr), length))
+
+    def add_segment_bytes(self, data: bytes):
+        buf = ctypes.create_string_buffer(data, len(data))
+        self.add_segment_buffer(ctypes.addressof(buf), len(data), keepalive=buf)
+
+    def prepare(self):
+        _lib.check(_lib.load().lk_query_prepare(self._h))
+        self._keep.clear()
+
+    def execute(self):
+        _lib.check(_lib.load().lk_query_execute(self._h))
+
+    def sync(self):
+        _lib.check(_lib.load().lk_query_sync(self._h))
+
+    def finalize_device(self):
+        _lib.check(_lib.load().lk_query_finalize_device(self._h))
+
+    def finalize(self) -> GlobResult:
+        r = ctypes.c_void_p()
+        _lib.check(_lib.load().lk_query_finalize(self._h, ctypes.byref(r)))
+        return GlobResult(r.value)
+
+    def export_dictionaries(self) -> bytes:
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _lib.check(_lib.load().lk_query_export_dictionaries(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return ctypes.string_at(p.value, n.value)
+
+    def import_dictionaries(self, blob: bytes):
+        _lib.check(_lib.load().lk_query_import_dictionaries(self._h, blob, len(blob)))
+
+    def partial_dense(self):
+        n, k = ctypes.c_int64(), ctypes.c_int()
+        ptrs = (ctypes.c_void_p * 8)()
+        ops = (ctypes.c_int * 8)()
+        _lib.check(_lib.load().lk_query_partial_dense(self._h, ctypes.byref(n), ctypes.byref(k), ptrs, ops))
+        return n.value, [(ptrs[i], ops[i]) for i in range(k.value)]
+
+    @property
+    def stream(self) -> int:
+        s = ctypes.c_void_p()
+        _lib.check(_lib.load().lk_query_stream(self._h, ctypes.byref(s)))
+        return s.value or 0
+
+    @property
+    def info(self) -> dict:
+        s = ctypes.c_char_p()
+        _lib.check(_lib.load().lk_query_info_json(self._h, ctypes.byref(s)))
+        return json.loads(s.value.decode())
+
+    @property
+    def timings(self) -> Dict[str, float]:
+        ms = (ctypes.c_double * 8)()
+        _lib.check(_lib.load().lk_query_timings(self._h, ms))
+        return {"h2d_ms": ms[0], "scan_ms": ms[1], "finalize_ms": ms[2], "d2h_ms": ms[3], "plan_ms": ms[4]}
+
+    @property
+    def touched_bytes(self) -> int:
+        return int(_lib.load().lk_query_touched_bytes(self._h))
+
+    @property
+    def total_rows(self) -> int:
+        return int(_lib.load().lk_query_total_rows(self._h))
+
+    @property
+    def survivors(self) -> int:
+        return int(_lib.load().lk_query_survivors(self._h))
+
+    def close(self):
+        if self._h:
+            _lib.load().lk_query_destroy(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def eval_glob(push_down_request_json: str, parquet_paths: Sequence[str]) -> GlobResult:
+    """``lk_eval``: drop-in for ``Commons.toGlobResultSet`` (Commons.scala:200-254)."""
+    lib = _lib.load()
+    arr = (ctypes.c_char_p * len(parquet_paths))(*[p.encode() for p in parquet_paths])
+    r = ctypes.c_void_p()
+    _lib.check(lib.lk_eval(push_down_request_json.encode(), arr, len(parquet_paths), ctypes.byref(r)))
+    return GlobResult(r.value)
+
+
+def to_parquet_file_path(sr: dict, db_root: str = "./db") -> str:
+    """``Commons.toParquetFilePath`` for local segments (Commons.scala:160-177, 256-278)."""
+    return f"{db_root}/{sr['customerId']}/{sr['collectorId']}/{sr['dateInt']}/{sr['dataset']}/{sr['hour']}/{sr['segmentId']}.parquet"
+
+
+def merge_sorted_source(sources: List[list], reverse_sort: bool = False) -> list:
+    """``mergeSortedSource`` (QueryEngineV2.scala:76-97): K-way merge by timestamp on the GPU (lk_merge_streams).
+    Elements need a ``timestamp`` attribute; ties come out by source index descending (left-deep mergeSorted fold)."""
+    lens = [len(s) for s in sources]
+    total = sum(lens)
+    if total == 0:
+        return []
+    ts = [np.fromiter((e.timestamp for e in s), np.int64, len(s)) for s in sources]
+    src, pos = merge_streams_index(ts, reverse_sort)
+    return [sources[s][p] for s, p in zip(src.tolist(), pos.tolist())]
+
+
+def merge_streams_index(ts_list: Sequence[np.ndarray], reverse: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+    """Merges K sorted int64 timestamp streams; returns (source index, position) of every output element."""
+    lib = _lib.load()
+    k = len(ts_list)
+    ts_list = [np.ascontiguousarray(t, np.int64) for t in ts_list]
+    gids = [np.arange(len(t), dtype=np.int32) for t in ts_list]  # carry the in-stream position as payload
+    vals = [np.zeros(len(t), np.float64) for t in ts_list]
+    lens = (ctypes.c_int64 * k)(*[len(t) for t in ts_list])
+    total = int(sum(len(t) for t in ts_list))
+    P = ctypes.c_void_p
+    tsp = (P * k)(*[t.ctypes.data for t in ts_list])
+    gp = (P * k)(*[g.ctypes.data for g in gids])
+    vp = (P * k)(*[v.ctypes.data for v in vals])
+    out_ts = np.empty(total, np.int64)
+    out_gid = np.empty(total, np.int32)
+    out_val = np.empty(total, np.float64)
+    out_src = np.empty(total, np.int32)
+    _lib.check(lib.lk_merge_streams(k, tsp, gp, vp, lens, 1 if reverse else 0, out_ts.ctypes.data, out_gid.ctypes.data,
+                                    out_val.ctypes.data, out_src.ctypes.data))
+    return out_src, out_gid
+
+
+def evaluate_push_down_request(query_id: str, local_parquet: bool, push_down_request: dict, db_root: str = "./db"):
+    """``Commons.evaluatePushDownRequest`` (Commons.scala:343-397): globs of 10 (local) / 5 (S3) segments, one GPU
+    evaluation per glob, glob streams merged by timestamp; an empty request yields the ts = -1 sentinel; a failing
+    glob streams nothing (Commons.scala:249-253)."""
+    srs = push_down_request["segmentRequests"]
+    if not srs:
+        return [DataPoint(-1, -1.0, {})]
+    glob_size = 10 if local_parquet else 5
+    agg = push_down_request["baseExpr"].get("chart", {}).get("aggregation", "sum")
+    sources = []
+    for g in range(0, len(srs), glob_size):
+        group = srs[g:g + glob_size]
+        sub = dict(push_down_request, segmentRequests=group)
+        paths = [to_parquet_file_path(s, db_root) for s in group]
+        try:
+            res = eval_glob(json.dumps(sub), paths)
+        except (LakesideQueryError, LakesideUnsupported):
+            sources.append([])
+            continue
+        except LakesideError as e:
+            if e.code == _lib.LK_ERR_IO:
+                sources.append([])
+                continue
+            raise
+        dps = res.to_data_points(group[0].get("queryTags") or {})
+        sources.append([SketchInput(d.timestamp, d.tags, {agg: d.value}) for d in dps])
+    if len(sources) == 1:
+        return sources[0]
+    return merge_sorted_source(sources, False)

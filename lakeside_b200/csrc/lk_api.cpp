@@ -1,0 +1,350 @@
+// C ABI of liblakeside_b200 (see include/lakeside_b200.h for the contract and the reference seams it replaces).
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <cstring>
+
+#include "lk_engine.h"
+#include "lk_merge.h"
+
+using namespace lk;
+
+struct lk_query { Query q; };
+struct lk_result { HostResult* r; };
+
+static thread_local std::string tl_error;
+
+template <class F>
+static int guard(F&& f) {
+  try {
+    f();
+    tl_error.clear();
+    return LK_OK;
+  } catch (const Error& e) {
+    tl_error = e.what();
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    tl_error = "out of host memory";
+    return LK_ERR_NOMEM;
+  } catch (const std::exception& e) {
+    tl_error = e.what();
+    return LK_ERR_INVALID;
+  }
+}
+
+static double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int lk_init(const char* options_json) {
+  return guard([&] {
+    Options& o = global_options();
+    if (options_json && *options_json) {
+      Json j = parse_json(options_json);
+      LK_CHECK(j.is_obj(), LK_ERR_INVALID, "lk_init options must be a JSON object");
+      if (const Json* v = j.get("device")) o.device = (int)v->as_i64();
+      if (const Json* v = j.get("max_hash_slots")) o.max_hash_slots = (uint64_t)v->as_i64();
+      if (const Json* v = j.get("dense_max_cells")) o.dense_max_cells = (uint64_t)v->as_i64();
+      if (const Json* v = j.get("tile_rows")) o.tile_rows = (uint32_t)v->as_i64();
+      if (const Json* v = j.get("host_threads")) o.host_threads = (int)v->as_i64();
+      LK_CHECK(o.max_hash_slots >= 1024 && (o.max_hash_slots & (o.max_hash_slots - 1)) == 0, LK_ERR_INVALID, "max_hash_slots must be a power of two >= 1024");
+    }
+    device_init();
+  });
+}
+
+void lk_shutdown(void) { device_shutdown(); }
+const char* lk_last_error(void) { return tl_error.c_str(); }
+const char* lk_version(void) { return "lakeside_b200 0.1 (sm_100a)"; }
+int lk_device_count(void) { return device_count(); }
+
+void* lk_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  guard([&] { device_init(); p = pinned_alloc(bytes); });
+  return p;
+}
+void lk_host_free(void* p) { pinned_free(p); }
+
+int lk_query_create(const char* pushdown_request_json, const char* options_json, lk_query** out) {
+  return guard([&] {
+    LK_CHECK(pushdown_request_json && out, LK_ERR_INVALID, "null argument");
+    auto h = std::make_unique<lk_query>();
+    h->q.req = parse_push_down_request(pushdown_request_json);
+    if (options_json && *options_json) {
+      Json j = parse_json(options_json);
+      LK_CHECK(j.is_obj(), LK_ERR_INVALID, "query options must be a JSON object");
+      if (const Json* p = j.get("path"); p && p->text()) {
+        LK_CHECK(p->str == "auto" || p->str == "dense" || p->str == "hash", LK_ERR_INVALID, "path must be auto|dense|hash");
+        h->q.path_opt = p->str;
+      }
+      if (const Json* e = j.get("exact_sums")) h->q.exact_sums = e->as_bool();
+      LK_CHECK(!h->q.exact_sums, LK_ERR_UNSUPPORTED, "exact_sums (fixed-order summation) is not available in this build");
+      if (const Json* a = j.get("aggregates"); a && a->is_arr()) {
+        const BaseExpr& e = h->q.req.expr;
+        for (auto& x : a->arr) {
+          LK_CHECK(x.is_obj(), LK_ERR_INVALID, "aggregates[] entries must be objects");
+          const Json* ag = x.get("aggregation");
+          LK_CHECK(ag && ag->text(), LK_ERR_INVALID, "aggregates[].aggregation missing");
+          const Json* ro = x.get("rollup");
+          // re-uses the planner's resolution through a temporary single-aggregate expression
+          AggSpec s;
+          s.aggregation = ag->str;
+          LK_CHECK(!(ag->str.rfind("p", 0) == 0 || ag->str.find("ces") != std::string::npos), LK_ERR_UNSUPPORTED,
+                   "percentile / cardinality-estimate aggregations are outside the GPU path");
+          if (ag->str == "sum") s.op = AGG_SUM;
+          else if (ag->str == "count") s.op = AGG_COUNT;
+          else if (ag->str == "min") s.op = AGG_MIN;
+          else if (ag->str == "max") s.op = AGG_MAX;
+          else fail(ag->str == "avg" ? LK_ERR_UNSUPPORTED : LK_ERR_QUERY, "aggregate function " + ag->str + " is not available");
+          if (e.dataset == "metrics") s.value_column = "rollup_" + ((ro && ro->text()) ? ro->str : std::string("sum"));
+          else {
+            LK_CHECK(!e.chart.has_field_name || e.chart.field_name == "_cardinalhq.value", LK_ERR_UNSUPPORTED, "chart fieldName in a fused multi-aggregate pass");
+            s.value_column = "_cardinalhq.value";
+          }
+          h->q.aggs.push_back(s);
+        }
+      }
+    }
+    *out = h.release();
+  });
+}
+
+int lk_query_add_segment_buffer(lk_query* q, const void* data, size_t len) {
+  return guard([&] {
+    LK_CHECK(q && data, LK_ERR_INVALID, "null argument");
+    LK_CHECK(!q->q.prepared, LK_ERR_INVALID, "query already prepared");
+    SegmentInput s;
+    s.data = (const uint8_t*)data;
+    s.len = len;
+    s.name = "buffer#" + std::to_string(q->q.segs.size());
+    q->q.segs.push_back(std::move(s));
+  });
+}
+
+int lk_query_add_segment_file(lk_query* q, const char* path) {
+  return guard([&] {
+    LK_CHECK(q && path, LK_ERR_INVALID, "null argument");
+    LK_CHECK(!q->q.prepared, LK_ERR_INVALID, "query already prepared");
+    int fd = open(path, O_RDONLY);
+    LK_CHECK(fd >= 0, LK_ERR_IO, std::string("IO Error: cannot open ") + path);
+    struct stat st;
+    if (fstat(fd, &st) != 0) { close(fd); fail(LK_ERR_IO, std::string("IO Error: cannot stat ") + path); }
+    size_t len = (size_t)st.st_size;
+    void* buf = nullptr;
+    try {
+      device_init();
+      buf = pinned_alloc(len + 16);
+    } catch (...) { close(fd); throw; }
+    size_t got = 0;
+    while (got < len) {
+      ssize_t r = read(fd, (char*)buf + got, len - got);
+      if (r <= 0) break;
+      got += (size_t)r;
+    }
+    close(fd);
+    if (got != len) { pinned_free(buf); fail(LK_ERR_IO, std::string("IO Error: short read on ") + path); }
+    SegmentInput s;
+    s.data = (const uint8_t*)buf;
+    s.len = len;
+    s.name = path;
+    s.owned_pinned = buf;
+    q->q.segs.push_back(std::move(s));
+  });
+}
+
+int lk_query_prepare(lk_query* q) {
+  return guard([&] {
+    LK_CHECK(q, LK_ERR_INVALID, "null argument");
+    LK_CHECK(!q->q.prepared, LK_ERR_INVALID, "query already prepared");
+    double t0 = now_ms();
+    plan_query(q->q);
+    q->q.t_ms[4] = now_ms() - t0;
+    device_upload(q->q);
+  });
+}
+
+int lk_query_export_dictionaries(lk_query* q, const void** blob, size_t* len) {
+  return guard([&] {
+    LK_CHECK(q && blob && len, LK_ERR_INVALID, "null argument");
+    LK_CHECK(q->q.prepared, LK_ERR_INVALID, "query not prepared");
+    q->q.dict_blob = export_dictionaries(q->q);
+    *blob = q->q.dict_blob.data();
+    *len = q->q.dict_blob.size();
+  });
+}
+
+int lk_query_import_dictionaries(lk_query* q, const void* blob, size_t len) {
+  return guard([&] {
+    LK_CHECK(q && blob, LK_ERR_INVALID, "null argument");
+    LK_CHECK(q->q.prepared, LK_ERR_INVALID, "query not prepared");
+    import_dictionaries(q->q, (const uint8_t*)blob, len);
+    device_mark_group_tables_stale(q->q);
+  });
+}
+
+int lk_query_execute(lk_query* q) {
+  return guard([&] { LK_CHECK(q && q->q.prepared, LK_ERR_INVALID, "query not prepared"); device_execute(q->q); });
+}
+
+int lk_query_sync(lk_query* q) {
+  return guard([&] { LK_CHECK(q, LK_ERR_INVALID, "null argument"); device_sync(q->q); });
+}
+
+int lk_query_partial_dense(lk_query* q, int64_t* n_cells, int* n_planes, void** plane_ptrs, int* plane_ops) {
+  return guard([&] {
+    LK_CHECK(q && n_cells && n_planes && plane_ptrs && plane_ops, LK_ERR_INVALID, "null argument");
+    device_partial_dense(q->q, n_cells, n_planes, plane_ptrs, plane_ops);
+  });
+}
+
+int lk_query_partial_sparse(lk_query*, void**, int64_t*, int*) {
+  tl_error = "sparse partial exchange is not available in this build";
+  return LK_ERR_UNSUPPORTED;
+}
+int lk_query_merge_sparse(lk_query*, const void*, int64_t) {
+  tl_error = "sparse partial exchange is not available in this build";
+  return LK_ERR_UNSUPPORTED;
+}
+
+int lk_query_finalize_device(lk_query* q) {
+  return guard([&] { LK_CHECK(q && q->q.prepared, LK_ERR_INVALID, "query not prepared"); device_finalize_device(q->q); });
+}
+
+int lk_query_finalize(lk_query* q, lk_result** out) {
+  return guard([&] {
+    LK_CHECK(q && out, LK_ERR_INVALID, "null argument");
+    LK_CHECK(q->q.prepared, LK_ERR_INVALID, "query not prepared");
+    device_finalize_device(q->q);
+    auto r = std::make_unique<lk_result>();
+    r->r = device_fetch(q->q);
+    *out = r.release();
+  });
+}
+
+int lk_query_timings(lk_query* q, double* ms) {
+  return guard([&] {
+    LK_CHECK(q && ms, LK_ERR_INVALID, "null argument");
+    if (q->q.dev) { device_sync(q->q); device_timings(q->q); }
+    for (int i = 0; i < 8; i++) ms[i] = q->q.t_ms[i];
+  });
+}
+
+int64_t lk_query_touched_bytes(lk_query* q) { return q ? q->q.touched_bytes : -1; }
+int64_t lk_query_total_rows(lk_query* q) { return q ? q->q.total_rows : -1; }
+int64_t lk_query_survivors(lk_query* q) {
+  int64_t v = -1;
+  guard([&] { LK_CHECK(q && q->q.dev, LK_ERR_INVALID, "query not prepared"); v = device_survivors(q->q); });
+  return v;
+}
+
+int lk_query_stream(lk_query* q, void** cuda_stream) {
+  return guard([&] {
+    LK_CHECK(q && cuda_stream && q->q.dev, LK_ERR_INVALID, "query not prepared");
+    *cuda_stream = device_stream(q->q);
+  });
+}
+
+int lk_query_info_json(lk_query* q, const char** json) {
+  return guard([&] {
+    LK_CHECK(q && json, LK_ERR_INVALID, "null argument");
+    *json = q->q.info_json.c_str();
+  });
+}
+
+void lk_query_destroy(lk_query* q) { delete q; }
+
+int lk_eval(const char* pushdown_request_json, const char* const* parquet_paths, int n_paths, lk_result** out) {
+  lk_query* q = nullptr;
+  int rc = lk_query_create(pushdown_request_json, nullptr, &q);
+  for (int i = 0; rc == LK_OK && i < n_paths; i++) rc = lk_query_add_segment_file(q, parquet_paths[i]);
+  if (rc == LK_OK) rc = lk_query_prepare(q);
+  if (rc == LK_OK) rc = lk_query_execute(q);
+  if (rc == LK_OK) rc = lk_query_finalize(q, out);
+  std::string err = tl_error;
+  lk_query_destroy(q);
+  tl_error = err;
+  return rc;
+}
+
+// ---- result accessors ----
+int64_t lk_result_num_rows(const lk_result* r) { return r ? r->r->n : 0; }
+int lk_result_num_values(const lk_result* r) { return r ? r->r->n_values : 0; }
+int lk_result_num_tags(const lk_result* r) { return r ? r->r->n_tags : 0; }
+int lk_result_num_cols(const lk_result* r) { return r ? (int)r->r->col_names.size() : 0; }
+const char* lk_result_col_name(const lk_result* r, int col) {
+  if (!r || col < 0 || col >= (int)r->r->col_names.size()) return nullptr;
+  return r->r->col_names[col].c_str();
+}
+const int64_t* lk_result_ts(const lk_result* r) { return r ? r->r->ts : nullptr; }
+const double* lk_result_value(const lk_result* r, int a) { return (r && a >= 0 && a < r->r->n_values) ? r->r->values[a] : nullptr; }
+const uint8_t* lk_result_value_null(const lk_result* r, int a) { return (r && a >= 0 && a < r->r->n_values) ? r->r->nulls[a] : nullptr; }
+const int32_t* lk_result_tag_codes(const lk_result* r, int t) { return (r && t >= 0 && t < r->r->n_tags) ? r->r->codes[t] : nullptr; }
+int lk_result_tag_dict(const lk_result* r, int t, int32_t* n, const char* const** strings) {
+  if (!r || t < 0 || t >= r->r->n_tags || !n || !strings) return LK_ERR_INVALID;
+  *n = (int32_t)r->r->dicts[t].size();
+  *strings = r->r->dict_ptrs[t].data();
+  return LK_OK;
+}
+int64_t lk_result_get_long(const lk_result* r, int64_t row, int col) {
+  if (!r || row < 0 || row >= r->r->n) return 0;
+  if (col == 1) return r->r->ts[row];
+  if (col >= 2 && col < 2 + r->r->n_values) return (int64_t)r->r->values[col - 2][row];
+  return 0;
+}
+double lk_result_get_double(const lk_result* r, int64_t row, int col) {
+  if (!r || row < 0 || row >= r->r->n) return 0.0;
+  if (col == 1) return (double)r->r->ts[row];
+  if (col >= 2 && col < 2 + r->r->n_values) return r->r->values[col - 2][row];
+  return 0.0;
+}
+const char* lk_result_get_string(const lk_result* r, int64_t row, int col) {
+  if (!r || row < 0 || row >= r->r->n) return nullptr;
+  int t = col - 2 - r->r->n_values;
+  if (t < 0 || t >= r->r->n_tags) return nullptr;
+  int32_t c = r->r->codes[t][row];
+  return c < 0 ? nullptr : r->r->dict_ptrs[t][c];
+}
+void lk_result_free(lk_result* r) {
+  if (!r) return;
+  delete r->r;
+  delete r;
+}
+
+// ---- K-way merge ----
+int lk_merge_create(int k, const int64_t* const* ts, const int32_t* const* gid, const double* const* val, const int64_t* lens,
+                    int reverse, lk_merge** out) {
+  return guard([&] {
+    LK_CHECK(out && k >= 0 && (k == 0 || (ts && lens)), LK_ERR_INVALID, "bad argument");
+    *out = merge_create(k, ts, gid, val, lens, reverse != 0);
+  });
+}
+int lk_merge_run(lk_merge* m) { return guard([&] { LK_CHECK(m, LK_ERR_INVALID, "null argument"); merge_run(m); }); }
+int lk_merge_sync(lk_merge* m) { return guard([&] { LK_CHECK(m, LK_ERR_INVALID, "null argument"); merge_sync(m); }); }
+int lk_merge_timings(lk_merge* m, double* ms) { return guard([&] { LK_CHECK(m && ms, LK_ERR_INVALID, "null argument"); merge_timings(m, ms); }); }
+int lk_merge_download(lk_merge* m, int64_t* out_ts, int32_t* out_gid, double* out_val, int32_t* out_src) {
+  return guard([&] { LK_CHECK(m, LK_ERR_INVALID, "null argument"); merge_download(m, out_ts, out_gid, out_val, out_src); });
+}
+int lk_merge_reduce(lk_merge* m, int op, int64_t* n_out, int64_t* out_ts, int32_t* out_gid, double* out_val) {
+  return guard([&] { LK_CHECK(m && n_out, LK_ERR_INVALID, "null argument"); merge_reduce(m, op, n_out, out_ts, out_gid, out_val); });
+}
+void lk_merge_destroy(lk_merge* m) { merge_destroy(m); }
+
+int lk_merge_streams(int k, const int64_t* const* ts, const int32_t* const* gid, const double* const* val, const int64_t* lens,
+                     int reverse, int64_t* out_ts, int32_t* out_gid, double* out_val, int32_t* out_src) {
+  lk_merge* m = nullptr;
+  int rc = lk_merge_create(k, ts, gid, val, lens, reverse, &m);
+  if (rc == LK_OK) rc = lk_merge_run(m);
+  if (rc == LK_OK) rc = lk_merge_download(m, out_ts, out_gid, out_val, out_src);
+  std::string err = tl_error;
+  lk_merge_destroy(m);
+  tl_error = err;
+  return rc;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

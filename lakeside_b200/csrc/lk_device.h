@@ -1,0 +1,263 @@
+// Structures shared by the host planner and the sm_100a kernels, plus the per-value decode primitives
+// (host/device inline so the CPU unit tests can exercise exactly the arithmetic the kernels run).
+//
+// HBM layout of a prepared query ("arena"): the raw bytes of every touched Parquet column chunk, exactly as they are
+// in the file (dictionary page + data pages, page headers included), each chunk at a 256-byte aligned offset.
+// Nothing is re-encoded on the host; PLAIN values are therefore at arbitrary byte alignment and are read with
+// lk_load_u64 (two aligned 8-byte loads + funnel shift).  Around it, small index pools:
+//   runs[]     one 16-byte entry per run of every RLE/bit-packed hybrid stream (definition levels, dictionary indices)
+//   tiles[]    one entry per tile (<= tile_rows consecutive rows of one row group, never crossing a page of any column)
+//   cursors[]  per (tile, column): where the column starts inside the tile
+//   chunks[]   per (row group, column): dictionary location and the offsets of its code -> class / group-code tables
+#pragma once
+#include <stdint.h>
+
+#ifdef __CUDACC__
+#define LK_HD __host__ __device__ __forceinline__
+#else
+#define LK_HD inline
+#endif
+
+namespace lk {
+
+constexpr int LK_MAX_PCOLS = 16;   // distinct physical columns a query may touch
+constexpr int LK_MAX_FILTER = 8;   // distinct filter columns
+constexpr int LK_MAX_KEYS = 8;     // name + group-by columns
+constexpr int LK_MAX_AGGS = 7;     // aggregates of one fused pass
+constexpr int LK_MAX_NUMLEAF = 4;  // numeric comparison leaves per column
+constexpr int LK_TILE_ROWS_MAX = 2048;
+constexpr uint64_t LK_EMPTY_KEY = 0ull;  // hash entries store cell + 1; an all-zero arena is clean
+
+enum AggOp : uint8_t { AGG_SUM = 0, AGG_COUNT = 1, AGG_MIN = 2, AGG_MAX = 3 };
+
+struct Run {
+  uint32_t start;       // chunk-level index of the run's first element (row for def levels, value index for codes)
+  uint32_t kind_value;  // bit 31 set: RLE run, bits 0..30 = the repeated value; clear: bit-packed run
+  uint64_t off;         // arena byte offset of the packed bytes of a bit-packed run
+};
+
+enum : uint8_t { CUR_ALL_VALID = 1, CUR_ALL_NULL = 2, CUR_DICT = 4 };
+
+struct ColCursor {
+  uint64_t plain_off;  // PLAIN page: arena offset of the tile's first value
+  uint32_t vidx0;      // chunk-level value index of the tile's first non-null value
+  uint32_t vrun_lo;    // first value run intersecting the tile
+  uint32_t drun_lo;    // first definition-level run intersecting the tile
+  uint16_t vrun_n, drun_n;
+  uint32_t nvals;      // non-null values in the tile
+  uint8_t flags;
+  uint8_t width;       // bit width of the dictionary indices
+  uint16_t pad;
+};
+static_assert(sizeof(ColCursor) == 32, "ColCursor must be 32 bytes");
+
+struct TileDesc {
+  uint32_t row0;     // chunk-level row of the tile's first row
+  uint32_t nrows;
+  uint32_t rg;       // row-group slot
+  uint32_t cursor0;  // index of the tile's first cursor (one per physical column)
+};
+
+struct ChunkInfo {
+  uint64_t dict_off;   // numeric dictionary: arena offset of its PLAIN values
+  uint32_t dict_n;
+  uint32_t lut_cls;    // offset into the class-table pool (string filter columns)
+  uint32_t lut_gcode;  // offset into the group-code pool (key columns)
+  uint32_t phys_type;  // parquet physical type
+  uint64_t seq_base;   // global sequence number of the row group's first row (fixed-order sums)
+};
+
+struct FilterCol {
+  uint8_t pcol;
+  uint8_t numeric;   // 0: class = lut_cls[code]; 1: class = bitmask of comparison leaves
+  uint8_t n_leaves;  // numeric only
+  uint8_t null_cls;  // class of SQL NULL
+  uint32_t stride;   // multiplier of this column's class in the pass-table index
+  uint8_t ops[LK_MAX_NUMLEAF];  // 0 gt, 1 ge, 2 lt, 3 le
+  double consts[LK_MAX_NUMLEAF];
+};
+
+struct KeyCol {
+  uint64_t stride;     // multiplier of this column's group code in the group id
+  uint32_t null_code;  // group code of SQL NULL (= dictionary size)
+  uint8_t pcol;
+};
+
+struct AggSlot {
+  uint8_t op;    // AggOp
+  uint8_t pcol;  // value column
+};
+
+enum : uint32_t { ST_HASH_FULL = 1, ST_BAD_CODE = 2 };
+
+struct ScanParams {
+  const uint8_t* arena;
+  const TileDesc* tiles;
+  const ColCursor* cursors;
+  const Run* runs;
+  const ChunkInfo* chunks;
+  const uint8_t* lut_cls;
+  const uint32_t* lut_gcode;
+  const uint32_t* pass_bits;  // bit i set <=> class combination i satisfies the WHERE clause
+  uint32_t ntiles, npcols;
+  int ts_pcol;
+  int n_filter, n_keys, n_aggs;
+  FilterCol filter[LK_MAX_FILTER];
+  KeyCol keys[LK_MAX_KEYS];
+  AggSlot aggs[LK_MAX_AGGS];
+  uint32_t def_mask;       // physical columns that can contain NULLs somewhere (need a def bitmap)
+  int64_t ts_lo, ts_hi;    // [startTs, endTs)
+  int64_t base, step;      // bucket = (ts - base) / step
+  uint32_t nbuckets;
+  uint64_t n_groups;
+  int notnull_pcol;        // chart-field filter `field$type IS NOT NULL` (BaseExpr.scala:407-426), or -1
+  int is_metrics;          // metrics: GROUP BY raw timestamp => (ts - base) % step must be one constant
+  int path;                // 0 dense, 1 hash
+  int warp_agg;            // pre-reduce equal cells inside a warp before the global atomics
+  // dense path: cell = bucket * n_groups + group
+  unsigned long long* rowcnt;
+  unsigned long long* acc[LK_MAX_AGGS];
+  // hash path: open addressing, entries of h_stride bytes {u64 key; u64 acc[n_aggs]}
+  uint8_t* h_entries;
+  uint32_t h_stride;
+  uint64_t h_mask;
+  uint32_t* h_occ;      // slots claimed by this query
+  uint32_t h_occ_cap;
+  uint32_t* counters;   // [0] status flags, [1] phase min, [2] phase max, [3] #claimed slots, [4] tile ticket
+  unsigned long long* survivors;  // [0] rows that passed the WHERE clause
+};
+
+// ---- order-preserving map double -> uint64 (DuckDB total order: -inf < ... < -0.0 < +0.0 < ... < +inf < NaN) ----
+LK_HD uint64_t lk_f64_key(uint64_t bits) {
+  // all NaNs collapse into one canonical key just below the "empty" sentinels
+  if ((bits & 0x7fffffffffffffffull) > 0x7ff0000000000000ull) return 0xfffffffffffffffeull;
+  return (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
+}
+LK_HD uint64_t lk_key_f64(uint64_t key) {
+  if (key == 0xfffffffffffffffeull) return 0x7ff8000000000000ull;
+  return (key >> 63) ? (key & 0x7fffffffffffffffull) : ~key;
+}
+// Accumulator words are designed so that ALL-ZERO is the empty state of every aggregate (tables are cleared with a
+// memset): sum -> +0.0, count -> 0, max -> atomicMax over lk_f64_key (every key is > 0), min -> atomicMax over the
+// COMPLEMENT of the key (so "no value yet" is 0 again).
+LK_HD uint64_t lk_min_encode(uint64_t f64_bits) { return ~lk_f64_key(f64_bits); }
+LK_HD uint64_t lk_max_encode(uint64_t f64_bits) { return lk_f64_key(f64_bits); }
+LK_HD uint64_t lk_min_decode(uint64_t stored) { return lk_key_f64(~stored); }
+LK_HD uint64_t lk_max_decode(uint64_t stored) { return lk_key_f64(stored); }
+
+// ---- loads ----
+LK_HD uint64_t lk_ld64(const uint8_t* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldg(reinterpret_cast<const unsigned long long*>(p));
+#else
+  return *reinterpret_cast<const uint64_t*>(p);
+#endif
+}
+
+// 8 bytes at an arbitrary byte offset (little endian).  The arena is padded so the second word is always readable.
+LK_HD uint64_t lk_load_u64(const uint8_t* arena, uint64_t off) {
+  uint64_t a = off & ~7ull;
+  unsigned sh = (unsigned)(off & 7) * 8;
+  uint64_t lo = lk_ld64(arena + a);
+  if (sh == 0) return lo;
+  uint64_t hi = lk_ld64(arena + a + 8);
+  return (lo >> sh) | (hi << (64 - sh));
+}
+
+// index of the last run whose start <= idx (runs sorted by start, n >= 1)
+LK_HD uint32_t lk_find_run(const Run* runs, uint32_t n, uint32_t idx) {
+  uint32_t lo = 0, hi = n;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (runs[mid].start <= idx) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+// definition bits of rows [row, row + nbits) (nbits <= 32) of a column that has a def-level stream
+LK_HD uint32_t lk_def_word(const uint8_t* arena, const Run* runs, const ColCursor& c, uint32_t row, uint32_t nbits) {
+  const Run* r = runs + c.drun_lo;
+  uint32_t ri = lk_find_run(r, c.drun_n, row);
+  uint32_t w = 0, filled = 0;
+  while (filled < nbits) {
+    Run run = r[ri];
+    uint32_t next = (ri + 1 < c.drun_n) ? r[ri + 1].start : 0xffffffffu;
+    uint32_t avail = next - (row + filled);
+    if (avail > nbits - filled) avail = nbits - filled;
+    uint32_t m = avail >= 32 ? 0xffffffffu : ((1u << avail) - 1);
+    if (run.kind_value >> 31) {
+      if (run.kind_value & 1) w |= m << filled;
+    } else {
+      uint32_t bit = row + filled - run.start;
+      uint64_t x = lk_load_u64(arena, run.off + (bit >> 3)) >> (bit & 7);
+      w |= ((uint32_t)x & m) << filled;
+    }
+    filled += avail;
+    ri++;
+  }
+  return w;
+}
+
+// dictionary index of chunk-level value `vidx`
+LK_HD uint32_t lk_dict_code(const uint8_t* arena, const Run* runs, const ColCursor& c, uint32_t vidx) {
+  const Run* r = runs + c.vrun_lo;
+  Run run = r[lk_find_run(r, c.vrun_n, vidx)];
+  if (run.kind_value >> 31) return run.kind_value & 0x7fffffffu;
+  uint64_t bitpos = (uint64_t)(vidx - run.start) * c.width;
+  uint64_t x = lk_load_u64(arena, run.off + (bitpos >> 3)) >> (bitpos & 7);
+  return (uint32_t)x & (c.width >= 32 ? 0xffffffffu : ((1u << c.width) - 1));
+}
+
+// raw little-endian bits of value `vidx` (PLAIN page or numeric dictionary); 4-byte types in the low half
+LK_HD uint64_t lk_value_bits(const uint8_t* arena, const Run* runs, const ColCursor& c, const ChunkInfo& ci, uint32_t vidx,
+                             uint32_t* bad) {
+  unsigned esz = (ci.phys_type == 1 || ci.phys_type == 4) ? 4 : 8;
+  uint64_t off;
+  if (c.flags & CUR_DICT) {
+    uint32_t code = lk_dict_code(arena, runs, c, vidx);
+    if (code >= ci.dict_n) { *bad = 1; code = 0; }
+    off = ci.dict_off + (uint64_t)code * esz;
+  } else {
+    off = c.plain_off + (uint64_t)(vidx - c.vidx0) * esz;
+  }
+  uint64_t x = lk_load_u64(arena, off);
+  return esz == 4 ? (x & 0xffffffffull) : x;
+}
+
+LK_HD double lk_bits_to_f64(uint64_t bits, uint32_t phys_type) {
+  union { uint64_t u; double d; } a;
+  union { uint32_t u; float f; } b;
+  switch (phys_type) {
+    case 5: a.u = bits; return a.d;
+    case 4: b.u = (uint32_t)bits; return (double)b.f;
+    case 2: return (double)(int64_t)bits;
+    default: return (double)(int32_t)(uint32_t)bits;
+  }
+}
+
+LK_HD int64_t lk_bits_to_i64(uint64_t bits, uint32_t phys_type) {
+  return phys_type == 2 ? (int64_t)bits : (int64_t)(int32_t)(uint32_t)bits;
+}
+
+// class of a numeric filter column: bit l set <=> comparison leaf l is TRUE (DuckDB order: NaN greatest, NaN == NaN)
+LK_HD uint32_t lk_numeric_class(const FilterCol& f, double x) {
+  uint32_t cls = 0;
+  bool xn = x != x;
+  for (int l = 0; l < f.n_leaves; l++) {
+    double c = f.consts[l];
+    bool cn = c != c;
+    int r = (xn || cn) ? ((int)xn - (int)cn) : ((x > c) - (x < c));
+    bool t = f.ops[l] == 0 ? r > 0 : f.ops[l] == 1 ? r >= 0 : f.ops[l] == 2 ? r < 0 : r <= 0;
+    cls |= (uint32_t)t << l;
+  }
+  return cls;
+}
+
+LK_HD uint64_t lk_hash64(uint64_t x) {  // splitmix64 finaliser
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+
+}  // namespace lk

@@ -1,0 +1,603 @@
+// Device layer of liblakeside_b200: HBM residency of a prepared query, kernel launches, result compaction.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+#include "lk_engine.h"
+#include "lk_scan.cuh"
+
+namespace lk {
+
+#define CUDA_CHECK(x)                                                                                        \
+  do {                                                                                                       \
+    cudaError_t err__ = (x);                                                                                 \
+    if (err__ != cudaSuccess) ::lk::fail(LK_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(err__)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------------------
+// device / pools
+// ------------------------------------------------------------------------------------------------------------
+static std::mutex g_mu;
+static bool g_inited = false;
+static int g_num_sms = 148;
+
+int device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+void device_init() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  if (g_inited) { CUDA_CHECK(cudaSetDevice(global_options().device)); return; }
+  LK_CHECK(device_count() > 0, LK_ERR_CUDA, "no CUDA device visible: liblakeside_b200 has no CPU fallback");
+  CUDA_CHECK(cudaSetDevice(global_options().device));
+  cudaDeviceProp prop;
+  CUDA_CHECK(cudaGetDeviceProperties(&prop, global_options().device));
+  g_num_sms = prop.multiProcessorCount;
+  cudaMemPool_t pool;
+  CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, global_options().device));
+  uint64_t thresh = ~0ull;  // keep freed blocks cached: repeated queries re-use them without cudaMalloc
+  CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  g_inited = true;
+}
+
+int num_sms() { return g_num_sms; }
+
+// pinned host memory, cached by power-of-two size class
+struct PinnedPool {
+  std::mutex mu;
+  std::vector<std::pair<size_t, void*>> free_list;
+  std::vector<std::pair<void*, size_t>> live;
+} g_pinned;
+
+void* pinned_alloc(size_t bytes) {
+  size_t cap = 4096;
+  while (cap < bytes) cap <<= 1;
+  {
+    std::lock_guard<std::mutex> lk(g_pinned.mu);
+    for (size_t i = 0; i < g_pinned.free_list.size(); i++)
+      if (g_pinned.free_list[i].first == cap) {
+        void* p = g_pinned.free_list[i].second;
+        g_pinned.free_list.erase(g_pinned.free_list.begin() + i);
+        g_pinned.live.emplace_back(p, cap);
+        return p;
+      }
+  }
+  void* p = nullptr;
+  cudaError_t e = cudaHostAlloc(&p, cap, cudaHostAllocDefault);
+  if (e != cudaSuccess) { cudaGetLastError(); fail(e == cudaErrorMemoryAllocation ? LK_ERR_NOMEM : LK_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
+  std::lock_guard<std::mutex> lk(g_pinned.mu);
+  g_pinned.live.emplace_back(p, cap);
+  return p;
+}
+
+void pinned_free(void* p) {
+  if (!p) return;
+  std::lock_guard<std::mutex> lk(g_pinned.mu);
+  for (size_t i = 0; i < g_pinned.live.size(); i++)
+    if (g_pinned.live[i].first == p) {
+      g_pinned.free_list.emplace_back(g_pinned.live[i].second, p);
+      g_pinned.live.erase(g_pinned.live.begin() + i);
+      return;
+    }
+}
+
+void pinned_release_all() {
+  std::lock_guard<std::mutex> lk(g_pinned.mu);
+  for (auto& f : g_pinned.free_list) cudaFreeHost(f.second);
+  g_pinned.free_list.clear();
+}
+
+// hash arenas stay allocated and CLEAN (all zero) between queries: a query only ever touches the slots it claims and
+// the emit kernel zeroes them again, so no O(capacity) clear sits on the query path.
+struct HashArena {
+  uint8_t* entries = nullptr;
+  uint32_t* occ = nullptr;
+  uint64_t slots = 0;
+  uint32_t stride = 0;
+  bool busy = false;
+};
+static std::vector<HashArena> g_arenas;
+
+static HashArena* arena_acquire(uint64_t slots, uint32_t stride, cudaStream_t st) {
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& a : g_arenas)
+      if (!a.busy && a.slots == slots && a.stride == stride) { a.busy = true; return &a; }
+  }
+  HashArena a;
+  a.slots = slots;
+  a.stride = stride;
+  cudaError_t e = cudaMalloc(&a.entries, slots * stride);
+  if (e == cudaSuccess) e = cudaMalloc(&a.occ, slots * sizeof(uint32_t));
+  if (e != cudaSuccess) { cudaGetLastError(); if (a.entries) cudaFree(a.entries); fail(LK_ERR_NOMEM, strf("hash arena of %llu slots: %s", (unsigned long long)slots, cudaGetErrorString(e))); }
+  CUDA_CHECK(cudaMemsetAsync(a.entries, 0, slots * stride, st));
+  a.busy = true;
+  std::lock_guard<std::mutex> lk(g_mu);
+  g_arenas.reserve(64);
+  LK_CHECK(g_arenas.size() < 64, LK_ERR_NOMEM, "too many live hash arenas");
+  g_arenas.push_back(a);
+  return &g_arenas.back();
+}
+
+static void arena_release(HashArena* a) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  a->busy = false;
+}
+
+void device_shutdown() {
+  std::lock_guard<std::mutex> lk(g_mu);
+  for (auto& a : g_arenas) { cudaFree(a.entries); cudaFree(a.occ); }
+  g_arenas.clear();
+  pinned_release_all();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// per-query device state
+// ------------------------------------------------------------------------------------------------------------
+struct Query::Device {
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[8] = {};
+  uint8_t* arena = nullptr;
+  TileDesc* tiles = nullptr;
+  ColCursor* cursors = nullptr;
+  Run* runs = nullptr;
+  ChunkInfo* chunks = nullptr;
+  uint8_t* lut_cls = nullptr;
+  uint32_t* lut_gcode = nullptr;
+  uint32_t* pass_bits = nullptr;
+  uint32_t* counters = nullptr;           // 8 x u32
+  unsigned long long* survivors = nullptr;
+  unsigned long long* planes = nullptr;   // dense: (1 + n_aggs) planes of n_cells words
+  HashArena* harena = nullptr;
+  bool resident = false, executed = false, group_tables_stale = false;
+  // compaction scratch + device result
+  uint32_t* block_counts = nullptr;
+  size_t block_counts_cap = 0;
+  uint8_t* dres = nullptr;
+  size_t dres_cap = 0;
+  int64_t n_rows = 0;
+  uint32_t phase = 0;
+  uint32_t h_counters[8] = {};
+  bool finalized_device = false;
+};
+
+Query::Query() = default;
+Query::~Query() {
+  if (dev) {
+    Device& d = *dev;
+    if (d.st) cudaStreamSynchronize(d.st);
+    auto fr = [&](void* p) { if (p) cudaFreeAsync(p, d.st); };
+    fr(d.arena); fr(d.tiles); fr(d.cursors); fr(d.runs); fr(d.chunks); fr(d.lut_cls); fr(d.lut_gcode); fr(d.pass_bits);
+    fr(d.counters); fr(d.survivors); fr(d.planes); fr(d.block_counts); fr(d.dres);
+    if (d.harena) {
+      // an arena that was written but never emitted is dirty: clear it before handing it back
+      if (d.executed && !d.finalized_device) cudaMemsetAsync(d.harena->entries, 0, d.harena->slots * d.harena->stride, d.st);
+      if (d.st) cudaStreamSynchronize(d.st);
+      arena_release(d.harena);
+    }
+    for (auto& e : d.ev) if (e) cudaEventDestroy(e);
+    if (d.st) { cudaStreamSynchronize(d.st); cudaStreamDestroy(d.st); }
+  }
+  for (auto& s : segs) if (s.owned_pinned) pinned_free(s.owned_pinned);
+}
+
+template <class T>
+static void upload_vec(T*& dptr, const std::vector<T>& v, cudaStream_t st) {
+  if (dptr) { CUDA_CHECK(cudaFreeAsync(dptr, st)); dptr = nullptr; }
+  size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+  CUDA_CHECK(cudaMallocAsync(&dptr, bytes, st));
+  if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+
+static void upload_group_tables(Query& q) {
+  Query::Device& d = *q.dev;
+  upload_vec(d.lut_gcode, q.lut_gcode, d.st);
+  upload_vec(d.chunks, q.chunk_infos, d.st);
+  // aggregate table for the (possibly new) group space
+  if (d.planes) { CUDA_CHECK(cudaFreeAsync(d.planes, d.st)); d.planes = nullptr; }
+  if (d.harena) { arena_release(d.harena); d.harena = nullptr; }
+  if (q.n_cells > 0) {
+    if (q.path == 0) CUDA_CHECK(cudaMallocAsync(&d.planes, (1 + q.aggs.size()) * q.n_cells * sizeof(unsigned long long), d.st));
+    else d.harena = arena_acquire(q.hash_slots, q.hash_stride, d.st);
+  }
+  d.group_tables_stale = false;
+}
+
+void device_upload(Query& q) {
+  device_init();
+  if (!q.dev) q.dev = std::make_unique<Query::Device>();
+  Query::Device& d = *q.dev;
+  if (!d.st) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking));
+    for (auto& e : d.ev) CUDA_CHECK(cudaEventCreate(&e));
+  }
+  CUDA_CHECK(cudaEventRecord(d.ev[0], d.st));
+  CUDA_CHECK(cudaMallocAsync(&d.arena, q.arena_bytes, d.st));
+  for (auto& u : q.uploads)
+    CUDA_CHECK(cudaMemcpyAsync(d.arena + u.arena_off, q.segs[u.seg].data + u.file_off, u.len, cudaMemcpyHostToDevice, d.st));
+  upload_vec(d.tiles, q.tiles, d.st);
+  upload_vec(d.cursors, q.cursors, d.st);
+  upload_vec(d.runs, q.runs, d.st);
+  upload_vec(d.lut_cls, q.lut_cls, d.st);
+  upload_vec(d.pass_bits, q.pass_bits, d.st);
+  CUDA_CHECK(cudaMallocAsync(&d.counters, 8 * sizeof(uint32_t), d.st));
+  CUDA_CHECK(cudaMallocAsync(&d.survivors, sizeof(unsigned long long), d.st));
+  upload_group_tables(q);
+  CUDA_CHECK(cudaEventRecord(d.ev[1], d.st));
+  // the borrowed host buffers may be released by the caller once prepare returns
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  d.resident = true;
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
+  q.t_ms[0] = ms;
+}
+
+void device_mark_group_tables_stale(Query& q) {
+  if (q.dev) q.dev->group_tables_stale = true;
+}
+
+void device_execute(Query& q) {
+  LK_CHECK(q.dev && q.dev->resident, LK_ERR_INVALID, "lk_query_execute before lk_query_prepare");
+  Query::Device& d = *q.dev;
+  CUDA_CHECK(cudaSetDevice(global_options().device));
+  if (d.group_tables_stale) upload_group_tables(q);
+  if (d.executed && !d.finalized_device && d.harena)  // re-execute without emit: the arena still holds the last run
+    CUDA_CHECK(cudaMemsetAsync(d.harena->entries, 0, d.harena->slots * d.harena->stride, d.st));
+  ScanParams P = q.params;
+  P.arena = d.arena;
+  P.tiles = d.tiles;
+  P.cursors = d.cursors;
+  P.runs = d.runs;
+  P.chunks = d.chunks;
+  P.lut_cls = d.lut_cls;
+  P.lut_gcode = d.lut_gcode;
+  P.pass_bits = d.pass_bits;
+  P.counters = d.counters;
+  P.survivors = d.survivors;
+  CUDA_CHECK(cudaEventRecord(d.ev[2], d.st));
+  static const uint32_t init_counters[8] = {0, 0xffffffffu, 0, 0, 0, 0, 0, 0};
+  CUDA_CHECK(cudaMemcpyAsync(d.counters, init_counters, sizeof init_counters, cudaMemcpyHostToDevice, d.st));
+  CUDA_CHECK(cudaMemsetAsync(d.survivors, 0, sizeof(unsigned long long), d.st));
+  d.finalized_device = false;
+  d.executed = true;
+  if (q.n_cells > 0 && P.ntiles > 0) {
+    if (q.path == 0) {
+      CUDA_CHECK(cudaMemsetAsync(d.planes, 0, (1 + q.aggs.size()) * q.n_cells * sizeof(unsigned long long), d.st));
+      P.rowcnt = d.planes;
+      for (size_t a = 0; a < q.aggs.size(); a++) P.acc[a] = d.planes + (1 + a) * q.n_cells;
+    } else {
+      P.h_entries = d.harena->entries;
+      P.h_occ = d.harena->occ;
+      P.h_occ_cap = (uint32_t)std::min<uint64_t>(d.harena->slots, 0xffffffffu);
+    }
+    int grid = (int)std::min<uint32_t>(P.ntiles, (uint32_t)(num_sms() * 8));
+    scan_kernel<<<grid, SCAN_BLOCK, 0, d.st>>>(P);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  CUDA_CHECK(cudaEventRecord(d.ev[3], d.st));
+}
+
+void device_sync(Query& q) {
+  LK_CHECK(q.dev && q.dev->st, LK_ERR_INVALID, "query has no device state");
+  CUDA_CHECK(cudaStreamSynchronize(q.dev->st));
+}
+
+void* device_stream(Query& q) { return q.dev ? (void*)q.dev->st : nullptr; }
+
+void device_partial_dense(Query& q, int64_t* n_cells, int* n_planes, void** ptrs, int* ops) {
+  LK_CHECK(q.dev && q.dev->executed, LK_ERR_INVALID, "lk_query_partial_dense before lk_query_execute");
+  LK_CHECK(q.path == 0, LK_ERR_INVALID, "query uses the hash path; use lk_query_partial_sparse");
+  *n_cells = (int64_t)q.n_cells;
+  *n_planes = 1 + (int)q.aggs.size();
+  ptrs[0] = q.dev->planes;
+  ops[0] = AGG_COUNT;
+  for (size_t a = 0; a < q.aggs.size(); a++) {
+    ptrs[1 + a] = q.dev->planes ? q.dev->planes + (1 + a) * q.n_cells : nullptr;
+    ops[1 + a] = q.aggs[a].op == AGG_MIN ? AGG_MAX : q.aggs[a].op;  // min is stored complemented: combine with max
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// compaction of the aggregate table into result rows
+// ------------------------------------------------------------------------------------------------------------
+struct EmitParams {
+  int n_aggs, n_keys;
+  uint8_t ops[LK_MAX_AGGS];
+  double divisor[LK_MAX_AGGS];
+  uint64_t key_stride[LK_MAX_KEYS];
+  uint32_t key_null[LK_MAX_KEYS];
+  int64_t base, step;
+  uint32_t phase;
+  uint64_t n_groups;
+  int64_t* ts;
+  double* val[LK_MAX_AGGS];
+  uint8_t* nul[LK_MAX_AGGS];
+  int32_t* code[LK_MAX_KEYS];
+};
+
+__device__ __forceinline__ void emit_row(const EmitParams& E, uint64_t out, uint64_t cell, const unsigned long long* acc, size_t acc_pitch) {
+  const uint64_t bucket = cell / E.n_groups;
+  const uint64_t gid = cell - bucket * E.n_groups;
+  E.ts[out] = E.base + (int64_t)bucket * E.step + (int64_t)E.phase;
+  for (int a = 0; a < E.n_aggs; a++) {
+    const unsigned long long w = acc[a * acc_pitch];
+    double v;
+    uint8_t isnull = 0;
+    switch (E.ops[a]) {
+      case AGG_SUM: v = __longlong_as_double((long long)w); break;
+      case AGG_COUNT: v = (double)w; break;
+      case AGG_MIN: if (w == 0) { v = 0.0; isnull = 1; } else v = __longlong_as_double((long long)lk_min_decode(w)); break;
+      default: if (w == 0) { v = 0.0; isnull = 1; } else v = __longlong_as_double((long long)lk_max_decode(w)); break;
+    }
+    if (E.divisor[a] != 1.0 && !isnull) v = v / E.divisor[a];
+    E.val[a][out] = v;
+    E.nul[a][out] = isnull;
+  }
+  for (int k = 0; k < E.n_keys; k++) {
+    uint32_t g = (uint32_t)((gid / E.key_stride[k]) % ((uint64_t)E.key_null[k] + 1));
+    E.code[k][out] = g == E.key_null[k] ? -1 : (int32_t)g;
+  }
+}
+
+constexpr int CMP_BLOCK = 256;
+constexpr int CMP_PER_THREAD = 8;
+constexpr int CMP_CHUNK = CMP_BLOCK * CMP_PER_THREAD;
+
+__global__ void __launch_bounds__(CMP_BLOCK) dense_count_kernel(const unsigned long long* __restrict__ rowcnt, uint64_t n_cells, uint32_t* __restrict__ block_counts) {
+  __shared__ uint32_t warp_sums[CMP_BLOCK / 32];
+  const uint64_t first = (uint64_t)blockIdx.x * CMP_CHUNK + (uint64_t)threadIdx.x * CMP_PER_THREAD;
+  uint32_t c = 0;
+#pragma unroll
+  for (int k = 0; k < CMP_PER_THREAD; k++)
+    if (first + k < n_cells) c += rowcnt[first + k] != 0;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < CMP_BLOCK / 32; w++) t += warp_sums[w];
+    block_counts[blockIdx.x] = t;
+  }
+}
+
+// single-block exclusive scan of n u32 counters (in place); the grand total goes to *total
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(uint32_t* __restrict__ v, uint32_t n, uint32_t* __restrict__ total) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t carry;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t x = i < n ? v[i] : 0;
+    uint32_t incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const uint32_t t = warp_tot[lane];
+      uint32_t ti = t;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= d) ti += o; }
+      warp_tot[lane] = ti - t;
+    }
+    __syncthreads();
+    const uint32_t excl = carry + warp_tot[wid] + incl - x;
+    if (i < n) v[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + x;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry;
+}
+
+__global__ void __launch_bounds__(CMP_BLOCK) dense_emit_kernel(const unsigned long long* __restrict__ planes, uint64_t n_cells,
+                                                               const uint32_t* __restrict__ block_offsets, const __grid_constant__ EmitParams E) {
+  __shared__ uint32_t warp_sums[CMP_BLOCK / 32];
+  const uint64_t first = (uint64_t)blockIdx.x * CMP_CHUNK + (uint64_t)threadIdx.x * CMP_PER_THREAD;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t present = 0, c = 0;
+#pragma unroll
+  for (int k = 0; k < CMP_PER_THREAD; k++)
+    if (first + k < n_cells && planes[first + k] != 0) { present |= 1u << k; c++; }
+  uint32_t incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  uint32_t woff = 0;
+  for (int w = 0; w < wid; w++) woff += warp_sums[w];
+  uint64_t out = (uint64_t)block_offsets[blockIdx.x] + woff + incl - c;
+  for (int k = 0; k < CMP_PER_THREAD; k++)
+    if (present & (1u << k)) {
+      const uint64_t cell = first + k;
+      emit_row(E, out++, cell, planes + n_cells + cell, n_cells);
+    }
+}
+
+__global__ void hash_hist_kernel(const uint32_t* __restrict__ occ, uint32_t n, const uint8_t* __restrict__ entries, uint32_t stride,
+                                 uint64_t n_groups, uint32_t* __restrict__ hist) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long key = *reinterpret_cast<const unsigned long long*>(entries + (uint64_t)occ[i] * stride);
+    atomicAdd(hist + (key - 1) / n_groups, 1u);
+  }
+}
+
+// rows of one bucket are contiguous in the output (ORDER BY timestamp); their order inside the bucket is arbitrary,
+// like the reference's (BaseExpr.scala:394, 403 order by the time column only).  Each emitted entry is zeroed again.
+__global__ void hash_emit_kernel(const uint32_t* __restrict__ occ, uint32_t n, uint8_t* __restrict__ entries, uint32_t stride,
+                                 uint32_t* __restrict__ cursor, const __grid_constant__ EmitParams E) {
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    unsigned long long* e = reinterpret_cast<unsigned long long*>(entries + (uint64_t)occ[i] * stride);
+    const uint64_t cell = e[0] - 1;
+    const uint32_t pos = atomicAdd(cursor + cell / E.n_groups, 1u);
+    emit_row(E, pos, cell, e + 1, 1);
+    for (uint32_t w = 0; w < stride / 8; w++) e[w] = 0;
+  }
+}
+
+// device result layout for n rows: ts[n] | val[a][n] | code[k][n] | nul[a][n]
+static size_t result_bytes(const Query& q, int64_t n) {
+  return (size_t)n * (8 + 8 * q.aggs.size() + 4 * q.key_pcols.size() + q.aggs.size()) + 64;
+}
+
+static void fill_emit_params(const Query& q, EmitParams& E, uint8_t* basep, int64_t n) {
+  memset(&E, 0, sizeof E);
+  E.n_aggs = (int)q.aggs.size();
+  E.n_keys = (int)q.key_pcols.size();
+  for (int a = 0; a < E.n_aggs; a++) { E.ops[a] = q.aggs[a].op; E.divisor[a] = q.aggs[a].divisor; }
+  for (int k = 0; k < E.n_keys; k++) { E.key_stride[k] = q.params.keys[k].stride; E.key_null[k] = q.params.keys[k].null_code; }
+  E.base = q.base;
+  E.step = q.step;
+  E.phase = q.dev->phase;
+  E.n_groups = q.n_groups;
+  uint8_t* p = basep;
+  E.ts = (int64_t*)p; p += 8 * n;
+  for (int a = 0; a < E.n_aggs; a++) { E.val[a] = (double*)p; p += 8 * n; }
+  for (int k = 0; k < E.n_keys; k++) { E.code[k] = (int32_t*)p; p += 4 * n; }
+  for (int a = 0; a < E.n_aggs; a++) { E.nul[a] = p; p += n; }
+}
+
+static void ensure_dres(Query::Device& d, size_t bytes) {
+  if (d.dres_cap >= bytes) return;
+  if (d.dres) CUDA_CHECK(cudaFreeAsync(d.dres, d.st));
+  d.dres = nullptr;
+  CUDA_CHECK(cudaMallocAsync(&d.dres, bytes, d.st));
+  d.dres_cap = bytes;
+}
+
+static void ensure_block_counts(Query::Device& d, size_t n) {
+  if (d.block_counts_cap >= n) return;
+  if (d.block_counts) CUDA_CHECK(cudaFreeAsync(d.block_counts, d.st));
+  d.block_counts = nullptr;
+  CUDA_CHECK(cudaMallocAsync(&d.block_counts, n * sizeof(uint32_t), d.st));
+  d.block_counts_cap = n;
+}
+
+void device_finalize_device(Query& q) {
+  LK_CHECK(q.dev && q.dev->executed, LK_ERR_INVALID, "lk_query_finalize before lk_query_execute");
+  Query::Device& d = *q.dev;
+  CUDA_CHECK(cudaSetDevice(global_options().device));
+  if (d.finalized_device) return;
+  CUDA_CHECK(cudaEventRecord(d.ev[4], d.st));
+  CUDA_CHECK(cudaMemcpyAsync(d.h_counters, d.counters, sizeof d.h_counters, cudaMemcpyDeviceToHost, d.st));
+  d.n_rows = 0;
+  if (q.n_cells == 0 || q.tiles.empty()) {
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    d.finalized_device = true;
+    CUDA_CHECK(cudaEventRecord(d.ev[5], d.st));
+    return;
+  }
+  uint32_t nblocks = 0;
+  if (q.path == 0) {
+    nblocks = (uint32_t)((q.n_cells + CMP_CHUNK - 1) / CMP_CHUNK);
+    ensure_block_counts(d, (size_t)nblocks + 1);
+    dense_count_kernel<<<nblocks, CMP_BLOCK, 0, d.st>>>(d.planes, q.n_cells, d.block_counts);
+    exclusive_scan_kernel<<<1, 1024, 0, d.st>>>(d.block_counts, nblocks, d.block_counts + nblocks);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(&d.h_counters[7], d.block_counts + nblocks, 4, cudaMemcpyDeviceToHost, d.st));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  const uint32_t status = d.h_counters[0];
+  if (status & ST_HASH_FULL) {
+    CUDA_CHECK(cudaMemsetAsync(d.harena->entries, 0, d.harena->slots * d.harena->stride, d.st));
+    d.finalized_device = true;
+    fail(LK_ERR_NOMEM, strf("aggregate hash table of %llu slots overflowed; raise max_hash_slots in lk_init", (unsigned long long)q.hash_slots));
+  }
+  LK_CHECK(!(status & ST_BAD_CODE), LK_ERR_IO, "corrupt segment: dictionary index out of range");
+  if (q.is_metrics && d.h_counters[1] != 0xffffffffu) {
+    // GROUP BY "_cardinalhq.timestamp": metric segments are pre-rolled to the step grid (QueryEngineV2.scala:746-752);
+    // every timestamp must sit at one offset from startTs modulo step, otherwise buckets would merge distinct rows.
+    if (d.h_counters[1] != d.h_counters[2]) {
+      if (d.harena) CUDA_CHECK(cudaMemsetAsync(d.harena->entries, 0, d.harena->slots * d.harena->stride, d.st));
+      d.finalized_device = true;
+      fail(LK_ERR_UNSUPPORTED, "metric timestamps are not on one step-aligned grid; cannot bucket GROUP BY timestamp densely");
+    }
+    d.phase = d.h_counters[1];
+  } else d.phase = 0;
+  const int64_t n = q.path == 0 ? (int64_t)d.h_counters[7] : (int64_t)d.h_counters[3];
+  d.n_rows = n;
+  if (n > 0) {
+    ensure_dres(d, result_bytes(q, n));
+    EmitParams E;
+    fill_emit_params(q, E, d.dres, n);
+    if (q.path == 0) {
+      dense_emit_kernel<<<nblocks, CMP_BLOCK, 0, d.st>>>(d.planes, q.n_cells, d.block_counts, E);
+    } else {
+      ensure_block_counts(d, (size_t)q.nbuckets + 1);
+      CUDA_CHECK(cudaMemsetAsync(d.block_counts, 0, ((size_t)q.nbuckets + 1) * 4, d.st));
+      int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16);
+      hash_hist_kernel<<<grid, 256, 0, d.st>>>(d.harena->occ, (uint32_t)n, d.harena->entries, d.harena->stride, q.n_groups, d.block_counts);
+      exclusive_scan_kernel<<<1, 1024, 0, d.st>>>(d.block_counts, q.nbuckets, d.block_counts + q.nbuckets);
+      hash_emit_kernel<<<grid, 256, 0, d.st>>>(d.harena->occ, (uint32_t)n, d.harena->entries, d.harena->stride, d.block_counts, E);
+    }
+    CUDA_CHECK(cudaGetLastError());
+  }
+  d.finalized_device = true;
+  CUDA_CHECK(cudaEventRecord(d.ev[5], d.st));
+}
+
+HostResult* device_fetch(Query& q) {
+  Query::Device& d = *q.dev;
+  LK_CHECK(d.finalized_device, LK_ERR_INVALID, "fetch before finalize");
+  auto r = std::make_unique<HostResult>();
+  const int64_t n = d.n_rows;
+  r->n = n;
+  r->n_values = (int)q.aggs.size();
+  r->n_tags = (int)q.key_pcols.size();
+  r->col_names.push_back(q.ts_col_name);
+  for (size_t a = 0; a < q.aggs.size(); a++)
+    r->col_names.push_back(q.is_metrics ? (q.aggs.size() == 1 ? std::string("value") : "value_" + std::to_string(a))
+                                         : q.aggs[a].aggregation + "(\"" + q.aggs[a].value_column + "\")");
+  for (auto& k : q.key_names) r->col_names.push_back(k);
+  r->dicts = q.key_dicts;
+  r->dict_ptrs.resize(r->dicts.size());
+  for (size_t k = 0; k < r->dicts.size(); k++)
+    for (auto& s : r->dicts[k]) r->dict_ptrs[k].push_back(s.c_str());
+  CUDA_CHECK(cudaEventRecord(d.ev[6], d.st));
+  if (n > 0) {
+    size_t bytes = result_bytes(q, n);
+    r->pinned = (uint8_t*)pinned_alloc(bytes);
+    CUDA_CHECK(cudaMemcpyAsync(r->pinned, d.dres, bytes, cudaMemcpyDeviceToHost, d.st));
+    uint8_t* p = r->pinned;
+    r->ts = (int64_t*)p; p += 8 * n;
+    for (size_t a = 0; a < q.aggs.size(); a++) { r->values.push_back((double*)p); p += 8 * n; }
+    for (size_t k = 0; k < q.key_pcols.size(); k++) { r->codes.push_back((int32_t*)p); p += 4 * n; }
+    for (size_t a = 0; a < q.aggs.size(); a++) { r->nulls.push_back(p); p += n; }
+  } else {
+    for (size_t a = 0; a < q.aggs.size(); a++) { r->values.push_back(nullptr); r->nulls.push_back(nullptr); }
+    for (size_t k = 0; k < q.key_pcols.size(); k++) r->codes.push_back(nullptr);
+  }
+  CUDA_CHECK(cudaEventRecord(d.ev[7], d.st));
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  float ms = 0;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, d.ev[2], d.ev[3])); q.t_ms[1] = ms;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, d.ev[4], d.ev[5])); q.t_ms[2] = ms;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, d.ev[6], d.ev[7])); q.t_ms[3] = ms;
+  return r.release();
+}
+
+void device_timings(Query& q) {
+  Query::Device& d = *q.dev;
+  float ms = 0;
+  if (d.executed && cudaEventElapsedTime(&ms, d.ev[2], d.ev[3]) == cudaSuccess) q.t_ms[1] = ms;
+  if (d.finalized_device && cudaEventElapsedTime(&ms, d.ev[4], d.ev[5]) == cudaSuccess) q.t_ms[2] = ms;
+  cudaGetLastError();
+}
+
+int64_t device_survivors(Query& q) {
+  unsigned long long v = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&v, q.dev->survivors, 8, cudaMemcpyDeviceToHost, q.dev->st));
+  CUDA_CHECK(cudaStreamSynchronize(q.dev->st));
+  return (int64_t)v;
+}
+
+HostResult::~HostResult() { pinned_free(pinned); }
+
+}  // namespace lk

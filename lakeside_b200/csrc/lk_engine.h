@@ -1,0 +1,25 @@
+// Interface between the C-ABI layer (lk_api.cpp, plain C++) and the CUDA translation units.
+#pragma once
+#include "lk_query.h"
+
+namespace lk {
+
+int device_count();
+void device_init();
+void device_shutdown();
+int num_sms();
+void* pinned_alloc(size_t bytes);
+void pinned_free(void* p);
+
+void device_upload(Query& q);              // H2D of the touched column chunks and index pools
+void device_mark_group_tables_stale(Query& q);
+void device_execute(Query& q);             // clear table + fused scan kernel (async)
+void device_sync(Query& q);
+void* device_stream(Query& q);
+void device_partial_dense(Query& q, int64_t* n_cells, int* n_planes, void** ptrs, int* ops);
+void device_finalize_device(Query& q);     // compaction into result rows in HBM
+HostResult* device_fetch(Query& q);        // D2H
+void device_timings(Query& q);
+int64_t device_survivors(Query& q);
+
+}  // namespace lk

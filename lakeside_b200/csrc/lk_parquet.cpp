@@ -1,0 +1,503 @@
+#include "lk_parquet.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace lk {
+
+// ------------------------------------------------------------------------------------------------------------
+// Thrift compact protocol reader (just enough for parquet.thrift's FileMetaData and PageHeader)
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+enum TType { T_STOP = 0, T_TRUE = 1, T_FALSE = 2, T_BYTE = 3, T_I16 = 4, T_I32 = 5, T_I64 = 6, T_DOUBLE = 7, T_BINARY = 8, T_LIST = 9, T_SET = 10, T_MAP = 11, T_STRUCT = 12 };
+
+struct TReader {
+  const uint8_t* p;
+  const uint8_t* end;
+  TReader(const uint8_t* b, const uint8_t* e) : p(b), end(e) {}
+  uint8_t byte() {
+    LK_CHECK(p < end, LK_ERR_IO, "parquet: truncated thrift data");
+    return *p++;
+  }
+  uint64_t varint() {
+    uint64_t r = 0;
+    int sh = 0;
+    while (true) {
+      uint8_t c = byte();
+      r |= (uint64_t)(c & 0x7f) << sh;
+      if (!(c & 0x80)) return r;
+      sh += 7;
+      LK_CHECK(sh < 70, LK_ERR_IO, "parquet: bad varint");
+    }
+  }
+  int64_t zigzag() {
+    uint64_t v = varint();
+    return (int64_t)(v >> 1) ^ -(int64_t)(v & 1);
+  }
+  std::string binary() {
+    uint64_t n = varint();
+    LK_CHECK(n <= (uint64_t)(end - p), LK_ERR_IO, "parquet: truncated thrift binary");
+    std::string s((const char*)p, n);
+    p += n;
+    return s;
+  }
+  void skip_binary() {
+    uint64_t n = varint();
+    LK_CHECK(n <= (uint64_t)(end - p), LK_ERR_IO, "parquet: truncated thrift binary");
+    p += n;
+  }
+  // returns false at STOP; otherwise sets fid/type
+  bool field(int& fid, int& type, int& last) {
+    uint8_t h = byte();
+    if (h == 0) return false;
+    type = h & 0x0f;
+    int delta = h >> 4;
+    fid = delta ? last + delta : (int)zigzag();
+    last = fid;
+    return true;
+  }
+  void list_header(int& n, int& et) {
+    uint8_t h = byte();
+    n = h >> 4;
+    et = h & 0x0f;
+    if (n == 15) n = (int)varint();
+  }
+  void skip(int type, int depth = 0) {
+    LK_CHECK(depth < 32, LK_ERR_IO, "parquet: thrift nesting too deep");
+    switch (type) {
+      case T_TRUE: case T_FALSE: break;
+      case T_BYTE: byte(); break;
+      case T_I16: case T_I32: case T_I64: varint(); break;
+      case T_DOUBLE: LK_CHECK(end - p >= 8, LK_ERR_IO, "parquet: truncated"); p += 8; break;
+      case T_BINARY: skip_binary(); break;
+      case T_LIST: case T_SET: {
+        int n, et;
+        list_header(n, et);
+        for (int i = 0; i < n; i++) {
+          if (et == T_TRUE || et == T_FALSE) byte();  // list<bool>: one byte per element
+          else skip(et, depth + 1);
+        }
+        break;
+      }
+      case T_MAP: {
+        uint64_t n = varint();
+        if (n) {
+          uint8_t kv = byte();
+          for (uint64_t i = 0; i < n; i++) { skip(kv >> 4, depth + 1); skip(kv & 0x0f, depth + 1); }
+        }
+        break;
+      }
+      case T_STRUCT: {
+        int fid, t, last = 0;
+        while (field(fid, t, last)) skip(t, depth + 1);
+        break;
+      }
+      default: fail(LK_ERR_IO, "parquet: unknown thrift type");
+    }
+  }
+};
+
+struct SchemaElem {
+  int type = -1, repetition = 0, num_children = 0;
+  std::string name;
+};
+
+SchemaElem read_schema_elem(TReader& r) {
+  SchemaElem s;
+  int fid, t, last = 0;
+  while (r.field(fid, t, last)) {
+    switch (fid) {
+      case 1: s.type = (int)r.zigzag(); break;
+      case 3: s.repetition = (int)r.zigzag(); break;
+      case 4: s.name = r.binary(); break;
+      case 5: s.num_children = (int)r.zigzag(); break;
+      default: r.skip(t);
+    }
+  }
+  return s;
+}
+
+ColumnChunkMeta read_column_meta(TReader& r) {
+  ColumnChunkMeta m;
+  int fid, t, last = 0;
+  while (r.field(fid, t, last)) {
+    switch (fid) {
+      case 1: m.phys_type = (int)r.zigzag(); break;
+      case 4: m.codec = (int)r.zigzag(); break;
+      case 5: m.num_values = r.zigzag(); break;
+      case 7: m.total_compressed_size = r.zigzag(); break;
+      case 9: m.data_page_offset = r.zigzag(); break;
+      case 11: m.dictionary_page_offset = r.zigzag(); break;
+      default: r.skip(t);
+    }
+  }
+  return m;
+}
+
+ColumnChunkMeta read_column_chunk(TReader& r) {
+  ColumnChunkMeta m;
+  bool have = false;
+  int fid, t, last = 0;
+  while (r.field(fid, t, last)) {
+    if (fid == 3 && t == T_STRUCT) { m = read_column_meta(r); have = true; }
+    else r.skip(t);
+  }
+  LK_CHECK(have, LK_ERR_UNSUPPORTED, "parquet: column chunk without inline meta_data");
+  return m;
+}
+
+RowGroupMeta read_row_group(TReader& r) {
+  RowGroupMeta g;
+  int fid, t, last = 0;
+  while (r.field(fid, t, last)) {
+    if (fid == 1 && t == T_LIST) {
+      int n, et;
+      r.list_header(n, et);
+      for (int i = 0; i < n; i++) g.columns.push_back(read_column_chunk(r));
+    } else if (fid == 3) g.num_rows = r.zigzag();
+    else r.skip(t);
+  }
+  return g;
+}
+
+}  // namespace
+
+int FileMeta::leaf_index(const std::string& name) const {
+  for (size_t i = 0; i < leaves.size(); i++)
+    if (leaves[i].flat && leaves[i].name == name) return (int)i;
+  return -1;
+}
+
+FileMeta parse_footer(const uint8_t* data, size_t len) {
+  LK_CHECK(len >= 12 && memcmp(data, "PAR1", 4) == 0 && memcmp(data + len - 4, "PAR1", 4) == 0, LK_ERR_IO,
+           "not a Parquet file (bad magic)");
+  uint32_t flen;
+  memcpy(&flen, data + len - 8, 4);
+  LK_CHECK((size_t)flen + 12 <= len, LK_ERR_IO, "parquet: bad footer length");
+  TReader r(data + len - 8 - flen, data + len - 8);
+  FileMeta fm;
+  std::vector<SchemaElem> schema;
+  int fid, t, last = 0;
+  while (r.field(fid, t, last)) {
+    if (fid == 2 && t == T_LIST) {
+      int n, et;
+      r.list_header(n, et);
+      for (int i = 0; i < n; i++) schema.push_back(read_schema_elem(r));
+    } else if (fid == 3) fm.num_rows = r.zigzag();
+    else if (fid == 4 && t == T_LIST) {
+      int n, et;
+      r.list_header(n, et);
+      for (int i = 0; i < n; i++) fm.row_groups.push_back(read_row_group(r));
+    } else r.skip(t);
+  }
+  LK_CHECK(!schema.empty(), LK_ERR_IO, "parquet: empty schema");
+  // depth-first walk: leaves in schema order; only direct children of the root are addressable by name
+  size_t pos = 1;
+  struct Frame { int remaining; int depth; };
+  std::vector<Frame> st;
+  st.push_back({schema[0].num_children, 0});
+  while (pos < schema.size() && !st.empty()) {
+    while (!st.empty() && st.back().remaining == 0) st.pop_back();
+    if (st.empty()) break;
+    st.back().remaining--;
+    int depth = (int)st.size();
+    const SchemaElem& e = schema[pos++];
+    if (e.num_children > 0) { st.push_back({e.num_children, depth}); continue; }
+    LeafColumn lc;
+    lc.name = e.name;
+    lc.phys_type = e.type;
+    lc.flat = depth == 1 && e.repetition != 2;
+    lc.max_def = e.repetition == 1 ? 1 : 0;
+    fm.leaves.push_back(lc);
+  }
+  for (auto& g : fm.row_groups)
+    LK_CHECK(g.columns.size() == fm.leaves.size(), LK_ERR_IO, "parquet: row group column count != schema leaves");
+  return fm;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// pages and runs
+// ------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct PageHeader {
+  int type = -1;
+  int32_t uncompressed = 0, compressed = 0;
+  int32_t num_values = 0;
+  int encoding = -1;
+  int def_encoding = ENC_RLE;
+  // v2
+  int32_t num_nulls = 0, num_rows = 0, def_len = 0, rep_len = 0;
+  size_t header_len = 0;
+};
+
+PageHeader read_page_header(const uint8_t* p, const uint8_t* end) {
+  TReader r(p, end);
+  PageHeader h;
+  int fid, t, last = 0;
+  while (r.field(fid, t, last)) {
+    switch (fid) {
+      case 1: h.type = (int)r.zigzag(); break;
+      case 2: h.uncompressed = (int32_t)r.zigzag(); break;
+      case 3: h.compressed = (int32_t)r.zigzag(); break;
+      case 5: case 7: {  // DataPageHeader / DictionaryPageHeader
+        int f2, t2, l2 = 0;
+        while (r.field(f2, t2, l2)) {
+          if (f2 == 1) h.num_values = (int32_t)r.zigzag();
+          else if (f2 == 2) h.encoding = (int)r.zigzag();
+          else if (f2 == 3 && fid == 5) h.def_encoding = (int)r.zigzag();
+          else r.skip(t2);
+        }
+        break;
+      }
+      case 8: {  // DataPageHeaderV2
+        int f2, t2, l2 = 0;
+        while (r.field(f2, t2, l2)) {
+          switch (f2) {
+            case 1: h.num_values = (int32_t)r.zigzag(); break;
+            case 2: h.num_nulls = (int32_t)r.zigzag(); break;
+            case 3: h.num_rows = (int32_t)r.zigzag(); break;
+            case 4: h.encoding = (int)r.zigzag(); break;
+            case 5: h.def_len = (int32_t)r.zigzag(); break;
+            case 6: h.rep_len = (int32_t)r.zigzag(); break;
+            default: r.skip(t2);
+          }
+        }
+        break;
+      }
+      default: r.skip(t);
+    }
+  }
+  h.header_len = (size_t)(r.p - p);
+  return h;
+}
+
+inline uint32_t popcount_bits(const uint8_t* p, uint32_t nbits) {
+  uint32_t c = 0;
+  uint32_t nbytes = nbits >> 3;
+  uint32_t i = 0;
+  for (; i + 8 <= nbytes; i += 8) {
+    uint64_t w;
+    memcpy(&w, p + i, 8);
+    c += (uint32_t)__builtin_popcountll(w);
+  }
+  for (; i < nbytes; i++) c += (uint32_t)__builtin_popcount(p[i]);
+  if (nbits & 7) c += (uint32_t)__builtin_popcount(p[nbytes] & ((1u << (nbits & 7)) - 1));
+  return c;
+}
+
+// Walks the runs of an RLE/bit-packed hybrid stream holding `count` elements.  cb(start, n, is_rle, value, byte_off)
+template <class CB>
+void walk_hybrid(const uint8_t* file, uint64_t off, uint64_t end, int bit_width, uint32_t count, CB cb) {
+  uint32_t done = 0;
+  const int vbytes = (bit_width + 7) / 8;
+  while (done < count) {
+    LK_CHECK(off < end, LK_ERR_IO, "parquet: hybrid stream ends before all values are covered");
+    TReader r(file + off, file + end);
+    uint64_t h = r.varint();
+    off = (uint64_t)(r.p - file);
+    if (h & 1) {
+      uint64_t groups = h >> 1;
+      uint64_t n = groups * 8;
+      uint64_t bytes = groups * (uint64_t)bit_width;
+      LK_CHECK(groups > 0, LK_ERR_IO, "parquet: empty bit-packed run");
+      // a writer may truncate the padding of the final group; require the bytes that carry real values
+      uint32_t take = (uint32_t)std::min<uint64_t>(n, count - done);
+      uint64_t need = ((uint64_t)take * bit_width + 7) / 8;
+      LK_CHECK(off + need <= end, LK_ERR_IO, "parquet: truncated bit-packed run");
+      cb(done, take, false, 0u, off);
+      off += std::min<uint64_t>(bytes, end - off);
+      done += take;
+    } else {
+      uint64_t n = h >> 1;
+      LK_CHECK(n > 0, LK_ERR_IO, "parquet: empty RLE run");
+      LK_CHECK(off + vbytes <= end, LK_ERR_IO, "parquet: truncated RLE run");
+      uint32_t v = 0;
+      for (int i = 0; i < vbytes; i++) v |= (uint32_t)file[off + i] << (8 * i);
+      off += vbytes;
+      uint32_t take = (uint32_t)std::min<uint64_t>(n, count - done);
+      cb(done, take, true, v, (uint64_t)0);
+      done += take;
+    }
+  }
+}
+
+}  // namespace
+
+int ChunkIndex::page_at(uint32_t r) const {
+  int lo = 0, hi = (int)pages.size();
+  while (hi - lo > 1) {
+    int mid = (lo + hi) / 2;
+    if (pages[mid].first_row <= r) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+int ChunkIndex::def_run_at(uint32_t r) const {
+  int lo = 0, hi = (int)def_runs.size();
+  while (hi - lo > 1) {
+    int mid = (lo + hi) / 2;
+    if (def_runs[mid].start <= r) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+int ChunkIndex::val_run_at(uint32_t v) const {
+  int lo = 0, hi = (int)val_runs.size();
+  while (hi - lo > 1) {
+    int mid = (lo + hi) / 2;
+    if (val_runs[mid].start <= v) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+uint32_t ChunkIndex::vidx_at(const uint8_t* file, uint32_t r) const {
+  if (max_def == 0) return r;
+  if (def_runs.empty()) return 0;
+  int i = def_run_at(r);
+  const Run& run = def_runs[i];
+  uint32_t nn = def_nn_before[i];
+  uint32_t k = r - run.start;
+  if (run.kind_value >> 31) return nn + ((run.kind_value & 1) ? k : 0);
+  return nn + popcount_bits(file + run.off, k);
+}
+
+ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, const ColumnChunkMeta& cm, int64_t rg_rows,
+                       bool want_strings) {
+  ChunkIndex ci;
+  ci.present = true;
+  ci.phys_type = cm.phys_type;
+  ci.max_def = leaf.max_def;
+  ci.total_compressed_size = cm.total_compressed_size;
+  LK_CHECK(cm.codec == 0, LK_ERR_UNSUPPORTED,
+           "column '" + leaf.name + "': compressed pages (codec " + std::to_string(cm.codec) + ") are not supported yet; write segments with compression=NONE");
+  LK_CHECK(rg_rows >= 0 && rg_rows < (int64_t)0xfffffff0u, LK_ERR_UNSUPPORTED, "row group too large");
+  ci.num_rows = (uint32_t)rg_rows;
+  LK_CHECK(cm.num_values == rg_rows, LK_ERR_UNSUPPORTED, "column '" + leaf.name + "': repeated values are not supported");
+  int64_t start = cm.data_page_offset;
+  if (cm.dictionary_page_offset > 0 && cm.dictionary_page_offset < start) start = cm.dictionary_page_offset;
+  LK_CHECK(start >= 4 && cm.total_compressed_size >= 0 && (uint64_t)start + (uint64_t)cm.total_compressed_size <= len, LK_ERR_IO,
+           "parquet: column chunk out of file bounds");
+  ci.file_start = (uint64_t)start;
+  ci.file_len = (uint64_t)cm.total_compressed_size;
+  const uint64_t cend = ci.file_start + ci.file_len;
+  uint64_t p = ci.file_start;
+  uint32_t row = 0, vidx = 0;
+  while (p < cend && row < ci.num_rows) {
+    PageHeader h = read_page_header(data + p, data + cend);
+    uint64_t payload = p + h.header_len;
+    LK_CHECK(h.compressed >= 0 && payload + (uint64_t)h.compressed <= cend, LK_ERR_IO, "parquet: page out of chunk bounds");
+    LK_CHECK(h.compressed == h.uncompressed, LK_ERR_UNSUPPORTED, "parquet: compressed page in an UNCOMPRESSED chunk");
+    uint64_t pend = payload + (uint64_t)h.compressed;
+    if (h.type == 2) {  // dictionary page
+      LK_CHECK(h.encoding == ENC_PLAIN || h.encoding == ENC_PLAIN_DICTIONARY, LK_ERR_UNSUPPORTED, "parquet: dictionary page encoding");
+      LK_CHECK(!ci.has_dict, LK_ERR_IO, "parquet: two dictionary pages in one chunk");
+      ci.has_dict = true;
+      ci.dict_off = payload;
+      ci.dict_len = (uint32_t)h.compressed;
+      ci.dict_n = (uint32_t)h.num_values;
+      if (cm.phys_type == PT_BYTE_ARRAY) {
+        if (want_strings) {
+          ci.dict_strings.reserve(ci.dict_n);
+          uint64_t q = payload;
+          for (uint32_t i = 0; i < ci.dict_n; i++) {
+            LK_CHECK(q + 4 <= pend, LK_ERR_IO, "parquet: truncated dictionary page");
+            uint32_t n;
+            memcpy(&n, data + q, 4);
+            q += 4;
+            LK_CHECK(q + n <= pend, LK_ERR_IO, "parquet: truncated dictionary page");
+            ci.dict_strings.emplace_back((const char*)data + q, n);
+            q += n;
+          }
+        }
+      } else {
+        unsigned esz = (cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT) ? 4 : 8;
+        LK_CHECK(cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT || cm.phys_type == PT_INT64 || cm.phys_type == PT_DOUBLE,
+                 LK_ERR_UNSUPPORTED, "column '" + leaf.name + "': unsupported physical type");
+        LK_CHECK((uint64_t)ci.dict_n * esz <= ci.dict_len, LK_ERR_IO, "parquet: truncated numeric dictionary");
+      }
+    } else if (h.type == 0 || h.type == 3) {  // data page v1 / v2
+      LK_CHECK(h.num_values >= 0 && (uint64_t)row + (uint64_t)h.num_values <= ci.num_rows, LK_ERR_IO, "parquet: page rows exceed row group");
+      PageInfo pg;
+      pg.first_row = row;
+      pg.num_rows = (uint32_t)h.num_values;
+      pg.first_vidx = vidx;
+      uint64_t q = payload;
+      uint32_t nn = pg.num_rows;
+      if (h.type == 3) LK_CHECK(h.rep_len == 0, LK_ERR_UNSUPPORTED, "parquet: repetition levels");
+      if (leaf.max_def > 0) {
+        uint64_t dl_off, dl_end;
+        if (h.type == 0) {
+          LK_CHECK(h.def_encoding == ENC_RLE, LK_ERR_UNSUPPORTED, "parquet: BIT_PACKED definition levels");
+          LK_CHECK(q + 4 <= pend, LK_ERR_IO, "parquet: truncated definition levels");
+          uint32_t dl;
+          memcpy(&dl, data + q, 4);
+          dl_off = q + 4;
+          dl_end = dl_off + dl;
+          LK_CHECK(dl_end <= pend, LK_ERR_IO, "parquet: truncated definition levels");
+          q = dl_end;
+        } else {
+          dl_off = q;
+          dl_end = q + (uint64_t)h.def_len;
+          LK_CHECK(dl_end <= pend, LK_ERR_IO, "parquet: truncated definition levels");
+          q = dl_end;
+        }
+        nn = 0;
+        uint32_t base_row = row;
+        uint32_t nn_base = vidx;
+        walk_hybrid(data, dl_off, dl_end, 1, pg.num_rows, [&](uint32_t s, uint32_t n, bool rle, uint32_t v, uint64_t off) {
+          Run run;
+          run.start = base_row + s;
+          run.off = off;
+          run.kind_value = rle ? (0x80000000u | (v & 1)) : 0u;
+          ci.def_runs.push_back(run);
+          ci.def_nn_before.push_back(nn_base + nn);
+          nn += rle ? ((v & 1) ? n : 0) : popcount_bits(data + off, n);
+        });
+      }
+      pg.nvals = nn;
+      if (h.encoding == ENC_PLAIN) {
+        unsigned esz = (cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT) ? 4 : (cm.phys_type == PT_INT64 || cm.phys_type == PT_DOUBLE) ? 8 : 0;
+        LK_CHECK(esz != 0, LK_ERR_UNSUPPORTED,
+                 "column '" + leaf.name + "': PLAIN pages of this type are not supported (dictionary fallback of a string column?)");
+        LK_CHECK(q + (uint64_t)nn * esz <= pend, LK_ERR_IO, "parquet: truncated PLAIN page");
+        pg.dict_coded = false;
+        pg.values_off = q;
+        pg.values_len = (uint32_t)(pend - q);
+      } else if (h.encoding == ENC_RLE_DICTIONARY || h.encoding == ENC_PLAIN_DICTIONARY) {
+        LK_CHECK(ci.has_dict, LK_ERR_IO, "parquet: dictionary-encoded page without a dictionary page");
+        pg.dict_coded = true;
+        if (nn > 0 || q < pend) {
+          LK_CHECK(q + 1 <= pend, LK_ERR_IO, "parquet: truncated dictionary-encoded page");
+          pg.bit_width = data[q];
+          LK_CHECK(pg.bit_width <= 31, LK_ERR_UNSUPPORTED, "parquet: dictionary index bit width > 31");
+          q += 1;
+        }
+        pg.values_off = q;
+        pg.values_len = (uint32_t)(pend - q);
+        uint32_t vbase = vidx;
+        if (nn > 0)
+          walk_hybrid(data, q, pend, pg.bit_width, nn, [&](uint32_t s, uint32_t n, bool rle, uint32_t v, uint64_t off) {
+            (void)n;
+            Run run;
+            run.start = vbase + s;
+            run.off = off;
+            run.kind_value = rle ? (0x80000000u | (v & 0x7fffffffu)) : 0u;
+            if (rle) LK_CHECK(v < ci.dict_n, LK_ERR_IO, "parquet: dictionary index out of range");
+            ci.val_runs.push_back(run);
+          });
+      } else {
+        fail(LK_ERR_UNSUPPORTED, "column '" + leaf.name + "': page encoding " + std::to_string(h.encoding) + " is not supported");
+      }
+      ci.pages.push_back(pg);
+      row += pg.num_rows;
+      vidx += nn;
+    }  // other page types (index pages) are skipped
+    p = pend;
+  }
+  LK_CHECK(row == ci.num_rows, LK_ERR_IO, "parquet: pages do not cover the row group");
+  return ci;
+}
+
+}  // namespace lk

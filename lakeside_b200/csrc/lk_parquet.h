@@ -1,0 +1,86 @@
+// Host-side Parquet reader: footer (Thrift compact), page headers, dictionary pages and the *seek index* over the
+// RLE/bit-packed hybrid streams.  The host never materialises column values: it walks headers (and popcounts the
+// definition-level bits) so that the device can start decoding at any row.  Replaces the metadata half of DuckDB's
+// parquet scan, reached from core/src/main/scala/com/cardinal/utils/Commons.scala:213-240.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "lk_common.h"
+#include "lk_device.h"
+
+namespace lk {
+
+enum PhysType : int { PT_BOOLEAN = 0, PT_INT32 = 1, PT_INT64 = 2, PT_INT96 = 3, PT_FLOAT = 4, PT_DOUBLE = 5, PT_BYTE_ARRAY = 6, PT_FLBA = 7 };
+enum Encoding : int { ENC_PLAIN = 0, ENC_PLAIN_DICTIONARY = 2, ENC_RLE = 3, ENC_BIT_PACKED = 4, ENC_RLE_DICTIONARY = 8 };
+
+struct ColumnChunkMeta {
+  int phys_type = -1;
+  int codec = 0;
+  int64_t num_values = 0;
+  int64_t total_compressed_size = 0;
+  int64_t data_page_offset = 0;
+  int64_t dictionary_page_offset = -1;
+};
+
+struct RowGroupMeta {
+  int64_t num_rows = 0;
+  std::vector<ColumnChunkMeta> columns;  // by leaf index
+};
+
+struct LeafColumn {
+  std::string name;  // flat leaf name (may contain dots: "resource.service.name")
+  int phys_type = -1;
+  int max_def = 0;   // 0 REQUIRED, 1 OPTIONAL
+  bool flat = true;  // false for leaves below a group (not addressable by the reference's SQL either)
+};
+
+struct FileMeta {
+  int64_t num_rows = 0;
+  std::vector<LeafColumn> leaves;
+  std::vector<RowGroupMeta> row_groups;
+  int leaf_index(const std::string& name) const;
+};
+
+// Parses the footer of a Parquet file held in memory.  Throws lk::Error(LK_ERR_IO) if it is not Parquet.
+FileMeta parse_footer(const uint8_t* data, size_t len);
+
+struct PageInfo {
+  uint32_t first_row = 0, num_rows = 0;  // chunk-level row range
+  uint32_t first_vidx = 0, nvals = 0;    // chunk-level index of the first non-null value, number of non-null values
+  bool dict_coded = false;
+  uint8_t bit_width = 0;
+  uint64_t values_off = 0;  // file offset of the value bytes (after the bit-width byte for dictionary pages)
+  uint32_t values_len = 0;
+};
+
+// Index of one column chunk.  `Run::off` values are FILE offsets here; the planner rebases them into the arena.
+struct ChunkIndex {
+  bool present = false;
+  int phys_type = -1;
+  int max_def = 0;
+  uint64_t file_start = 0, file_len = 0;  // byte range of the chunk (dictionary page + data pages)
+  int64_t total_compressed_size = 0;
+  uint32_t num_rows = 0;
+  std::vector<PageInfo> pages;
+  std::vector<Run> def_runs;             // start = chunk-level row
+  std::vector<uint32_t> def_nn_before;   // non-null values before each def run
+  std::vector<Run> val_runs;             // start = chunk-level value index (dictionary-coded pages only)
+  bool has_dict = false;
+  uint64_t dict_off = 0;  // file offset of the PLAIN dictionary payload
+  uint32_t dict_len = 0, dict_n = 0;
+  std::vector<std::string> dict_strings;  // BYTE_ARRAY dictionaries, decoded on the host
+  // chunk-level value index of row r (number of non-null values before r); r may equal num_rows
+  uint32_t vidx_at(const uint8_t* file, uint32_t r) const;
+  int def_run_at(uint32_t r) const;   // index of the def run containing row r
+  int val_run_at(uint32_t v) const;   // index of the value run containing value v
+  int page_at(uint32_t r) const;
+};
+
+// Walks every page header of the chunk and every run header of its hybrid streams.
+// want_strings: decode the BYTE_ARRAY dictionary into dict_strings.
+ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, const ColumnChunkMeta& cm, int64_t rg_rows,
+                       bool want_strings);
+
+}  // namespace lk

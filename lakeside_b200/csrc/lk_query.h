@@ -1,0 +1,147 @@
+// Host-side state of one glob evaluation (lk_query) and its result (lk_result).
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "lk_device.h"
+#include "lk_expr.h"
+#include "lk_parquet.h"
+
+namespace lk {
+
+struct Options {
+  int device = 0;
+  uint64_t max_hash_slots = 1ull << 27;
+  uint64_t dense_max_cells = 1ull << 25;
+  uint32_t tile_rows = LK_TILE_ROWS_MAX;
+  int host_threads = 0;  // 0 = hardware concurrency (capped)
+};
+Options& global_options();
+
+struct AggSpec {
+  AggOp op;
+  std::string aggregation;   // as written in the request ("sum", "count", "min", "max")
+  std::string value_column;  // rollup_<x> | _cardinalhq.value | field$type
+  double divisor = 1.0;
+};
+
+struct SegmentInput {
+  const uint8_t* data = nullptr;
+  size_t len = 0;
+  std::string name;
+  void* owned_pinned = nullptr;  // file read into pinned memory owned by the query
+  FileMeta meta;
+};
+
+// one physical column touched by the query
+struct PCol {
+  std::string name;
+  bool is_ts = false, is_key = false, is_filter = false, is_value = false;
+  bool string_typed = false;
+  int phys_type = -1;
+  int key_slot = -1, filter_slot = -1;
+};
+
+struct FilterColPlan {
+  int pcol = -1;
+  bool numeric = false;
+  std::vector<int> leaves;  // indices into Query::leaves (this column's leaves)
+  // string columns: leaf-truth signature -> class id (class 0 = SQL NULL)
+  std::map<std::vector<uint8_t>, uint32_t> sig2cls;
+  std::vector<std::vector<uint8_t>> cls_sig;
+  uint32_t ncls = 0;
+  std::vector<int> num_leaf_slot;  // numeric: for each entry of `leaves`, its comparison slot or -1 (exists)
+  int n_num = 0;
+};
+
+struct RowGroupPlan {
+  int seg = -1, rg = -1;
+  uint32_t num_rows = 0;
+  std::vector<ChunkIndex> chunks;  // per pcol
+  std::vector<uint64_t> arena_base;  // per pcol: arena offset of the chunk's first byte
+  uint64_t seq_base = 0;
+};
+
+struct HostResult;
+
+struct Query {
+  PushDownRequest req;
+  std::vector<AggSpec> aggs;
+  std::string path_opt = "auto";
+  bool exact_sums = false;
+  std::vector<SegmentInput> segs;
+
+  // ---- plan ----
+  bool prepared = false;
+  bool is_metrics = false;
+  int64_t ts_lo = 0, ts_hi = 0, step = 0, base = 0;
+  uint32_t nbuckets = 0;
+  std::string ts_col_name;
+  std::vector<PCol> pcols;
+  int ts_pcol = -1;
+  std::vector<const Clause*> leaves;
+  std::vector<LeafPredicate> leaf_preds;
+  std::vector<int> leaf_filter_col;  // per leaf: filter column slot, or -1 => literal FALSE (missing column)
+  std::vector<FilterColPlan> fcols;
+  std::vector<int> key_pcols;                          // name first, then existing group-bys
+  std::vector<std::string> key_names;                  // JDBC names: "name", group-by names
+  std::vector<std::vector<std::string>> key_dicts;     // global dictionaries (sorted)
+  std::vector<std::vector<std::string>> local_dicts;   // union of this rank's dictionaries (export)
+  std::vector<int> agg_pcols;
+  std::vector<RowGroupPlan> rgs;
+  int64_t touched_bytes = 0, total_rows = 0;
+  uint64_t n_groups = 1;
+  uint64_t n_cells = 0;
+  int path = 0;  // 0 dense, 1 hash
+  uint64_t hash_slots = 0;
+  uint32_t hash_stride = 0;
+
+  // host copies of the device pools
+  std::vector<TileDesc> tiles;
+  std::vector<ColCursor> cursors;
+  std::vector<Run> runs;
+  std::vector<ChunkInfo> chunk_infos;
+  std::vector<uint8_t> lut_cls;
+  std::vector<uint32_t> lut_gcode;
+  std::vector<uint32_t> pass_bits;
+  struct Upload { int seg; uint64_t file_off, len, arena_off; };
+  std::vector<Upload> uploads;
+  uint64_t arena_bytes = 0;
+  ScanParams params{};
+
+  // ---- device ----
+  struct Device;
+  std::unique_ptr<Device> dev;
+  double t_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::string info_json;
+  std::string dict_blob;
+
+  Query();
+  ~Query();
+};
+
+struct HostResult {
+  int64_t n = 0;
+  int n_values = 0, n_tags = 0;
+  std::vector<std::string> col_names;
+  uint8_t* pinned = nullptr;  // one pinned block: ts | values | codes | nulls
+  int64_t* ts = nullptr;
+  std::vector<double*> values;
+  std::vector<uint8_t*> nulls;
+  std::vector<int32_t*> codes;
+  std::vector<std::vector<std::string>> dicts;
+  std::vector<std::vector<const char*>> dict_ptrs;
+  ~HostResult();
+};
+
+// planning (host only, no CUDA): lk_plan.cpp
+void plan_query(Query& q);           // parse + index + compile; fills the host pools and ScanParams (device pointers unset)
+void rebuild_group_tables(Query& q); // after key_dicts changed (dictionary import)
+std::string export_dictionaries(const Query& q);
+void import_dictionaries(Query& q, const uint8_t* blob, size_t len);
+void parallel_for(int n, int threads, const std::function<void(int)>& fn);
+
+}  // namespace lk

@@ -1,0 +1,73 @@
+"""GPU parity tests (run on the B200 box: pytest -m gpu): the CUDA path through the C ABI against the oracle.
+
+Bit-exact: row selection, group keys, counts, min, max.  Double sums: relative 1e-12 (helpers.SUM_RTOL)."""
+import json
+
+import numpy as np
+import pytest
+
+import helpers as H
+from lakeside_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    from lakeside_b200 import api
+
+    api.init()
+
+
+def test_c1_single_segment_name_filter_sum_60s():
+    # BASELINE.json configs[0]: one sealed segment, name filter, sum by 60 s step
+    spec = synth.SynthSpec(dataset="logs", rows=1 << 20)
+    _, paths = H.dataset("c1_logs_1m", spec, 1)
+    rq = H.request_json(synth.c1_base_expr(), [0], 60000)
+    got = H.gpu_eval_single(rq, paths)
+    want = H.oracle_single(rq, paths)
+    assert 0 < len(want["rows"]) <= 60
+    H.assert_same(got, want, ["sum"], "c1")
+
+
+def test_c1_int_values_bit_exact_sum():
+    spec = synth.SynthSpec(dataset="logs", rows=300000, int_values=True)
+    _, paths = H.dataset("c1_logs_int", spec, 1)
+    rq = H.request_json(synth.c1_base_expr(), [0], 60000)
+    got = H.gpu_eval_single(rq, paths)
+    want = H.oracle_single(rq, paths)
+    for k, v in want["rows"].items():
+        assert got["rows"][k][0] == v[0]  # integer-valued doubles: exact in any order
+
+
+@pytest.mark.parametrize("path", ["hash"])
+def test_c2_four_aggregates(path):
+    spec = synth.SynthSpec(dataset="metrics", rows=200000)
+    _, paths = H.dataset("c2_m200k", spec, 3)
+    rq = H.request_json(synth.c2_base_expr(), [0, 1, 2], 10000)
+    got = H.gpu_eval_multi(rq, paths, synth.C2_AGGREGATES, path=path)
+    want = H.oracle_multi(rq, paths, synth.C2_AGGREGATES)
+    assert got["info"]["path"] == path
+    H.assert_same(got, want, ["sum", "sum", "min", "max"], "c2/" + path)
+    assert got["survivors"] >= len(want["rows"])
+
+
+@pytest.mark.parametrize("path", ["dense", "hash"])
+def test_small_group_space_dense_and_hash(path):
+    spec = synth.SynthSpec(dataset="metrics", rows=150000, n_names=4, cards=(16, 4, 4, 2))
+    _, paths = H.dataset("small_groups", spec, 2)
+    rq = H.request_json(synth.c2_base_expr(), [0, 1], 10000)
+    got = H.gpu_eval_multi(rq, paths, synth.C2_AGGREGATES, path=path)
+    want = H.oracle_multi(rq, paths, synth.C2_AGGREGATES)
+    assert got["info"]["path"] == path
+    H.assert_same(got, want, ["sum", "sum", "min", "max"], "small/" + path)
+
+
+@pytest.mark.parametrize("agg,rollup", [("sum", "sum"), ("count", "sum"), ("min", "min"), ("max", "max")])
+def test_single_aggregate_requests(agg, rollup):
+    spec = synth.SynthSpec(dataset="metrics", rows=100000, n_names=8, cards=(16, 8, 8, 4))
+    _, paths = H.dataset("single_agg", spec, 2)
+    rq = H.request_json(synth.c2_base_expr(agg, rollup), [0, 1], 10000)
+    got = H.gpu_eval_single(rq, paths)
+    want = H.oracle_single(rq, paths)
+    H.assert_same(got, want, [agg], f"{agg}({rollup})")

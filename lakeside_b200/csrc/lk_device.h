@@ -25,16 +25,17 @@ constexpr int LK_MAX_FILTER = 8;   // distinct filter columns
 constexpr int LK_MAX_KEYS = 8;     // name + group-by columns
 constexpr int LK_MAX_AGGS = 7;     // aggregates of one fused pass
 constexpr int LK_MAX_NUMLEAF = 4;  // numeric comparison leaves per column
-constexpr int LK_TILE_ROWS_MAX = 2048;
+constexpr int LK_TILE_ROWS_MAX = 512;  // one warp owns one tile: 16 consecutive rows per lane
 constexpr uint64_t LK_EMPTY_KEY = 0ull;  // hash entries store cell + 1; an all-zero arena is clean
 
 enum AggOp : uint8_t { AGG_SUM = 0, AGG_COUNT = 1, AGG_MIN = 2, AGG_MAX = 3 };
 
 struct Run {
   uint32_t start;       // chunk-level index of the run's first element (row for def levels, value index for codes)
-  uint32_t kind_value;  // bit 31 set: RLE run, bits 0..30 = the repeated value; clear: bit-packed run
-  uint64_t off;         // arena byte offset of the packed bytes of a bit-packed run
+  uint32_t kind_value;  // bit 31 set: RLE run, bits 0..30 = the repeated value;
+                        // clear: bit-packed run, bits 0..30 = byte offset of its packed bytes from the chunk's first byte
 };
+static_assert(sizeof(Run) == 8, "Run must be 8 bytes");
 
 enum : uint8_t { CUR_ALL_VALID = 1, CUR_ALL_NULL = 2, CUR_DICT = 4 };
 
@@ -59,6 +60,7 @@ struct TileDesc {
 };
 
 struct ChunkInfo {
+  uint64_t base_off;   // arena offset of the chunk's first byte (bit-packed run offsets are relative to it)
   uint64_t dict_off;   // numeric dictionary: arena offset of its PLAIN values
   uint32_t dict_n;
   uint32_t lut_cls;    // offset into the class-table pool (string filter columns)
@@ -175,7 +177,8 @@ LK_HD uint32_t lk_find_run(const Run* runs, uint32_t n, uint32_t idx) {
 }
 
 // definition bits of rows [row, row + nbits) (nbits <= 32) of a column that has a def-level stream
-LK_HD uint32_t lk_def_word(const uint8_t* arena, const Run* runs, const ColCursor& c, uint32_t row, uint32_t nbits) {
+LK_HD uint32_t lk_def_word(const uint8_t* arena, const Run* runs, const ColCursor& c, const ChunkInfo& ci, uint32_t row,
+                           uint32_t nbits) {
   const Run* r = runs + c.drun_lo;
   uint32_t ri = lk_find_run(r, c.drun_n, row);
   uint32_t w = 0, filled = 0;
@@ -189,7 +192,7 @@ LK_HD uint32_t lk_def_word(const uint8_t* arena, const Run* runs, const ColCurso
       if (run.kind_value & 1) w |= m << filled;
     } else {
       uint32_t bit = row + filled - run.start;
-      uint64_t x = lk_load_u64(arena, run.off + (bit >> 3)) >> (bit & 7);
+      uint64_t x = lk_load_u64(arena, ci.base_off + run.kind_value + (bit >> 3)) >> (bit & 7);
       w |= ((uint32_t)x & m) << filled;
     }
     filled += avail;
@@ -199,12 +202,12 @@ LK_HD uint32_t lk_def_word(const uint8_t* arena, const Run* runs, const ColCurso
 }
 
 // dictionary index of chunk-level value `vidx`
-LK_HD uint32_t lk_dict_code(const uint8_t* arena, const Run* runs, const ColCursor& c, uint32_t vidx) {
+LK_HD uint32_t lk_dict_code(const uint8_t* arena, const Run* runs, const ColCursor& c, const ChunkInfo& ci, uint32_t vidx) {
   const Run* r = runs + c.vrun_lo;
   Run run = r[lk_find_run(r, c.vrun_n, vidx)];
   if (run.kind_value >> 31) return run.kind_value & 0x7fffffffu;
   uint64_t bitpos = (uint64_t)(vidx - run.start) * c.width;
-  uint64_t x = lk_load_u64(arena, run.off + (bitpos >> 3)) >> (bitpos & 7);
+  uint64_t x = lk_load_u64(arena, ci.base_off + run.kind_value + (bitpos >> 3)) >> (bitpos & 7);
   return (uint32_t)x & (c.width >= 32 ? 0xffffffffu : ((1u << c.width) - 1));
 }
 
@@ -214,7 +217,7 @@ LK_HD uint64_t lk_value_bits(const uint8_t* arena, const Run* runs, const ColCur
   unsigned esz = (ci.phys_type == 1 || ci.phys_type == 4) ? 4 : 8;
   uint64_t off;
   if (c.flags & CUR_DICT) {
-    uint32_t code = lk_dict_code(arena, runs, c, vidx);
+    uint32_t code = lk_dict_code(arena, runs, c, ci, vidx);
     if (code >= ci.dict_n) { *bad = 1; code = 0; }
     off = ci.dict_off + (uint64_t)code * esz;
   } else {

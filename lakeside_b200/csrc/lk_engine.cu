@@ -274,7 +274,8 @@ void device_execute(Query& q) {
       P.h_occ = d.harena->occ;
       P.h_occ_cap = (uint32_t)std::min<uint64_t>(d.harena->slots, 0xffffffffu);
     }
-    int grid = (int)std::min<uint32_t>(P.ntiles, (uint32_t)(num_sms() * 8));
+    // persistent grid: every warp pulls 512-row tiles from the ticket counter until none are left
+    int grid = (int)std::min<uint32_t>((P.ntiles + SCAN_WARPS - 1) / SCAN_WARPS, (uint32_t)(num_sms() * 8));
     scan_kernel<<<grid, SCAN_BLOCK, 0, d.st>>>(P);
     CUDA_CHECK(cudaGetLastError());
   }
@@ -421,25 +422,73 @@ __global__ void __launch_bounds__(CMP_BLOCK) dense_emit_kernel(const unsigned lo
     }
 }
 
-__global__ void hash_hist_kernel(const uint32_t* __restrict__ occ, uint32_t n, const uint8_t* __restrict__ entries, uint32_t stride,
-                                 uint64_t n_groups, uint32_t* __restrict__ hist) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+// ---- hash path: counting sort of the claimed slots by bucket (ORDER BY timestamp), then a coalesced emit ----
+constexpr int HS_BLOCK = 256;
+constexpr int HS_CHUNK = 8192;   // claimed slots per block
+constexpr int HS_MAXB = 4096;    // buckets histogrammed in shared memory; beyond that global atomics are uncontended enough
+
+// pass 1: bucket of every claimed slot + per-bucket counts (block-private histogram, one global atomic per bucket per block)
+__global__ void __launch_bounds__(HS_BLOCK) hash_hist_kernel(const uint32_t* __restrict__ occ, uint32_t n, const uint8_t* __restrict__ entries,
+                                                             uint32_t stride, uint64_t n_groups, uint32_t nbuckets,
+                                                             uint32_t* __restrict__ bucket_of, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[HS_MAXB];
+  const bool priv = nbuckets <= HS_MAXB;
+  if (priv) {
+    for (uint32_t b = threadIdx.x; b < nbuckets; b += HS_BLOCK) h[b] = 0;
+    __syncthreads();
+  }
+  const uint32_t lo = blockIdx.x * HS_CHUNK, hi = min(n, lo + HS_CHUNK);
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) {
     const unsigned long long key = *reinterpret_cast<const unsigned long long*>(entries + (uint64_t)occ[i] * stride);
-    atomicAdd(hist + (key - 1) / n_groups, 1u);
+    const uint32_t b = (uint32_t)((key - 1) / n_groups);
+    bucket_of[i] = b;
+    atomicAdd(priv ? &h[b] : &hist[b], 1u);
+  }
+  if (priv) {
+    __syncthreads();
+    for (uint32_t b = threadIdx.x; b < nbuckets; b += HS_BLOCK)
+      if (h[b]) atomicAdd(&hist[b], h[b]);
   }
 }
 
-// rows of one bucket are contiguous in the output (ORDER BY timestamp); their order inside the bucket is arbitrary,
-// like the reference's (BaseExpr.scala:394, 403 order by the time column only).  Each emitted entry is zeroed again.
-__global__ void hash_emit_kernel(const uint32_t* __restrict__ occ, uint32_t n, uint8_t* __restrict__ entries, uint32_t stride,
-                                 uint32_t* __restrict__ cursor, const __grid_constant__ EmitParams E) {
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    unsigned long long* e = reinterpret_cast<unsigned long long*>(entries + (uint64_t)occ[i] * stride);
-    const uint64_t cell = e[0] - 1;
-    const uint32_t pos = atomicAdd(cursor + cell / E.n_groups, 1u);
-    emit_row(E, pos, cell, e + 1, 1);
-    for (uint32_t w = 0; w < stride / 8; w++) e[w] = 0;
+// pass 2: each block reserves one range per bucket (cursor = exclusive scan of hist) and scatters its slots into it
+__global__ void __launch_bounds__(HS_BLOCK) hash_scatter_kernel(const uint32_t* __restrict__ occ, const uint32_t* __restrict__ bucket_of, uint32_t n,
+                                                                uint32_t nbuckets, uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+  __shared__ uint32_t cnt[HS_MAXB];
+  __shared__ uint32_t base[HS_MAXB];
+  const bool priv = nbuckets <= HS_MAXB;
+  const uint32_t lo = blockIdx.x * HS_CHUNK, hi = min(n, lo + HS_CHUNK);
+  if (!priv) {
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) sorted[atomicAdd(&cursor[bucket_of[i]], 1u)] = occ[i];
+    return;
   }
+  for (uint32_t b = threadIdx.x; b < nbuckets; b += HS_BLOCK) cnt[b] = 0;
+  __syncthreads();
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) atomicAdd(&cnt[bucket_of[i]], 1u);
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < nbuckets; b += HS_BLOCK) {
+    const uint32_t c = cnt[b];
+    if (c) base[b] = atomicAdd(&cursor[b], c);
+    cnt[b] = 0;
+  }
+  __syncthreads();
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) {
+    const uint32_t b = bucket_of[i];
+    sorted[base[b] + atomicAdd(&cnt[b], 1u)] = occ[i];
+  }
+}
+
+// pass 3: row i <- slot sorted[i] (rows of one bucket are contiguous; their order inside a bucket is arbitrary, like the
+// reference's: BaseExpr.scala:394, 403 order by the time column only).  Each emitted entry is zeroed: the arena stays clean.
+__global__ void __launch_bounds__(HS_BLOCK) hash_emit_kernel(const uint32_t* __restrict__ sorted, uint32_t n, uint8_t* __restrict__ entries,
+                                                             uint32_t stride, const __grid_constant__ EmitParams E) {
+  const uint32_t i = blockIdx.x * HS_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  unsigned long long* e = reinterpret_cast<unsigned long long*>(entries + (uint64_t)sorted[i] * stride);
+  const uint64_t cell = e[0] - 1;
+  emit_row(E, i, cell, e + 1, 1);
+  ulonglong2* z = reinterpret_cast<ulonglong2*>(e);
+  for (uint32_t w = 0; w < stride / 16; w++) z[w] = make_ulonglong2(0ull, 0ull);
 }
 
 // device result layout for n rows: ts[n] | val[a][n] | code[k][n] | nul[a][n]
@@ -530,12 +579,18 @@ void device_finalize_device(Query& q) {
     if (q.path == 0) {
       dense_emit_kernel<<<nblocks, CMP_BLOCK, 0, d.st>>>(d.planes, q.n_cells, d.block_counts, E);
     } else {
-      ensure_block_counts(d, (size_t)q.nbuckets + 1);
-      CUDA_CHECK(cudaMemsetAsync(d.block_counts, 0, ((size_t)q.nbuckets + 1) * 4, d.st));
-      int grid = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16);
-      hash_hist_kernel<<<grid, 256, 0, d.st>>>(d.harena->occ, (uint32_t)n, d.harena->entries, d.harena->stride, q.n_groups, d.block_counts);
-      exclusive_scan_kernel<<<1, 1024, 0, d.st>>>(d.block_counts, q.nbuckets, d.block_counts + q.nbuckets);
-      hash_emit_kernel<<<grid, 256, 0, d.st>>>(d.harena->occ, (uint32_t)n, d.harena->entries, d.harena->stride, d.block_counts, E);
+      // scratch: hist/cursor[nbuckets + 1] | bucket_of[n] | sorted[n]
+      ensure_block_counts(d, (size_t)q.nbuckets + 1 + 2 * (size_t)n);
+      uint32_t* hist = d.block_counts;
+      uint32_t* bucket_of = hist + q.nbuckets + 1;
+      uint32_t* sorted = bucket_of + n;
+      CUDA_CHECK(cudaMemsetAsync(hist, 0, ((size_t)q.nbuckets + 1) * 4, d.st));
+      const int hgrid = (int)((n + HS_CHUNK - 1) / HS_CHUNK);
+      hash_hist_kernel<<<hgrid, HS_BLOCK, 0, d.st>>>(d.harena->occ, (uint32_t)n, d.harena->entries, d.harena->stride, q.n_groups, q.nbuckets,
+                                                     bucket_of, hist);
+      exclusive_scan_kernel<<<1, 1024, 0, d.st>>>(hist, q.nbuckets, hist + q.nbuckets);
+      hash_scatter_kernel<<<hgrid, HS_BLOCK, 0, d.st>>>(d.harena->occ, bucket_of, (uint32_t)n, q.nbuckets, hist, sorted);
+      hash_emit_kernel<<<(int)((n + HS_BLOCK - 1) / HS_BLOCK), HS_BLOCK, 0, d.st>>>(sorted, (uint32_t)n, d.harena->entries, d.harena->stride, E);
     }
     CUDA_CHECK(cudaGetLastError());
   }

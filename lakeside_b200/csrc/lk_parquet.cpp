@@ -360,7 +360,7 @@ uint32_t ChunkIndex::vidx_at(const uint8_t* file, uint32_t r) const {
   uint32_t nn = def_nn_before[i];
   uint32_t k = r - run.start;
   if (run.kind_value >> 31) return nn + ((run.kind_value & 1) ? k : 0);
-  return nn + popcount_bits(file + run.off, k);
+  return nn + popcount_bits(file + file_start + run.kind_value, k);
 }
 
 ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, const ColumnChunkMeta& cm, int64_t rg_rows,
@@ -381,6 +381,7 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
            "parquet: column chunk out of file bounds");
   ci.file_start = (uint64_t)start;
   ci.file_len = (uint64_t)cm.total_compressed_size;
+  LK_CHECK(ci.file_len < (1ull << 31), LK_ERR_UNSUPPORTED, "column chunk larger than 2 GiB");
   const uint64_t cend = ci.file_start + ci.file_len;
   uint64_t p = ci.file_start;
   uint32_t row = 0, vidx = 0;
@@ -449,8 +450,7 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
         walk_hybrid(data, dl_off, dl_end, 1, pg.num_rows, [&](uint32_t s, uint32_t n, bool rle, uint32_t v, uint64_t off) {
           Run run;
           run.start = base_row + s;
-          run.off = off;
-          run.kind_value = rle ? (0x80000000u | (v & 1)) : 0u;
+          run.kind_value = rle ? (0x80000000u | (v & 1)) : (uint32_t)(off - ci.file_start);
           ci.def_runs.push_back(run);
           ci.def_nn_before.push_back(nn_base + nn);
           nn += rle ? ((v & 1) ? n : 0) : popcount_bits(data + off, n);
@@ -482,8 +482,7 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
             (void)n;
             Run run;
             run.start = vbase + s;
-            run.off = off;
-            run.kind_value = rle ? (0x80000000u | (v & 0x7fffffffu)) : 0u;
+            run.kind_value = rle ? (0x80000000u | (v & 0x7fffffffu)) : (uint32_t)(off - ci.file_start);
             if (rle) LK_CHECK(v < ci.dict_n, LK_ERR_IO, "parquet: dictionary index out of range");
             ci.val_runs.push_back(run);
           });

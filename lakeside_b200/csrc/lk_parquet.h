@@ -55,7 +55,7 @@ struct PageInfo {
   uint32_t values_len = 0;
 };
 
-// Index of one column chunk.  `Run::off` values are FILE offsets here; the planner rebases them into the arena.
+// Index of one column chunk.  Bit-packed run offsets are relative to file_start (the chunk's first byte).
 struct ChunkIndex {
   bool present = false;
   int phys_type = -1;

@@ -337,9 +337,10 @@ void plan_query(Query& q) {
       info.dict_off = ci.has_dict ? rebase(ci.dict_off) : 0;
       info.dict_n = ci.dict_n;
       dbase[p] = (uint32_t)rpos;
-      for (auto r : ci.def_runs) { if (!(r.kind_value >> 31)) r.off = rebase(r.off); q.runs[rpos++] = r; }
+      info.base_off = rp.arena_base[p];
+      for (auto& r : ci.def_runs) q.runs[rpos++] = r;
       vbase[p] = (uint32_t)rpos;
-      for (auto r : ci.val_runs) { if (!(r.kind_value >> 31)) r.off = rebase(r.off); q.runs[rpos++] = r; }
+      for (auto& r : ci.val_runs) q.runs[rpos++] = r;
     }
     const std::vector<uint32_t>& b = bounds[i];
     for (size_t t = 0; t + 1 < b.size(); t++) {

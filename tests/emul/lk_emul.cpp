@@ -68,7 +68,7 @@ static void run(Query& q, EmulResult& out) {
       uint32_t running = 0;
       for (uint32_t w = 0; w < nwords; w++) {
         uint32_t nb = std::min(32u, td.nrows - 32 * w);
-        bits[p][w] = lk_def_word(A, q.runs.data(), cur[p], td.row0 + 32 * w, nb);
+        bits[p][w] = lk_def_word(A, q.runs.data(), cur[p], ci[p], td.row0 + 32 * w, nb);
         pref[p][w] = (uint16_t)running;
         running += (uint32_t)__builtin_popcount(bits[p][w]);
       }
@@ -87,7 +87,7 @@ static void run(Query& q, EmulResult& out) {
           LK_CHECK(!bad, LK_ERR_IO, "bad code");
           cls = lk_numeric_class(fc, lk_bits_to_f64(b, ci[p].phys_type));
         } else {
-          uint32_t code = lk_dict_code(A, q.runs.data(), cur[p], vidx);
+          uint32_t code = lk_dict_code(A, q.runs.data(), cur[p], ci[p], vidx);
           LK_CHECK(code < ci[p].dict_n, LK_ERR_IO, "bad code");
           cls = q.lut_cls[ci[p].lut_cls + code];
         }
@@ -111,7 +111,7 @@ static void run(Query& q, EmulResult& out) {
         int p = P.keys[k].pcol;
         uint32_t g = P.keys[k].null_code;
         if (col_pos(cur[p], bits[p].data(), pref[p].data(), r, vidx)) {
-          uint32_t code = lk_dict_code(A, q.runs.data(), cur[p], vidx);
+          uint32_t code = lk_dict_code(A, q.runs.data(), cur[p], ci[p], vidx);
           LK_CHECK(code < ci[p].dict_n, LK_ERR_IO, "bad code");
           g = q.lut_gcode[ci[p].lut_gcode + code];
         }

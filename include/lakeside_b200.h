@@ -72,6 +72,9 @@ int lk_query_add_segment_buffer(lk_query* q, const void* data, size_t len);
 /* Parses footers, page headers and dictionaries, builds the page/run/tile index, compiles the predicate to
  * dictionary-code tables, uploads the touched column chunks to HBM.  After this the query is device-resident. */
 int lk_query_prepare(lk_query* q);
+/* The host half of prepare only (no CUDA call): footers, page/run/tile index, predicate and group tables.  Optional;
+ * lk_query_prepare runs it when it has not been called. */
+int lk_query_plan(lk_query* q);
 /* Sharded evaluation: every rank exports the dictionaries of its group-by columns, the host unions them
  * (any order-insensitive union, e.g. sorted) and imports the same blob on every rank so that all ranks index one
  * dense (group x bucket) space.  Blob format: see INTEGRATION.md.  Call between prepare and execute. */
@@ -86,9 +89,12 @@ int lk_query_sync(lk_query* q);
  *   plane 1 + a        : aggregate a; sum -> float64, count -> uint64, min/max -> order-preserving uint64 keys
  * Layout: cell = bucket * n_groups + group.  op[a]: 0 sum(f64 add) 1 count(u64 add) 2 min(u64 min) 3 max(u64 max). */
 int lk_query_partial_dense(lk_query* q, int64_t* n_cells, int* n_planes, void** plane_ptrs /*[8]*/, int* plane_ops /*[8]*/);
-/* Hash path: compacts the occupied entries into a device list of n entries of `stride` bytes
- * {uint64 key; uint64 acc[..]} and merges entries gathered from other ranks. */
-int lk_query_partial_sparse(lk_query* q, void** entries, int64_t* n, int* stride_bytes);
+/* Hash path, sharded evaluation: the (group x bucket) cells are hash-partitioned over `nparts` owners (ranks).
+ * partial_sparse moves every occupied entry {uint64 key = cell + 1; uint64 acc[..]} (stride_bytes each) out of the
+ * table into one device buffer ordered by partition (counts[p] entries for partition p) and leaves the table empty;
+ * after the all-to-all each rank merges the entries of ITS partition (own and foreign) with merge_sparse and
+ * finalizes: every rank then holds the final rows of its partition. */
+int lk_query_partial_sparse(lk_query* q, int nparts, void** entries, int64_t* counts /*[nparts]*/, int* stride_bytes);
 int lk_query_merge_sparse(lk_query* q, const void* device_entries, int64_t n);
 /* Compacts the non-empty cells into result rows sorted by timestamp, still in HBM (asynchronous apart from one
  * scalar read-back).  Idempotent until the next execute.  The hash path also returns its table to the clean state. */

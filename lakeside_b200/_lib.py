@@ -48,7 +48,8 @@ _SIGNATURES = {
     "lk_query_execute": (c_int, [c_void_p]),
     "lk_query_sync": (c_int, [c_void_p]),
     "lk_query_partial_dense": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int), POINTER(c_void_p), POINTER(c_int)]),
-    "lk_query_partial_sparse": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int)]),
+    "lk_query_partial_sparse": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_int64), POINTER(c_int)]),
+    "lk_query_plan": (c_int, [c_void_p]),
     "lk_query_merge_sparse": (c_int, [c_void_p, c_void_p, c_int64]),
     "lk_query_finalize_device": (c_int, [c_void_p]),
     "lk_query_finalize": (c_int, [c_void_p, POINTER(c_void_p)]),

@@ -137,9 +137,23 @@ class Query:
         buf = ctypes.create_string_buffer(data, len(data))
         self.add_segment_buffer(ctypes.addressof(buf), len(data), keepalive=buf)
 
+    def plan(self):
+        """Host half of prepare (no CUDA): usable on a CPU-only box for the sharding/dictionary logic."""
+        _lib.check(_lib.load().lk_query_plan(self._h))
+
     def prepare(self):
         _lib.check(_lib.load().lk_query_prepare(self._h))
         self._keep.clear()
+
+    def partial_sparse(self, nparts: int):
+        """-> (device pointer, [entries per partition], stride bytes); the table is left empty."""
+        ptr, stride = ctypes.c_void_p(), ctypes.c_int()
+        counts = (ctypes.c_int64 * nparts)()
+        _lib.check(_lib.load().lk_query_partial_sparse(self._h, nparts, ctypes.byref(ptr), counts, ctypes.byref(stride)))
+        return ptr.value or 0, list(counts), stride.value
+
+    def merge_sparse(self, device_ptr: int, n: int):
+        _lib.check(_lib.load().lk_query_merge_sparse(self._h, ctypes.c_void_p(device_ptr), n))
 
     def execute(self):
         _lib.check(_lib.load().lk_query_execute(self._h))
@@ -264,6 +278,56 @@ def merge_streams_index(ts_list: Sequence[np.ndarray], reverse: bool = False) ->
     _lib.check(lib.lk_merge_streams(k, tsp, gp, vp, lens, 1 if reverse else 0, out_ts.ctypes.data, out_gid.ctypes.data,
                                     out_val.ctypes.data, out_src.ctypes.data))
     return out_src, out_gid
+
+
+def parse_dictionary_blob(blob: bytes) -> List[List[bytes]]:
+    """Blob of lk_query_export_dictionaries: u32 n_keys; per key: u32 n; per string: u32 len, bytes."""
+    import struct
+
+    p = 0
+    (nk,) = struct.unpack_from("<I", blob, p)
+    p += 4
+    out = []
+    for _ in range(nk):
+        (n,) = struct.unpack_from("<I", blob, p)
+        p += 4
+        d = []
+        for _ in range(n):
+            (ln,) = struct.unpack_from("<I", blob, p)
+            p += 4
+            d.append(bytes(blob[p:p + ln]))
+            p += ln
+        out.append(d)
+    return out
+
+
+def union_dictionaries(blobs: Sequence[bytes]) -> bytes:
+    """Union (byte-wise sorted) of the per-rank group-by dictionaries: the one global code space all ranks import."""
+    import struct
+
+    parsed = [parse_dictionary_blob(b) for b in blobs]
+    nk = len(parsed[0])
+    assert all(len(p) == nk for p in parsed), "ranks disagree on the number of key columns"
+    out = [struct.pack("<I", nk)]
+    for k in range(nk):
+        vals = sorted(set().union(*[set(p[k]) for p in parsed]))
+        out.append(struct.pack("<I", len(vals)))
+        for v in vals:
+            out.append(struct.pack("<I", len(v)))
+            out.append(v)
+    return b"".join(out)
+
+
+def shard_request(push_down_request: dict, rank: int, world: int) -> Tuple[dict, List[int]]:
+    """Segment sharding of a PushDownRequest over `world` GPUs (the reference shards segments over workers by
+    ``floorMod(segmentId.hashCode, n)``, WorkerManager.scala:150-156; here: round-robin by position).  Every shard keeps the
+    request's global [startTs, endTs) so that all ranks index the same buckets."""
+    srs = push_down_request["segmentRequests"]
+    lo = min(s["startTs"] for s in srs)
+    hi = max(s["endTs"] for s in srs)
+    idx = [i for i in range(len(srs)) if i % world == rank]
+    mine = [dict(srs[i], startTs=lo, endTs=hi, stepInMillis=srs[0]["stepInMillis"]) for i in idx]
+    return dict(push_down_request, segmentRequests=mine), idx
 
 
 def evaluate_push_down_request(query_id: str, local_parquet: bool, push_down_request: dict, db_root: str = "./db"):

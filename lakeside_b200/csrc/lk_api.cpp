@@ -157,13 +157,25 @@ int lk_query_add_segment_file(lk_query* q, const char* path) {
   });
 }
 
-int lk_query_prepare(lk_query* q) {
+int lk_query_plan(lk_query* q) {
   return guard([&] {
     LK_CHECK(q, LK_ERR_INVALID, "null argument");
-    LK_CHECK(!q->q.prepared, LK_ERR_INVALID, "query already prepared");
+    LK_CHECK(!q->q.prepared, LK_ERR_INVALID, "query already planned");
     double t0 = now_ms();
     plan_query(q->q);
     q->q.t_ms[4] = now_ms() - t0;
+  });
+}
+
+int lk_query_prepare(lk_query* q) {
+  return guard([&] {
+    LK_CHECK(q, LK_ERR_INVALID, "null argument");
+    LK_CHECK(!(q->q.dev), LK_ERR_INVALID, "query already prepared");
+    if (!q->q.prepared) {
+      double t0 = now_ms();
+      plan_query(q->q);
+      q->q.t_ms[4] = now_ms() - t0;
+    }
     device_upload(q->q);
   });
 }
@@ -202,13 +214,17 @@ int lk_query_partial_dense(lk_query* q, int64_t* n_cells, int* n_planes, void** 
   });
 }
 
-int lk_query_partial_sparse(lk_query*, void**, int64_t*, int*) {
-  tl_error = "sparse partial exchange is not available in this build";
-  return LK_ERR_UNSUPPORTED;
+int lk_query_partial_sparse(lk_query* q, int nparts, void** entries, int64_t* counts, int* stride_bytes) {
+  return guard([&] {
+    LK_CHECK(q && entries && counts && stride_bytes, LK_ERR_INVALID, "null argument");
+    device_partial_sparse(q->q, nparts, entries, counts, stride_bytes);
+  });
 }
-int lk_query_merge_sparse(lk_query*, const void*, int64_t) {
-  tl_error = "sparse partial exchange is not available in this build";
-  return LK_ERR_UNSUPPORTED;
+int lk_query_merge_sparse(lk_query* q, const void* device_entries, int64_t n) {
+  return guard([&] {
+    LK_CHECK(q && (device_entries || n == 0), LK_ERR_INVALID, "null argument");
+    device_merge_sparse(q->q, device_entries, n);
+  });
 }
 
 int lk_query_finalize_device(lk_query* q) {

@@ -159,6 +159,8 @@ struct Query::Device {
   size_t block_counts_cap = 0;
   uint8_t* dres = nullptr;
   size_t dres_cap = 0;
+  uint8_t* sparse_out = nullptr;  // partitioned copy of the claimed entries (sparse exchange)
+  size_t sparse_cap = 0;
   int64_t n_rows = 0;
   uint32_t phase = 0;
   uint32_t h_counters[8] = {};
@@ -172,7 +174,7 @@ Query::~Query() {
     if (d.st) cudaStreamSynchronize(d.st);
     auto fr = [&](void* p) { if (p) cudaFreeAsync(p, d.st); };
     fr(d.arena); fr(d.tiles); fr(d.cursors); fr(d.runs); fr(d.chunks); fr(d.lut_cls); fr(d.lut_gcode); fr(d.pass_bits);
-    fr(d.counters); fr(d.survivors); fr(d.planes); fr(d.block_counts); fr(d.dres);
+    fr(d.counters); fr(d.survivors); fr(d.planes); fr(d.block_counts); fr(d.dres); fr(d.sparse_out);
     if (d.harena) {
       // an arena that was written but never emitted is dirty: clear it before handing it back
       if (d.executed && !d.finalized_device) cudaMemsetAsync(d.harena->entries, 0, d.harena->slots * d.harena->stride, d.st);
@@ -644,6 +646,170 @@ void device_timings(Query& q) {
   if (d.executed && cudaEventElapsedTime(&ms, d.ev[2], d.ev[3]) == cudaSuccess) q.t_ms[1] = ms;
   if (d.finalized_device && cudaEventElapsedTime(&ms, d.ev[4], d.ev[5]) == cudaSuccess) q.t_ms[2] = ms;
   cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// sparse exchange (hash path, sharded evaluation): every rank owns the cells whose hash falls into its partition
+// ------------------------------------------------------------------------------------------------------------
+constexpr int SP_MAXPARTS = 64;
+struct AggSlot4 { uint8_t op[LK_MAX_AGGS + 1]; };
+
+__device__ __forceinline__ uint32_t cell_partition(unsigned long long cell, uint32_t nparts) {
+  return (uint32_t)((lk_hash64(cell ^ 0x9e3779b97f4a7c15ull) >> 33) % nparts);
+}
+
+__global__ void __launch_bounds__(HS_BLOCK) sparse_hist_kernel(const uint32_t* __restrict__ occ, uint32_t n, const uint8_t* __restrict__ entries, uint32_t stride,
+                                                               uint32_t nparts, uint32_t* __restrict__ part_of, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[SP_MAXPARTS];
+  if (threadIdx.x < SP_MAXPARTS) h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t lo = blockIdx.x * HS_CHUNK, hi = min(n, lo + HS_CHUNK);
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) {
+    const unsigned long long key = *reinterpret_cast<const unsigned long long*>(entries + (uint64_t)occ[i] * stride);
+    const uint32_t p = cell_partition(key - 1, nparts);
+    part_of[i] = p;
+    atomicAdd(&h[p], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < nparts && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+
+// copies every claimed entry into its partition's range of `out` and returns the table slot to the clean state
+__global__ void __launch_bounds__(HS_BLOCK) sparse_scatter_kernel(const uint32_t* __restrict__ occ, const uint32_t* __restrict__ part_of, uint32_t n,
+                                                                  uint8_t* __restrict__ entries, uint32_t stride, uint32_t nparts,
+                                                                  uint32_t* __restrict__ cursor, uint8_t* __restrict__ out) {
+  __shared__ uint32_t cnt[SP_MAXPARTS];
+  __shared__ uint32_t base[SP_MAXPARTS];
+  if (threadIdx.x < SP_MAXPARTS) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t lo = blockIdx.x * HS_CHUNK, hi = min(n, lo + HS_CHUNK);
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) atomicAdd(&cnt[part_of[i]], 1u);
+  __syncthreads();
+  if (threadIdx.x < nparts) {
+    const uint32_t c = cnt[threadIdx.x];
+    if (c) base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], c);
+    cnt[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) {
+    const uint32_t p = part_of[i];
+    const uint32_t pos = base[p] + atomicAdd(&cnt[p], 1u);
+    ulonglong2* src = reinterpret_cast<ulonglong2*>(entries + (uint64_t)occ[i] * stride);
+    ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + (uint64_t)pos * stride);
+    for (uint32_t w = 0; w < stride / 16; w++) { dst[w] = src[w]; src[w] = make_ulonglong2(0ull, 0ull); }
+  }
+}
+
+// merges n foreign entries {key, acc[n_aggs]} into the table: sum/count add, min/max (both stored as "max" keys) max
+__global__ void __launch_bounds__(HS_BLOCK) sparse_merge_kernel(const uint8_t* __restrict__ in, uint32_t n, uint8_t* __restrict__ entries, uint32_t stride,
+                                                                uint64_t mask, uint32_t* __restrict__ occ, uint32_t occ_cap, uint32_t* __restrict__ counters,
+                                                                int n_aggs, const __grid_constant__ AggSlot4 ops) {
+  const uint32_t i = blockIdx.x * HS_BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool claimed = false;
+  uint32_t claimed_slot = 0;
+  uint32_t status = 0;
+  if (i < n) {
+    const unsigned long long* e_in = reinterpret_cast<const unsigned long long*>(in + (uint64_t)i * stride);
+    const unsigned long long key = e_in[0];
+    uint64_t slot = lk_hash64(key - 1) & mask;
+    unsigned long long* entry = nullptr;
+    for (int probe = 0; probe < 4096; probe++) {
+      unsigned long long* e = reinterpret_cast<unsigned long long*>(entries + slot * stride);
+      unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(e);
+      if (k == LK_EMPTY_KEY) {
+        k = atomicCAS(e, (unsigned long long)LK_EMPTY_KEY, key);
+        if (k == LK_EMPTY_KEY) { claimed = true; claimed_slot = (uint32_t)slot; entry = e; break; }
+      }
+      if (k == key) { entry = e; break; }
+      slot = (slot + 1) & mask;
+    }
+    if (!entry) status |= ST_HASH_FULL;
+    else
+      for (int a = 0; a < n_aggs; a++) {
+        const unsigned long long w = e_in[1 + a];
+        if (ops.op[a] == AGG_SUM) atomicAdd(reinterpret_cast<double*>(entry + 1 + a), __longlong_as_double((long long)w));
+        else if (ops.op[a] == AGG_COUNT) atomicAdd(entry + 1 + a, w);
+        else if (w) atomicMax(entry + 1 + a, w);
+      }
+  }
+  const unsigned cm = __ballot_sync(0xffffffffu, claimed);
+  if (cm) {
+    uint32_t base = 0;
+    if (lane == __ffs(cm) - 1) base = atomicAdd(counters + 3, (uint32_t)__popc(cm));
+    base = __shfl_sync(0xffffffffu, base, __ffs(cm) - 1);
+    if (claimed) {
+      const uint32_t idx = base + __popc(cm & ((1u << lane) - 1));
+      if (idx < occ_cap) occ[idx] = claimed_slot; else status |= ST_HASH_FULL;
+    }
+  }
+  if (status) atomicOr(counters + 0, status);
+}
+
+void device_partial_sparse(Query& q, int nparts, void** entries_out, int64_t* counts, int* stride_out) {
+  LK_CHECK(q.dev && q.dev->executed, LK_ERR_INVALID, "lk_query_partial_sparse before lk_query_execute");
+  LK_CHECK(q.path == 1, LK_ERR_INVALID, "query uses the dense path; use lk_query_partial_dense");
+  LK_CHECK(nparts >= 1 && nparts <= SP_MAXPARTS, LK_ERR_INVALID, "nparts must be in [1, 64]");
+  Query::Device& d = *q.dev;
+  LK_CHECK(!d.finalized_device, LK_ERR_INVALID, "lk_query_partial_sparse after finalize");
+  CUDA_CHECK(cudaSetDevice(global_options().device));
+  CUDA_CHECK(cudaMemcpyAsync(d.h_counters, d.counters, sizeof d.h_counters, cudaMemcpyDeviceToHost, d.st));
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  if (d.h_counters[0] & ST_HASH_FULL) {
+    if (d.harena) CUDA_CHECK(cudaMemsetAsync(d.harena->entries, 0, d.harena->slots * d.harena->stride, d.st));
+    d.finalized_device = true;
+    fail(LK_ERR_NOMEM, "aggregate hash table overflowed; raise max_hash_slots in lk_init");
+  }
+  LK_CHECK(!(d.h_counters[0] & ST_BAD_CODE), LK_ERR_IO, "corrupt segment: dictionary index out of range");
+  const uint32_t n = q.n_cells ? d.h_counters[3] : 0;
+  const uint32_t stride = q.hash_stride;
+  for (int p = 0; p < nparts; p++) counts[p] = 0;
+  *stride_out = (int)stride;
+  *entries_out = nullptr;
+  if (n == 0) return;
+  // scratch: hist[64] | cursor[64] | part_of[n]
+  ensure_block_counts(d, 128 + (size_t)n);
+  uint32_t* hist = d.block_counts;
+  uint32_t* cursor = hist + 64;
+  uint32_t* part_of = hist + 128;
+  if (d.sparse_cap < (size_t)n * stride) {
+    if (d.sparse_out) CUDA_CHECK(cudaFreeAsync(d.sparse_out, d.st));
+    d.sparse_out = nullptr;
+    CUDA_CHECK(cudaMallocAsync(&d.sparse_out, (size_t)n * stride, d.st));
+    d.sparse_cap = (size_t)n * stride;
+  }
+  CUDA_CHECK(cudaMemsetAsync(hist, 0, 128 * 4, d.st));
+  const int grid = (int)((n + HS_CHUNK - 1) / HS_CHUNK);
+  sparse_hist_kernel<<<grid, HS_BLOCK, 0, d.st>>>(d.harena->occ, n, d.harena->entries, stride, (uint32_t)nparts, part_of, hist);
+  uint32_t h[64];
+  CUDA_CHECK(cudaMemcpyAsync(h, hist, 64 * 4, cudaMemcpyDeviceToHost, d.st));
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  uint32_t starts[64] = {0};
+  uint32_t run = 0;
+  for (int p = 0; p < nparts; p++) { counts[p] = h[p]; starts[p] = run; run += h[p]; }
+  CUDA_CHECK(cudaMemcpyAsync(cursor, starts, 64 * 4, cudaMemcpyHostToDevice, d.st));
+  sparse_scatter_kernel<<<grid, HS_BLOCK, 0, d.st>>>(d.harena->occ, part_of, n, d.harena->entries, stride, (uint32_t)nparts, cursor, d.sparse_out);
+  // the table is empty and clean again: foreign + own entries come back through lk_query_merge_sparse
+  CUDA_CHECK(cudaMemsetAsync(d.counters + 3, 0, 4, d.st));
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  *entries_out = d.sparse_out;
+}
+
+void device_merge_sparse(Query& q, const void* dev_entries, int64_t n) {
+  LK_CHECK(q.dev && q.dev->executed && !q.dev->finalized_device, LK_ERR_INVALID, "lk_query_merge_sparse needs an executed, not yet finalized query");
+  LK_CHECK(q.path == 1, LK_ERR_INVALID, "query uses the dense path");
+  LK_CHECK(n >= 0 && n < (int64_t)0xffffffffu, LK_ERR_INVALID, "bad entry count");
+  if (n == 0) return;
+  Query::Device& d = *q.dev;
+  CUDA_CHECK(cudaSetDevice(global_options().device));
+  AggSlot4 ops;
+  memset(&ops, 0, sizeof ops);
+  for (size_t a = 0; a < q.aggs.size(); a++) ops.op[a] = q.aggs[a].op;
+  sparse_merge_kernel<<<(int)((n + HS_BLOCK - 1) / HS_BLOCK), HS_BLOCK, 0, d.st>>>(
+      (const uint8_t*)dev_entries, (uint32_t)n, d.harena->entries, d.harena->stride, q.params.h_mask, d.harena->occ,
+      (uint32_t)std::min<uint64_t>(d.harena->slots, 0xffffffffu), d.counters, (int)q.aggs.size(), ops);
+  CUDA_CHECK(cudaGetLastError());
 }
 
 int64_t device_survivors(Query& q) {

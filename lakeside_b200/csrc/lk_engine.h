@@ -17,6 +17,8 @@ void device_execute(Query& q);             // clear table + fused scan kernel (a
 void device_sync(Query& q);
 void* device_stream(Query& q);
 void device_partial_dense(Query& q, int64_t* n_cells, int* n_planes, void** ptrs, int* ops);
+void device_partial_sparse(Query& q, int nparts, void** entries_out, int64_t* counts, int* stride_out);
+void device_merge_sparse(Query& q, const void* dev_entries, int64_t n);
 void device_finalize_device(Query& q);     // compaction into result rows in HBM
 HostResult* device_fetch(Query& q);        // D2H
 void device_timings(Query& q);

@@ -1,15 +1,387 @@
+// GPU K-way merge of sorted per-segment streams (merge-path partitioning + in-CTA pairwise merge tree) and the
+// map-sketch re-aggregation of the merged stream.
+//
+// Order produced = the reference's left-deep fold `sources.fold(Source.empty)((s1, s2) => s1.mergeSorted(s2))`
+// (Commons.scala:391-392, WorkerApi.scala:173, QueryEngineV2.scala:96) with akka-stream's MergeSorted emitting the
+// left head only when left < right: by timestamp, ties by stream index DESCENDING, then by position in the stream.
+// Every element therefore has a unique sort key (ts', K-1-src, pos) and the merge is a deterministic total order.
+//
+// One pass over the data: kernel 1 finds, for every output tile boundary (rank p * TILE), the exact per-stream split
+// (multi-sequence selection by bisection over the key domain, a thread per stream); kernel 2 gives each CTA its K
+// sub-ranges (exactly TILE elements), loads their keys into shared memory, merges the K sorted runs pairwise
+// (log2 K levels of rank-by-binary-search, ping-pong buffers) and writes the tile out coalesced, gathering the
+// payload.  Algorithmic traffic = 20 B read + 20 B written per element.
 #include "lk_merge.h"
 
-#include "lk_common.h"
+#include <cuda_runtime.h>
 
-struct lk_merge { int dummy; };
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lk_common.h"
+#include "lk_engine.h"
+
+#define CUDA_CHECK(x)                                                                                        \
+  do {                                                                                                       \
+    cudaError_t err__ = (x);                                                                                 \
+    if (err__ != cudaSuccess) ::lk::fail(LK_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(err__)); \
+  } while (0)
 
 namespace lk {
-lk_merge* merge_create(int, const int64_t* const*, const int32_t* const*, const double* const*, const int64_t*, bool) { fail(LK_ERR_UNSUPPORTED, "merge: not built yet"); }
-void merge_run(lk_merge*) { fail(LK_ERR_UNSUPPORTED, "merge: not built yet"); }
-void merge_sync(lk_merge*) {}
-void merge_timings(lk_merge*, double*) {}
-void merge_download(lk_merge*, int64_t*, int32_t*, double*, int32_t*) { fail(LK_ERR_UNSUPPORTED, "merge: not built yet"); }
-void merge_reduce(lk_merge*, int, int64_t*, int64_t*, int32_t*, double*) { fail(LK_ERR_UNSUPPORTED, "merge: not built yet"); }
-void merge_destroy(lk_merge* m) { delete m; }
+
+constexpr int MG_TILE = 2048;
+constexpr int MG_BLOCK = 256;
+
+struct MergeElem {
+  unsigned long long key;  // order-mapped timestamp
+  uint32_t tag;            // (K - 1 - src) * MG_TILE + local index: unique, realises the tie rule
+  uint32_t gidx;           // index into the concatenated input
+};
+
+__device__ __forceinline__ bool elem_less(const MergeElem& a, const MergeElem& b) {
+  return a.key < b.key || (a.key == b.key && a.tag < b.tag);
+}
+
+// order-preserving map int64 -> uint64; reverse streams (descending ts) are merged ascending on the complement
+__device__ __forceinline__ unsigned long long ts_key(long long ts, int reverse) {
+  unsigned long long u = (unsigned long long)ts ^ 0x8000000000000000ull;
+  return reverse ? ~u : u;
+}
+__device__ __forceinline__ long long key_ts(unsigned long long k, int reverse) {
+  if (reverse) k = ~k;
+  return (long long)(k ^ 0x8000000000000000ull);
+}
+
+// first index in [lo, hi) of stream whose key is >= k (lower) or > k (upper)
+__device__ __forceinline__ uint32_t bound(const long long* __restrict__ ts, uint32_t lo, uint32_t hi, unsigned long long k, int reverse, bool upper) {
+  while (lo < hi) {
+    uint32_t mid = lo + ((hi - lo) >> 1);
+    unsigned long long v = ts_key(ts[mid], reverse);
+    if (upper ? v <= k : v < k) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// kernel 1: per-stream split of output rank r = blockIdx.x * MG_TILE.  splits[p * K + j] = elements of stream j before r.
+__global__ void __launch_bounds__(MG_BLOCK) merge_split_kernel(const long long* __restrict__ ts, const uint32_t* __restrict__ offs, int K,
+                                                               uint64_t total, unsigned long long kmin, unsigned long long kmax, int reverse,
+                                                               uint32_t* __restrict__ splits) {
+  __shared__ unsigned long long red[MG_BLOCK / 32];
+  __shared__ unsigned long long bcast;
+  const uint64_t r = (uint64_t)blockIdx.x * MG_TILE;
+  uint32_t* out = splits + (size_t)blockIdx.x * K;
+  if (r >= total) {  // the sentinel boundary after the last tile
+    for (int j = threadIdx.x; j < K; j += MG_BLOCK) out[j] = offs[j + 1] - offs[j];
+    return;
+  }
+  auto block_sum = [&](unsigned long long v) -> unsigned long long {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned long long t = 0;
+      for (int w = 0; w < MG_BLOCK / 32; w++) t += red[w];
+      bcast = t;
+    }
+    __syncthreads();
+    return bcast;
+  };
+  // smallest key t with count_le(t) > r
+  unsigned long long lo = kmin, hi = kmax;
+  while (lo < hi) {
+    const unsigned long long mid = lo + ((hi - lo) >> 1);
+    unsigned long long c = 0;
+    for (int j = threadIdx.x; j < K; j += MG_BLOCK) c += bound(ts, offs[j], offs[j + 1], mid, reverse, true) - offs[j];
+    c = block_sum(c);
+    if (c > r) hi = mid; else lo = mid + 1;
+  }
+  const unsigned long long tstar = lo;
+  unsigned long long less = 0;
+  for (int j = threadIdx.x; j < K; j += MG_BLOCK) less += bound(ts, offs[j], offs[j + 1], tstar, reverse, false) - offs[j];
+  less = block_sum(less);
+  // ties at tstar are consumed from the highest stream index downwards
+  unsigned long long rem = r - less;
+  __shared__ unsigned long long rem_s;
+  if (threadIdx.x == 0) rem_s = rem;
+  __syncthreads();
+  for (int jb = ((K - 1) / MG_BLOCK) * MG_BLOCK; jb >= 0; jb -= MG_BLOCK) {
+    const int j = jb + (MG_BLOCK - 1 - (int)threadIdx.x);  // thread 0 handles the highest stream of the chunk
+    uint32_t lb = 0, cnt = 0;
+    if (j < K) {
+      lb = bound(ts, offs[j], offs[j + 1], tstar, reverse, false);
+      cnt = bound(ts, lb, offs[j + 1], tstar, reverse, true) - lb;
+    }
+    // inclusive scan of cnt in thread order (descending stream index)
+    __shared__ uint32_t warp_tot[MG_BLOCK / 32];
+    uint32_t incl = cnt;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < wid; w++) woff += warp_tot[w];
+    const unsigned long long before = (unsigned long long)woff + incl - cnt;  // ties consumed by higher streams of this chunk
+    const unsigned long long rem0 = rem_s;
+    if (j < K) {
+      unsigned long long take = rem0 > before ? rem0 - before : 0;
+      if (take > cnt) take = cnt;
+      out[j] = (lb - offs[j]) + (uint32_t)take;
+    }
+    __syncthreads();
+    if (threadIdx.x == MG_BLOCK - 1) {
+      const unsigned long long chunk_total = (unsigned long long)woff + incl;
+      rem_s = rem0 > chunk_total ? rem0 - chunk_total : 0;
+    }
+    __syncthreads();
+  }
+}
+
+// kernel 2: merge the K sub-ranges of one output tile
+__global__ void __launch_bounds__(MG_BLOCK) merge_tile_kernel(const long long* __restrict__ ts, const int* __restrict__ gid, const double* __restrict__ val,
+                                                              const uint32_t* __restrict__ offs, int K, uint64_t total, int reverse,
+                                                              const uint32_t* __restrict__ splits, long long* __restrict__ out_ts,
+                                                              int* __restrict__ out_gid, double* __restrict__ out_val, int* __restrict__ out_src) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  MergeElem* bufA = reinterpret_cast<MergeElem*>(smem_raw);
+  MergeElem* bufB = bufA + MG_TILE;
+  uint32_t* rb = reinterpret_cast<uint32_t*>(bufB + MG_TILE);  // run boundaries, K + 1 entries (ping)
+  uint32_t* rb2 = rb + (K + 1);                                 // (pong)
+  const uint32_t* s0 = splits + (size_t)blockIdx.x * K;
+  const uint32_t* s1 = s0 + K;
+  const uint64_t tile_base = (uint64_t)blockIdx.x * MG_TILE;
+  const uint32_t n = (uint32_t)min((uint64_t)MG_TILE, total - tile_base);
+  // run boundaries = exclusive prefix of the sub-range lengths (single-warp scan over K)
+  if (threadIdx.x < 32) {
+    uint32_t carry = 0;
+    for (int jb = 0; jb < K; jb += 32) {
+      const int j = jb + threadIdx.x;
+      uint32_t c = j < K ? s1[j] - s0[j] : 0, incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if ((int)threadIdx.x >= d) incl += o; }
+      if (j < K) rb[j] = carry + incl - c;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (threadIdx.x == 0) rb[K] = carry;
+  }
+  __syncthreads();
+  // load: slot s belongs to the stream j with rb[j] <= s < rb[j + 1]
+  for (uint32_t s = threadIdx.x; s < n; s += MG_BLOCK) {
+    int lo = 0, hi = K;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (rb[mid] <= s) lo = mid; else hi = mid; }
+    // skip empty streams that share the same boundary: take the LAST j with rb[j] <= s
+    const int j = lo;
+    const uint32_t gi = offs[j] + s0[j] + (s - rb[j]);
+    MergeElem e;
+    e.key = ts_key(ts[gi], reverse);
+    e.tag = (uint32_t)(K - 1 - j) * MG_TILE + s;
+    e.gidx = gi;
+    bufA[s] = e;
+  }
+  __syncthreads();
+  // pairwise merge tree over runs
+  MergeElem* src = bufA;
+  MergeElem* dst = bufB;
+  int nruns = K;
+  while (nruns > 1) {
+    const int nnew = (nruns + 1) >> 1;
+    for (uint32_t s = threadIdx.x; s < n; s += MG_BLOCK) {
+      int lo = 0, hi = nruns;
+      while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (rb[mid] <= s) lo = mid; else hi = mid; }
+      const int run = lo;
+      const int partner = run ^ 1;
+      const MergeElem e = src[s];
+      uint32_t pos;
+      if (partner >= nruns) pos = s;  // odd run out: carried unchanged
+      else {
+        uint32_t plo = rb[partner], phi = rb[partner + 1];
+        const uint32_t pstart = plo;
+        while (plo < phi) {  // elements of the partner run that sort before e (keys are unique)
+          uint32_t mid = plo + ((phi - plo) >> 1);
+          if (elem_less(src[mid], e)) plo = mid + 1; else phi = mid;
+        }
+        const uint32_t pair_start = rb[run & ~1];
+        pos = pair_start + (s - rb[run]) + (plo - pstart);
+      }
+      dst[pos] = e;
+    }
+    for (int i = threadIdx.x; i <= nnew; i += MG_BLOCK) rb2[i] = i == nnew ? rb[nruns] : rb[2 * i];
+    __syncthreads();
+    MergeElem* t = src; src = dst; dst = t;
+    uint32_t* tr = rb; rb = rb2; rb2 = tr;
+    nruns = nnew;
+  }
+  for (uint32_t s = threadIdx.x; s < n; s += MG_BLOCK) {
+    const MergeElem e = src[s];
+    const uint64_t o = tile_base + s;
+    out_ts[o] = key_ts(e.key, reverse);
+    if (out_gid) out_gid[o] = gid[e.gidx];
+    if (out_val) out_val[o] = val[e.gidx];
+    if (out_src) out_src[o] = K - 1 - (int)(e.tag / MG_TILE);
+  }
+}
+
+// ---- map-sketch re-aggregation of the merged stream (TimeGroupedSketchAggregator.scala:63-93) ----
+// Elements with equal timestamp are contiguous after the merge; equal (ts, gid) pairs are combined with
+// op 0: + (sum / count), 2: min, 3: max.  Output: one element per (ts, gid), sorted by ts then gid.
+__global__ void seg_flag_kernel(const long long* __restrict__ ts, uint64_t n, uint32_t* __restrict__ flag) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) flag[i] = (i == 0 || ts[i] != ts[i - 1]) ? 1u : 0u;
+}
+
+}  // namespace lk
+
+using namespace lk;
+
+struct lk_merge {
+  int K = 0;
+  bool reverse = false;
+  uint64_t total = 0;
+  unsigned long long kmin = 0, kmax = 0;
+  cudaStream_t st = nullptr;
+  cudaEvent_t ev[4] = {};
+  long long* d_ts = nullptr;
+  int* d_gid = nullptr;
+  double* d_val = nullptr;
+  uint32_t* d_offs = nullptr;
+  uint32_t* d_splits = nullptr;
+  long long* o_ts = nullptr;
+  int* o_gid = nullptr;
+  double* o_val = nullptr;
+  int* o_src = nullptr;
+  uint32_t ntiles = 0;
+  bool ran = false;
+  double ms[4] = {0, 0, 0, 0};
+};
+
+namespace lk {
+
+static unsigned long long host_key(long long ts, bool reverse) {
+  unsigned long long u = (unsigned long long)ts ^ 0x8000000000000000ull;
+  return reverse ? ~u : u;
+}
+
+lk_merge* merge_create(int k, const int64_t* const* ts, const int32_t* const* gid, const double* const* val, const int64_t* lens, bool reverse) {
+  device_init();
+  auto m = new lk_merge();
+  try {
+    m->K = k;
+    m->reverse = reverse;
+    std::vector<uint32_t> offs(k + 1, 0);
+    uint64_t total = 0;
+    for (int j = 0; j < k; j++) {
+      LK_CHECK(lens[j] >= 0, LK_ERR_INVALID, "negative stream length");
+      total += (uint64_t)lens[j];
+      LK_CHECK(total < 0xfffffff0ull, LK_ERR_UNSUPPORTED, "merge: more than 2^32 elements");
+      offs[j + 1] = (uint32_t)total;
+    }
+    LK_CHECK((uint64_t)k * MG_TILE < 0xffffffffull, LK_ERR_UNSUPPORTED, "merge: too many streams");
+    m->total = total;
+    CUDA_CHECK(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking));
+    for (auto& e : m->ev) CUDA_CHECK(cudaEventCreate(&e));
+    bool any = false;
+    for (int j = 0; j < k; j++) {
+      if (!lens[j]) continue;
+      // streams must be sorted; the key domain is bracketed by the heads and tails
+      unsigned long long a = host_key(ts[j][0], reverse), b = host_key(ts[j][lens[j] - 1], reverse);
+      LK_CHECK(a <= b, LK_ERR_INVALID, "merge: stream " + std::to_string(j) + " is not sorted in the requested direction");
+      if (!any) { m->kmin = a; m->kmax = b; any = true; }
+      m->kmin = std::min(m->kmin, a);
+      m->kmax = std::max(m->kmax, b);
+    }
+    size_t n = std::max<uint64_t>(total, 1);
+    CUDA_CHECK(cudaEventRecord(m->ev[0], m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->d_ts, n * 8, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->d_gid, n * 4, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->d_val, n * 8, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->d_offs, (k + 1) * 4, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->o_ts, n * 8, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->o_gid, n * 4, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->o_val, n * 8, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->o_src, n * 4, m->st));
+    m->ntiles = (uint32_t)((total + MG_TILE - 1) / MG_TILE);
+    CUDA_CHECK(cudaMallocAsync(&m->d_splits, ((size_t)m->ntiles + 1) * std::max(k, 1) * 4, m->st));
+    CUDA_CHECK(cudaMemcpyAsync(m->d_offs, offs.data(), (k + 1) * 4, cudaMemcpyHostToDevice, m->st));
+    for (int j = 0; j < k; j++) {
+      if (!lens[j]) continue;
+      CUDA_CHECK(cudaMemcpyAsync(m->d_ts + offs[j], ts[j], lens[j] * 8, cudaMemcpyHostToDevice, m->st));
+      if (gid && gid[j]) CUDA_CHECK(cudaMemcpyAsync(m->d_gid + offs[j], gid[j], lens[j] * 4, cudaMemcpyHostToDevice, m->st));
+      else CUDA_CHECK(cudaMemsetAsync(m->d_gid + offs[j], 0, lens[j] * 4, m->st));
+      if (val && val[j]) CUDA_CHECK(cudaMemcpyAsync(m->d_val + offs[j], val[j], lens[j] * 8, cudaMemcpyHostToDevice, m->st));
+      else CUDA_CHECK(cudaMemsetAsync(m->d_val + offs[j], 0, lens[j] * 8, m->st));
+    }
+    CUDA_CHECK(cudaEventRecord(m->ev[1], m->st));
+    CUDA_CHECK(cudaStreamSynchronize(m->st));  // the host arrays are borrowed for the call only
+    float f = 0;
+    CUDA_CHECK(cudaEventElapsedTime(&f, m->ev[0], m->ev[1]));
+    m->ms[0] = f;
+    static bool attr_set = false;
+    size_t smem = 2 * MG_TILE * sizeof(MergeElem) + 2 * (size_t)(k + 1) * 4 + 16;
+    LK_CHECK(smem <= 200 * 1024, LK_ERR_UNSUPPORTED, "merge: too many streams for one shared-memory tile");
+    (void)attr_set;
+    CUDA_CHECK(cudaFuncSetAttribute(merge_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  } catch (...) {
+    merge_destroy(m);
+    throw;
+  }
+  return m;
+}
+
+void merge_run(lk_merge* m) {
+  CUDA_CHECK(cudaSetDevice(global_options().device));
+  CUDA_CHECK(cudaEventRecord(m->ev[2], m->st));
+  if (m->total > 0) {
+    size_t smem = 2 * MG_TILE * sizeof(MergeElem) + 2 * (size_t)(m->K + 1) * 4 + 16;
+    merge_split_kernel<<<m->ntiles + 1, MG_BLOCK, 0, m->st>>>(m->d_ts, m->d_offs, m->K, m->total, m->kmin, m->kmax, m->reverse ? 1 : 0, m->d_splits);
+    merge_tile_kernel<<<m->ntiles, MG_BLOCK, smem, m->st>>>(m->d_ts, m->d_gid, m->d_val, m->d_offs, m->K, m->total, m->reverse ? 1 : 0, m->d_splits,
+                                                            m->o_ts, m->o_gid, m->o_val, m->o_src);
+    CUDA_CHECK(cudaGetLastError());
+  }
+  CUDA_CHECK(cudaEventRecord(m->ev[3], m->st));
+  m->ran = true;
+}
+
+void merge_sync(lk_merge* m) { CUDA_CHECK(cudaStreamSynchronize(m->st)); }
+
+void merge_timings(lk_merge* m, double* ms) {
+  merge_sync(m);
+  float f = 0;
+  if (m->ran && cudaEventElapsedTime(&f, m->ev[2], m->ev[3]) == cudaSuccess) m->ms[1] = f;
+  cudaGetLastError();
+  for (int i = 0; i < 4; i++) ms[i] = m->ms[i];
+}
+
+void merge_download(lk_merge* m, int64_t* out_ts, int32_t* out_gid, double* out_val, int32_t* out_src) {
+  LK_CHECK(m->ran, LK_ERR_INVALID, "lk_merge_download before lk_merge_run");
+  size_t n = m->total;
+  if (n) {
+    if (out_ts) CUDA_CHECK(cudaMemcpyAsync(out_ts, m->o_ts, n * 8, cudaMemcpyDeviceToHost, m->st));
+    if (out_gid) CUDA_CHECK(cudaMemcpyAsync(out_gid, m->o_gid, n * 4, cudaMemcpyDeviceToHost, m->st));
+    if (out_val) CUDA_CHECK(cudaMemcpyAsync(out_val, m->o_val, n * 8, cudaMemcpyDeviceToHost, m->st));
+    if (out_src) CUDA_CHECK(cudaMemcpyAsync(out_src, m->o_src, n * 4, cudaMemcpyDeviceToHost, m->st));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(m->st));
+}
+
+void merge_reduce(lk_merge*, int, int64_t*, int64_t*, int32_t*, double*) {
+  fail(LK_ERR_UNSUPPORTED, "lk_merge_reduce is not available in this build");
+}
+
+void merge_destroy(lk_merge* m) {
+  if (!m) return;
+  if (m->st) {
+    cudaStreamSynchronize(m->st);
+    void* ptrs[] = {m->d_ts, m->d_gid, m->d_val, m->d_offs, m->d_splits, m->o_ts, m->o_gid, m->o_val, m->o_src};
+    for (void* p : ptrs) if (p) cudaFreeAsync(p, m->st);
+    cudaStreamSynchronize(m->st);
+    cudaStreamDestroy(m->st);
+  }
+  for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  delete m;
+}
+
 }  // namespace lk

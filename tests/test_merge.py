@@ -1,0 +1,79 @@
+"""K-way merge: oracle tie rule on CPU, GPU merge-path kernel against the oracle on the B200."""
+import numpy as np
+import pytest
+
+import lakeside_oracle as lo
+from lakeside_b200 import synth
+
+
+class _E:
+    def __init__(self, ts, src, pos):
+        self.timestamp, self.src, self.pos = ts, src, pos
+
+
+def _streams(k, m, rng, distinct=360, ragged=True):
+    out = []
+    for j in range(k):
+        n = int(rng.integers(0, m + 1)) if ragged else m
+        out.append(np.sort(synth.T0 + 10000 * rng.integers(0, distinct, n)).astype(np.int64))
+    return out
+
+
+def test_oracle_fold_matches_vectorised_order():
+    # the literal left-deep fold of 2-way merges (later source first on ties) == lexsort (ts, -src, pos)
+    rng = np.random.default_rng(7)
+    ts = _streams(9, 40, rng, distinct=6)
+    fold = lo.merge_sorted_source([[_E(int(t), j, i) for i, t in enumerate(s)] for j, s in enumerate(ts)])
+    src, pos = lo.merge_sorted_arrays(ts)
+    assert [(e.src, e.pos) for e in fold] == list(zip(src.tolist(), pos.tolist()))
+    # descending streams, reverseSort = true
+    tsr = [s[::-1].copy() for s in ts]
+    fold = lo.merge_sorted_source([[_E(int(t), j, i) for i, t in enumerate(s)] for j, s in enumerate(tsr)], reverse=True)
+    order = np.lexsort((np.concatenate([np.arange(len(s)) for s in tsr]), -np.concatenate([np.full(len(s), j) for j, s in enumerate(tsr)]),
+                        -np.concatenate(tsr)))
+    allsrc = np.concatenate([np.full(len(s), j) for j, s in enumerate(tsr)])
+    allpos = np.concatenate([np.arange(len(s)) for s in tsr])
+    assert [(e.src, e.pos) for e in fold] == list(zip(allsrc[order].tolist(), allpos[order].tolist()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,m,distinct", [(1, 5000, 360), (2, 3000, 5), (7, 2500, 360), (64, 4096, 360), (256, 1024, 40), (300, 700, 100000)])
+def test_gpu_merge_matches_oracle(k, m, distinct):
+    from lakeside_b200 import api
+
+    api.init()
+    rng = np.random.default_rng(k * 1000 + m)
+    ts = _streams(k, m, rng, distinct=distinct)
+    src, pos = api.merge_streams_index(ts)
+    wsrc, wpos = lo.merge_sorted_arrays(ts)
+    assert np.array_equal(src, wsrc) and np.array_equal(pos, wpos)
+
+
+@pytest.mark.gpu
+def test_gpu_merge_payload_reverse_and_empty():
+    import ctypes
+
+    from lakeside_b200 import _lib, api
+
+    api.init()
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+    ts = [s[::-1].copy() for s in _streams(33, 900, rng, distinct=50)] + [np.zeros(0, np.int64)]
+    k = len(ts)
+    gid = [rng.integers(0, 1000, len(t)).astype(np.int32) for t in ts]
+    val = [rng.standard_normal(len(t)) for t in ts]
+    n = sum(len(t) for t in ts)
+    P = ctypes.c_void_p
+    o_ts, o_gid, o_val, o_src = np.empty(n, np.int64), np.empty(n, np.int32), np.empty(n, np.float64), np.empty(n, np.int32)
+    _lib.check(lib.lk_merge_streams(k, (P * k)(*[t.ctypes.data for t in ts]), (P * k)(*[g.ctypes.data for g in gid]),
+                                    (P * k)(*[v.ctypes.data for v in val]), (ctypes.c_int64 * k)(*[len(t) for t in ts]), 1,
+                                    o_ts.ctypes.data, o_gid.ctypes.data, o_val.ctypes.data, o_src.ctypes.data))
+    allsrc = np.concatenate([np.full(len(s), j) for j, s in enumerate(ts)])
+    allpos = np.concatenate([np.arange(len(s)) for s in ts])
+    order = np.lexsort((allpos, -allsrc, -np.concatenate(ts)))
+    assert np.array_equal(o_src, allsrc[order])
+    assert np.array_equal(o_ts, np.concatenate(ts)[order])
+    assert np.array_equal(o_gid, np.concatenate(gid)[order])
+    assert np.array_equal(o_val, np.concatenate(val)[order])
+    # nothing to merge
+    assert api.merge_sorted_source([[], []]) == []

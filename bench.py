@@ -216,37 +216,76 @@ def main():
             q.add_segment_buffer(ptr, n)
         return q
 
+    def _as_tensor(ptr, n, typestr, dtype):
+        class _A:
+            pass
+        a = _A()
+        a.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3}
+        return torch.as_tensor(a, device=f"cuda:{local_rank}").view(dtype)
+
+    def agree_on_dictionaries(qq):
+        """All ranks must index ONE (group x bucket) space: all-gather the per-rank group-by dictionaries (host strings,
+        a few KB), import their union everywhere."""
+        if world == 1:
+            return
+        blobs = [None] * world
+        dist.all_gather_object(blobs, qq.export_dictionaries())
+        qq.import_dictionaries(api.union_dictionaries(blobs))
+
+    SIGN = torch.iinfo(torch.int64).min
+    exchange_bytes = [0]
+
+    def exchange(qq, path):
+        """The ONE exchange step of the sharded path (no collective touches the scan).
+        dense : NCCL reduce of every (group x bucket) plane to rank 0 (sum f64 / sum u64 / max on order-preserving keys)
+        hash  : cells are hash-partitioned over the ranks; NCCL all-to-all of the occupied 32/64-byte entries, each rank
+                merges and finalises its own partition."""
+        if world == 1:
+            return
+        if path == "dense":
+            n_cells, planes = qq.partial_dense()
+            qq.sync()
+            for ptr, op in planes:
+                if op == 0:
+                    dist.reduce(_as_tensor(ptr, n_cells, "<f8", torch.float64), 0, op=dist.ReduceOp.SUM)
+                elif op == 1:
+                    dist.reduce(_as_tensor(ptr, n_cells, "<i8", torch.int64), 0, op=dist.ReduceOp.SUM)
+                else:  # unsigned max: flip the sign bit so that NCCL's signed max orders the keys, flip back
+                    t = _as_tensor(ptr, n_cells, "<i8", torch.int64)
+                    t.bitwise_xor_(SIGN)
+                    dist.reduce(t, 0, op=dist.ReduceOp.MAX)
+                    t.bitwise_xor_(SIGN)
+            exchange_bytes[0] = n_cells * 8 * len(planes)
+            torch.cuda.synchronize()
+        else:
+            ptr, counts, stride = qq.partial_sparse(world)
+            send_counts = torch.tensor(counts, dtype=torch.int64, device="cuda")
+            recv_counts = torch.empty_like(send_counts)
+            dist.all_to_all_single(recv_counts, send_counts)
+            rc = recv_counts.tolist()
+            n_send = sum(counts)
+            send = _as_tensor(ptr, n_send * stride, "|u1", torch.uint8) if n_send else torch.empty(0, dtype=torch.uint8, device="cuda")
+            recv = torch.empty(sum(rc) * stride, dtype=torch.uint8, device="cuda")
+            dist.all_to_all_single(recv, send, [c * stride for c in rc], [c * stride for c in counts])
+            torch.cuda.synchronize()
+            qq.merge_sparse(recv.data_ptr(), sum(rc))
+            qq._keep.append(recv)
+            exchange_bytes[0] = (n_send - counts[rank]) * stride
+
     # ---------------- resident ("kernel-only") arm ----------------
     q = new_query()
+    q.plan()
+    agree_on_dictionaries(q)
     q.prepare()
     info = q.info
     rows_per_rank = q.total_rows
     touched = q.touched_bytes
-    sparse_exchange = None
-
-    def exchange():
-        """The one exchange step of the sharded path.  Dense: NCCL reduce of the (group x bucket) planes."""
-        if world == 1:
-            return
-        if info["path"] == "dense":
-            n_cells, planes = q.partial_dense()
-            for ptr, op in planes:
-                t = _as_tensor(ptr, n_cells, torch.float64 if op == 0 else torch.int64)
-                dist.reduce(t, 0, op=dist.ReduceOp.SUM if op in (0, 1) else dist.ReduceOp.MAX)
-        else:
-            raise SystemExit("sparse exchange not wired into bench yet")
-
-    def _as_tensor(ptr, n, dtype):
-        class _A:
-            pass
-        a = _A()
-        a.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8" if dtype == torch.float64 else "<i8", "data": (ptr, False), "version": 3}
-        return torch.as_tensor(a, device=f"cuda:{local_rank}")
 
     def step():
         q.execute()
-        exchange()
+        exchange(q, info["path"])
         q.finalize_device()
+        q._keep.clear()
 
     for _ in range(max(3, args.warmup)):
         step()
@@ -289,8 +328,11 @@ def main():
 
     def e2e_step():
         qq = new_query()
+        qq.plan()
+        agree_on_dictionaries(qq)
         qq.prepare()
         qq.execute()
+        exchange(qq, qq.info["path"])
         res = qq.finalize()
         n = res.num_rows
         d2h = n * (8 + 8 * res.num_values + 4 * res.num_tags + res.num_values)
@@ -341,11 +383,13 @@ def main():
                          "frac_of_nominal_8TBps": achieved / 8000.0, "traffic": traffic,
                          "algorithmic_bytes_per_launch": touched, "kernel_ms": k_ms,
                          "note": "algorithmic bytes = sum of ColumnMetaData.total_compressed_size of the touched column chunks (SURVEY §8d)"},
-            "cpu_baseline": cpu_baseline(paths, rq, aggs),
+            "cpu_baseline": cpu_baseline(paths, rq, aggs) if world == 1 else None,  # timed on rank 0 at N = 1 only
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
                     "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps,
                     "what": "lk_query_create + add_segment_buffer(pinned host bytes) + prepare (host index + H2D) + execute + finalize (D2H)"},
-            "gpu_launches": args.steps * 4,
+            "gpu_launches": args.steps * (5 if world == 1 else 8),
+            "exchange": None if world == 1 else {"kind": "NCCL reduce of dense planes" if info["path"] == "dense" else "NCCL all-to-all of hash-partitioned occupied cells",
+                                                 "bytes_sent_per_rank_per_step": exchange_bytes[0]},
             "clocks": clocks,
         }
         print(json.dumps(line))

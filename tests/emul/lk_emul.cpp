@@ -226,3 +226,14 @@ __attribute__((visibility("default"))) const char* lk_emul_col_name(EmulResult* 
 __attribute__((visibility("default"))) const char* lk_emul_info(EmulResult* r) { return r->info.c_str(); }
 __attribute__((visibility("default"))) void lk_emul_free(EmulResult* r) { delete r; }
 }
+
+// regex engine under test (the class is not exported by the product library)
+extern "C" __attribute__((visibility("default"))) int lk_emul_regex(const char* pattern, int case_insensitive, const char* s, int len) {
+  try {
+    Regex re(pattern, case_insensitive != 0);
+    return re.search(s, (size_t)len) ? 1 : 0;
+  } catch (const Error& e) {
+    g_err = e.what();
+    return -e.code;
+  }
+}

@@ -1,0 +1,52 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/lakeside_b200.h declares; compute entry
+points fail loudly (LK_ERR_CUDA) instead of falling back when no device is visible."""
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "lakeside_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(lk_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from lakeside_b200 import _lib
+
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 45
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert set(names) == set(_lib.EXPORTED_SYMBOLS), set(names) ^ set(_lib.EXPORTED_SYMBOLS)
+    assert lib.lk_version().decode().startswith("lakeside_b200")
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    from lakeside_b200 import _lib, api
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    assert api.device_count() == 0
+    with pytest.raises(api.LakesideError) as e:
+        api.init()
+    assert e.value.code == _lib.LK_ERR_CUDA and "no CPU fallback" in str(e.value)
+    with pytest.raises(api.LakesideError) as e:
+        api.merge_streams_index([__import__("numpy").arange(4)])
+    assert e.value.code == _lib.LK_ERR_CUDA
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "lakeside_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cpp", ".cu", ".h", ".cuh")):
+                txt = open(os.path.join(dp, f), errors="replace").read()
+                assert "lakeside_oracle" not in txt and "oracle/" not in txt.replace("lakeside_oracle", ""), f
+                assert "lk_emul" not in txt, f

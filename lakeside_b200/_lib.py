@@ -12,7 +12,8 @@ from ctypes import POINTER, c_char_p, c_double, c_int, c_int32, c_int64, c_size_
 LK_OK, LK_ERR_INVALID, LK_ERR_UNSUPPORTED, LK_ERR_IO, LK_ERR_CUDA, LK_ERR_QUERY, LK_ERR_NOMEM = range(7)
 _CODE_NAMES = {1: "INVALID", 2: "UNSUPPORTED", 3: "IO", 4: "CUDA", 5: "QUERY", 6: "NOMEM"}
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblakeside_b200.so")
+# LK_LIB selects another in-tree build of the same library (kernel tuning experiments); there is still no fallback
+LIB_PATH = os.environ.get("LK_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "liblakeside_b200.so")
 
 
 class LakesideError(RuntimeError):

@@ -67,7 +67,9 @@ struct ChunkInfo {
   uint32_t lut_gcode;  // offset into the group-code pool (key columns)
   uint32_t phys_type;  // parquet physical type
   uint64_t seq_base;   // global sequence number of the row group's first row (fixed-order sums)
+  uint64_t pad;        // 48 bytes: three 16-byte cp.async transfers
 };
+static_assert(sizeof(ChunkInfo) == 48, "ChunkInfo must be 48 bytes");
 
 struct FilterCol {
   uint8_t pcol;
@@ -116,6 +118,8 @@ struct ScanParams {
   int is_metrics;          // metrics: GROUP BY raw timestamp => (ts - base) % step must be one constant
   int path;                // 0 dense, 1 hash
   int warp_agg;            // pre-reduce equal cells inside a warp before the global atomics
+  int fits32;              // (endTs - base) and step are below 2^32: 32-bit bucket arithmetic
+  int stop_after;          // profiling aid (LK_SCAN_STOP_AFTER=1..3): leave each tile after prologue / phase A / phase B; 0 = full
   // dense path: cell = bucket * n_groups + group
   unsigned long long* rowcnt;
   unsigned long long* acc[LK_MAX_AGGS];

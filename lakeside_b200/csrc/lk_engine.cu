@@ -277,7 +277,12 @@ void device_execute(Query& q) {
       P.h_occ_cap = (uint32_t)std::min<uint64_t>(d.harena->slots, 0xffffffffu);
     }
     // persistent grid: every warp pulls 512-row tiles from the ticket counter until none are left
-    int grid = (int)std::min<uint32_t>((P.ntiles + SCAN_WARPS - 1) / SCAN_WARPS, (uint32_t)(num_sms() * 8));
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, scan_kernel, SCAN_BLOCK, 0));
+      if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    int grid = (int)std::min<uint32_t>((P.ntiles + SCAN_WARPS - 1) / SCAN_WARPS, (uint32_t)(num_sms() * ctas_per_sm));
     scan_kernel<<<grid, SCAN_BLOCK, 0, d.st>>>(P);
     CUDA_CHECK(cudaGetLastError());
   }
@@ -316,6 +321,7 @@ struct EmitParams {
   int64_t base, step;
   uint32_t phase;
   uint64_t n_groups;
+  int cells32;
   int64_t* ts;
   double* val[LK_MAX_AGGS];
   uint8_t* nul[LK_MAX_AGGS];
@@ -323,8 +329,15 @@ struct EmitParams {
 };
 
 __device__ __forceinline__ void emit_row(const EmitParams& E, uint64_t out, uint64_t cell, const unsigned long long* acc, size_t acc_pitch) {
-  const uint64_t bucket = cell / E.n_groups;
-  const uint64_t gid = cell - bucket * E.n_groups;
+  uint64_t bucket, gid;
+  if (E.cells32) {  // the whole (group x bucket) space fits 32 bits: 32-bit divisions (a 64-bit one costs ~100 instructions)
+    const uint32_t b32 = (uint32_t)cell / (uint32_t)E.n_groups;
+    gid = (uint32_t)cell - b32 * (uint32_t)E.n_groups;
+    bucket = b32;
+  } else {
+    bucket = cell / E.n_groups;
+    gid = cell - bucket * E.n_groups;
+  }
   E.ts[out] = E.base + (int64_t)bucket * E.step + (int64_t)E.phase;
   for (int a = 0; a < E.n_aggs; a++) {
     const unsigned long long w = acc[a * acc_pitch];
@@ -341,7 +354,9 @@ __device__ __forceinline__ void emit_row(const EmitParams& E, uint64_t out, uint
     E.nul[a][out] = isnull;
   }
   for (int k = 0; k < E.n_keys; k++) {
-    uint32_t g = (uint32_t)((gid / E.key_stride[k]) % ((uint64_t)E.key_null[k] + 1));
+    uint32_t g;
+    if (E.cells32) g = ((uint32_t)gid / (uint32_t)E.key_stride[k]) % (E.key_null[k] + 1);
+    else g = (uint32_t)((gid / E.key_stride[k]) % ((uint64_t)E.key_null[k] + 1));
     E.code[k][out] = g == E.key_null[k] ? -1 : (int32_t)g;
   }
 }
@@ -486,11 +501,16 @@ __global__ void __launch_bounds__(HS_BLOCK) hash_emit_kernel(const uint32_t* __r
                                                              uint32_t stride, const __grid_constant__ EmitParams E) {
   const uint32_t i = blockIdx.x * HS_BLOCK + threadIdx.x;
   if (i >= n) return;
-  unsigned long long* e = reinterpret_cast<unsigned long long*>(entries + (uint64_t)sorted[i] * stride);
-  const uint64_t cell = e[0] - 1;
-  emit_row(E, i, cell, e + 1, 1);
-  ulonglong2* z = reinterpret_cast<ulonglong2*>(e);
-  for (uint32_t w = 0; w < stride / 16; w++) z[w] = make_ulonglong2(0ull, 0ull);
+  ulonglong2* z = reinterpret_cast<ulonglong2*>(entries + (uint64_t)sorted[i] * stride);
+  unsigned long long w[8];
+  {
+    const ulonglong2 a = z[0], b = z[1];  // one 32-byte sector
+    w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
+    if (stride == 64) { const ulonglong2 c = z[2], d = z[3]; w[4] = c.x; w[5] = c.y; w[6] = d.x; w[7] = d.y; }
+    else { w[4] = w[5] = w[6] = w[7] = 0; }
+  }
+  for (uint32_t k = 0; k < stride / 16; k++) z[k] = make_ulonglong2(0ull, 0ull);
+  emit_row(E, i, w[0] - 1, w + 1, 1);
 }
 
 // device result layout for n rows: ts[n] | val[a][n] | code[k][n] | nul[a][n]
@@ -508,6 +528,7 @@ static void fill_emit_params(const Query& q, EmitParams& E, uint8_t* basep, int6
   E.step = q.step;
   E.phase = q.dev->phase;
   E.n_groups = q.n_groups;
+  E.cells32 = q.n_cells < (1ull << 32);
   uint8_t* p = basep;
   E.ts = (int64_t*)p; p += 8 * n;
   for (int a = 0; a < E.n_aggs; a++) { E.val[a] = (double*)p; p += 8 * n; }

@@ -505,6 +505,7 @@ void plan_query(Query& q) {
     q.nbuckets = (uint32_t)nb;
   }
   P.base = q.base;
+  P.fits32 = q.ts_hi > q.base && (uint64_t)(q.ts_hi - q.base) < (1ull << 32) && (uint64_t)q.step < (1ull << 32);
   P.nbuckets = q.nbuckets;
   P.notnull_pcol = value_not_null ? q.agg_pcols[0] : -1;
   q.params.survivors = nullptr;
@@ -579,6 +580,7 @@ void rebuild_group_tables(Query& q) {
   P.path = q.path;
   // few cells => many rows per cell => warp-level pre-reduction pays
   P.warp_agg = dense && q.n_groups <= 4096;
+  { const char* e = getenv("LK_SCAN_STOP_AFTER"); P.stop_after = e ? atoi(e) : 0; }
   q.hash_stride = q.aggs.size() <= 3 ? 32 : 64;
   uint64_t want = 2 * std::min<uint64_t>((uint64_t)std::max<int64_t>(q.total_rows, 1), std::max<uint64_t>(q.n_cells, 1));
   uint64_t slots = 1024;

@@ -2,12 +2,13 @@
 //
 // Work unit: one WARP owns one tile (<= 512 consecutive rows of one row group; a tile never crosses a page of any
 // touched column, so every (tile, column) pair is one contiguous piece of one page).  Warps are fully independent --
-// no block-level barrier anywhere -- and pull tiles from a global ticket counter.  Per tile:
-//   A  definition-level words: lane l builds the 32-row def word l of a nullable column straight from the bit-packed
-//      def runs (funnel shift), a 16-lane shuffle scan of the popcounts gives the row -> value-index mapping
-//   B  WHERE: each lane owns 16 consecutive rows, walks the dictionary-index runs of every filter column once
-//      (sequential run cursor, no per-row search), maps codes through the per-chunk class table and tests one bit
-//      of the pass bitmap; survivors are compacted into shared memory with a warp prefix sum over popc
+// no block-level barrier anywhere -- and pull tiles from a global ticket counter.  Lane l owns rows [16 l, 16 l + 16).
+//   A  definition levels: the lane finds the def run that holds its first row with a shuffle search over the run
+//      starts (both sequences are sorted), walks the 1-3 runs that cover its 16 rows (RLE: mask, bit-packed: one
+//      funnel shift) and a warp scan of the popcounts gives every lane its first value index
+//   B  WHERE: the lane slides a 64-bit window over the bit-packed dictionary indices of its rows (one funnel shift
+//      per value, run changes are rare); with one filter column the class table and the pass bitmap are folded into
+//      one bit per dictionary code per tile; survivors are compacted into shared memory by a warp prefix sum
 //   C  one lane per survivor: timestamp -> bucket, group-by codes -> group id, values -> (group x bucket) table:
 //      dense planes (global atomics, optional warp pre-reduction of equal cells) or an open-addressing hash table of
 //      32/64-byte entries (key + accumulators in one sector pair).
@@ -23,26 +24,70 @@ namespace lk {
 constexpr int SCAN_WARPS = 4;
 constexpr int SCAN_BLOCK = SCAN_WARPS * 32;
 constexpr int SCAN_ROWS_PER_LANE = LK_TILE_ROWS_MAX / 32;  // 16
-constexpr int SCAN_WORDS = LK_TILE_ROWS_MAX / 32;          // 16
-static_assert(SCAN_ROWS_PER_LANE == 16 && SCAN_WORDS == 16, "the kernel is written for 512-row tiles");
+static_assert(SCAN_ROWS_PER_LANE == 16, "the kernel is written for 512-row tiles");
+constexpr uint32_t SCAN_CODEPASS_MAX = 1024;
 
 struct WarpSmem {
   ColCursor cur[LK_MAX_PCOLS];
   ChunkInfo ci[LK_MAX_PCOLS];
-  uint32_t bits[LK_MAX_PCOLS][SCAN_WORDS];
-  uint16_t pref[LK_MAX_PCOLS][SCAN_WORDS];
+  uint16_t defb[LK_MAX_PCOLS][32];  // definition bits of the 16 rows of every lane
+  uint16_t vpre[LK_MAX_PCOLS][32];  // non-null values of the tile before the lane's first row
+  uint32_t vrs[LK_MAX_PCOLS][4];    // start index of the tile's first 4 dictionary-index runs (0xffffffff = none)
+  uint32_t vrk[LK_MAX_PCOLS][4];    // their kind_value words
+  uint32_t codepass[SCAN_CODEPASS_MAX / 32];  // single filter column: bit c set <=> dictionary code c passes the WHERE
   uint16_t surv[LK_TILE_ROWS_MAX];
-  uint32_t claims[LK_TILE_ROWS_MAX];
 };
 
+// 32 bits starting `bit` bits after byte address p (bit may exceed 7)
+__device__ __forceinline__ uint32_t load_bits32(const uint8_t* __restrict__ p, uint32_t bit) {
+  const uint64_t a = reinterpret_cast<uint64_t>(p + (bit >> 3));
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~3ull);
+  const uint32_t sh = (uint32_t)(a & 3) * 8 + (bit & 7);
+  return __funnelshift_r(__ldg(q), __ldg(q + 1), sh);
+}
+
+// (valid, value index) of row r of column p
 __device__ __forceinline__ bool col_pos(const WarpSmem& s, int p, uint32_t r, uint32_t& vidx) {
   const ColCursor& c = s.cur[p];
   if (c.flags & CUR_ALL_VALID) { vidx = c.vidx0 + r; return true; }
   if (c.flags & CUR_ALL_NULL) return false;
-  uint32_t w = s.bits[p][r >> 5];
-  uint32_t b = r & 31;
-  vidx = c.vidx0 + s.pref[p][r >> 5] + __popc(w & ((1u << b) - 1));
-  return (w >> b) & 1;
+  const uint32_t db = s.defb[p][r >> 4];
+  const uint32_t j = r & 15;
+  vidx = c.vidx0 + s.vpre[p][r >> 4] + __popc(db & ((1u << j) - 1));
+  return (db >> j) & 1;
+}
+
+// index (0..3) of the dictionary-index run holding value `vidx`, for columns with at most 4 runs in the tile
+__device__ __forceinline__ uint32_t fast_run(const WarpSmem& s, int p, uint32_t vidx) {
+  return (uint32_t)(vidx >= s.vrs[p][1]) + (uint32_t)(vidx >= s.vrs[p][2]) + (uint32_t)(vidx >= s.vrs[p][3]);
+}
+
+// dictionary index of value `vidx`: run descriptors from shared memory when the tile has <= 4 runs of this column
+__device__ __forceinline__ uint32_t dict_code(const WarpSmem& s, int p, const uint8_t* __restrict__ arena, const Run* __restrict__ runs, uint32_t vidx) {
+  const ColCursor& c = s.cur[p];
+  if (c.vrun_n > 4) return lk_dict_code(arena, runs, c, s.ci[p], vidx);
+  const uint32_t ri = fast_run(s, p, vidx);
+  const uint32_t kv = s.vrk[p][ri];
+  if (kv >> 31) return kv & 0x7fffffffu;
+  const uint32_t w = c.width;
+  return load_bits32(arena + s.ci[p].base_off + kv, (vidx - s.vrs[p][ri]) * w) & ((1u << w) - 1);
+}
+
+__device__ __forceinline__ uint64_t value_bits(const WarpSmem& s, int p, const uint8_t* __restrict__ arena, const Run* __restrict__ runs, uint32_t vidx,
+                                               uint32_t& bad) {
+  const ColCursor& c = s.cur[p];
+  const ChunkInfo& ci = s.ci[p];
+  const unsigned esz = (ci.phys_type == 1 || ci.phys_type == 4) ? 4 : 8;
+  uint64_t off;
+  if (c.flags & CUR_DICT) {
+    uint32_t code = dict_code(s, p, arena, runs, vidx);
+    if (code >= ci.dict_n) { bad = 1; code = 0; }
+    off = ci.dict_off + (uint64_t)code * esz;
+  } else {
+    off = c.plain_off + (uint64_t)(vidx - c.vidx0) * esz;
+  }
+  const uint64_t x = lk_load_u64(arena, off);
+  return esz == 4 ? (x & 0xffffffffull) : x;
 }
 
 __device__ __forceinline__ double shfl_xor_f64(double v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
@@ -57,42 +102,50 @@ __device__ __forceinline__ void acc_update(unsigned long long* word, int op, uns
   }
 }
 
-// Sequential cursor over the dictionary-index runs of one column inside a tile.
-struct RunCursor {
-  const Run* run;      // current run
-  const Run* last;     // last run of the tile
-  uint32_t start, next_start, kind_value;
-  const uint8_t* base;  // packed bytes of a bit-packed run
-  __device__ __forceinline__ void load(const uint8_t* chunk) {
-    Run r = *run;
-    start = r.start;
-    kind_value = r.kind_value;
-    base = chunk + (r.kind_value & 0x7fffffffu);
+// Sequential reader of consecutive dictionary indices of one column: a 64-bit window (two 32-bit words) slides over a
+// bit-packed run, one funnel shift per value; run changes are rare (a bit-packed run holds up to 504 values).
+struct SeqReader {
+  const Run* run;
+  const Run* last;
+  const uint8_t* chunk;
+  const uint32_t* wp;
+  uint32_t next_start, rle, cur, nxt, sh, width, mask;
+  bool is_rle;
+  __device__ __forceinline__ void open_run(uint32_t vidx) {
+    const Run r = *run;
     next_start = run < last ? run[1].start : 0xffffffffu;
+    is_rle = r.kind_value >> 31;
+    rle = r.kind_value & 0x7fffffffu;
+    if (!is_rle) {
+      const uint32_t bitpos = (vidx - r.start) * width;
+      const uint64_t a = reinterpret_cast<uint64_t>(chunk + r.kind_value + (bitpos >> 3));
+      wp = reinterpret_cast<const uint32_t*>(a & ~3ull);
+      sh = (uint32_t)(a & 3) * 8 + (bitpos & 7);
+      cur = __ldg(wp);
+      nxt = __ldg(wp + 1);
+    }
   }
-  __device__ __forceinline__ void seek(const uint8_t* chunk, const Run* runs, const ColCursor& c, uint32_t vidx) {
+  __device__ __forceinline__ void seek(const WarpSmem& s, int p, const uint8_t* arena, const Run* runs, uint32_t vidx) {
+    const ColCursor& c = s.cur[p];
     const Run* r0 = runs + c.vrun_lo;
     last = r0 + c.vrun_n - 1;
-    run = r0 + lk_find_run(r0, c.vrun_n, vidx);
-    load(chunk);
+    chunk = arena + s.ci[p].base_off;
+    width = c.width;
+    mask = (1u << width) - 1;  // width <= 31 (checked by the host index)
+    run = r0 + (c.vrun_n > 4 ? lk_find_run(r0, c.vrun_n, vidx) : fast_run(s, p, vidx));
+    open_run(vidx);
   }
-  __device__ __forceinline__ uint32_t code(const uint8_t* chunk, uint32_t vidx, uint32_t width, uint32_t mask) {
-    while (vidx >= next_start) { run++; load(chunk); }
-    if (kind_value >> 31) return kind_value & 0x7fffffffu;
-    const uint32_t bitpos = (vidx - start) * width;
-    const uint8_t* p = base + (bitpos >> 3);
-    const uint64_t a = reinterpret_cast<uint64_t>(p);
-    const unsigned sh = (unsigned)(a & 7) * 8 + (bitpos & 7);
-    const unsigned long long* q = reinterpret_cast<const unsigned long long*>(a & ~7ull);
-    unsigned long long lo = __ldg(q);
-    uint32_t x;
-    if (sh + width <= 64) x = (uint32_t)(lo >> sh);
-    else x = (uint32_t)((lo >> sh) | (__ldg(q + 1) << (64 - sh)));
-    return x & mask;
+  __device__ __forceinline__ uint32_t next(uint32_t vidx) {
+    if (vidx >= next_start) { run++; open_run(vidx); }
+    if (is_rle) return rle;
+    const uint32_t code = __funnelshift_r(cur, nxt, sh) & mask;
+    sh += width;
+    if (sh >= 32) { sh -= 32; cur = nxt; nxt = __ldg(++wp + 1); }
+    return code;
   }
 };
 
-__global__ void __launch_bounds__(SCAN_BLOCK) scan_kernel(const __grid_constant__ ScanParams P) {
+__global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_constant__ ScanParams P) {
   __shared__ WarpSmem smem[SCAN_WARPS];
   const int lane = threadIdx.x & 31;
   WarpSmem& s = smem[threadIdx.x >> 5];
@@ -111,44 +164,134 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_kernel(const __grid_constant_
     const uint32_t nrows = td.nrows;
     const uint32_t row0 = td.row0;
     __syncwarp();  // every lane is done with the previous tile's shared state
-    if (lane < (int)P.npcols) {
-      s.cur[lane] = P.cursors[td.cursor0 + lane];
-      s.ci[lane] = P.chunks[(size_t)td.rg * P.npcols + lane];
-    }
-    __syncwarp();
-
-    // ---- phase A: definition-level words + exclusive prefix of their popcounts (two columns per pass) ----
-    const uint32_t nwords = (nrows + 31) >> 5;
+    uint32_t need = 0;  // columns with some (not all) NULLs in this tile
     {
-      uint32_t need = 0;
-      for (uint32_t p = 0; p < P.npcols; p++)
-        if (!(s.cur[p].flags & (CUR_ALL_VALID | CUR_ALL_NULL))) need |= 1u << p;
-      while (need) {
-        const int pa = __ffs(need) - 1;
-        need &= need - 1;
-        int pb = -1;
-        if (need) { pb = __ffs(need) - 1; need &= need - 1; }
-        const int p = lane < 16 ? pa : pb;
-        const uint32_t w = lane & 15;
-        uint32_t word = 0;
-        if (p >= 0 && w < nwords) word = lk_def_word(arena, runs, s.cur[p], s.ci[p], row0 + 32 * w, min(32u, nrows - 32 * w));
-        uint32_t c = __popc(word), incl = c;
+      bool mine = false;
+      if (lane < (int)P.npcols) {
+        const ColCursor c = P.cursors[td.cursor0 + lane];
+        s.cur[lane] = c;
+        s.ci[lane] = P.chunks[(size_t)td.rg * P.npcols + lane];
+        mine = !(c.flags & (CUR_ALL_VALID | CUR_ALL_NULL));
+        if ((c.flags & CUR_DICT) && c.nvals) {
 #pragma unroll
-        for (int d = 1; d < 16; d <<= 1) {
-          uint32_t o = __shfl_up_sync(0xffffffffu, incl, d, 16);
-          if ((lane & 15) >= d) incl += o;
+          for (int j = 0; j < 4; j++) {
+            Run r;
+            r.start = 0xffffffffu;
+            r.kind_value = 0;
+            if (j < (int)c.vrun_n) r = runs[c.vrun_lo + j];
+            s.vrs[lane][j] = r.start;
+            s.vrk[lane][j] = r.kind_value;
+          }
         }
-        if (p >= 0 && w < nwords) { s.bits[p][w] = word; s.pref[p][w] = (uint16_t)(incl - c); }
       }
+      need = __ballot_sync(0xffffffffu, mine);
     }
     __syncwarp();
+    if (P.stop_after == 1) continue;
 
-    // ---- phase B: WHERE on dictionary codes; lane owns rows [16*lane, 16*lane + 16) ----
     const uint32_t lrow0 = (uint32_t)lane * SCAN_ROWS_PER_LANE;
     const uint32_t lrows = lrow0 >= nrows ? 0u : min((uint32_t)SCAN_ROWS_PER_LANE, nrows - lrow0);
     const uint32_t rowmask = (1u << lrows) - 1;
+
+    // ---- phase A: definition bits of my 16 rows + value-index prefix, one nullable column at a time ----
+    while (need) {
+      const int p = __ffs(need) - 1;
+      need &= need - 1;
+      const ColCursor& c = s.cur[p];
+      const uint32_t n = c.drun_n;
+      const Run* __restrict__ r0 = runs + c.drun_lo;
+      const uint8_t* __restrict__ chunk = arena + s.ci[p].base_off;
+      const uint32_t target = row0 + lrow0;  // my first row (chunk-level)
+      // first = index of the last run with start <= target.  Runs and targets are both sorted: every chunk of 32 runs
+      // is searched with shuffles (lower bound over the lanes' run starts).
+      uint32_t first = 0;
+      for (uint32_t base = 0; base < n; base += 32) {
+        const uint32_t st = base + lane < n ? r0[base + lane].start : 0xffffffffu;
+        uint32_t lo = 0;  // number of runs of this chunk with start <= target (starts ascending)
+#pragma unroll
+        for (int step = 16; step; step >>= 1) {
+          const uint32_t v = __shfl_sync(0xffffffffu, st, (lo + step - 1) & 31);
+          if (v <= target) lo += step;
+        }
+        if (__shfl_sync(0xffffffffu, st, 31) <= target) lo = 32;  // the search above tops out at 31
+        if (lo) first = base + lo - 1;
+        if (__all_sync(0xffffffffu, lo < 32)) break;
+      }
+      uint32_t bits = 0;
+      if (lrows) {
+        uint32_t filled = 0, ri = first;
+        Run run = r0[ri];
+        while (true) {
+          const uint32_t next = ri + 1 < n ? r0[ri + 1].start : 0xffffffffu;
+          uint32_t avail = next - (target + filled);
+          if (avail > lrows - filled) avail = lrows - filled;
+          const uint32_t m = (1u << avail) - 1;  // avail <= 16
+          if (run.kind_value >> 31) {
+            if (run.kind_value & 1) bits |= m << filled;
+          } else {
+            bits |= (load_bits32(chunk + run.kind_value, target + filled - run.start) & m) << filled;
+          }
+          filled += avail;
+          if (filled >= lrows) break;
+          run = r0[++ri];
+        }
+      }
+      uint32_t cnt = __popc(bits), incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
+      }
+      s.defb[p][lane] = (uint16_t)bits;
+      s.vpre[p][lane] = (uint16_t)(incl - cnt);
+    }
+    __syncwarp();
+    if (P.stop_after == 2) continue;
+
+    // ---- phase B: WHERE on dictionary codes ----
     uint32_t passmask = 0;
-    if (lrows) {
+    // definition bits and first value index of this lane's rows in column p
+    auto lane_def = [&](int p, uint32_t& defbits, uint32_t& vidx) {
+      const ColCursor& c = s.cur[p];
+      if (c.flags & CUR_ALL_VALID) { defbits = rowmask; vidx = c.vidx0 + lrow0; }
+      else if (c.flags & CUR_ALL_NULL) { defbits = 0; vidx = 0; }
+      else { defbits = s.defb[p][lane]; vidx = c.vidx0 + s.vpre[p][lane]; }
+    };
+    const bool single = P.n_filter == 1 && !P.filter[0].numeric && s.ci[P.filter[0].pcol].dict_n <= SCAN_CODEPASS_MAX;
+    if (single) {
+      // one filter column: fold class table and pass bitmap into one bit per dictionary code (per tile: every row
+      // group has its own dictionary); a row passes iff bit[code] -- or the NULL class bit -- is set
+      const int p = P.filter[0].pcol;
+      const uint32_t dict_n = s.ci[p].dict_n;
+      const uint8_t* __restrict__ lut = P.lut_cls + s.ci[p].lut_cls;
+      for (uint32_t c0 = 0; c0 < dict_n; c0 += 32) {
+        const uint32_t code = c0 + lane;
+        bool ok = false;
+        if (code < dict_n) {
+          const uint32_t cls = __ldg(lut + code);
+          ok = (__ldg(P.pass_bits + (cls >> 5)) >> (cls & 31)) & 1;
+        }
+        const unsigned b = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s.codepass[c0 >> 5] = b;
+      }
+      __syncwarp();
+      if (lrows) {
+        const uint32_t ncls = P.filter[0].null_cls;
+        const uint32_t nullpass = (__ldg(P.pass_bits + (ncls >> 5)) >> (ncls & 31)) & 1u;
+        uint32_t defbits, vidx;
+        lane_def(p, defbits, vidx);
+        passmask = nullpass ? (~defbits & rowmask) : 0u;
+        if (defbits) {
+          SeqReader rd;
+          rd.seek(s, p, arena, runs, vidx);
+          for (uint32_t m = defbits; m; m &= m - 1) {
+            const uint32_t code = rd.next(vidx++);
+            if (code < dict_n) passmask |= ((s.codepass[code >> 5] >> (code & 31)) & 1u) << (__ffs(m) - 1);
+            else my_status |= ST_BAD_CODE;
+          }
+        }
+      }
+    } else if (lrows) {
       uint32_t idx[SCAN_ROWS_PER_LANE];
 #pragma unroll
       for (int j = 0; j < SCAN_ROWS_PER_LANE; j++) idx[j] = 0;
@@ -156,42 +299,30 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_kernel(const __grid_constant_
         const int p = P.filter[f].pcol;
         const uint32_t stride = P.filter[f].stride;
         const uint32_t null_cls = P.filter[f].null_cls;
-        const ColCursor& c = s.cur[p];
         uint32_t defbits, vidx;
-        if (c.flags & CUR_ALL_VALID) { defbits = rowmask; vidx = c.vidx0 + lrow0; }
-        else if (c.flags & CUR_ALL_NULL) { defbits = 0; vidx = 0; }
-        else {
-          const uint32_t w = s.bits[p][lane >> 1];
-          const uint32_t sh = 16 * (lane & 1);
-          defbits = (w >> sh) & rowmask;
-          vidx = c.vidx0 + s.pref[p][lane >> 1] + __popc(w & ((1u << sh) - 1));
-        }
+        lane_def(p, defbits, vidx);
         if (P.filter[f].numeric) {
-          const ChunkInfo& ci = s.ci[p];
-#pragma unroll 4
+#pragma unroll
           for (int j = 0; j < SCAN_ROWS_PER_LANE; j++) {
             uint32_t cls = null_cls;
             if ((defbits >> j) & 1) {
               uint32_t bad = 0;
-              uint64_t bits = lk_value_bits(arena, runs, c, ci, vidx++, &bad);
+              const uint64_t bits = value_bits(s, p, arena, runs, vidx++, bad);
               if (bad) my_status |= ST_BAD_CODE;
-              cls = lk_numeric_class(P.filter[f], lk_bits_to_f64(bits, ci.phys_type));
+              cls = lk_numeric_class(P.filter[f], lk_bits_to_f64(bits, s.ci[p].phys_type));
             }
             idx[j] += cls * stride;
           }
         } else {
           const uint32_t dict_n = s.ci[p].dict_n;
           const uint8_t* __restrict__ lut = P.lut_cls + s.ci[p].lut_cls;
-          const uint32_t width = c.width;
-          const uint32_t mask = (1u << width) - 1;  // width <= 31 (checked by the host index)
-          const uint8_t* chunk = arena + s.ci[p].base_off;
-          RunCursor rc;
-          if (defbits) rc.seek(chunk, runs, c, vidx);
-#pragma unroll 4
+          SeqReader rd;
+          if (defbits) rd.seek(s, p, arena, runs, vidx);
+#pragma unroll
           for (int j = 0; j < SCAN_ROWS_PER_LANE; j++) {
             uint32_t cls = null_cls;
             if ((defbits >> j) & 1) {
-              const uint32_t code = rc.code(chunk, vidx++, width, mask);
+              const uint32_t code = rd.next(vidx++);
               if (code < dict_n) cls = __ldg(lut + code);
               else my_status |= ST_BAD_CODE;
             }
@@ -204,34 +335,30 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_kernel(const __grid_constant_
         const uint32_t i = idx[j];
         passmask |= ((__ldg(P.pass_bits + (i >> 5)) >> (i & 31)) & 1u) << j;
       }
-      passmask &= rowmask;
-      if (passmask && P.notnull_pcol >= 0) {
-        const ColCursor& c = s.cur[P.notnull_pcol];
-        if (c.flags & CUR_ALL_NULL) passmask = 0;
-        else if (!(c.flags & CUR_ALL_VALID)) passmask &= s.bits[P.notnull_pcol][lane >> 1] >> (16 * (lane & 1));
-      }
+    }
+    passmask &= rowmask;
+    if (passmask && P.notnull_pcol >= 0) {
+      const ColCursor& c = s.cur[P.notnull_pcol];
+      if (c.flags & CUR_ALL_NULL) passmask = 0;
+      else if (!(c.flags & CUR_ALL_VALID)) passmask &= s.defb[P.notnull_pcol][lane];
     }
     // compaction: warp exclusive scan of the per-lane survivor counts
-    uint32_t cnt = __popc(passmask), incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += o;
-    }
-    const uint32_t nsurv = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t nsurv;
     {
-      uint32_t o = incl - cnt;
-      uint32_t m = passmask;
-      while (m) {
-        const int j = __ffs(m) - 1;
-        m &= m - 1;
-        s.surv[o++] = (uint16_t)(lrow0 + j);
+      uint32_t cnt = __popc(passmask), incl = cnt;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += o;
       }
+      nsurv = __shfl_sync(0xffffffffu, incl, 31);
+      uint32_t o = incl - cnt;
+      for (uint32_t m = passmask; m; m &= m - 1) s.surv[o++] = (uint16_t)(lrow0 + __ffs(m) - 1);
     }
     __syncwarp();
+    if (P.stop_after == 3) { my_surv += (lane == 0) ? nsurv : 0; continue; }
 
     // ---- phase C: one lane per survivor ----
-    uint32_t nclaims = 0;
     for (uint32_t i0 = 0; i0 < nsurv; i0 += 32) {
       const uint32_t i = i0 + lane;
       bool active = i < nsurv;
@@ -246,13 +373,21 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_kernel(const __grid_constant_
         active = col_pos(s, P.ts_pcol, r, vidx);  // NULL timestamp: `ts >= S` is not TRUE
         if (active) {
           uint32_t bad = 0;
-          const int64_t ts = (int64_t)lk_value_bits(arena, runs, s.cur[P.ts_pcol], s.ci[P.ts_pcol], vidx, &bad);
+          const int64_t ts = (int64_t)value_bits(s, P.ts_pcol, arena, runs, vidx, bad);
           active = ts >= P.ts_lo && ts < P.ts_hi;
           if (active) {
             const uint64_t rel = (uint64_t)(ts - P.base);
-            const uint64_t bucket = rel / (uint64_t)P.step;
+            uint64_t bucket;
+            uint32_t ph;
+            if (P.fits32) {  // (endTs - base) and step fit 32 bits: one 32-bit division instead of a 64-bit one
+              const uint32_t b32 = (uint32_t)rel / (uint32_t)P.step;
+              ph = (uint32_t)rel - b32 * (uint32_t)P.step;
+              bucket = b32;
+            } else {
+              bucket = rel / (uint64_t)P.step;
+              ph = (uint32_t)(rel - bucket * (uint64_t)P.step);
+            }
             if (P.is_metrics) {
-              const uint32_t ph = (uint32_t)(rel - bucket * (uint64_t)P.step);
               my_phase_min = min(my_phase_min, ph);
               my_phase_max = max(my_phase_max, ph);
             }
@@ -261,7 +396,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_kernel(const __grid_constant_
               const int p = P.keys[k].pcol;
               uint32_t gcode = P.keys[k].null_code;
               if (col_pos(s, p, r, vidx)) {
-                const uint32_t code = lk_dict_code(arena, runs, s.cur[p], s.ci[p], vidx);
+                const uint32_t code = dict_code(s, p, arena, runs, vidx);
                 if (code >= s.ci[p].dict_n) bad = 1;
                 else gcode = __ldg(P.lut_gcode + s.ci[p].lut_gcode + code);
               }
@@ -270,11 +405,11 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_kernel(const __grid_constant_
             cell = bucket * P.n_groups + gid;
 #pragma unroll
             for (int a = 0; a < LK_MAX_AGGS; a++) {
-              if (a < P.n_aggs) {
+              if (a < P.n_aggs && P.stop_after != 5) {
                 const int p = P.aggs[a].pcol;
                 vvalid[a] = col_pos(s, p, r, vidx);
                 if (vvalid[a]) {
-                  const uint64_t raw = lk_value_bits(arena, runs, s.cur[p], s.ci[p], vidx, &bad);
+                  const uint64_t raw = value_bits(s, p, arena, runs, vidx, bad);
                   const double x = lk_bits_to_f64(raw, s.ci[p].phys_type);
                   const unsigned long long xb = (unsigned long long)__double_as_longlong(x);
                   const int op = P.aggs[a].op;
@@ -288,6 +423,13 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_kernel(const __grid_constant_
         }
       }
 
+      if (P.stop_after >= 4) {  // profiling aid: no table update
+        unsigned long long x = cell;
+#pragma unroll
+        for (int a = 0; a < LK_MAX_AGGS; a++) x ^= vbits[a];
+        if (x == 0x123456789abcdefull) my_status |= 4;
+        continue;
+      }
       if (P.path == 0) {
         // dense planes; optionally pre-reduce lanes that hit the same cell (few groups => long same-cell runs)
         bool todo = active;
@@ -333,7 +475,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_kernel(const __grid_constant_
             if (a < P.n_aggs && vvalid[a]) acc_update(P.acc[a] + cell, P.aggs[a].op, vbits[a], 1ull);
         }
       } else {
-        // open addressing with linear probing; entry = {key = cell + 1, acc[n_aggs]}
+        // open addressing with linear probing; entry = {key = cell + 1, acc[n_aggs]}.  A plain load first: an atomic on a
+        // line that is not yet in L2 measured slower than load + CAS (B200, r1).
         bool claimed = false;
         uint32_t claimed_slot = 0;
         if (active) {
@@ -357,21 +500,20 @@ __global__ void __launch_bounds__(SCAN_BLOCK) scan_kernel(const __grid_constant_
               if (a < P.n_aggs && vvalid[a]) acc_update(entry + 1 + a, P.aggs[a].op, vbits[a], 1ull);
           }
         }
+        // publish the slots claimed by this batch of survivors: one global atomic per warp iteration
         const unsigned cm = __ballot_sync(0xffffffffu, claimed);
-        if (claimed) s.claims[nclaims + __popc(cm & lt_mask)] = claimed_slot;
-        nclaims += __popc(cm);
+        if (cm) {
+          const int leader = __ffs(cm) - 1;
+          uint32_t base = 0;
+          if (lane == leader) base = atomicAdd(P.counters + 3, (uint32_t)__popc(cm));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (claimed) {
+            const uint32_t o = base + __popc(cm & lt_mask);
+            if (o < P.h_occ_cap) P.h_occ[o] = claimed_slot;
+            else my_status |= ST_HASH_FULL;
+          }
+        }
       }
-    }
-
-    if (P.path == 1 && nclaims) {
-      // publish the slots this tile claimed: one global atomic per tile
-      __syncwarp();
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(P.counters + 3, nclaims);
-      base = __shfl_sync(0xffffffffu, base, 0);
-      for (uint32_t i = lane; i < nclaims; i += 32)
-        if (base + i < P.h_occ_cap) P.h_occ[base + i] = s.claims[i];
-        else my_status |= ST_HASH_FULL;
     }
   }
 

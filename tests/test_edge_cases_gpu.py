@@ -63,7 +63,8 @@ def test_jdbc_style_row_access_and_data_points():
     odps = lo.to_data_points(want, {"q": "tags"})
     key = lambda d: (d.timestamp, tuple(sorted(d.tags.items())))
     assert sorted(map(key, dps)) == sorted(map(key, odps))
-    assert {key(d): d.value for d in dps} == {key(d): d.value for d in odps}
+    # dropped tags ("" / "null" / NULL) can make several rows share one tag map: compare as multisets
+    assert sorted((key(d), d.value) for d in dps) == sorted((key(d), d.value) for d in odps)
     assert all("missing.group" not in d.tags for d in dps)
     for row in range(min(res.num_rows, 50)):
         assert res.get_long(row, 1) == int(res.ts[row])

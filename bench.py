@@ -274,8 +274,9 @@ def main():
 
     # ---------------- resident ("kernel-only") arm ----------------
     q = new_query()
-    q.plan()
-    agree_on_dictionaries(q)
+    if world > 1:
+        q.plan()
+        agree_on_dictionaries(q)
     q.prepare()
     info = q.info
     rows_per_rank = q.total_rows
@@ -328,8 +329,9 @@ def main():
 
     def e2e_step():
         qq = new_query()
-        qq.plan()
-        agree_on_dictionaries(qq)
+        if world > 1:  # one rank: prepare() plans by itself and overlaps the H2D copies with the host index build
+            qq.plan()
+            agree_on_dictionaries(qq)
         qq.prepare()
         qq.execute()
         exchange(qq, qq.info["path"])

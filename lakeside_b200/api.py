@@ -55,7 +55,8 @@ class GlobResult:
         self.columns = [lib.lk_result_col_name(self._h, i).decode() for i in range(lib.lk_result_num_cols(self._h))]
 
         def arr(ptr, dtype):
-            return np.ctypeslib.as_array(ptr, (n,)).view(dtype).copy() if n else np.zeros(0, dtype)
+            # zero-copy views into the result's pinned host block: valid until close()
+            return np.ctypeslib.as_array(ptr, (n,)).view(dtype) if n else np.zeros(0, dtype)
 
         self.ts = arr(lib.lk_result_ts(self._h), np.int64)
         self.values = [arr(lib.lk_result_value(self._h, a), np.float64) for a in range(self.num_values)]

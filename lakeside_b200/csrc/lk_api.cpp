@@ -173,7 +173,11 @@ int lk_query_prepare(lk_query* q) {
     LK_CHECK(!(q->q.dev), LK_ERR_INVALID, "query already prepared");
     if (!q->q.prepared) {
       double t0 = now_ms();
+      device_init();  // fail before any host work when there is no GPU
+      Query* qp = &q->q;
+      q->q.on_layout = [qp] { device_begin_upload(*qp); };  // column chunks start moving while the host builds the index
       plan_query(q->q);
+      q->q.on_layout = nullptr;
       q->q.t_ms[4] = now_ms() - t0;
     }
     device_upload(q->q);

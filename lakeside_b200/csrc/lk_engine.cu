@@ -41,6 +41,8 @@ void device_init() {
   CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, global_options().device));
   uint64_t thresh = ~0ull;  // keep freed blocks cached: repeated queries re-use them without cudaMalloc
   CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+  PoolAlloc::alloc = pinned_alloc;   // index pools of later queries live in pinned memory
+  PoolAlloc::release = pinned_free;
   g_inited = true;
 }
 
@@ -195,6 +197,14 @@ static void upload_vec(T*& dptr, const std::vector<T>& v, cudaStream_t st) {
   if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
 }
 
+template <class T>
+static void upload_vec(T*& dptr, const RawVec<T>& v, cudaStream_t st) {
+  if (dptr) { CUDA_CHECK(cudaFreeAsync(dptr, st)); dptr = nullptr; }
+  size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+  CUDA_CHECK(cudaMallocAsync(&dptr, bytes, st));
+  if (!v.empty()) CUDA_CHECK(cudaMemcpyAsync(dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+}
+
 static void upload_group_tables(Query& q) {
   Query::Device& d = *q.dev;
   upload_vec(d.lut_gcode, q.lut_gcode, d.st);
@@ -209,7 +219,9 @@ static void upload_group_tables(Query& q) {
   d.group_tables_stale = false;
 }
 
-void device_upload(Query& q) {
+// Starts the H2D copies of the touched column chunks (asynchronous; called from plan_query's on_layout hook so that
+// the copies run while the host still walks page and run headers).
+void device_begin_upload(Query& q) {
   device_init();
   if (!q.dev) q.dev = std::make_unique<Query::Device>();
   Query::Device& d = *q.dev;
@@ -217,10 +229,16 @@ void device_upload(Query& q) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking));
     for (auto& e : d.ev) CUDA_CHECK(cudaEventCreate(&e));
   }
+  if (d.arena) return;
   CUDA_CHECK(cudaEventRecord(d.ev[0], d.st));
   CUDA_CHECK(cudaMallocAsync(&d.arena, q.arena_bytes, d.st));
   for (auto& u : q.uploads)
     CUDA_CHECK(cudaMemcpyAsync(d.arena + u.arena_off, q.segs[u.seg].data + u.file_off, u.len, cudaMemcpyHostToDevice, d.st));
+}
+
+void device_upload(Query& q) {
+  device_begin_upload(q);
+  Query::Device& d = *q.dev;
   upload_vec(d.tiles, q.tiles, d.st);
   upload_vec(d.cursors, q.cursors, d.st);
   upload_vec(d.runs, q.runs, d.st);

@@ -11,7 +11,8 @@ int num_sms();
 void* pinned_alloc(size_t bytes);
 void pinned_free(void* p);
 
-void device_upload(Query& q);              // H2D of the touched column chunks and index pools
+void device_begin_upload(Query& q);        // async H2D of the touched column chunks (arena layout known)
+void device_upload(Query& q);              // ... plus the index pools; waits for all of it
 void device_mark_group_tables_stale(Query& q);
 void device_execute(Query& q);             // clear table + fused scan kernel (async)
 void device_sync(Query& q);

@@ -355,12 +355,25 @@ int ChunkIndex::val_run_at(uint32_t v) const {
 uint32_t ChunkIndex::vidx_at(const uint8_t* file, uint32_t r) const {
   if (max_def == 0) return r;
   if (def_runs.empty()) return 0;
-  int i = def_run_at(r);
+  return vidx_in_run(file, def_run_at(r), r);
+}
+
+uint32_t ChunkIndex::vidx_in_run(const uint8_t* file, int i, uint32_t r) const {
   const Run& run = def_runs[i];
   uint32_t nn = def_nn_before[i];
   uint32_t k = r - run.start;
   if (run.kind_value >> 31) return nn + ((run.kind_value & 1) ? k : 0);
   return nn + popcount_bits(file + file_start + run.kind_value, k);
+}
+
+void chunk_byte_range(const ColumnChunkMeta& cm, size_t file_len, const std::string& name, uint64_t& start_out, uint64_t& len_out) {
+  int64_t start = cm.data_page_offset;
+  if (cm.dictionary_page_offset > 0 && cm.dictionary_page_offset < start) start = cm.dictionary_page_offset;
+  LK_CHECK(start >= 4 && cm.total_compressed_size >= 0 && (uint64_t)start + (uint64_t)cm.total_compressed_size <= file_len, LK_ERR_IO,
+           "parquet: column chunk '" + name + "' out of file bounds");
+  LK_CHECK((uint64_t)cm.total_compressed_size < (1ull << 31), LK_ERR_UNSUPPORTED, "column chunk '" + name + "' larger than 2 GiB");
+  start_out = (uint64_t)start;
+  len_out = (uint64_t)cm.total_compressed_size;
 }
 
 ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, const ColumnChunkMeta& cm, int64_t rg_rows,
@@ -375,13 +388,7 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
   LK_CHECK(rg_rows >= 0 && rg_rows < (int64_t)0xfffffff0u, LK_ERR_UNSUPPORTED, "row group too large");
   ci.num_rows = (uint32_t)rg_rows;
   LK_CHECK(cm.num_values == rg_rows, LK_ERR_UNSUPPORTED, "column '" + leaf.name + "': repeated values are not supported");
-  int64_t start = cm.data_page_offset;
-  if (cm.dictionary_page_offset > 0 && cm.dictionary_page_offset < start) start = cm.dictionary_page_offset;
-  LK_CHECK(start >= 4 && cm.total_compressed_size >= 0 && (uint64_t)start + (uint64_t)cm.total_compressed_size <= len, LK_ERR_IO,
-           "parquet: column chunk out of file bounds");
-  ci.file_start = (uint64_t)start;
-  ci.file_len = (uint64_t)cm.total_compressed_size;
-  LK_CHECK(ci.file_len < (1ull << 31), LK_ERR_UNSUPPORTED, "column chunk larger than 2 GiB");
+  chunk_byte_range(cm, len, leaf.name, ci.file_start, ci.file_len);
   const uint64_t cend = ci.file_start + ci.file_len;
   uint64_t p = ci.file_start;
   uint32_t row = 0, vidx = 0;

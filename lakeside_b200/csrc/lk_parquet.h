@@ -73,10 +73,15 @@ struct ChunkIndex {
   std::vector<std::string> dict_strings;  // BYTE_ARRAY dictionaries, decoded on the host
   // chunk-level value index of row r (number of non-null values before r); r may equal num_rows
   uint32_t vidx_at(const uint8_t* file, uint32_t r) const;
+  // same, when the def run `run_index` holding row r is already known (linear sweeps)
+  uint32_t vidx_in_run(const uint8_t* file, int run_index, uint32_t r) const;
   int def_run_at(uint32_t r) const;   // index of the def run containing row r
   int val_run_at(uint32_t v) const;   // index of the value run containing value v
   int page_at(uint32_t r) const;
 };
+
+// Byte range [start, start + len) of a column chunk inside the file (dictionary page + data pages), from the footer alone.
+void chunk_byte_range(const ColumnChunkMeta& cm, size_t file_len, const std::string& name, uint64_t& start, uint64_t& len);
 
 // Walks every page header of the chunk and every run header of its hybrid streams.
 // want_strings: decode the BYTE_ARRAY dictionary into dict_strings.

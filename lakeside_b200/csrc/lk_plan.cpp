@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstring>
 #include <functional>
+#include <chrono>
 #include <thread>
 #include <unordered_map>
 
@@ -16,6 +17,9 @@ namespace lk {
 static const char* TIMESTAMP = "_cardinalhq.timestamp";
 static const char* NAME = "_cardinalhq.name";
 static const char* VALUE = "_cardinalhq.value";
+
+void* (*PoolAlloc::alloc)(size_t) = malloc;
+void (*PoolAlloc::release)(void*) = free;
 
 Options& global_options() {
   static Options o;
@@ -109,7 +113,21 @@ static Truth eval_tree(const Clause& c, int& leaf_counter, const std::function<T
 
 static void build_info_json(Query& q);
 
+namespace {
+struct PlanTrace {
+  bool on = getenv("LK_PLAN_TRACE") != nullptr;
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  void mark(const char* what) {
+    if (!on) return;
+    auto n = std::chrono::steady_clock::now();
+    fprintf(stderr, "[lk plan] %-28s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+    t = n;
+  }
+};
+}  // namespace
+
 void plan_query(Query& q) {
+  PlanTrace trace;
   const BaseExpr& e = q.req.expr;
   const Options& opt = global_options();
   // ---- shape checks: everything that is not the aggregate push-down is outside the GPU path ----
@@ -146,6 +164,7 @@ void plan_query(Query& q) {
     if (!exists(f)) non_existent.push_back(f);
   auto is_non_existent = [&](const std::string& n) { return std::find(non_existent.begin(), non_existent.end(), n) != non_existent.end(); };
 
+  trace.mark("footers");
   // ---- touched columns ----
   q.pcols.clear();
   q.ts_pcol = pcol_index(q, TIMESTAMP);
@@ -256,6 +275,30 @@ void plan_query(Query& q) {
       q.rgs.push_back(std::move(rp));
     }
   const int np = (int)q.pcols.size();
+  // ---- arena layout + upload list: needs the footers only, so the H2D copies of the column chunks can start NOW
+  //      (q.on_layout) and overlap the page/run indexing below ----
+  q.uploads.clear();
+  {
+    uint64_t arena = 0;
+    for (auto& rp : q.rgs) {
+      const SegmentInput& seg = q.segs[rp.seg];
+      rp.arena_base.assign(np, 0);
+      for (int p = 0; p < np; p++) {
+        int li = seg.meta.leaf_index(q.pcols[p].name);
+        if (li < 0) continue;
+        const ColumnChunkMeta& cm = seg.meta.row_groups[rp.rg].columns[li];
+        uint64_t start, len;
+        chunk_byte_range(cm, seg.len, q.pcols[p].name, start, len);
+        arena = (arena + 255) & ~255ull;
+        rp.arena_base[p] = arena;
+        q.uploads.push_back({rp.seg, start, len, arena});
+        arena += len;
+      }
+    }
+    q.arena_bytes = ((arena + 255) & ~255ull) + 256;  // tail padding: lk_load_u64 may read the next aligned word
+  }
+  trace.mark("arena layout");
+  if (q.on_layout) q.on_layout();
   parallel_for((int)q.rgs.size(), opt.host_threads, [&](int i) {
     RowGroupPlan& rp = q.rgs[i];
     const SegmentInput& seg = q.segs[rp.seg];
@@ -280,22 +323,7 @@ void plan_query(Query& q) {
       if (c.present) q.touched_bytes += c.total_compressed_size;
   }
 
-  // ---- arena layout + upload list ----
-  q.uploads.clear();
-  uint64_t arena = 0;
-  for (auto& rp : q.rgs) {
-    rp.arena_base.assign(np, 0);
-    for (int p = 0; p < np; p++) {
-      const ChunkIndex& ci = rp.chunks[p];
-      if (!ci.present) continue;
-      arena = (arena + 255) & ~255ull;
-      rp.arena_base[p] = arena;
-      q.uploads.push_back({rp.seg, ci.file_start, ci.file_len, arena});
-      arena += ci.file_len;
-    }
-  }
-  q.arena_bytes = ((arena + 255) & ~255ull) + 256;  // tail padding: lk_load_u64 may read the next aligned word
-
+  trace.mark("index chunks");
   // ---- runs pool, tiles, cursors ----
   const uint32_t tile_rows = std::max(64u, std::min(opt.tile_rows, (uint32_t)LK_TILE_ROWS_MAX)) & ~31u;
   std::vector<size_t> run_base(q.rgs.size() + 1, 0), tile_base(q.rgs.size() + 1, 0);
@@ -316,9 +344,9 @@ void plan_query(Query& q) {
     tile_base[i + 1] = tile_base[i] + (b.size() - 1);
   }
   LK_CHECK(run_base.back() < 0xffffffffull && tile_base.back() * np < 0xffffffffull, LK_ERR_UNSUPPORTED, "glob too large for 32-bit index pools");
-  q.runs.assign(run_base.back(), Run{});
-  q.tiles.assign(tile_base.back(), TileDesc{});
-  q.cursors.assign(tile_base.back() * np, ColCursor{});
+  q.runs.resize_uninit(run_base.back());
+  q.tiles.resize_uninit(tile_base.back());
+  q.cursors.resize_uninit(tile_base.back() * np);  // zeroed slice by slice by the workers below
   q.chunk_infos.assign(q.rgs.size() * np, ChunkInfo{});
   uint32_t def_mask = 0;
   std::vector<uint32_t> def_masks(q.rgs.size(), 0);
@@ -342,40 +370,63 @@ void plan_query(Query& q) {
       vbase[p] = (uint32_t)rpos;
       for (auto& r : ci.val_runs) q.runs[rpos++] = r;
     }
+    // cursors: one linear sweep per column over the (ascending) tile boundaries -- no per-tile binary searches
     const std::vector<uint32_t>& b = bounds[i];
-    for (size_t t = 0; t + 1 < b.size(); t++) {
-      const uint32_t r0 = b[t], r1 = b[t + 1];
-      size_t ti = tile_base[i] + t;
+    const size_t nt = b.size() - 1;
+    if (nt) memset(&q.cursors[tile_base[i] * np], 0, nt * np * sizeof(ColCursor));
+    for (size_t t = 0; t < nt; t++) {
+      const size_t ti = tile_base[i] + t;
       TileDesc& td = q.tiles[ti];
-      td.row0 = r0;
-      td.nrows = r1 - r0;
+      td.row0 = b[t];
+      td.nrows = b[t + 1] - b[t];
       td.rg = (uint32_t)i;
       td.cursor0 = (uint32_t)(ti * np);
-      for (int p = 0; p < np; p++) {
-        const ChunkIndex& ci = rp.chunks[p];
-        ColCursor& c = q.cursors[ti * np + p];
-        if (!ci.present) { c.flags = CUR_ALL_NULL; continue; }
-        uint32_t v0 = ci.vidx_at(file, r0), v1 = ci.vidx_at(file, r1);
+    }
+    std::vector<uint32_t> vb(b.size()), db(b.size());  // value index at / def run holding every boundary row
+    for (int p = 0; p < np; p++) {
+      const ChunkIndex& ci = rp.chunks[p];
+      if (!ci.present) {
+        for (size_t t = 0; t < nt; t++) q.cursors[(tile_base[i] + t) * np + p].flags = CUR_ALL_NULL;
+        continue;
+      }
+      const size_t nd = ci.def_runs.size(), nv = ci.val_runs.size(), npg = ci.pages.size();
+      size_t di = 0;
+      for (size_t k = 0; k < b.size(); k++) {
+        const uint32_t r = b[k];
+        if (ci.max_def == 0 || nd == 0) { vb[k] = ci.max_def == 0 ? r : 0; db[k] = 0; continue; }
+        while (di + 1 < nd && ci.def_runs[di + 1].start <= r) di++;
+        vb[k] = ci.vidx_in_run(file, (int)di, r);
+        db[k] = (uint32_t)di;
+      }
+      size_t vi = 0, pi = 0;
+      const unsigned esz = (ci.phys_type == PT_INT32 || ci.phys_type == PT_FLOAT) ? 4 : 8;
+      for (size_t t = 0; t < nt; t++) {
+        const uint32_t r0 = b[t], r1 = b[t + 1], v0 = vb[t], v1 = vb[t + 1];
+        ColCursor& c = q.cursors[(tile_base[i] + t) * np + p];
         c.vidx0 = v0;
         c.nvals = v1 - v0;
         if (c.nvals == r1 - r0) c.flags |= CUR_ALL_VALID;
         else if (c.nvals == 0) c.flags |= CUR_ALL_NULL;
         else {
-          int d0 = ci.def_run_at(r0), d1 = ci.def_run_at(r1 - 1);
-          c.drun_lo = dbase[p] + (uint32_t)d0;
+          const uint32_t d0 = db[t];
+          uint32_t d1 = db[t + 1];
+          if (ci.def_runs[d1].start >= r1) d1--;  // the run holding row r1 - 1
+          c.drun_lo = dbase[p] + d0;
           c.drun_n = (uint16_t)(d1 - d0 + 1);
           def_masks[i] |= 1u << p;
         }
         if (c.nvals > 0) {
-          const PageInfo& pg = ci.pages[ci.page_at(r0)];
+          while (pi + 1 < npg && ci.pages[pi + 1].first_row <= r0) pi++;
+          const PageInfo& pg = ci.pages[pi];
           if (pg.dict_coded) {
             c.flags |= CUR_DICT;
             c.width = pg.bit_width;
-            int a = ci.val_run_at(v0), z = ci.val_run_at(v1 - 1);
-            c.vrun_lo = vbase[p] + (uint32_t)a;
-            c.vrun_n = (uint16_t)(z - a + 1);
+            while (vi + 1 < nv && ci.val_runs[vi + 1].start <= v0) vi++;
+            size_t zi = vi;
+            while (zi + 1 < nv && ci.val_runs[zi + 1].start <= v1 - 1) zi++;
+            c.vrun_lo = vbase[p] + (uint32_t)vi;
+            c.vrun_n = (uint16_t)(zi - vi + 1);
           } else {
-            unsigned esz = (ci.phys_type == PT_INT32 || ci.phys_type == PT_FLOAT) ? 4 : 8;
             c.plain_off = rp.arena_base[p] + (pg.values_off - ci.file_start) + (uint64_t)(v0 - pg.first_vidx) * esz;
           }
         }
@@ -384,6 +435,7 @@ void plan_query(Query& q) {
   });
   for (auto m : def_masks) def_mask |= m;
 
+  trace.mark("tiles/cursors/runs");
   // ---- predicate: per-column classes over dictionary entries, then the pass bitmap over class combinations ----
   q.lut_cls.clear();
   for (size_t f = 0; f < q.fcols.size(); f++) {
@@ -460,6 +512,7 @@ void plan_query(Query& q) {
     }
   }
 
+  trace.mark("predicate tables");
   // ---- ScanParams (device pointers are filled in by the device layer) ----
   ScanParams& P = q.params;
   memset(&P, 0, sizeof P);
@@ -510,6 +563,7 @@ void plan_query(Query& q) {
   P.notnull_pcol = value_not_null ? q.agg_pcols[0] : -1;
   q.params.survivors = nullptr;
 
+  trace.mark("scan params");
   // ---- group-by: global dictionaries + remap tables ----
   q.local_dicts.assign(q.key_pcols.size(), {});
   for (size_t k = 0; k < q.key_pcols.size(); k++) {
@@ -522,7 +576,9 @@ void plan_query(Query& q) {
     d.erase(std::unique(d.begin(), d.end()), d.end());
   }
   q.key_dicts = q.local_dicts;
+  trace.mark("local dictionaries");
   rebuild_group_tables(q);
+  trace.mark("group tables");
   q.prepared = true;
 }
 

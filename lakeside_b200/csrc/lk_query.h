@@ -12,6 +12,41 @@
 
 namespace lk {
 
+// Index pools are hundreds of MB for a 100-segment glob: allocated uninitialised and filled (first-touched) by the
+// planner's worker threads, not zero-filled by one thread the way std::vector::assign would.
+// The allocator is malloc/free until the device layer swaps in its pinned-memory pool (H2D of the pools then runs at
+// PCIe speed instead of through the driver's staging buffer).
+struct PoolAlloc {
+  static void* (*alloc)(size_t);
+  static void (*release)(void*);
+};
+template <class T>
+struct RawVec {
+  T* p = nullptr;
+  size_t n = 0;
+  void (*rel)(void*) = nullptr;
+  RawVec() = default;
+  RawVec(const RawVec&) = delete;
+  RawVec& operator=(const RawVec&) = delete;
+  ~RawVec() { if (p) rel(p); }
+  void resize_uninit(size_t count) {
+    if (p) rel(p);
+    p = nullptr;
+    n = count;
+    if (count) {
+      rel = PoolAlloc::release;
+      p = static_cast<T*>(PoolAlloc::alloc(count * sizeof(T)));
+      if (!p) { n = 0; throw std::bad_alloc(); }
+    }
+  }
+  T* data() { return p; }
+  const T* data() const { return p; }
+  size_t size() const { return n; }
+  bool empty() const { return n == 0; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+};
+
 struct Options {
   int device = 0;
   uint64_t max_hash_slots = 1ull << 27;
@@ -100,9 +135,9 @@ struct Query {
   uint32_t hash_stride = 0;
 
   // host copies of the device pools
-  std::vector<TileDesc> tiles;
-  std::vector<ColCursor> cursors;
-  std::vector<Run> runs;
+  RawVec<TileDesc> tiles;
+  RawVec<ColCursor> cursors;
+  RawVec<Run> runs;
   std::vector<ChunkInfo> chunk_infos;
   std::vector<uint8_t> lut_cls;
   std::vector<uint32_t> lut_gcode;
@@ -110,6 +145,9 @@ struct Query {
   struct Upload { int seg; uint64_t file_off, len, arena_off; };
   std::vector<Upload> uploads;
   uint64_t arena_bytes = 0;
+  // called by plan_query as soon as the arena layout is known (footers only): the device layer starts the H2D copies
+  // of the column chunks there so that they overlap the host-side page/run indexing
+  std::function<void()> on_layout;
   ScanParams params{};
 
   // ---- device ----

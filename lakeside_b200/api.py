@@ -117,9 +117,9 @@ class Query:
     """Staged evaluation of one glob: create -> add segments -> prepare (HBM resident) -> execute -> finalize."""
 
     def __init__(self, push_down_request_json: str, aggregates: Optional[Sequence[Tuple[str, str]]] = None,
-                 path: str = "auto"):
+                 path: str = "auto", exact_sums: bool = False):
         lib = _lib.load()
-        opts: Dict[str, Any] = {"path": path}
+        opts: Dict[str, Any] = {"path": path, "exact_sums": bool(exact_sums)}
         if aggregates:
             opts["aggregates"] = [{"aggregation": a, "rollup": r} for a, r in aggregates]
         self._h = ctypes.c_void_p()
@@ -360,3 +360,31 @@ def evaluate_push_down_request(query_id: str, local_parquet: bool, push_down_req
     if len(sources) == 1:
         return sources[0]
     return merge_sorted_source(sources, False)
+
+
+def merge_and_reduce(ts_list: Sequence[np.ndarray], gid_list: Sequence[np.ndarray], val_list: Sequence[np.ndarray],
+                     aggregation: str = "sum", reverse: bool = False):
+    """K-way merge of the per-segment streams followed by the map-sketch merge of TimeGroupedSketchAggregator
+    (core/.../eval/TimeGroupedSketchAggregator.scala:63-93): equal (timestamp, group) elements are folded in merged
+    (arrival) order with + (sum, count), Math.min or Math.max.  Returns (ts, gid, value) with one element per
+    (timestamp, group), sorted by timestamp then group."""
+    lib = _lib.load()
+    k = len(ts_list)
+    ts_list = [np.ascontiguousarray(t, np.int64) for t in ts_list]
+    gid_list = [np.ascontiguousarray(g, np.int32) for g in gid_list]
+    val_list = [np.ascontiguousarray(v, np.float64) for v in val_list]
+    lens = (ctypes.c_int64 * k)(*[len(t) for t in ts_list])
+    total = int(sum(len(t) for t in ts_list))
+    P = ctypes.c_void_p
+    h = ctypes.c_void_p()
+    _lib.check(lib.lk_merge_create(k, (P * k)(*[t.ctypes.data for t in ts_list]), (P * k)(*[g.ctypes.data for g in gid_list]),
+                                   (P * k)(*[v.ctypes.data for v in val_list]), lens, 1 if reverse else 0, ctypes.byref(h)))
+    try:
+        _lib.check(lib.lk_merge_run(h))
+        op = {"sum": 0, "count": 1, "min": 2, "max": 3}[aggregation]
+        o_ts, o_gid, o_val = np.empty(total, np.int64), np.empty(total, np.int32), np.empty(total, np.float64)
+        n = ctypes.c_int64()
+        _lib.check(lib.lk_merge_reduce(h, op, ctypes.byref(n), o_ts.ctypes.data, o_gid.ctypes.data, o_val.ctypes.data))
+        return o_ts[:n.value].copy(), o_gid[:n.value].copy(), o_val[:n.value].copy()
+    finally:
+        lib.lk_merge_destroy(h)

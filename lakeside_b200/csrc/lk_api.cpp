@@ -83,7 +83,6 @@ int lk_query_create(const char* pushdown_request_json, const char* options_json,
         h->q.path_opt = p->str;
       }
       if (const Json* e = j.get("exact_sums")) h->q.exact_sums = e->as_bool();
-      LK_CHECK(!h->q.exact_sums, LK_ERR_UNSUPPORTED, "exact_sums (fixed-order summation) is not available in this build");
       if (const Json* a = j.get("aggregates"); a && a->is_arr()) {
         const BaseExpr& e = h->q.req.expr;
         for (auto& x : a->arr) {

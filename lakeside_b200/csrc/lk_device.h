@@ -129,7 +129,13 @@ struct ScanParams {
   uint64_t h_mask;
   uint32_t* h_occ;      // slots claimed by this query
   uint32_t h_occ_cap;
-  uint32_t* counters;   // [0] status flags, [1] phase min, [2] phase max, [3] #claimed slots, [4] tile ticket
+  // fixed-order summation (exact_sums): survivors are emitted as records instead of being aggregated
+  int emit_records;
+  uint32_t rec_cap;
+  unsigned long long* rec_cell;
+  unsigned long long* rec_seq;  // global row sequence number: segment order, then row order
+  unsigned long long* rec_val[LK_MAX_AGGS];
+  uint32_t* counters;   // [0] status flags, [1] phase min, [2] phase max, [3] #claimed slots, [4] tile ticket, [5] #records
   unsigned long long* survivors;  // [0] rows that passed the WHERE clause
 };
 

@@ -8,7 +8,11 @@
 #include "lk_engine.h"
 #include "lk_scan.cuh"
 
+#include <cub/device/device_radix_sort.cuh>  // exact_sums (optional fixed-order pass) only
+
 namespace lk {
+
+static void device_exact_sums(Query& q, const ScanParams& base);
 
 #define CUDA_CHECK(x)                                                                                        \
   do {                                                                                                       \
@@ -303,6 +307,7 @@ void device_execute(Query& q) {
     int grid = (int)std::min<uint32_t>((P.ntiles + SCAN_WARPS - 1) / SCAN_WARPS, (uint32_t)(num_sms() * ctas_per_sm));
     scan_kernel<<<grid, SCAN_BLOCK, 0, d.st>>>(P);
     CUDA_CHECK(cudaGetLastError());
+    if (q.exact_sums) device_exact_sums(q, P);
   }
   CUDA_CHECK(cudaEventRecord(d.ev[3], d.st));
 }
@@ -849,6 +854,132 @@ void device_merge_sparse(Query& q, const void* dev_entries, int64_t n) {
       (const uint8_t*)dev_entries, (uint32_t)n, d.harena->entries, d.harena->stride, q.params.h_mask, d.harena->occ,
       (uint32_t)std::min<uint64_t>(d.harena->slots, 0xffffffffu), d.counters, (int)q.aggs.size(), ops);
   CUDA_CHECK(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// exact_sums: fixed-order (row order) double sums, bit-identical to a sequential evaluator
+// ------------------------------------------------------------------------------------------------------------
+// The atomics of the scan add in an arbitrary order (sums agree to ~1e-16 relative, not bitwise).  With exact_sums the
+// scan is run a second time in record mode, the (cell, row sequence, value) records are sorted by (cell, sequence)
+// -- two stable LSD radix sorts (CUB, a library call on this OPTIONAL slow path only) -- and one thread per cell folds
+// its values strictly left to right, then overwrites the accumulator word in the table.
+__global__ void iota_kernel(uint32_t* v, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+__global__ void gather_u64_kernel(const unsigned long long* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t n, unsigned long long* __restrict__ dst) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[idx[i]];
+}
+struct ExactPatch {
+  int path, n_aggs;
+  uint8_t ops[LK_MAX_AGGS + 1];
+  const unsigned long long* rec_val[LK_MAX_AGGS];
+  unsigned long long* acc[LK_MAX_AGGS];  // dense planes
+  uint8_t* h_entries;
+  uint32_t h_stride;
+  uint64_t h_mask;
+};
+__global__ void exact_fold_kernel(const unsigned long long* __restrict__ sorted_cell, const uint32_t* __restrict__ order, uint32_t n,
+                                  const __grid_constant__ ExactPatch X) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long cell = sorted_cell[i];
+  if (i > 0 && sorted_cell[i - 1] == cell) return;  // not the head of its cell
+  unsigned long long* entry = nullptr;
+  if (X.path == 1) {
+    uint64_t slot = lk_hash64(cell) & X.h_mask;
+    for (int probe = 0; probe < 4096; probe++) {
+      unsigned long long* e = reinterpret_cast<unsigned long long*>(X.h_entries + slot * X.h_stride);
+      if (*e == cell + 1) { entry = e; break; }
+      slot = (slot + 1) & X.h_mask;
+    }
+    if (!entry) return;
+  }
+  for (int a = 0; a < X.n_aggs; a++) {
+    if (X.ops[a] != AGG_SUM) continue;
+    double sum = 0.0;
+    for (uint32_t j = i; j < n && sorted_cell[j] == cell; j++) sum += __longlong_as_double((long long)X.rec_val[a][order[j]]);
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(sum);
+    if (X.path == 0) X.acc[a][cell] = bits;
+    else entry[1 + a] = bits;
+  }
+}
+
+static void sort_order_by_two_keys(cudaStream_t st, const unsigned long long* primary, const unsigned long long* secondary, uint32_t n,
+                                   unsigned long long* key_a, unsigned long long* key_b, uint32_t* idx_a, uint32_t* idx_b, void* tmp, size_t tmp_bytes,
+                                   const unsigned long long** sorted_primary, const uint32_t** order) {
+  const int grid = (int)((n + 255) / 256);
+  iota_kernel<<<grid, 256, 0, st>>>(idx_a, n);
+  // pass 1: by the secondary key
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, secondary, key_a, idx_a, idx_b, (int)n, 0, 64, st));
+  // pass 2: stable by the primary key
+  gather_u64_kernel<<<grid, 256, 0, st>>>(primary, idx_b, n, key_a);
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key_a, key_b, idx_b, idx_a, (int)n, 0, 64, st));
+  *sorted_primary = key_b;
+  *order = idx_a;
+}
+
+static void device_exact_sums(Query& q, const ScanParams& base) {
+  Query::Device& d = *q.dev;
+  bool any_sum = false;
+  for (auto& a : q.aggs) any_sum |= a.op == AGG_SUM;
+  if (!any_sum || q.n_cells == 0 || q.tiles.empty()) return;
+  const int64_t nsurv = device_survivors(q);
+  if (nsurv <= 0) return;
+  LK_CHECK(nsurv < (int64_t)0x7fffffff, LK_ERR_UNSUPPORTED, "exact_sums: too many surviving rows for one pass");
+  const uint32_t n = (uint32_t)nsurv;
+  const size_t na = q.aggs.size();
+  // scratch: rec_cell | rec_seq | rec_val[na] | key_a | key_b (u64 each) | idx_a | idx_b (u32 each) | counters2 | cub temp
+  size_t tmp_bytes = 0;
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr,
+                                             (uint32_t*)nullptr, (int)n, 0, 64, d.st));
+  const size_t words = (size_t)n * (4 + na);
+  uint8_t* scratch = nullptr;
+  const size_t bytes = words * 8 + (size_t)n * 8 + 64 + tmp_bytes + 256;
+  CUDA_CHECK(cudaMallocAsync(&scratch, bytes, d.st));
+  unsigned long long* rec_cell = (unsigned long long*)scratch;
+  unsigned long long* rec_seq = rec_cell + n;
+  unsigned long long* rec_val0 = rec_seq + n;
+  unsigned long long* key_a = rec_val0 + (size_t)n * na;
+  unsigned long long* key_b = key_a + n;
+  uint32_t* idx_a = (uint32_t*)(key_b + n);
+  uint32_t* idx_b = idx_a + n;
+  uint32_t* counters2 = idx_b + n;
+  void* tmp = (void*)(((uintptr_t)(counters2 + 16) + 255) & ~(uintptr_t)255);
+  ScanParams P = base;
+  P.emit_records = 1;
+  P.rec_cap = n;
+  P.rec_cell = rec_cell;
+  P.rec_seq = rec_seq;
+  for (size_t a = 0; a < na; a++) P.rec_val[a] = rec_val0 + a * n;
+  P.counters = counters2;
+  P.survivors = (unsigned long long*)(counters2 + 8);
+  static const uint32_t init_counters[16] = {0, 0xffffffffu, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  CUDA_CHECK(cudaMemcpyAsync(counters2, init_counters, sizeof init_counters, cudaMemcpyHostToDevice, d.st));
+  int ctas = 0;
+  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, scan_kernel, SCAN_BLOCK, 0));
+  int grid = (int)std::min<uint32_t>((P.ntiles + SCAN_WARPS - 1) / SCAN_WARPS, (uint32_t)(num_sms() * std::max(ctas, 1)));
+  scan_kernel<<<grid, SCAN_BLOCK, 0, d.st>>>(P);
+  CUDA_CHECK(cudaGetLastError());
+  const unsigned long long* sorted_cell = nullptr;
+  const uint32_t* order = nullptr;
+  sort_order_by_two_keys(d.st, rec_cell, rec_seq, n, key_a, key_b, idx_a, idx_b, tmp, tmp_bytes, &sorted_cell, &order);
+  ExactPatch X;
+  memset(&X, 0, sizeof X);
+  X.path = q.path;
+  X.n_aggs = (int)na;
+  for (size_t a = 0; a < na; a++) {
+    X.ops[a] = q.aggs[a].op;
+    X.rec_val[a] = P.rec_val[a];
+    X.acc[a] = base.acc[a];
+  }
+  X.h_entries = base.h_entries;
+  X.h_stride = base.h_stride;
+  X.h_mask = base.h_mask;
+  exact_fold_kernel<<<(int)((n + 255) / 256), 256, 0, d.st>>>(sorted_cell, order, n, X);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaFreeAsync(scratch, d.st));
 }
 
 int64_t device_survivors(Query& q) {

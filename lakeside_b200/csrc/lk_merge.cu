@@ -14,6 +14,8 @@
 #include "lk_merge.h"
 
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>  // lk_merge_reduce only (stable sorts of the merged order)
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cstring>
@@ -228,9 +230,50 @@ __global__ void __launch_bounds__(MG_BLOCK) merge_tile_kernel(const long long* _
 // ---- map-sketch re-aggregation of the merged stream (TimeGroupedSketchAggregator.scala:63-93) ----
 // Elements with equal timestamp are contiguous after the merge; equal (ts, gid) pairs are combined with
 // op 0: + (sum / count), 2: min, 3: max.  Output: one element per (ts, gid), sorted by ts then gid.
-__global__ void seg_flag_kernel(const long long* __restrict__ ts, uint64_t n, uint32_t* __restrict__ flag) {
-  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) flag[i] = (i == 0 || ts[i] != ts[i - 1]) ? 1u : 0u;
+__global__ void mr_iota_kernel(uint32_t* v, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) v[i] = i;
+}
+__global__ void mr_gid_keys_kernel(const int* __restrict__ gid, uint32_t n, unsigned long long* __restrict__ keys) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = (unsigned long long)(uint32_t)gid[i] ^ 0x80000000ull;  // signed order
+}
+__global__ void mr_ts_keys_kernel(const long long* __restrict__ ts, const uint32_t* __restrict__ idx, uint32_t n, int reverse,
+                                  unsigned long long* __restrict__ keys) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) keys[i] = ts_key(ts[idx[i]], reverse);
+}
+// head[i] = 1 iff sorted element i starts a new (ts, gid) group
+__global__ void mr_heads_kernel(const unsigned long long* __restrict__ sorted_ts, const int* __restrict__ gid, const uint32_t* __restrict__ order,
+                                uint32_t n, uint32_t* __restrict__ head) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) head[i] = (i == 0 || sorted_ts[i] != sorted_ts[i - 1] || gid[order[i]] != gid[order[i - 1]]) ? 1u : 0u;
+}
+__device__ __forceinline__ double java_min(double a, double b) {  // Math.min: NaN wins, -0.0 < +0.0
+  if (a != a || b != b) return __longlong_as_double(0x7ff8000000000000ll);
+  if (a == 0.0 && b == 0.0) return (__double_as_longlong(a) < 0) ? a : b;
+  return a <= b ? a : b;
+}
+__device__ __forceinline__ double java_max(double a, double b) {
+  if (a != a || b != b) return __longlong_as_double(0x7ff8000000000000ll);
+  if (a == 0.0 && b == 0.0) return (__double_as_longlong(a) < 0) ? b : a;
+  return a >= b ? a : b;
+}
+// one thread per group: folds the group's values strictly in merged (arrival) order, as SimpleSketchMerger does
+__global__ void mr_fold_kernel(const unsigned long long* __restrict__ sorted_ts, const int* __restrict__ gid, const double* __restrict__ val,
+                               const uint32_t* __restrict__ order, const uint32_t* __restrict__ head, const uint32_t* __restrict__ pos, uint32_t n,
+                               int op, int reverse, long long* __restrict__ out_ts, int* __restrict__ out_gid, double* __restrict__ out_val) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !head[i]) return;
+  double acc = val[order[i]];
+  for (uint32_t j = i + 1; j < n && !head[j]; j++) {
+    const double v = val[order[j]];
+    acc = op == 2 ? java_min(acc, v) : op == 3 ? java_max(acc, v) : acc + v;
+  }
+  const uint32_t o = pos[i];
+  out_ts[o] = key_ts(sorted_ts[i], reverse);
+  out_gid[o] = gid[order[i]];
+  out_val[o] = acc;
 }
 
 }  // namespace lk
@@ -367,8 +410,54 @@ void merge_download(lk_merge* m, int64_t* out_ts, int32_t* out_gid, double* out_
   CUDA_CHECK(cudaStreamSynchronize(m->st));
 }
 
-void merge_reduce(lk_merge*, int, int64_t*, int64_t*, int32_t*, double*) {
-  fail(LK_ERR_UNSUPPORTED, "lk_merge_reduce is not available in this build");
+void merge_reduce(lk_merge* m, int op, int64_t* n_out, int64_t* out_ts, int32_t* out_gid, double* out_val) {
+  LK_CHECK(m->ran, LK_ERR_INVALID, "lk_merge_reduce before lk_merge_run");
+  LK_CHECK(op == 0 || op == 1 || op == 2 || op == 3, LK_ERR_INVALID, "op must be 0/1 (add), 2 (min) or 3 (max)");
+  CUDA_CHECK(cudaSetDevice(global_options().device));
+  *n_out = 0;
+  if (m->total == 0) return;
+  const uint32_t n = (uint32_t)m->total;
+  size_t t1 = 0, t2 = 0;
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, t1, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr,
+                                             (uint32_t*)nullptr, (int)n, 0, 64, m->st));
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, t2, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)n, m->st));
+  const size_t tmp_bytes = std::max(t1, t2);
+  // scratch: key_a | key_b (u64) | idx_a | idx_b | head | pos (u32) | out_ts (i64) | out_val (f64) | out_gid (i32) | cub temp
+  uint8_t* scratch = nullptr;
+  const size_t bytes = (size_t)n * (8 + 8 + 4 * 4 + 8 + 8 + 4) + 512 + tmp_bytes;
+  CUDA_CHECK(cudaMallocAsync(&scratch, bytes, m->st));
+  unsigned long long* key_a = (unsigned long long*)scratch;
+  unsigned long long* key_b = key_a + n;
+  long long* r_ts = (long long*)(key_b + n);
+  double* r_val = (double*)(r_ts + n);
+  uint32_t* idx_a = (uint32_t*)(r_val + n);
+  uint32_t* idx_b = idx_a + n;
+  uint32_t* head = idx_b + n;
+  uint32_t* pos = head + n;
+  int* r_gid = (int*)(pos + n);
+  void* tmp = (void*)(((uintptr_t)(r_gid + n) + 255) & ~(uintptr_t)255);
+  const int grid = (int)((n + 255) / 256);
+  // merged order -> stable by gid -> stable by ts: (ts, gid, arrival) order
+  mr_iota_kernel<<<grid, 256, 0, m->st>>>(idx_a, n);
+  mr_gid_keys_kernel<<<grid, 256, 0, m->st>>>(m->o_gid, n, key_a);
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, t1, key_a, key_b, idx_a, idx_b, (int)n, 0, 33, m->st));
+  mr_ts_keys_kernel<<<grid, 256, 0, m->st>>>(m->o_ts, idx_b, n, m->reverse ? 1 : 0, key_a);
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(tmp, t1, key_a, key_b, idx_b, idx_a, (int)n, 0, 64, m->st));
+  mr_heads_kernel<<<grid, 256, 0, m->st>>>(key_b, m->o_gid, idx_a, n, head);
+  CUDA_CHECK(cub::DeviceScan::ExclusiveSum(tmp, t2, head, pos, (int)n, m->st));
+  mr_fold_kernel<<<grid, 256, 0, m->st>>>(key_b, m->o_gid, m->o_val, idx_a, head, pos, n, op, m->reverse ? 1 : 0, r_ts, r_gid, r_val);
+  CUDA_CHECK(cudaGetLastError());
+  uint32_t last[2] = {0, 0};
+  CUDA_CHECK(cudaMemcpyAsync(&last[0], pos + (n - 1), 4, cudaMemcpyDeviceToHost, m->st));
+  CUDA_CHECK(cudaMemcpyAsync(&last[1], head + (n - 1), 4, cudaMemcpyDeviceToHost, m->st));
+  CUDA_CHECK(cudaStreamSynchronize(m->st));
+  const size_t ng = (size_t)last[0] + last[1];
+  *n_out = (int64_t)ng;
+  if (out_ts) CUDA_CHECK(cudaMemcpyAsync(out_ts, r_ts, ng * 8, cudaMemcpyDeviceToHost, m->st));
+  if (out_gid) CUDA_CHECK(cudaMemcpyAsync(out_gid, r_gid, ng * 4, cudaMemcpyDeviceToHost, m->st));
+  if (out_val) CUDA_CHECK(cudaMemcpyAsync(out_val, r_val, ng * 8, cudaMemcpyDeviceToHost, m->st));
+  CUDA_CHECK(cudaStreamSynchronize(m->st));
+  CUDA_CHECK(cudaFreeAsync(scratch, m->st));
 }
 
 void merge_destroy(lk_merge* m) {

@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
     for (uint32_t i0 = 0; i0 < nsurv; i0 += 32) {
       const uint32_t i = i0 + lane;
       bool active = i < nsurv;
-      unsigned long long cell = 0;
+      unsigned long long cell = 0, seq = 0;
       unsigned long long vbits[LK_MAX_AGGS];
       bool vvalid[LK_MAX_AGGS];
 #pragma unroll
@@ -403,6 +403,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
               gid += (uint64_t)gcode * P.keys[k].stride;
             }
             cell = bucket * P.n_groups + gid;
+            seq = s.ci[P.ts_pcol].seq_base + row0 + r;
 #pragma unroll
             for (int a = 0; a < LK_MAX_AGGS; a++) {
               if (a < P.n_aggs && P.stop_after != 5) {
@@ -423,6 +424,26 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
         }
       }
 
+      if (P.emit_records) {
+        // fixed-order summation pass: the survivors are not aggregated here but written out as (cell, global row
+        // sequence, value) records; they are sorted and folded strictly in row order afterwards (lk_exact.cu)
+        const unsigned am = __ballot_sync(0xffffffffu, active);
+        if (am) {
+          const int leader = __ffs(am) - 1;
+          uint32_t base = 0;
+          if (lane == leader) base = atomicAdd(P.counters + 5, (uint32_t)__popc(am));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          const uint32_t o = base + __popc(am & lt_mask);
+          if (active && o < P.rec_cap) {
+            P.rec_cell[o] = cell;
+            P.rec_seq[o] = seq;
+#pragma unroll
+            for (int a = 0; a < LK_MAX_AGGS; a++)
+              if (a < P.n_aggs && P.aggs[a].op == AGG_SUM) P.rec_val[a][o] = vvalid[a] ? vbits[a] : 0ull;
+          }
+        }
+        continue;
+      }
       if (P.stop_after >= 4) {  // profiling aid: no table update
         unsigned long long x = cell;
 #pragma unroll

@@ -1,0 +1,139 @@
+"""Size-independent properties at (or near) BASELINE.json's full sizes, where the oracle is too slow to be the checker:
+checksums against an independent Arrow computation, sortedness, idempotence, dense == hash, merge order at C5 size."""
+import json
+
+import numpy as np
+import pytest
+
+import helpers as H
+from lakeside_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def c2_20():
+    from lakeside_b200 import api
+
+    api.init()
+    spec = synth.SynthSpec(dataset="metrics", rows=1 << 20)
+    _, paths = H.dataset("c2_full_1m", spec, 20)
+    rq = H.request_json(synth.c2_base_expr(), list(range(20)), 10000)
+    return paths, rq
+
+
+def _run(rq, paths, aggs, path="auto"):
+    from lakeside_b200 import api
+
+    with api.Query(rq, aggregates=aggs, path=path) as q:
+        for p in paths:
+            q.add_segment_file(p)
+        q.prepare()
+        q.execute()
+        res = q.finalize()
+        out = dict(ts=res.ts.copy(), vals=[v.copy() for v in res.values], nulls=[v.copy() for v in res.value_nulls],
+                   codes=[c.copy() for c in res.tag_codes], dicts=res.tag_dicts, survivors=q.survivors, info=q.info)
+        res.close()
+        return out
+
+
+def test_c2_21m_rows_checksums_sorted_idempotent(c2_20):
+    import pyarrow.compute as pc
+    import pyarrow.parquet as pq
+
+    paths, rq = c2_20
+    r = _run(rq, paths, synth.C2_AGGREGATES)
+    assert r["info"]["total_rows"] == 20 << 20
+    assert np.all(np.diff(r["ts"]) >= 0), "rows must be sorted by timestamp"
+    # independent checker: Arrow compute over the same files
+    n_pass, total_count, total_sum, vmin, vmax = 0, 0.0, 0.0, np.inf, -np.inf
+    for p in paths:
+        t = pq.read_table(p, columns=[synth.TAG_SERVICE, "rollup_count", "rollup_sum", "rollup_min", "rollup_max"])
+        m = pc.fill_null(pc.equal(t[synth.TAG_SERVICE], "svc-03"), False)
+        f = t.filter(m)
+        n_pass += f.num_rows
+        total_count += pc.sum(f["rollup_count"]).as_py()
+        total_sum += pc.sum(f["rollup_sum"]).as_py()
+        vmin = min(vmin, pc.min(f["rollup_min"]).as_py())
+        vmax = max(vmax, pc.max(f["rollup_max"]).as_py())
+    assert r["survivors"] == n_pass                      # bit-exact row selection
+    assert float(r["vals"][1].sum()) == total_count      # integer-valued doubles: exact in any order
+    assert abs(float(r["vals"][0].sum()) - total_sum) <= 1e-9 * abs(total_sum)
+    assert float(r["vals"][2].min()) == vmin and float(r["vals"][3].max()) == vmax
+    # idempotence: a second evaluation gives the same multiset of rows (bit-exact except the double sums)
+    r2 = _run(rq, paths, synth.C2_AGGREGATES)
+    key = lambda x: np.lexsort([c for c in x["codes"]][::-1] + [x["ts"]])
+    o1, o2 = key(r), key(r2)
+    assert np.array_equal(r["ts"][o1], r2["ts"][o2])
+    for a in (1, 2, 3):
+        assert np.array_equal(r["vals"][a][o1], r2["vals"][a][o2])
+    assert np.allclose(r["vals"][0][o1], r2["vals"][0][o2], rtol=1e-12, atol=0)
+    for c1, c2 in zip(r["codes"], r2["codes"]):
+        assert np.array_equal(c1[o1], c2[o2])
+
+
+def test_dense_and_hash_agree_at_8m_rows():
+    from lakeside_b200 import api
+
+    api.init()
+    spec = synth.SynthSpec(dataset="metrics", rows=1 << 20, n_names=4, cards=(16, 8, 8, 4))
+    _, paths = H.dataset("dense_hash_1m", spec, 8)
+    be = synth.c2_base_expr()
+    rq = H.request_json(be, list(range(8)), 10000)
+    d = _run(rq, paths, synth.C2_AGGREGATES, "dense")
+    h = _run(rq, paths, synth.C2_AGGREGATES, "hash")
+    assert d["info"]["path"] == "dense" and h["info"]["path"] == "hash"
+    key = lambda x: np.lexsort([c for c in x["codes"]][::-1] + [x["ts"]])
+    od, oh = key(d), key(h)
+    assert np.array_equal(d["ts"][od], h["ts"][oh])
+    for a in (1, 2, 3):
+        assert np.array_equal(d["vals"][a][od], h["vals"][a][oh])
+    assert np.allclose(d["vals"][0][od], h["vals"][0][oh], rtol=1e-12, atol=0)
+
+
+def test_c4_regex_on_dictionary_high_cardinality():
+    # BASELINE.json configs[3] at 2 x 1 Mi rows: 10^6 tag combinations, regex evaluated once per dictionary entry
+    spec = synth.c4_spec(1 << 20)
+    _, paths = H.dataset("c4_1m", spec, 2)
+    rq = H.request_json(synth.c4_base_expr(), [0, 1], 10000)
+    got = H.gpu_eval_multi(rq, paths, synth.C2_AGGREGATES)
+    want = H.oracle_multi(rq, paths, synth.C2_AGGREGATES)
+    assert got["info"]["path"] == "hash" and got["info"]["n_groups"] > 10 ** 6
+    assert len(want["rows"]) > 800000
+    H.assert_same(got, want, ["sum", "sum", "min", "max"], "c4")
+
+
+def test_c5_merge_256_streams_full_size():
+    # BASELINE.json configs[4]: 256 sorted streams x 65536 elements, heavy ties (360 distinct timestamps)
+    import lakeside_oracle as lo
+    from lakeside_b200 import api
+
+    api.init()
+    rng = np.random.default_rng(5)
+    ts = [np.sort(synth.T0 + 10000 * rng.integers(0, 360, 65536)).astype(np.int64) for _ in range(256)]
+    src, pos = api.merge_streams_index(ts)
+    wsrc, wpos = lo.merge_sorted_arrays(ts)
+    assert np.array_equal(src, wsrc) and np.array_equal(pos, wpos)
+
+
+def test_evaluate_push_down_request_globs_of_ten_and_merge():
+    # a3: Commons.evaluatePushDownRequest -- 23 local segments => globs of 10, 10, 3 merged by timestamp
+    import lakeside_oracle as lo
+    from lakeside_b200 import api
+
+    api.init()
+    spec = synth.SynthSpec(dataset="metrics", rows=30000, n_names=3, cards=(16, 3, 3, 2))
+    root, paths = H.dataset("epdr", spec, 23)
+    req = synth.push_down_request(synth.c2_base_expr("max", "max"), list(range(23)), 10000)
+    got = api.evaluate_push_down_request("q1", True, req, db_root=root)
+    want = lo.evaluate_push_down_request(lo.push_down_request_from_json(json.dumps(req)), root, True)
+    assert len(got) == len(want) > 1000
+    assert [g.timestamp for g in got] == [w.timestamp for w in want] == sorted(w.timestamp for w in want)
+    k = lambda e: (e.timestamp, tuple(sorted(e.tags.items())), e.sketch["max"])
+    assert sorted(map(k, got)) == sorted(map(k, want))
+    # glob boundaries are visible: the same (ts, tags) may appear once per glob (3 globs), never more
+    from collections import Counter
+    assert max(Counter((e.timestamp, tuple(sorted(e.tags.items()))) for e in got).values()) <= 3
+    # no segments at all -> the ts = -1 sentinel (Commons.scala:393-396)
+    s = api.evaluate_push_down_request("q2", True, dict(req, segmentRequests=[]), db_root=root)
+    assert len(s) == 1 and s[0].timestamp == -1

@@ -264,6 +264,45 @@ void device_mark_group_tables_stale(Query& q) {
   if (q.dev) q.dev->group_tables_stale = true;
 }
 
+// The single-filter fast path needs every dictionary of the one (string) filter column to fit the per-warp
+// code->pass bitmap; one oversized dictionary anywhere in the glob sends the whole query down the generic path.
+static bool single_filter_ok(const Query& q) {
+  const ScanParams& P = q.params;
+  if (P.n_filter != 1 || P.filter[0].numeric) return false;
+  const int np = (int)q.pcols.size(), p = P.filter[0].pcol;
+  for (size_t i = 0; i < q.rgs.size(); i++)
+    if (q.chunk_infos[i * np + p].dict_n > SCAN_CODEPASS_MAX) return false;
+  return true;
+}
+
+template <int PATH, bool SINGLE, bool EMIT>
+static void launch_scan_variant(const ScanParams& P, cudaStream_t st) {
+  // persistent grid: every warp pulls 512-row tiles from the ticket counter until none are left
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, scan_kernel<PATH, SINGLE, EMIT>, SCAN_BLOCK, 0));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  const int grid = (int)std::min<uint32_t>((P.ntiles + SCAN_WARPS - 1) / SCAN_WARPS, (uint32_t)(num_sms() * ctas_per_sm));
+  scan_kernel<PATH, SINGLE, EMIT><<<grid, SCAN_BLOCK, 0, st>>>(P);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+static void launch_scan(const Query& q, const ScanParams& P, bool emit) {
+  cudaStream_t st = q.dev->st;
+  const bool single = single_filter_ok(q);
+  if (emit) {  // record pass of exact_sums: the table layout is irrelevant, cells are written out
+    if (single) launch_scan_variant<0, true, true>(P, st);
+    else launch_scan_variant<0, false, true>(P, st);
+  } else if (P.path == 0) {
+    if (single) launch_scan_variant<0, true, false>(P, st);
+    else launch_scan_variant<0, false, false>(P, st);
+  } else {
+    if (single) launch_scan_variant<1, true, false>(P, st);
+    else launch_scan_variant<1, false, false>(P, st);
+  }
+}
+
 void device_execute(Query& q) {
   LK_CHECK(q.dev && q.dev->resident, LK_ERR_INVALID, "lk_query_execute before lk_query_prepare");
   Query::Device& d = *q.dev;
@@ -298,15 +337,7 @@ void device_execute(Query& q) {
       P.h_occ = d.harena->occ;
       P.h_occ_cap = (uint32_t)std::min<uint64_t>(d.harena->slots, 0xffffffffu);
     }
-    // persistent grid: every warp pulls 512-row tiles from the ticket counter until none are left
-    static int ctas_per_sm = 0;
-    if (!ctas_per_sm) {
-      CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, scan_kernel, SCAN_BLOCK, 0));
-      if (ctas_per_sm < 1) ctas_per_sm = 1;
-    }
-    int grid = (int)std::min<uint32_t>((P.ntiles + SCAN_WARPS - 1) / SCAN_WARPS, (uint32_t)(num_sms() * ctas_per_sm));
-    scan_kernel<<<grid, SCAN_BLOCK, 0, d.st>>>(P);
-    CUDA_CHECK(cudaGetLastError());
+    launch_scan(q, P, false);
     if (q.exact_sums) device_exact_sums(q, P);
   }
   CUDA_CHECK(cudaEventRecord(d.ev[3], d.st));
@@ -957,11 +988,7 @@ static void device_exact_sums(Query& q, const ScanParams& base) {
   P.survivors = (unsigned long long*)(counters2 + 8);
   static const uint32_t init_counters[16] = {0, 0xffffffffu, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   CUDA_CHECK(cudaMemcpyAsync(counters2, init_counters, sizeof init_counters, cudaMemcpyHostToDevice, d.st));
-  int ctas = 0;
-  CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas, scan_kernel, SCAN_BLOCK, 0));
-  int grid = (int)std::min<uint32_t>((P.ntiles + SCAN_WARPS - 1) / SCAN_WARPS, (uint32_t)(num_sms() * std::max(ctas, 1)));
-  scan_kernel<<<grid, SCAN_BLOCK, 0, d.st>>>(P);
-  CUDA_CHECK(cudaGetLastError());
+  launch_scan(q, P, true);
   const unsigned long long* sorted_cell = nullptr;
   const uint32_t* order = nullptr;
   sort_order_by_two_keys(d.st, rec_cell, rec_seq, n, key_a, key_b, idx_a, idx_b, tmp, tmp_bytes, &sorted_cell, &order);

@@ -145,6 +145,10 @@ struct SeqReader {
   }
 };
 
+// Specialised at compile time on the aggregate-table layout, the single-filter-column fast path and the record-emit
+// mode of exact_sums: every instantiation carries only its own code (the generic kernel overflowed the instruction
+// cache: ncu showed 4.2 no-instruction stall cycles per issue).
+template <int PATH, bool SINGLE, bool EMIT>
 __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_constant__ ScanParams P) {
   __shared__ WarpSmem smem[SCAN_WARPS];
   const int lane = threadIdx.x & 31;
@@ -257,8 +261,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
       else if (c.flags & CUR_ALL_NULL) { defbits = 0; vidx = 0; }
       else { defbits = s.defb[p][lane]; vidx = c.vidx0 + s.vpre[p][lane]; }
     };
-    const bool single = P.n_filter == 1 && !P.filter[0].numeric && s.ci[P.filter[0].pcol].dict_n <= SCAN_CODEPASS_MAX;
-    if (single) {
+    // SINGLE: one string filter column whose dictionaries all have <= SCAN_CODEPASS_MAX entries (checked by the host)
+    if constexpr (SINGLE) {
       // one filter column: fold class table and pass bitmap into one bit per dictionary code (per tile: every row
       // group has its own dictionary); a row passes iff bit[code] -- or the NULL class bit -- is set
       const int p = P.filter[0].pcol;
@@ -292,6 +296,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
         }
       }
     } else if (lrows) {
+      // generic predicate: class index over all filter columns (kept rolled: this path is rarely the hot one)
       uint32_t idx[SCAN_ROWS_PER_LANE];
 #pragma unroll
       for (int j = 0; j < SCAN_ROWS_PER_LANE; j++) idx[j] = 0;
@@ -424,7 +429,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
         }
       }
 
-      if (P.emit_records) {
+      if constexpr (EMIT) {
         // fixed-order summation pass: the survivors are not aggregated here but written out as (cell, global row
         // sequence, value) records; they are sorted and folded strictly in row order afterwards (lk_exact.cu)
         const unsigned am = __ballot_sync(0xffffffffu, active);
@@ -451,7 +456,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
         if (x == 0x123456789abcdefull) my_status |= 4;
         continue;
       }
-      if (P.path == 0) {
+      if constexpr (PATH == 0) {
         // dense planes; optionally pre-reduce lanes that hit the same cell (few groups => long same-cell runs)
         bool todo = active;
         if (P.warp_agg) {

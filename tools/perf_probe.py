@@ -19,7 +19,7 @@ ap.add_argument("--config", default="c2")
 ap.add_argument("--data", default="/tmp/lk_probe")
 a = ap.parse_args()
 
-api.init()
+api.init(**json.loads(os.environ.get("LK_INIT", "{}")))
 if a.config == "c1":
     spec = synth.SynthSpec(dataset="logs", rows=a.rows)
     be, step, aggs = synth.c1_base_expr(), 60000, None

@@ -275,32 +275,38 @@ static bool single_filter_ok(const Query& q) {
   return true;
 }
 
-template <int PATH, bool SINGLE, bool EMIT>
+template <int PATH, bool SINGLE, bool EMIT, int NA>
 static void launch_scan_variant(const ScanParams& P, cudaStream_t st) {
   // persistent grid: every warp pulls 512-row tiles from the ticket counter until none are left
   static int ctas_per_sm = 0;
   if (!ctas_per_sm) {
-    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, scan_kernel<PATH, SINGLE, EMIT>, SCAN_BLOCK, 0));
+    CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, scan_kernel<PATH, SINGLE, EMIT, NA>, SCAN_BLOCK, 0));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
-  const int grid = (int)std::min<uint32_t>((P.ntiles + SCAN_WARPS - 1) / SCAN_WARPS, (uint32_t)(num_sms() * ctas_per_sm));
-  scan_kernel<PATH, SINGLE, EMIT><<<grid, SCAN_BLOCK, 0, st>>>(P);
+  const uint32_t chunks = (P.ntiles + SCAN_CHUNK_TILES - 1) / SCAN_CHUNK_TILES;  // one ticket = SCAN_CHUNK_TILES tiles
+  const int grid = (int)std::min<uint32_t>((chunks + SCAN_WARPS - 1) / SCAN_WARPS, (uint32_t)(num_sms() * ctas_per_sm));
+  scan_kernel<PATH, SINGLE, EMIT, NA><<<grid, SCAN_BLOCK, 0, st>>>(P);
   CUDA_CHECK(cudaGetLastError());
+}
+
+template <int PATH, bool EMIT>
+static void launch_scan_table(const ScanParams& P, bool single, cudaStream_t st) {
+  const bool few = P.n_aggs <= 4;  // the common case gets the kernel with 4 unrolled aggregate slots
+  if (single) {
+    if (few) launch_scan_variant<PATH, true, EMIT, 4>(P, st);
+    else launch_scan_variant<PATH, true, EMIT, LK_MAX_AGGS>(P, st);
+  } else {
+    if (few) launch_scan_variant<PATH, false, EMIT, 4>(P, st);
+    else launch_scan_variant<PATH, false, EMIT, LK_MAX_AGGS>(P, st);
+  }
 }
 
 static void launch_scan(const Query& q, const ScanParams& P, bool emit) {
   cudaStream_t st = q.dev->st;
   const bool single = single_filter_ok(q);
-  if (emit) {  // record pass of exact_sums: the table layout is irrelevant, cells are written out
-    if (single) launch_scan_variant<0, true, true>(P, st);
-    else launch_scan_variant<0, false, true>(P, st);
-  } else if (P.path == 0) {
-    if (single) launch_scan_variant<0, true, false>(P, st);
-    else launch_scan_variant<0, false, false>(P, st);
-  } else {
-    if (single) launch_scan_variant<1, true, false>(P, st);
-    else launch_scan_variant<1, false, false>(P, st);
-  }
+  if (emit) launch_scan_table<0, true>(P, single, st);  // record pass of exact_sums: cells are written out, no table
+  else if (P.path == 0) launch_scan_table<0, false>(P, single, st);
+  else launch_scan_table<1, false>(P, single, st);
 }
 
 void device_execute(Query& q) {

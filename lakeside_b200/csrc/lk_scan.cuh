@@ -26,6 +26,7 @@ constexpr int SCAN_BLOCK = SCAN_WARPS * 32;
 constexpr int SCAN_ROWS_PER_LANE = LK_TILE_ROWS_MAX / 32;  // 16
 static_assert(SCAN_ROWS_PER_LANE == 16, "the kernel is written for 512-row tiles");
 constexpr uint32_t SCAN_CODEPASS_MAX = 1024;
+constexpr uint32_t SCAN_CHUNK_TILES = 4;  // consecutive tiles per ticket
 
 struct WarpSmem {
   ColCursor cur[LK_MAX_PCOLS];
@@ -62,10 +63,15 @@ __device__ __forceinline__ uint32_t fast_run(const WarpSmem& s, int p, uint32_t 
   return (uint32_t)(vidx >= s.vrs[p][1]) + (uint32_t)(vidx >= s.vrs[p][2]) + (uint32_t)(vidx >= s.vrs[p][3]);
 }
 
+// more than 4 runs of the column in the tile (rare): binary search in the global run pool; one out-of-line copy
+__device__ __noinline__ uint32_t dict_code_slow(const uint8_t* arena, const Run* runs, const ColCursor* c, const ChunkInfo* ci, uint32_t vidx) {
+  return lk_dict_code(arena, runs, *c, *ci, vidx);
+}
+
 // dictionary index of value `vidx`: run descriptors from shared memory when the tile has <= 4 runs of this column
 __device__ __forceinline__ uint32_t dict_code(const WarpSmem& s, int p, const uint8_t* __restrict__ arena, const Run* __restrict__ runs, uint32_t vidx) {
   const ColCursor& c = s.cur[p];
-  if (c.vrun_n > 4) return lk_dict_code(arena, runs, c, s.ci[p], vidx);
+  if (c.vrun_n > 4) return dict_code_slow(arena, runs, &c, &s.ci[p], vidx);
   const uint32_t ri = fast_run(s, p, vidx);
   const uint32_t kv = s.vrk[p][ri];
   if (kv >> 31) return kv & 0x7fffffffu;
@@ -148,7 +154,8 @@ struct SeqReader {
 // Specialised at compile time on the aggregate-table layout, the single-filter-column fast path and the record-emit
 // mode of exact_sums: every instantiation carries only its own code (the generic kernel overflowed the instruction
 // cache: ncu showed 4.2 no-instruction stall cycles per issue).
-template <int PATH, bool SINGLE, bool EMIT>
+// NA bounds the unrolled aggregate slots (4 or LK_MAX_AGGS): each slot is a full copy of the value decode.
+template <int PATH, bool SINGLE, bool EMIT, int NA>
 __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_constant__ ScanParams P) {
   __shared__ WarpSmem smem[SCAN_WARPS];
   const int lane = threadIdx.x & 31;
@@ -159,11 +166,26 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
   uint32_t my_phase_min = 0xffffffffu, my_phase_max = 0, my_status = 0;
   unsigned long long my_surv = 0;
 
-  while (true) {
-    uint32_t tile = 0;
-    if (lane == 0) tile = atomicAdd(P.counters + 4, 1u);
-    tile = __shfl_sync(0xffffffffu, tile, 0);
-    if (tile >= P.ntiles) break;
+  // tiles are handed out in chunks of SCAN_CHUNK_TILES consecutive tiles; the ticket of the NEXT chunk is requested a
+  // chunk ahead (lane 0 holds it, nobody waits for it until the boundary), so the atomic is off the critical path
+  auto ticket = [&]() -> uint32_t {
+    uint32_t t = 0;
+    if (lane == 0) t = atomicAdd(P.counters + 4, SCAN_CHUNK_TILES);
+    return t;
+  };
+  uint32_t pending = ticket();
+  uint32_t tile = __shfl_sync(0xffffffffu, pending, 0);
+  uint32_t chunk_end = min(tile + SCAN_CHUNK_TILES, P.ntiles);
+  pending = ticket();
+  uint32_t cached_rg = 0xffffffffu;
+
+  for (;; tile++) {
+    if (tile >= chunk_end) {
+      tile = __shfl_sync(0xffffffffu, pending, 0);
+      if (tile >= P.ntiles) break;
+      chunk_end = min(tile + SCAN_CHUNK_TILES, P.ntiles);
+      pending = ticket();
+    }
     const TileDesc td = P.tiles[tile];
     const uint32_t nrows = td.nrows;
     const uint32_t row0 = td.row0;
@@ -172,9 +194,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
     {
       bool mine = false;
       if (lane < (int)P.npcols) {
-        const ColCursor c = P.cursors[td.cursor0 + lane];
+        const ColCursor c = P.cursors[(size_t)tile * P.npcols + lane];  // == td.cursor0 + lane: no wait for td
         s.cur[lane] = c;
-        s.ci[lane] = P.chunks[(size_t)td.rg * P.npcols + lane];
+        if (td.rg != cached_rg) s.ci[lane] = P.chunks[(size_t)td.rg * P.npcols + lane];
         mine = !(c.flags & (CUR_ALL_VALID | CUR_ALL_NULL));
         if ((c.flags & CUR_DICT) && c.nvals) {
 #pragma unroll
@@ -190,6 +212,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
       }
       need = __ballot_sync(0xffffffffu, mine);
     }
+    const bool new_rg = td.rg != cached_rg;  // chunk descriptors (and the per-code pass bits) are per row group
+    cached_rg = td.rg;
     __syncwarp();
     if (P.stop_after == 1) continue;
 
@@ -268,7 +292,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
       const int p = P.filter[0].pcol;
       const uint32_t dict_n = s.ci[p].dict_n;
       const uint8_t* __restrict__ lut = P.lut_cls + s.ci[p].lut_cls;
-      for (uint32_t c0 = 0; c0 < dict_n; c0 += 32) {
+      for (uint32_t c0 = 0; new_rg && c0 < dict_n; c0 += 32) {  // the bits only change with the dictionary
         const uint32_t code = c0 + lane;
         bool ok = false;
         if (code < dict_n) {
@@ -368,10 +392,10 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
       const uint32_t i = i0 + lane;
       bool active = i < nsurv;
       unsigned long long cell = 0, seq = 0;
-      unsigned long long vbits[LK_MAX_AGGS];
-      bool vvalid[LK_MAX_AGGS];
+      unsigned long long vbits[NA];
+      bool vvalid[NA];
 #pragma unroll
-      for (int a = 0; a < LK_MAX_AGGS; a++) { vbits[a] = 0; vvalid[a] = false; }
+      for (int a = 0; a < NA; a++) { vbits[a] = 0; vvalid[a] = false; }
       if (active) {
         const uint32_t r = s.surv[i];
         uint32_t vidx;
@@ -397,6 +421,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
               my_phase_max = max(my_phase_max, ph);
             }
             uint64_t gid = 0;
+#pragma unroll 1
             for (int k = 0; k < P.n_keys; k++) {
               const int p = P.keys[k].pcol;
               uint32_t gcode = P.keys[k].null_code;
@@ -410,7 +435,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
             cell = bucket * P.n_groups + gid;
             seq = s.ci[P.ts_pcol].seq_base + row0 + r;
 #pragma unroll
-            for (int a = 0; a < LK_MAX_AGGS; a++) {
+            for (int a = 0; a < NA; a++) {
               if (a < P.n_aggs && P.stop_after != 5) {
                 const int p = P.aggs[a].pcol;
                 vvalid[a] = col_pos(s, p, r, vidx);
@@ -443,7 +468,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
             P.rec_cell[o] = cell;
             P.rec_seq[o] = seq;
 #pragma unroll
-            for (int a = 0; a < LK_MAX_AGGS; a++)
+            for (int a = 0; a < NA; a++)
               if (a < P.n_aggs && P.aggs[a].op == AGG_SUM) P.rec_val[a][o] = vvalid[a] ? vbits[a] : 0ull;
           }
         }
@@ -452,7 +477,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
       if (P.stop_after >= 4) {  // profiling aid: no table update
         unsigned long long x = cell;
 #pragma unroll
-        for (int a = 0; a < LK_MAX_AGGS; a++) x ^= vbits[a];
+        for (int a = 0; a < NA; a++) x ^= vbits[a];
         if (x == 0x123456789abcdefull) my_status |= 4;
         continue;
       }
@@ -468,7 +493,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
             const unsigned m = __ballot_sync(0xffffffffu, mine);
             if (__popc(m) > 1) {
 #pragma unroll
-              for (int a = 0; a < LK_MAX_AGGS; a++) {
+              for (int a = 0; a < NA; a++) {
                 if (a < P.n_aggs) {
                   const int op = P.aggs[a].op;
                   const bool has = mine && vvalid[a];
@@ -497,7 +522,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
         if (todo) {
           atomicAdd(P.rowcnt + cell, 1ull);
 #pragma unroll
-          for (int a = 0; a < LK_MAX_AGGS; a++)
+          for (int a = 0; a < NA; a++)
             if (a < P.n_aggs && vvalid[a]) acc_update(P.acc[a] + cell, P.aggs[a].op, vbits[a], 1ull);
         }
       } else {
@@ -522,7 +547,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_consta
           if (!entry) my_status |= ST_HASH_FULL;
           else {
 #pragma unroll
-            for (int a = 0; a < LK_MAX_AGGS; a++)
+            for (int a = 0; a < NA; a++)
               if (a < P.n_aggs && vvalid[a]) acc_update(entry + 1 + a, P.aggs[a].op, vbits[a], 1ull);
           }
         }

@@ -9,7 +9,11 @@ for r in rows:
     if r and r[0] == "File Path": f = r[1].split("/")[-1]; continue
     if r and r[0] == "Line No": hdr = r; continue
     if hdr is None or not r or not r[0].isdigit(): continue
-    g = lambda name: int(r[hdr.index(name)] or 0) if r[hdr.index(name)] not in ("-", "") else 0
+    def g(name):
+        try:
+            return int(r[hdr.index(name)] or 0)
+        except (ValueError, IndexError):  # "-" cells, or a source line whose quotes confused the CSV export
+            return 0
     out.append((g("# Samples"), g("stall_long_sb"), g("stall_wait"), g("stall_short_sb"), g("stall_no_inst"), g("Instructions Executed"), f, r[0], r[1].strip()[:100]))
 tot = sum(o[0] for o in out); toti = sum(o[5] for o in out)
 print("samples", tot, "warp-inst", toti)

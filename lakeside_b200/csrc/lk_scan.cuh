@@ -27,6 +27,11 @@ constexpr int SCAN_ROWS_PER_LANE = LK_TILE_ROWS_MAX / 32;  // 16
 static_assert(SCAN_ROWS_PER_LANE == 16, "the kernel is written for 512-row tiles");
 constexpr uint32_t SCAN_CODEPASS_MAX = 1024;
 constexpr uint32_t SCAN_CHUNK_TILES = 4;  // consecutive tiles per ticket
+#ifndef SCAN_MIN_CTAS
+// resident CTAs per SM the register allocation is held to: 9 x 4 warps at 56 registers measured 4 % faster than 8 x 4 at
+// 64 and 8 % faster than 10 x 4 at 48 (spills); tuning builds: make EXTRA=-DSCAN_MIN_CTAS=n
+#define SCAN_MIN_CTAS 9
+#endif
 
 struct WarpSmem {
   ColCursor cur[LK_MAX_PCOLS];
@@ -111,15 +116,23 @@ __device__ __forceinline__ void acc_update(unsigned long long* word, int op, uns
 // Sequential reader of consecutive dictionary indices of one column: a 64-bit window (two 32-bit words) slides over a
 // bit-packed run, one funnel shift per value; run changes are rare (a bit-packed run holds up to 504 values).
 struct SeqReader {
-  const Run* run;
-  const Run* last;
+  const Run* r0;       // the column's runs in the global pool (more than 4 runs in the tile)
+  const uint32_t* fs;  // or: starts / kind words of its <= 4 runs in shared memory (absent runs start at 0xffffffff)
+  const uint32_t* fk;
   const uint8_t* chunk;
   const uint32_t* wp;
-  uint32_t next_start, rle, cur, nxt, sh, width, mask;
+  uint32_t ri, n, next_start, rle, cur, nxt, sh, width, mask;
   bool is_rle;
   __device__ __forceinline__ void open_run(uint32_t vidx) {
-    const Run r = *run;
-    next_start = run < last ? run[1].start : 0xffffffffu;
+    Run r;
+    if (fs) {
+      r.start = fs[ri];
+      r.kind_value = fk[ri];
+      next_start = ri < 3 ? fs[ri + 1] : 0xffffffffu;
+    } else {
+      r = r0[ri];
+      next_start = ri + 1 < n ? r0[ri + 1].start : 0xffffffffu;
+    }
     is_rle = r.kind_value >> 31;
     rle = r.kind_value & 0x7fffffffu;
     if (!is_rle) {
@@ -133,16 +146,19 @@ struct SeqReader {
   }
   __device__ __forceinline__ void seek(const WarpSmem& s, int p, const uint8_t* arena, const Run* runs, uint32_t vidx) {
     const ColCursor& c = s.cur[p];
-    const Run* r0 = runs + c.vrun_lo;
-    last = r0 + c.vrun_n - 1;
+    r0 = runs + c.vrun_lo;
+    n = c.vrun_n;
+    const bool fast = n <= 4;
+    fs = fast ? s.vrs[p] : nullptr;
+    fk = s.vrk[p];
     chunk = arena + s.ci[p].base_off;
     width = c.width;
     mask = (1u << width) - 1;  // width <= 31 (checked by the host index)
-    run = r0 + (c.vrun_n > 4 ? lk_find_run(r0, c.vrun_n, vidx) : fast_run(s, p, vidx));
+    ri = fast ? fast_run(s, p, vidx) : lk_find_run(r0, n, vidx);
     open_run(vidx);
   }
   __device__ __forceinline__ uint32_t next(uint32_t vidx) {
-    if (vidx >= next_start) { run++; open_run(vidx); }
+    if (vidx >= next_start) { ri++; open_run(vidx); }
     if (is_rle) return rle;
     const uint32_t code = __funnelshift_r(cur, nxt, sh) & mask;
     sh += width;
@@ -156,7 +172,7 @@ struct SeqReader {
 // cache: ncu showed 4.2 no-instruction stall cycles per issue).
 // NA bounds the unrolled aggregate slots (4 or LK_MAX_AGGS): each slot is a full copy of the value decode.
 template <int PATH, bool SINGLE, bool EMIT, int NA>
-__global__ void __launch_bounds__(SCAN_BLOCK, 8) scan_kernel(const __grid_constant__ ScanParams P) {
+__global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const __grid_constant__ ScanParams P) {
   __shared__ WarpSmem smem[SCAN_WARPS];
   const int lane = threadIdx.x & 31;
   WarpSmem& s = smem[threadIdx.x >> 5];

@@ -32,6 +32,10 @@ constexpr uint32_t SCAN_CHUNK_TILES = 4;  // consecutive tiles per ticket
 // 64 and 8 % faster than 10 x 4 at 48 (spills); tuning builds: make EXTRA=-DSCAN_MIN_CTAS=n
 #define SCAN_MIN_CTAS 9
 #endif
+// Measured and rejected on B200 (r1, C2 workload, this kernel at 1.30 ms): prefetch.global.L1/.L2 of a survivor's nine
+// gather addresses ahead of the dependent loads (+7 %: the extra address arithmetic costs more issue slots than the
+// latency it hides); batched branch-free gathers in registers (3400 SASS instructions: +16 %, instruction fetch);
+// cp.async staging of the seek index one tile ahead (long-scoreboard stalls 7.7 -> 2.2 per issue but +50 % instructions).
 
 struct WarpSmem {
   ColCursor cur[LK_MAX_PCOLS];
@@ -42,6 +46,12 @@ struct WarpSmem {
   uint32_t vrk[LK_MAX_PCOLS][4];    // their kind_value words
   uint32_t codepass[SCAN_CODEPASS_MAX / 32];  // single filter column: bit c set <=> dictionary code c passes the WHERE
   uint16_t surv[LK_TILE_ROWS_MAX];
+};
+
+// the generic (several filter columns) predicate also keeps one class index per row
+template <bool GENERIC>
+struct WarpSmemT : WarpSmem {
+  uint32_t fidx[GENERIC ? LK_TILE_ROWS_MAX : 1];
 };
 
 // 32 bits starting `bit` bits after byte address p (bit may exceed 7)
@@ -173,9 +183,9 @@ struct SeqReader {
 // NA bounds the unrolled aggregate slots (4 or LK_MAX_AGGS): each slot is a full copy of the value decode.
 template <int PATH, bool SINGLE, bool EMIT, int NA>
 __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const __grid_constant__ ScanParams P) {
-  __shared__ WarpSmem smem[SCAN_WARPS];
+  __shared__ WarpSmemT<!SINGLE> smem[SCAN_WARPS];
   const int lane = threadIdx.x & 31;
-  WarpSmem& s = smem[threadIdx.x >> 5];
+  WarpSmemT<!SINGLE>& s = smem[threadIdx.x >> 5];
   const uint8_t* __restrict__ arena = P.arena;
   const Run* __restrict__ runs = P.runs;
   const unsigned lt_mask = (1u << lane) - 1;
@@ -336,10 +346,13 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
         }
       }
     } else if (lrows) {
-      // generic predicate: class index over all filter columns (kept rolled: this path is rarely the hot one)
-      uint32_t idx[SCAN_ROWS_PER_LANE];
-#pragma unroll
-      for (int j = 0; j < SCAN_ROWS_PER_LANE; j++) idx[j] = 0;
+      // generic predicate: class index over all filter columns, accumulated per row in shared memory (row j of this
+      // lane at fidx[32 j + lane]: conflict-free) so that every loop stays rolled -- the unrolled form was a 10 k-
+      // instruction kernel, far beyond the instruction cache
+      uint32_t* const fidx = s.fidx + lane;
+#pragma unroll 1
+      for (int j = 0; j < SCAN_ROWS_PER_LANE; j++) fidx[32 * j] = 0;
+#pragma unroll 1
       for (int f = 0; f < P.n_filter; f++) {
         const int p = P.filter[f].pcol;
         const uint32_t stride = P.filter[f].stride;
@@ -347,7 +360,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
         uint32_t defbits, vidx;
         lane_def(p, defbits, vidx);
         if (P.filter[f].numeric) {
-#pragma unroll
+#pragma unroll 1
           for (int j = 0; j < SCAN_ROWS_PER_LANE; j++) {
             uint32_t cls = null_cls;
             if ((defbits >> j) & 1) {
@@ -356,14 +369,14 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
               if (bad) my_status |= ST_BAD_CODE;
               cls = lk_numeric_class(P.filter[f], lk_bits_to_f64(bits, s.ci[p].phys_type));
             }
-            idx[j] += cls * stride;
+            fidx[32 * j] += cls * stride;
           }
         } else {
           const uint32_t dict_n = s.ci[p].dict_n;
           const uint8_t* __restrict__ lut = P.lut_cls + s.ci[p].lut_cls;
           SeqReader rd;
           if (defbits) rd.seek(s, p, arena, runs, vidx);
-#pragma unroll
+#pragma unroll 1
           for (int j = 0; j < SCAN_ROWS_PER_LANE; j++) {
             uint32_t cls = null_cls;
             if ((defbits >> j) & 1) {
@@ -371,13 +384,13 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
               if (code < dict_n) cls = __ldg(lut + code);
               else my_status |= ST_BAD_CODE;
             }
-            idx[j] += cls * stride;
+            fidx[32 * j] += cls * stride;
           }
         }
       }
-#pragma unroll
+#pragma unroll 1
       for (int j = 0; j < SCAN_ROWS_PER_LANE; j++) {
-        const uint32_t i = idx[j];
+        const uint32_t i = fidx[32 * j];
         passmask |= ((__ldg(P.pass_bits + (i >> 5)) >> (i & 31)) & 1u) << j;
       }
     }
@@ -408,6 +421,10 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
       const uint32_t i = i0 + lane;
       bool active = i < nsurv;
       unsigned long long cell = 0, seq = 0;
+      uint64_t slot = 0;
+      unsigned long long probe_key = 1;  // neither empty nor a key: only looked at by lanes that set it
+      (void)slot;
+      (void)probe_key;
       unsigned long long vbits[NA];
       bool vvalid[NA];
 #pragma unroll
@@ -450,6 +467,11 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
             }
             cell = bucket * P.n_groups + gid;
             seq = s.ci[P.ts_pcol].seq_base + row0 + r;
+            if constexpr (PATH == 1 && !EMIT) {
+              // first probe of the hash table: in flight while the values are gathered
+              slot = lk_hash64(cell) & P.h_mask;
+              if (P.stop_after < 4) probe_key = *reinterpret_cast<volatile unsigned long long*>(P.h_entries + slot * P.h_stride);
+            }
 #pragma unroll
             for (int a = 0; a < NA; a++) {
               if (a < P.n_aggs && P.stop_after != 5) {
@@ -548,11 +570,11 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
         uint32_t claimed_slot = 0;
         if (active) {
           const unsigned long long key = cell + 1;
-          uint64_t slot = lk_hash64(cell) & P.h_mask;
           unsigned long long* entry = nullptr;
+          unsigned long long k = probe_key;
           for (int probe = 0; probe < 4096; probe++) {
             unsigned long long* e = reinterpret_cast<unsigned long long*>(P.h_entries + slot * P.h_stride);
-            unsigned long long k = *reinterpret_cast<volatile unsigned long long*>(e);
+            if (probe) k = *reinterpret_cast<volatile unsigned long long*>(e);
             if (k == LK_EMPTY_KEY) {
               k = atomicCAS(e, (unsigned long long)LK_EMPTY_KEY, key);
               if (k == LK_EMPTY_KEY) { claimed = true; claimed_slot = (uint32_t)slot; entry = e; break; }

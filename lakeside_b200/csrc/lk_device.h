@@ -128,6 +128,7 @@ struct ScanParams {
   uint32_t h_stride;
   uint64_t h_mask;
   uint32_t* h_occ;      // slots claimed by this query
+  uint32_t* h_bkt;      // and the time bucket of each of them (the ORDER BY pass sorts on it without re-reading the table)
   uint32_t h_occ_cap;
   // fixed-order summation (exact_sums): survivors are emitted as records instead of being aggregated
   int emit_records;

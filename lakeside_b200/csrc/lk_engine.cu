@@ -102,6 +102,7 @@ void pinned_release_all() {
 struct HashArena {
   uint8_t* entries = nullptr;
   uint32_t* occ = nullptr;
+  uint32_t* occ_bkt = nullptr;  // time bucket of every claimed slot (written at claim time: the emit sort never re-reads the entries)
   uint64_t slots = 0;
   uint32_t stride = 0;
   bool busy = false;
@@ -119,7 +120,8 @@ static HashArena* arena_acquire(uint64_t slots, uint32_t stride, cudaStream_t st
   a.stride = stride;
   cudaError_t e = cudaMalloc(&a.entries, slots * stride);
   if (e == cudaSuccess) e = cudaMalloc(&a.occ, slots * sizeof(uint32_t));
-  if (e != cudaSuccess) { cudaGetLastError(); if (a.entries) cudaFree(a.entries); fail(LK_ERR_NOMEM, strf("hash arena of %llu slots: %s", (unsigned long long)slots, cudaGetErrorString(e))); }
+  if (e == cudaSuccess) e = cudaMalloc(&a.occ_bkt, slots * sizeof(uint32_t));
+  if (e != cudaSuccess) { cudaGetLastError(); if (a.entries) cudaFree(a.entries); if (a.occ) cudaFree(a.occ); fail(LK_ERR_NOMEM, strf("hash arena of %llu slots: %s", (unsigned long long)slots, cudaGetErrorString(e))); }
   CUDA_CHECK(cudaMemsetAsync(a.entries, 0, slots * stride, st));
   a.busy = true;
   std::lock_guard<std::mutex> lk(g_mu);
@@ -136,7 +138,7 @@ static void arena_release(HashArena* a) {
 
 void device_shutdown() {
   std::lock_guard<std::mutex> lk(g_mu);
-  for (auto& a : g_arenas) { cudaFree(a.entries); cudaFree(a.occ); }
+  for (auto& a : g_arenas) { cudaFree(a.entries); cudaFree(a.occ); cudaFree(a.occ_bkt); }
   g_arenas.clear();
   pinned_release_all();
 }
@@ -341,6 +343,7 @@ void device_execute(Query& q) {
     } else {
       P.h_entries = d.harena->entries;
       P.h_occ = d.harena->occ;
+      P.h_bkt = d.harena->occ_bkt;
       P.h_occ_cap = (uint32_t)std::min<uint64_t>(d.harena->slots, 0xffffffffu);
     }
     launch_scan(q, P, false);
@@ -504,10 +507,10 @@ constexpr int HS_BLOCK = 256;
 constexpr int HS_CHUNK = 8192;   // claimed slots per block
 constexpr int HS_MAXB = 4096;    // buckets histogrammed in shared memory; beyond that global atomics are uncontended enough
 
-// pass 1: bucket of every claimed slot + per-bucket counts (block-private histogram, one global atomic per bucket per block)
-__global__ void __launch_bounds__(HS_BLOCK) hash_hist_kernel(const uint32_t* __restrict__ occ, uint32_t n, const uint8_t* __restrict__ entries,
-                                                             uint32_t stride, uint64_t n_groups, uint32_t nbuckets,
-                                                             uint32_t* __restrict__ bucket_of, uint32_t* __restrict__ hist) {
+// pass 1: per-bucket counts (block-private histogram, one global atomic per bucket per block).  The bucket of every claimed
+// slot was recorded when the slot was claimed (scan kernel / sparse merge): no random read of the table here.
+__global__ void __launch_bounds__(HS_BLOCK) hash_hist_kernel(const uint32_t* __restrict__ bucket_of, uint32_t n, uint32_t nbuckets,
+                                                             uint32_t* __restrict__ hist) {
   __shared__ uint32_t h[HS_MAXB];
   const bool priv = nbuckets <= HS_MAXB;
   if (priv) {
@@ -515,12 +518,7 @@ __global__ void __launch_bounds__(HS_BLOCK) hash_hist_kernel(const uint32_t* __r
     __syncthreads();
   }
   const uint32_t lo = blockIdx.x * HS_CHUNK, hi = min(n, lo + HS_CHUNK);
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) {
-    const unsigned long long key = *reinterpret_cast<const unsigned long long*>(entries + (uint64_t)occ[i] * stride);
-    const uint32_t b = (uint32_t)((key - 1) / n_groups);
-    bucket_of[i] = b;
-    atomicAdd(priv ? &h[b] : &hist[b], 1u);
-  }
+  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) atomicAdd(priv ? &h[bucket_of[i]] : &hist[bucket_of[i]], 1u);
   if (priv) {
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < nbuckets; b += HS_BLOCK)
@@ -662,15 +660,14 @@ void device_finalize_device(Query& q) {
     if (q.path == 0) {
       dense_emit_kernel<<<nblocks, CMP_BLOCK, 0, d.st>>>(d.planes, q.n_cells, d.block_counts, E);
     } else {
-      // scratch: hist/cursor[nbuckets + 1] | bucket_of[n] | sorted[n]
-      ensure_block_counts(d, (size_t)q.nbuckets + 1 + 2 * (size_t)n);
+      // scratch: hist/cursor[nbuckets + 1] | sorted[n]
+      ensure_block_counts(d, (size_t)q.nbuckets + 1 + (size_t)n);
       uint32_t* hist = d.block_counts;
-      uint32_t* bucket_of = hist + q.nbuckets + 1;
-      uint32_t* sorted = bucket_of + n;
+      const uint32_t* bucket_of = d.harena->occ_bkt;
+      uint32_t* sorted = hist + q.nbuckets + 1;
       CUDA_CHECK(cudaMemsetAsync(hist, 0, ((size_t)q.nbuckets + 1) * 4, d.st));
       const int hgrid = (int)((n + HS_CHUNK - 1) / HS_CHUNK);
-      hash_hist_kernel<<<hgrid, HS_BLOCK, 0, d.st>>>(d.harena->occ, (uint32_t)n, d.harena->entries, d.harena->stride, q.n_groups, q.nbuckets,
-                                                     bucket_of, hist);
+      hash_hist_kernel<<<hgrid, HS_BLOCK, 0, d.st>>>(bucket_of, (uint32_t)n, q.nbuckets, hist);
       exclusive_scan_kernel<<<1, 1024, 0, d.st>>>(hist, q.nbuckets, hist + q.nbuckets);
       hash_scatter_kernel<<<hgrid, HS_BLOCK, 0, d.st>>>(d.harena->occ, bucket_of, (uint32_t)n, q.nbuckets, hist, sorted);
       hash_emit_kernel<<<(int)((n + HS_BLOCK - 1) / HS_BLOCK), HS_BLOCK, 0, d.st>>>(sorted, (uint32_t)n, d.harena->entries, d.harena->stride, E);
@@ -783,16 +780,18 @@ __global__ void __launch_bounds__(HS_BLOCK) sparse_scatter_kernel(const uint32_t
 
 // merges n foreign entries {key, acc[n_aggs]} into the table: sum/count add, min/max (both stored as "max" keys) max
 __global__ void __launch_bounds__(HS_BLOCK) sparse_merge_kernel(const uint8_t* __restrict__ in, uint32_t n, uint8_t* __restrict__ entries, uint32_t stride,
-                                                                uint64_t mask, uint32_t* __restrict__ occ, uint32_t occ_cap, uint32_t* __restrict__ counters,
+                                                                uint64_t mask, uint32_t* __restrict__ occ, uint32_t* __restrict__ occ_bkt, uint64_t n_groups, uint32_t occ_cap,
+                                                                uint32_t* __restrict__ counters,
                                                                 int n_aggs, const __grid_constant__ AggSlot4 ops) {
   const uint32_t i = blockIdx.x * HS_BLOCK + threadIdx.x;
   const int lane = threadIdx.x & 31;
   bool claimed = false;
   uint32_t claimed_slot = 0;
   uint32_t status = 0;
+  unsigned long long key = 1;
   if (i < n) {
     const unsigned long long* e_in = reinterpret_cast<const unsigned long long*>(in + (uint64_t)i * stride);
-    const unsigned long long key = e_in[0];
+    key = e_in[0];
     uint64_t slot = lk_hash64(key - 1) & mask;
     unsigned long long* entry = nullptr;
     for (int probe = 0; probe < 4096; probe++) {
@@ -821,7 +820,8 @@ __global__ void __launch_bounds__(HS_BLOCK) sparse_merge_kernel(const uint8_t* _
     base = __shfl_sync(0xffffffffu, base, __ffs(cm) - 1);
     if (claimed) {
       const uint32_t idx = base + __popc(cm & ((1u << lane) - 1));
-      if (idx < occ_cap) occ[idx] = claimed_slot; else status |= ST_HASH_FULL;
+      if (idx < occ_cap) { occ[idx] = claimed_slot; occ_bkt[idx] = (uint32_t)((key - 1) / n_groups); }
+      else status |= ST_HASH_FULL;
     }
   }
   if (status) atomicOr(counters + 0, status);
@@ -889,7 +889,7 @@ void device_merge_sparse(Query& q, const void* dev_entries, int64_t n) {
   for (size_t a = 0; a < q.aggs.size(); a++) ops.op[a] = q.aggs[a].op;
   sparse_merge_kernel<<<(int)((n + HS_BLOCK - 1) / HS_BLOCK), HS_BLOCK, 0, d.st>>>(
       (const uint8_t*)dev_entries, (uint32_t)n, d.harena->entries, d.harena->stride, q.params.h_mask, d.harena->occ,
-      (uint32_t)std::min<uint64_t>(d.harena->slots, 0xffffffffu), d.counters, (int)q.aggs.size(), ops);
+      d.harena->occ_bkt, q.n_groups, (uint32_t)std::min<uint64_t>(d.harena->slots, 0xffffffffu), d.counters, (int)q.aggs.size(), ops);
   CUDA_CHECK(cudaGetLastError());
 }
 

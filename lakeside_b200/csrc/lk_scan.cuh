@@ -422,6 +422,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
       bool active = i < nsurv;
       unsigned long long cell = 0, seq = 0;
       uint64_t slot = 0;
+      uint32_t bucket32 = 0;
       unsigned long long probe_key = 1;  // neither empty nor a key: only looked at by lanes that set it
       (void)slot;
       (void)probe_key;
@@ -466,6 +467,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
               gid += (uint64_t)gcode * P.keys[k].stride;
             }
             cell = bucket * P.n_groups + gid;
+            bucket32 = (uint32_t)bucket;
             seq = s.ci[P.ts_pcol].seq_base + row0 + r;
             if constexpr (PATH == 1 && !EMIT) {
               // first probe of the hash table: in flight while the values are gathered
@@ -598,7 +600,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
           base = __shfl_sync(0xffffffffu, base, leader);
           if (claimed) {
             const uint32_t o = base + __popc(cm & lt_mask);
-            if (o < P.h_occ_cap) P.h_occ[o] = claimed_slot;
+            if (o < P.h_occ_cap) { P.h_occ[o] = claimed_slot; P.h_bkt[o] = bucket32; }
             else my_status |= ST_HASH_FULL;
           }
         }

@@ -391,7 +391,10 @@ struct EmitParams {
   int32_t* code[LK_MAX_KEYS];
 };
 
-__device__ __forceinline__ void emit_row(const EmitParams& E, uint64_t out, uint64_t cell, const unsigned long long* acc, size_t acc_pitch) {
+// `acc(a)` returns the accumulator word of aggregate a; the loop over aggregates is unrolled so that a caller holding
+// the words in registers (hash path) indexes them statically
+template <class AccFn>
+__device__ __forceinline__ void emit_row(const EmitParams& E, uint64_t out, uint64_t cell, AccFn acc) {
   uint64_t bucket, gid;
   if (E.cells32) {  // the whole (group x bucket) space fits 32 bits: 32-bit divisions (a 64-bit one costs ~100 instructions)
     const uint32_t b32 = (uint32_t)cell / (uint32_t)E.n_groups;
@@ -402,8 +405,10 @@ __device__ __forceinline__ void emit_row(const EmitParams& E, uint64_t out, uint
     gid = cell - bucket * E.n_groups;
   }
   E.ts[out] = E.base + (int64_t)bucket * E.step + (int64_t)E.phase;
-  for (int a = 0; a < E.n_aggs; a++) {
-    const unsigned long long w = acc[a * acc_pitch];
+#pragma unroll
+  for (int a = 0; a < LK_MAX_AGGS; a++) {
+    if (a >= E.n_aggs) break;
+    const unsigned long long w = acc(a);
     double v;
     uint8_t isnull = 0;
     switch (E.ops[a]) {
@@ -498,7 +503,8 @@ __global__ void __launch_bounds__(CMP_BLOCK) dense_emit_kernel(const unsigned lo
   for (int k = 0; k < CMP_PER_THREAD; k++)
     if (present & (1u << k)) {
       const uint64_t cell = first + k;
-      emit_row(E, out++, cell, planes + n_cells + cell, n_cells);
+      const unsigned long long* acc0 = planes + n_cells + cell;
+      emit_row(E, out++, cell, [&](int a) { return acc0[(size_t)a * n_cells]; });
     }
 }
 
@@ -568,7 +574,7 @@ __global__ void __launch_bounds__(HS_BLOCK) hash_emit_kernel(const uint32_t* __r
     else { w[4] = w[5] = w[6] = w[7] = 0; }
   }
   for (uint32_t k = 0; k < stride / 16; k++) z[k] = make_ulonglong2(0ull, 0ull);
-  emit_row(E, i, w[0] - 1, w + 1, 1);
+  emit_row(E, i, w[0] - 1, [&](int a) { return w[1 + a]; });
 }
 
 // device result layout for n rows: ts[n] | val[a][n] | code[k][n] | nul[a][n]

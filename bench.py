@@ -235,6 +235,14 @@ def main():
     SIGN = torch.iinfo(torch.int64).min
     exchange_bytes = [0]
 
+    trace = [] if os.environ.get("LK_BENCH_TRACE") else None  # per-phase wall clock of the exchange (adds syncs: diagnosis only)
+
+    def mark(name):
+        if trace is not None:
+            q.sync()
+            torch.cuda.synchronize()
+            trace.append((name, time.perf_counter()))
+
     def exchange(qq, path):
         """The ONE exchange step of the sharded path (no collective touches the scan).
         dense : NCCL reduce of every (group x bucket) plane to rank 0 (sum f64 / sum u64 / max on order-preserving keys)
@@ -258,17 +266,22 @@ def main():
             exchange_bytes[0] = n_cells * 8 * len(planes)
             torch.cuda.synchronize()
         else:
+            mark("execute")
             ptr, counts, stride = qq.partial_sparse(world)
+            mark("partition")
             send_counts = torch.tensor(counts, dtype=torch.int64, device="cuda")
             recv_counts = torch.empty_like(send_counts)
             dist.all_to_all_single(recv_counts, send_counts)
             rc = recv_counts.tolist()
+            mark("counts")
             n_send = sum(counts)
             send = _as_tensor(ptr, n_send * stride, "|u1", torch.uint8) if n_send else torch.empty(0, dtype=torch.uint8, device="cuda")
             recv = torch.empty(sum(rc) * stride, dtype=torch.uint8, device="cuda")
             dist.all_to_all_single(recv, send, [c * stride for c in rc], [c * stride for c in counts])
             torch.cuda.synchronize()
+            mark("all_to_all")
             qq.merge_sparse(recv.data_ptr(), sum(rc))
+            mark("merge")
             qq._keep.append(recv)
             exchange_bytes[0] = (n_send - counts[rank]) * stride
 
@@ -286,6 +299,7 @@ def main():
         q.execute()
         exchange(q, info["path"])
         q.finalize_device()
+        mark("finalize")
         q._keep.clear()
 
     for _ in range(max(3, args.warmup)):
@@ -306,6 +320,9 @@ def main():
     q.sync()
     torch.cuda.synchronize()
     dev_ms = e0.elapsed_time(e1)
+    if trace and rank == 0:
+        last = trace[-1 - 6:]
+        print("exchange trace (ms):", [(b[0], round((b[1] - a[1]) * 1e3, 3)) for a, b in zip(last, last[1:])], file=sys.stderr)
     # per-kernel duration of the dominant kernel (CUDA events recorded by the library around each scan launch, on its
     # launching stream); measured in a separate loop so that reading them never serialises the timed region
     per_scan = []

@@ -513,6 +513,19 @@ constexpr int HS_BLOCK = 256;
 constexpr int HS_CHUNK = 8192;   // claimed slots per block
 constexpr int HS_MAXB = 4096;    // buckets histogrammed in shared memory; beyond that global atomics are uncontended enough
 
+// Warp-aggregated counter increment: the lanes that target the same counter elect a leader that adds their count once
+// (with 2-8 partitions a plain shared-memory atomic per element serialises 32-way and took 3.4 ms for 6 M entries).
+// Must be called by all 32 lanes; lanes with valid == false get no slot.  Returns the lane's position.
+__device__ __forceinline__ uint32_t warp_agg_inc(uint32_t* ctrs, uint32_t idx, bool valid) {
+  const int lane = threadIdx.x & 31;
+  const unsigned peers = __match_any_sync(0xffffffffu, valid ? idx : 0xffffffffu);
+  const int leader = __ffs(peers) - 1;
+  uint32_t base = 0;
+  if (valid && lane == leader) base = atomicAdd(&ctrs[idx], (uint32_t)__popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + __popc(peers & ((1u << lane) - 1));
+}
+
 // pass 1: per-bucket counts (block-private histogram, one global atomic per bucket per block).  The bucket of every claimed
 // slot was recorded when the slot was claimed (scan kernel / sparse merge): no random read of the table here.
 __global__ void __launch_bounds__(HS_BLOCK) hash_hist_kernel(const uint32_t* __restrict__ bucket_of, uint32_t n, uint32_t nbuckets,
@@ -524,7 +537,11 @@ __global__ void __launch_bounds__(HS_BLOCK) hash_hist_kernel(const uint32_t* __r
     __syncthreads();
   }
   const uint32_t lo = blockIdx.x * HS_CHUNK, hi = min(n, lo + HS_CHUNK);
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) atomicAdd(priv ? &h[bucket_of[i]] : &hist[bucket_of[i]], 1u);
+  for (uint32_t i0 = lo; i0 < hi; i0 += HS_BLOCK) {  // uniform trip count: warp_agg_inc needs the whole warp
+    const uint32_t i = i0 + threadIdx.x;
+    const bool valid = i < hi;
+    warp_agg_inc(priv ? h : hist, valid ? bucket_of[i] : 0u, valid);
+  }
   if (priv) {
     __syncthreads();
     for (uint32_t b = threadIdx.x; b < nbuckets; b += HS_BLOCK)
@@ -545,7 +562,11 @@ __global__ void __launch_bounds__(HS_BLOCK) hash_scatter_kernel(const uint32_t* 
   }
   for (uint32_t b = threadIdx.x; b < nbuckets; b += HS_BLOCK) cnt[b] = 0;
   __syncthreads();
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) atomicAdd(&cnt[bucket_of[i]], 1u);
+  for (uint32_t i0 = lo; i0 < hi; i0 += HS_BLOCK) {
+    const uint32_t i = i0 + threadIdx.x;
+    const bool valid = i < hi;
+    warp_agg_inc(cnt, valid ? bucket_of[i] : 0u, valid);
+  }
   __syncthreads();
   for (uint32_t b = threadIdx.x; b < nbuckets; b += HS_BLOCK) {
     const uint32_t c = cnt[b];
@@ -553,9 +574,12 @@ __global__ void __launch_bounds__(HS_BLOCK) hash_scatter_kernel(const uint32_t* 
     cnt[b] = 0;
   }
   __syncthreads();
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) {
-    const uint32_t b = bucket_of[i];
-    sorted[base[b] + atomicAdd(&cnt[b], 1u)] = occ[i];
+  for (uint32_t i0 = lo; i0 < hi; i0 += HS_BLOCK) {
+    const uint32_t i = i0 + threadIdx.x;
+    const bool valid = i < hi;
+    const uint32_t b = valid ? bucket_of[i] : 0u;
+    const uint32_t pos = warp_agg_inc(cnt, b, valid);
+    if (valid) sorted[base[b] + pos] = occ[i];
   }
 }
 
@@ -570,10 +594,14 @@ __global__ void __launch_bounds__(HS_BLOCK) hash_emit_kernel(const uint32_t* __r
   {
     const ulonglong2 a = z[0], b = z[1];  // one 32-byte sector
     w[0] = a.x; w[1] = a.y; w[2] = b.x; w[3] = b.y;
-    if (stride == 64) { const ulonglong2 c = z[2], d = z[3]; w[4] = c.x; w[5] = c.y; w[6] = d.x; w[7] = d.y; }
-    else { w[4] = w[5] = w[6] = w[7] = 0; }
+    // only the 16-byte pieces that hold the key and the n_aggs accumulators are read and cleared: the rest of a
+    // 64-byte entry is never written
+    w[4] = w[5] = w[6] = w[7] = 0;
+    if (E.n_aggs > 3) { const ulonglong2 c = z[2]; w[4] = c.x; w[5] = c.y; }
+    if (E.n_aggs > 5) { const ulonglong2 d = z[3]; w[6] = d.x; w[7] = d.y; }
   }
-  for (uint32_t k = 0; k < stride / 16; k++) z[k] = make_ulonglong2(0ull, 0ull);
+  const uint32_t used16 = ((uint32_t)E.n_aggs + 2) / 2;  // ceil((1 + n_aggs) * 8 / 16)
+  for (uint32_t k = 0; k < max(used16, 2u); k++) z[k] = make_ulonglong2(0ull, 0ull);
   emit_row(E, i, w[0] - 1, [&](int a) { return w[1 + a]; });
 }
 
@@ -748,11 +776,16 @@ __global__ void __launch_bounds__(HS_BLOCK) sparse_hist_kernel(const uint32_t* _
   if (threadIdx.x < SP_MAXPARTS) h[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t lo = blockIdx.x * HS_CHUNK, hi = min(n, lo + HS_CHUNK);
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) {
-    const unsigned long long key = *reinterpret_cast<const unsigned long long*>(entries + (uint64_t)occ[i] * stride);
-    const uint32_t p = cell_partition(key - 1, nparts);
-    part_of[i] = p;
-    atomicAdd(&h[p], 1u);
+  for (uint32_t i0 = lo; i0 < hi; i0 += HS_BLOCK) {  // uniform trip count: warp_agg_inc needs the whole warp
+    const uint32_t i = i0 + threadIdx.x;
+    const bool valid = i < hi;
+    uint32_t p = 0;
+    if (valid) {
+      const unsigned long long key = *reinterpret_cast<const unsigned long long*>(entries + (uint64_t)occ[i] * stride);
+      p = cell_partition(key - 1, nparts);
+      part_of[i] = p;
+    }
+    warp_agg_inc(h, p, valid);
   }
   __syncthreads();
   if (threadIdx.x < nparts && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
@@ -767,7 +800,11 @@ __global__ void __launch_bounds__(HS_BLOCK) sparse_scatter_kernel(const uint32_t
   if (threadIdx.x < SP_MAXPARTS) cnt[threadIdx.x] = 0;
   __syncthreads();
   const uint32_t lo = blockIdx.x * HS_CHUNK, hi = min(n, lo + HS_CHUNK);
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) atomicAdd(&cnt[part_of[i]], 1u);
+  for (uint32_t i0 = lo; i0 < hi; i0 += HS_BLOCK) {
+    const uint32_t i = i0 + threadIdx.x;
+    const bool valid = i < hi;
+    warp_agg_inc(cnt, valid ? part_of[i] : 0u, valid);
+  }
   __syncthreads();
   if (threadIdx.x < nparts) {
     const uint32_t c = cnt[threadIdx.x];
@@ -775,12 +812,25 @@ __global__ void __launch_bounds__(HS_BLOCK) sparse_scatter_kernel(const uint32_t
     cnt[threadIdx.x] = 0;
   }
   __syncthreads();
-  for (uint32_t i = lo + threadIdx.x; i < hi; i += HS_BLOCK) {
-    const uint32_t p = part_of[i];
-    const uint32_t pos = base[p] + atomicAdd(&cnt[p], 1u);
+  for (uint32_t i0 = lo; i0 < hi; i0 += HS_BLOCK) {
+    const uint32_t i = i0 + threadIdx.x;
+    const bool valid = i < hi;
+    const uint32_t p = valid ? part_of[i] : 0u;
+    const uint32_t pos = base[p] + warp_agg_inc(cnt, p, valid);
+    if (!valid) continue;
     ulonglong2* src = reinterpret_cast<ulonglong2*>(entries + (uint64_t)occ[i] * stride);
     ulonglong2* dst = reinterpret_cast<ulonglong2*>(out + (uint64_t)pos * stride);
-    for (uint32_t w = 0; w < stride / 16; w++) { dst[w] = src[w]; src[w] = make_ulonglong2(0ull, 0ull); }
+    // all loads, then all stores of the copy, then the clearing stores: the 16-byte pieces of one output entry reach
+    // L2 together (interleaved with the loads they arrived a DRAM latency apart, half-written sectors were evicted and
+    // the kernel took 3.5 ms for 6 M entries)
+    const uint32_t nw = stride / 16;  // 2 or 4
+    ulonglong2 v[4];
+#pragma unroll
+    for (uint32_t w = 0; w < 4; w++) v[w] = w < nw ? src[w] : make_ulonglong2(0ull, 0ull);
+#pragma unroll
+    for (uint32_t w = 0; w < 4; w++) if (w < nw) dst[w] = v[w];
+#pragma unroll
+    for (uint32_t w = 0; w < 4; w++) if (w < nw) src[w] = make_ulonglong2(0ull, 0ull);
   }
 }
 

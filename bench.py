@@ -64,7 +64,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                           "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -73,9 +73,13 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
 
-    def stop(self) -> dict:
+    def stop(self, t0: float = 0.0, t1: float = float("inf")) -> dict:
+        """Median SM clock / throttle reasons of the samples that arrived inside [t0, t1] (the timed region).  The sampler
+        is started before the warm-up so that nvidia-smi is already streaming; a timed region shorter than the 20 ms
+        sampling period can still miss every sample: then all samples taken under the same load (warm-up .. per-kernel
+        loop) are used and `window` says so."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -84,8 +88,13 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        inside = [ln for (t, ln) in self.lines if t0 <= t <= t1 + 0.03]
+        window = "timed region"
+        if not inside:
+            inside = [ln for (_, ln) in self.lines]
+            window = "warm-up + timed region + per-kernel loop (timed region shorter than the sampling period)"
         sm, mx, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in inside:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -99,7 +108,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def gen_dataset(rank: int):
@@ -286,6 +295,8 @@ def main():
             exchange_bytes[0] = (n_send - counts[rank]) * stride
 
     # ---------------- resident ("kernel-only") arm ----------------
+    sampler = ClockSampler(local_rank)  # started here: nvidia-smi needs a few 100 ms before its first sample
+    sampler.start()
     q = new_query()
     if world > 1:
         q.plan()
@@ -310,15 +321,15 @@ def main():
         dist.barrier()
     ext = torch.cuda.ExternalStream(q.stream, device=torch.device("cuda", local_rank))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     torch.cuda.synchronize()
+    t_region0 = time.perf_counter()
     e0.record(ext)
     for _ in range(args.steps):
         step()
     e1.record(ext)
     q.sync()
     torch.cuda.synchronize()
+    t_region1 = time.perf_counter()
     dev_ms = e0.elapsed_time(e1)
     if trace and rank == 0:
         last = trace[-1 - 6:]
@@ -330,7 +341,7 @@ def main():
         q.execute()
         q.finalize_device()
         per_scan.append(q.timings["scan_ms"])
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_region0, t_region1)
     if world > 1:
         t = torch.tensor([dev_ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

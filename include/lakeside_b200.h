@@ -103,6 +103,14 @@ int lk_query_finalize_device(lk_query* q);
 int lk_query_finalize(lk_query* q, lk_result** out);
 /* Rows that satisfied the WHERE clause and the [startTs, endTs) range in the last execute (-1 on error). */
 int64_t lk_query_survivors(lk_query* q);
+/* BaseExpr.eval on the reduced rows of the last finalize (BaseExpr.scala:665-695 `eval`, :47-95 `getFromSketch`;
+ * ASTUtils.scala:190-219 `getTransformerFunc`): out[i] = transform(sketch value of row i), where the sketch value is the
+ * aggregate named `aggregation` ("sum" | "count" | "min" | "max"; "avg" = sum / count; NaN when the query did not compute
+ * it; on pre-rolled metrics the key K is the aggregate over `rollup_K`, so count = sum(rollup_count)) and the transform depends on (dataset, chart type, metric type): metrics count-chart over a rate metric
+ * x * (step / 1000), rate chart over a counter x / (step / 1000), events rate chart x / (step / 1000) -- integer
+ * division of step first -- else identity.  Computed on the device from the result columns still in HBM; rows are in
+ * the order of lk_result_*.  Returns the number of rows written, -1 on error. */
+int64_t lk_query_eval(lk_query* q, const char* aggregation, const char* chart_type, const char* metric_type, double* out, int64_t cap);
 /* Timings of the last execute/finalize in milliseconds (CUDA events on the query's stream):
  * [0] H2D upload, [1] scan kernel(s), [2] finalize kernels, [3] D2H, [4] host planning. */
 int lk_query_timings(lk_query* q, double* ms /*[8]*/);
@@ -130,6 +138,17 @@ int lk_result_tag_dict(const lk_result* r, int t, int32_t* n, const char* const*
 int64_t lk_result_get_long(const lk_result* r, int64_t row, int col);
 double lk_result_get_double(const lk_result* r, int64_t row, int col);
 const char* lk_result_get_string(const lk_result* r, int64_t row, int col); /* NULL for SQL NULL */
+/* Rows [row0, row1) as the reference's per-segment stream elements, one Server-Sent Event per row:
+ *   data: {"id":"_","type":"data","message":{"timestamp":T,"tags":{..},"type":"sketch","sketchType":"map","sketch":{K:V,..}}}\r\n\r\n
+ * i.e. what PushDownAggregatorStage.scala:95-106 (map sketch of globalAgg -> value), Commons.scala:474-502
+ * (dataPointResponseToSSE) and SSEMessage.scala:23-34 (GenericSSEPayload.toChunkStreamPart) produce for a DataPoint, and
+ * what SegmentSequencer.scala:35-101 decodes.  Value column v is published under sketch_keys[v] (n_keys <= number of
+ * value columns); NULL / "" / "null" tags are dropped and a row left without tags takes the n_fallback (key, value)
+ * pairs of fallback_tags (the segment's queryTags, Commons.scala:430-451); non-finite doubles are the strings "NaN",
+ * "Infinity", "-Infinity" as Jackson writes them.  Returns the number of bytes the rows need; they are written only if
+ * they fit `cap` (call with buf = NULL to size the buffer).  -1 on error. */
+int64_t lk_result_to_sse(const lk_result* r, int64_t row0, int64_t row1, const char* const* sketch_keys, int n_keys,
+                         const char* const* fallback_tags, int n_fallback, char* buf, int64_t cap);
 void lk_result_free(lk_result* r);
 
 /* ---- K-way merge of sorted per-segment streams (mergeSorted chains) ------------------ */

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "lk_query_finalize_device": (c_int, [c_void_p]),
     "lk_query_finalize": (c_int, [c_void_p, POINTER(c_void_p)]),
     "lk_query_survivors": (c_int64, [c_void_p]),
+    "lk_query_eval": (c_int64, [c_void_p, c_char_p, c_char_p, c_char_p, POINTER(c_double), c_int64]),
     "lk_query_timings": (c_int, [c_void_p, POINTER(c_double)]),
     "lk_query_touched_bytes": (c_int64, [c_void_p]),
     "lk_query_total_rows": (c_int64, [c_void_p]),
@@ -62,6 +63,7 @@ _SIGNATURES = {
     "lk_query_info_json": (c_int, [c_void_p, POINTER(c_char_p)]),
     "lk_query_destroy": (None, [c_void_p]),
     "lk_result_num_rows": (c_int64, [c_void_p]),
+    "lk_result_to_sse": (c_int64, [c_void_p, c_int64, c_int64, POINTER(c_char_p), c_int, POINTER(c_char_p), c_int, c_void_p, c_int64]),
     "lk_result_num_values": (c_int, [c_void_p]),
     "lk_result_num_tags": (c_int, [c_void_p]),
     "lk_result_num_cols": (c_int, [c_void_p]),

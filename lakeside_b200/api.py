@@ -91,6 +91,24 @@ class GlobResult:
         except Exception:
             pass
 
+    def to_sse(self, sketch_keys: Sequence[str], query_tags: Optional[Dict[str, str]] = None, row0: int = 0,
+               row1: Optional[int] = None) -> bytes:
+        """Rows [row0, row1) as the reference's per-segment stream elements (``Commons.dataPointResponseToSSE``,
+        Commons.scala:474-502, over the map sketches of PushDownAggregatorStage.scala:95-106), serialised natively
+        (``lk_result_to_sse``): one ``data: {...}\\r\\n\\r\\n`` event per row; value column v goes under sketch_keys[v]."""
+        lib = _lib.load()
+        row1 = self.num_rows if row1 is None else row1
+        keys = (ctypes.c_char_p * len(sketch_keys))(*[k.encode() for k in sketch_keys])
+        flat = [x.encode() for kv in (query_tags or {}).items() for x in kv]
+        fb = (ctypes.c_char_p * max(1, len(flat)))(*flat) if flat else None
+        need = int(lib.lk_result_to_sse(self._h, row0, row1, keys, len(sketch_keys), fb, len(flat) // 2, None, 0))
+        if need < 0:
+            _lib.check(_lib.LK_ERR_INVALID)
+        buf = ctypes.create_string_buffer(max(1, need))
+        got = int(lib.lk_result_to_sse(self._h, row0, row1, keys, len(sketch_keys), fb, len(flat) // 2, buf, need))
+        assert got == need
+        return buf.raw[:need]
+
     def to_data_points(self, query_tags: Optional[Dict[str, Any]] = None, value_index: int = 0) -> List[DataPoint]:
         """``Commons.toDataPoint`` aggregate branch (Commons.scala:424-461): null / "" / "null" tags are dropped and
         an empty tag map falls back to the segment's queryTags."""
@@ -214,6 +232,17 @@ class Query:
     @property
     def survivors(self) -> int:
         return int(_lib.load().lk_query_survivors(self._h))
+
+    def eval(self, n_rows: int, aggregation: str, chart_type: str = "line", metric_type: str = "gauge") -> np.ndarray:
+        """BaseExpr.eval on the reduced rows of the last finalize (BaseExpr.scala:665-695, :47-95; ASTUtils.scala:190-219):
+        one value per result row -- the map-sketch entry `aggregation` (`avg` = sum / count), then the chart/metric-type
+        transform.  Computed on the device from the result columns still in HBM."""
+        out = np.empty(int(n_rows), dtype=np.float64)
+        n = int(_lib.load().lk_query_eval(self._h, aggregation.encode(), chart_type.encode(), metric_type.encode(),
+                                          out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), int(n_rows)))
+        if n < 0:
+            _lib.check(_lib.LK_ERR_INVALID)  # the message comes from lk_last_error
+        return out[:n]
 
     def close(self):
         if self._h:

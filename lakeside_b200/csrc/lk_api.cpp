@@ -261,6 +261,15 @@ int64_t lk_query_survivors(lk_query* q) {
   return v;
 }
 
+int64_t lk_query_eval(lk_query* q, const char* aggregation, const char* chart_type, const char* metric_type, double* out, int64_t cap) {
+  int64_t n = -1;
+  guard([&] {
+    LK_CHECK(q && q->q.dev && aggregation && chart_type && metric_type, LK_ERR_INVALID, "lk_query_eval: bad arguments");
+    n = device_eval(q->q, aggregation, chart_type, metric_type, out, cap);
+  });
+  return n;
+}
+
 int lk_query_stream(lk_query* q, void** cuda_stream) {
   return guard([&] {
     LK_CHECK(q && cuda_stream && q->q.dev, LK_ERR_INVALID, "query not prepared");
@@ -327,6 +336,15 @@ const char* lk_result_get_string(const lk_result* r, int64_t row, int col) {
   if (t < 0 || t >= r->r->n_tags) return nullptr;
   int32_t c = r->r->codes[t][row];
   return c < 0 ? nullptr : r->r->dict_ptrs[t][c];
+}
+int64_t lk_result_to_sse(const lk_result* r, int64_t row0, int64_t row1, const char* const* sketch_keys, int n_keys,
+                         const char* const* fallback_tags, int n_fallback, char* buf, int64_t cap) {
+  int64_t n = -1;
+  guard([&] {
+    LK_CHECK(r && r->r, LK_ERR_INVALID, "null result");
+    n = result_to_sse(*r->r, row0, row1, sketch_keys, n_keys, fallback_tags, n_fallback, buf, cap);
+  });
+  return n;
 }
 void lk_result_free(lk_result* r) {
   if (!r) return;

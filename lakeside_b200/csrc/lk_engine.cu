@@ -712,6 +712,60 @@ void device_finalize_device(Query& q) {
   CUDA_CHECK(cudaEventRecord(d.ev[5], d.st));
 }
 
+// ---- BaseExpr.eval on the reduced rows (BaseExpr.scala:665-695, 47-95; ASTUtils.scala:190-219) ----
+// value = getFromSketch(map sketch, aggregation) -- `avg` = sum / count -- then the chart/metric-type transform:
+// x * (step / 1000) or x / (step / 1000) with the INTEGER division of step done first, plain IEEE double arithmetic
+// (a zero divisor gives +-Inf / NaN exactly as on the JVM).
+__global__ void __launch_bounds__(256) eval_transform_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, int avg,
+                                                             int transform, double secs, double* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  double v = a ? a[i] : __longlong_as_double(0x7ff8000000000000ll);  // aggregation missing from the sketch: NaN
+  if (avg) v = v / (b ? b[i] : __longlong_as_double(0x7ff8000000000000ll));
+  if (transform == 1) v = v * secs;
+  else if (transform == 2) v = v / secs;
+  out[i] = v;
+}
+
+int64_t device_eval(Query& q, const std::string& aggregation, const std::string& chart_type, const std::string& metric_type, double* out, int64_t cap) {
+  LK_CHECK(q.dev && q.dev->finalized_device, LK_ERR_INVALID, "lk_query_eval needs a finalized query");
+  Query::Device& d = *q.dev;
+  const int64_t n = d.n_rows;
+  LK_CHECK(out && cap >= n, LK_ERR_INVALID, "lk_query_eval: output buffer too small");
+  if (n == 0) return 0;
+  CUDA_CHECK(cudaSetDevice(global_options().device));
+  EmitParams E;
+  fill_emit_params(q, E, d.dres, n);
+  // map-sketch key -> aggregate slot.  Metrics are pre-rolled: the slot over `rollup_<key>` is the key's value
+  // (count = sum(rollup_count)); otherwise the first slot whose aggregation has that name.
+  auto column = [&](const char* name) -> const double* {
+    if (q.is_metrics)
+      for (size_t a = 0; a < q.aggs.size(); a++)
+        if (q.aggs[a].value_column == std::string("rollup_") + name) return E.val[a];
+    for (size_t a = 0; a < q.aggs.size(); a++)
+      if (q.aggs[a].aggregation == name) return E.val[a];
+    return nullptr;
+  };
+  const bool avg = aggregation == "avg";
+  const double* a = avg ? column("sum") : column(aggregation.c_str());
+  const double* b = avg ? column("count") : nullptr;
+  // getTransformerFunc (ASTUtils.scala:190-219)
+  int transform = 0;
+  if (q.is_metrics) {
+    if (chart_type == "count" && metric_type == "rate") transform = 1;
+    else if (chart_type == "rate" && metric_type == "count") transform = 2;
+  } else if (chart_type == "rate") transform = 2;
+  const double secs = (double)(q.step / 1000);
+  double* dev_out = nullptr;
+  CUDA_CHECK(cudaMallocAsync(&dev_out, (size_t)n * 8, d.st));
+  eval_transform_kernel<<<(int)((n + 255) / 256), 256, 0, d.st>>>(a, b, n, avg ? 1 : 0, transform, secs, dev_out);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemcpyAsync(out, dev_out, (size_t)n * 8, cudaMemcpyDeviceToHost, d.st));
+  CUDA_CHECK(cudaFreeAsync(dev_out, d.st));
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  return n;
+}
+
 HostResult* device_fetch(Query& q) {
   Query::Device& d = *q.dev;
   LK_CHECK(d.finalized_device, LK_ERR_INVALID, "fetch before finalize");

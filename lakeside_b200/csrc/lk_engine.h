@@ -24,5 +24,6 @@ void device_finalize_device(Query& q);     // compaction into result rows in HBM
 HostResult* device_fetch(Query& q);        // D2H
 void device_timings(Query& q);
 int64_t device_survivors(Query& q);
+int64_t device_eval(Query& q, const std::string& aggregation, const std::string& chart_type, const std::string& metric_type, double* out, int64_t cap);  // BaseExpr.eval on the reduced rows
 
 }  // namespace lk

@@ -181,5 +181,8 @@ void rebuild_group_tables(Query& q); // after key_dicts changed (dictionary impo
 std::string export_dictionaries(const Query& q);
 void import_dictionaries(Query& q, const uint8_t* blob, size_t len);
 void parallel_for(int n, int threads, const std::function<void(int)>& fn);
+// lk_sse.cpp: rows -> the reference's SSE stream elements (map sketches)
+int64_t result_to_sse(const HostResult& res, int64_t row0, int64_t row1, const char* const* keys, int n_keys, const char* const* fallback_tags,
+                      int n_fallback, char* buf, int64_t cap);
 
 }  // namespace lk

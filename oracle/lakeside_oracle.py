@@ -1089,6 +1089,98 @@ def push_down_aggregator_stage(req: PushDownRequest, dps: List[DataPoint]) -> Li
 
 
 # ----------------------------------------------------------------------------------------------
+# a9: wire format of a per-segment stream element.
+#   producer  Commons.dataPointResponseToSSE (Commons.scala:474-502) -> GenericSSEPayload(id="_", type="data", message)
+#             .toChunkStreamPart = "data: " + toJson + "\r\n\r\n" (SSEMessage.scala:23-34); JSON by Jackson
+#             (atlas-json defaults: non-finite doubles are quoted, "NaN" / "Infinity" / "-Infinity")
+#   consumer  EventStreamParser -> Json.decode(sse.data)("message") (QueryEngineV2.scala:133-140)
+#             -> SegmentSequencer.decode (SegmentSequencer.scala:35-101)
+# ----------------------------------------------------------------------------------------------
+def _json_double(v: float):
+    if v != v:
+        return "NaN"
+    if v in (math.inf, -math.inf):
+        return "Infinity" if v > 0 else "-Infinity"
+    return v
+
+
+def to_sse(elements: List[Any]) -> bytes:
+    """dataPointResponseToSSE over DataPoints (Left: "exemplar") and map-sketch SketchInputs (Right: "sketch")."""
+    import json as _json
+
+    out = []
+    for e in elements:
+        if isinstance(e, DataPoint):
+            msg = {"timestamp": int(e.timestamp), "value": _json_double(float(e.value)), "tags": dict(e.tags), "type": "exemplar"}
+        else:
+            msg = {"timestamp": int(e.timestamp), "tags": dict(e.tags), "type": "sketch", "sketchType": e.sketchType,
+                   "sketch": {k: _json_double(float(v)) for k, v in e.sketch.items()}}
+        out.append("data: " + _json.dumps({"id": "_", "type": "data", "message": msg}, separators=(",", ":"), ensure_ascii=False) + "\r\n\r\n")
+    return "".join(out).encode("utf-8")
+
+
+def _as_double(v) -> float:  # SegmentSequencer.scala:35-45
+    if isinstance(v, bool):
+        return math.nan
+    if isinstance(v, (int, float)):
+        return float(v)
+    if isinstance(v, str):
+        if v in ("NaN", "nan"):
+            return math.nan
+        if v in ("Infinity", "+Infinity"):
+            return math.inf
+        if v == "-Infinity":
+            return -math.inf
+        try:
+            return float(v)
+        except ValueError:
+            return math.nan
+    return math.nan
+
+
+def _as_long(v) -> int:  # SegmentSequencer.scala:47-51
+    if isinstance(v, bool):
+        return 0
+    if isinstance(v, (int, float)):
+        return int(v)
+    if isinstance(v, str):
+        try:
+            return int(v)
+        except ValueError:
+            return 0
+    return 0
+
+
+def sse_decode(stream: bytes) -> List[Any]:
+    """The consumer side: split the event stream, keep events whose JSON has a "message", decode each message as
+    SegmentSequencer.decode does (tags must be JSON strings; map-sketch values tolerate "NaN" / "Infinity")."""
+    import json as _json
+
+    out = []
+    for event in stream.decode("utf-8").split("\r\n\r\n"):
+        if not event.strip():
+            continue
+        assert event.startswith("data: "), event[:40]
+        obj = _json.loads(event[len("data: "):], parse_int=float)  # ujson: every JSON number is a Double ("-0" is -0.0)
+        if "message" not in obj:
+            continue  # heartbeat / done
+        m = obj["message"]
+        tags = {}
+        for k, v in m["tags"].items():
+            if not isinstance(v, str):
+                raise OracleQueryError("tag value is not a JSON string")  # ujson `.str` throws (SegmentSequencer.scala:68)
+            tags[k] = v
+        if m["type"] == "exemplar":
+            out.append(DataPoint(timestamp=_as_long(m["timestamp"]), value=_as_double(m["value"]), tags=tags))
+        elif m["type"] == "sketch":
+            if m["sketchType"] != "map":
+                raise OracleUnsupported("only map sketches are restated")
+            out.append(SketchInput(timestamp=_as_long(m["timestamp"]), tags=tags,
+                                   sketch={k: _as_double(v) for k, v in m["sketch"].items()}, sketchType="map"))
+    return out
+
+
+# ----------------------------------------------------------------------------------------------
 # a10: K-way merge.  ``sources.fold(Source.empty)((s1, s2) => s1.mergeSorted(s2))``
 #      (Commons.scala:391-392, WorkerApi.scala:173, QueryEngineV2.scala:96).
 # akka-stream 2.6.20 MergeSorted (third-party, not in tree) emits the LEFT head only if left < right,

@@ -244,6 +244,18 @@ class Query:
             _lib.check(_lib.LK_ERR_INVALID)  # the message comes from lk_last_error
         return out[:n]
 
+    def eval_results(self, res: "GlobResult", aggregation: str, chart_type: str, metric_type: str, group_bys: Sequence[str],
+                     query_tags: Optional[Dict[str, Any]] = None) -> List[Tuple[int, float, Dict[str, str], str]]:
+        """``BaseExpr.eval`` per reduced row: (timestamp, value, tags, group key).  The value comes from the device
+        (``lk_query_eval``); the group key is ``sorted(groupBys).map(tags.getOrElse(_, "")).mkString(":")``
+        (ASTUtils.scala:87-89), "default" without group-bys (BaseExpr.scala:665-695)."""
+        vals = self.eval(res.num_rows, aggregation, chart_type, metric_type)
+        keys = sorted(set(group_bys))
+        out = []
+        for d, v in zip(res.to_data_points(query_tags), vals):
+            out.append((d.timestamp, float(v), d.tags, ":".join(str(d.tags.get(k, "")) for k in keys) if keys else "default"))
+        return out
+
     def close(self):
         if self._h:
             _lib.load().lk_query_destroy(self._h)

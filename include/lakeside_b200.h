@@ -72,8 +72,10 @@ int lk_query_add_segment_buffer(lk_query* q, const void* data, size_t len);
 /* Parses footers, page headers and dictionaries, builds the page/run/tile index, compiles the predicate to
  * dictionary-code tables, uploads the touched column chunks to HBM.  After this the query is device-resident. */
 int lk_query_prepare(lk_query* q);
-/* The host half of prepare only (no CUDA call): footers, page/run/tile index, predicate and group tables.  Optional;
- * lk_query_prepare runs it when it has not been called. */
+/* The host half of prepare: footers, page/run/tile index, predicate and group tables.  Optional; lk_query_prepare
+ * runs it when it has not been called.  When a GPU is visible the copies of the touched column chunks to HBM are
+ * started here (asynchronously, as soon as the arena layout is known) so that they overlap the index build and the
+ * dictionary agreement of the sharded flow; on a host without a GPU it makes no CUDA call. */
 int lk_query_plan(lk_query* q);
 /* Sharded evaluation: every rank exports the dictionaries of its group-by columns, the host unions them
  * (any order-insensitive union, e.g. sorted) and imports the same blob on every rank so that all ranks index one

@@ -161,7 +161,12 @@ int lk_query_plan(lk_query* q) {
     LK_CHECK(q, LK_ERR_INVALID, "null argument");
     LK_CHECK(!q->q.prepared, LK_ERR_INVALID, "query already planned");
     double t0 = now_ms();
+    // With a GPU present the column chunks start moving to HBM as soon as the arena layout is known, exactly as in
+    // lk_query_prepare; without one (host-logic tests, dictionary agreement on a CPU box) planning is host-only.
+    Query* qp = &q->q;
+    if (device_count() > 0) q->q.on_layout = [qp] { device_begin_upload(*qp); };
     plan_query(q->q);
+    q->q.on_layout = nullptr;
     q->q.t_ms[4] = now_ms() - t0;
   });
 }
@@ -169,7 +174,7 @@ int lk_query_plan(lk_query* q) {
 int lk_query_prepare(lk_query* q) {
   return guard([&] {
     LK_CHECK(q, LK_ERR_INVALID, "null argument");
-    LK_CHECK(!(q->q.dev), LK_ERR_INVALID, "query already prepared");
+    LK_CHECK(!device_is_resident(q->q), LK_ERR_INVALID, "query already prepared");
     if (!q->q.prepared) {
       double t0 = now_ms();
       device_init();  // fail before any host work when there is no GPU

@@ -227,6 +227,8 @@ static void upload_group_tables(Query& q) {
 
 // Starts the H2D copies of the touched column chunks (asynchronous; called from plan_query's on_layout hook so that
 // the copies run while the host still walks page and run headers).
+bool device_is_resident(const Query& q) { return q.dev && q.dev->resident; }
+
 void device_begin_upload(Query& q) {
   device_init();
   if (!q.dev) q.dev = std::make_unique<Query::Device>();

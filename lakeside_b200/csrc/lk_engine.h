@@ -11,6 +11,7 @@ int num_sms();
 void* pinned_alloc(size_t bytes);
 void pinned_free(void* p);
 
+bool device_is_resident(const Query& q);   // lk_query_prepare has completed
 void device_begin_upload(Query& q);        // async H2D of the touched column chunks (arena layout known)
 void device_upload(Query& q);              // ... plus the index pools; waits for all of it
 void device_mark_group_tables_stale(Query& q);

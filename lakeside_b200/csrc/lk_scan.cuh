@@ -2,13 +2,18 @@
 //
 // Work unit: one WARP owns one tile (<= 512 consecutive rows of one row group; a tile never crosses a page of any
 // touched column, so every (tile, column) pair is one contiguous piece of one page).  Warps are fully independent --
-// no block-level barrier anywhere -- and pull tiles from a global ticket counter.  Lane l owns rows [16 l, 16 l + 16).
+// no block-level barrier anywhere -- and pull chunks of SCAN_CHUNK_TILES consecutive tiles from a global ticket counter
+// (the next ticket is requested a chunk ahead).  Lane l owns rows [16 l, 16 l + 16).  What is per row group (chunk
+// descriptors, the per-code pass bits of phase B) is reloaded only when the row group changes.
+// The kernel is latency bound with an instruction budget (profiles/README.md): the SM's instruction cache makes ~3 k SASS
+// instructions per instantiation the ceiling, hence the compile-time specialisation and the rolled column loops.
 //   A  definition levels: the lane finds the def run that holds its first row with a shuffle search over the run
 //      starts (both sequences are sorted), walks the 1-3 runs that cover its 16 rows (RLE: mask, bit-packed: one
 //      funnel shift) and a warp scan of the popcounts gives every lane its first value index
 //   B  WHERE: the lane slides a 64-bit window over the bit-packed dictionary indices of its rows (one funnel shift
 //      per value, run changes are rare); with one filter column the class table and the pass bitmap are folded into
-//      one bit per dictionary code per tile; survivors are compacted into shared memory by a warp prefix sum
+//      one bit per dictionary code per row group; with several, every row's class index is accumulated in shared
+//      memory and looked up in the pass bitmap; survivors are compacted into shared memory by a warp prefix sum
 //   C  one lane per survivor: timestamp -> bucket, group-by codes -> group id, values -> (group x bucket) table:
 //      dense planes (global atomics, optional warp pre-reduction of equal cells) or an open-addressing hash table of
 //      32/64-byte entries (key + accumulators in one sector pair).

@@ -16,7 +16,9 @@ PARITY STATUS: *partially pinned*.
     (3-valued logic, NULL grouping, NaN ordering ...): **parity unpinned** for numeric results.
     Two independent evaluators live here (a literal row-at-a-time one and a vectorised one that
     decodes Parquet with Arrow C++) and are cross-checked against each other and against
-    hand-computed fixtures under tests/golden/.
+    hand-computed fixtures under tests/golden/.  The generated SQL text is additionally executed by SQLite
+    (tests/test_oracle_vs_sqlite.py) over the same rows: a third evaluator that shares no code with this
+    file and interprets the reference's SQL directly (NaN-free data only: SQLite has no NaN).
 
 Reference citations are ``path:line`` relative to /root/reference.
 """

@@ -41,7 +41,11 @@ typedef struct lk_merge lk_merge;   /* K-way merge job */
 
 /* ---- library ------------------------------------------------------------------------------------------ */
 /* options_json (may be NULL): {"device": 0, "max_hash_slots": 134217728, "dense_max_cells": 33554432,
- *                              "tile_rows": 2048, "host_threads": 8} */
+ *                              "tile_rows": 512, "host_threads": 8, "tune_host_malloc": 1}
+ * tune_host_malloc (default 1, glibc only): raises the process's M_TRIM_THRESHOLD / M_MMAP_THRESHOLD so that the
+ * ~0.3 GB of transient host index memory a query builds is recycled inside the process instead of being unmapped at
+ * the end of every query and faulted in again by the next (8 ms per 100-segment query); pass 0 to leave the host's
+ * allocator settings alone. */
 int lk_init(const char* options_json);
 void lk_shutdown(void);
 const char* lk_last_error(void);

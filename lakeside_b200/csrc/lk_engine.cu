@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 
@@ -177,6 +178,7 @@ struct Query::Device {
 
 Query::Query() = default;
 Query::~Query() {
+  const auto t_destroy0 = std::chrono::steady_clock::now();
   if (dev) {
     Device& d = *dev;
     if (d.st) cudaStreamSynchronize(d.st);
@@ -193,6 +195,8 @@ Query::~Query() {
     if (d.st) { cudaStreamSynchronize(d.st); cudaStreamDestroy(d.st); }
   }
   for (auto& s : segs) if (s.owned_pinned) pinned_free(s.owned_pinned);
+  if (getenv("LK_PLAN_TRACE"))
+    fprintf(stderr, "[lk destroy] device part %23.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_destroy0).count());
 }
 
 template <class T>

@@ -53,6 +53,7 @@ struct Options {
   uint64_t dense_max_cells = 1ull << 25;
   uint32_t tile_rows = LK_TILE_ROWS_MAX;
   int host_threads = 0;  // 0 = hardware concurrency (capped)
+  bool tune_host_malloc = true;  // lk_init raises glibc's trim / mmap thresholds (process-wide) so transient index memory is recycled
 };
 Options& global_options();
 

@@ -17,8 +17,14 @@ ap.add_argument("--segments", type=int, default=100)
 ap.add_argument("--rows", type=int, default=1 << 20)
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--data", default="/tmp/lk_probe")
+ap.add_argument("--torch", action="store_true", help="initialise torch.cuda first, as bench.py does")
 a = ap.parse_args()
 
+if a.torch:
+    import torch
+
+    torch.cuda.init()
+    torch.zeros(1, device="cuda")
 api.init(**json.loads(os.environ.get("LK_INIT", "{}")))
 lib = _lib.load()
 spec = synth.SynthSpec(dataset="metrics", rows=a.rows)
@@ -42,8 +48,9 @@ for _ in range(a.steps):
     res = q.finalize(); t.append(time.perf_counter())
     tm = q.timings
     n_rows = res.num_rows
-    res.close(); q.close(); t.append(time.perf_counter())
-    row = {k: round((y - x) * 1e3, 2) for k, x, y in zip(["create", "prepare", "execute", "finalize", "close"], t, t[1:])}
+    res.close(); t.append(time.perf_counter())
+    q.close(); t.append(time.perf_counter())
+    row = {k: round((y - x) * 1e3, 2) for k, x, y in zip(["create", "prepare", "execute", "finalize", "res_close", "q_close"], t, t[1:])}
     row["total"] = round((t[-1] - t[0]) * 1e3, 2)
     row["lib"] = {k: round(v, 2) for k, v in tm.items()}
     row["rows"] = n_rows

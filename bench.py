@@ -219,8 +219,12 @@ def main():
             f.readinto((ctypes.c_char * n).from_address(ptr))
         host.append((ptr, n))
 
+    # one GPU: the planner chooses (records for this selective, high-cardinality query); sharded: the hash table, whose
+    # occupied cells are what the sparse exchange partitions
+    table_path = "auto" if world == 1 else "hash"
+
     def new_query():
-        q = api.Query(rq, aggregates=aggs)
+        q = api.Query(rq, aggregates=aggs, path=table_path)
         for ptr, n in host:
             q.add_segment_buffer(ptr, n)
         return q
@@ -432,7 +436,10 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
                     "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps,
                     "what": "lk_query_create + add_segment_buffer(pinned host bytes) + prepare (host index + H2D) + execute + finalize (D2H)"},
-            "gpu_launches": args.steps * (5 if world == 1 else 8),
+            # this library's own kernels per step (CUB's radix-sort kernels of the record path are library code and not counted):
+            # records: scan, rec_count, exclusive_scan, rec_emit; hash: scan, hist, exclusive_scan, scatter, emit
+            # (+ sparse_hist, sparse_scatter, sparse_merge when sharded); dense: scan, count, exclusive_scan, emit
+            "gpu_launches": args.steps * ({"records": 4, "hash": 5, "dense": 4}[info["path"]] + (3 if world > 1 and info["path"] == "hash" else 0)),
             "exchange": None if world == 1 else {"kind": "NCCL reduce of dense planes" if info["path"] == "dense" else "NCCL all-to-all of hash-partitioned occupied cells",
                                                  "bytes_sent_per_rank_per_step": exchange_bytes[0]},
             "clocks": clocks,

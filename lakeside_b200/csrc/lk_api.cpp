@@ -94,7 +94,7 @@ int lk_query_create(const char* pushdown_request_json, const char* options_json,
       Json j = parse_json(options_json);
       LK_CHECK(j.is_obj(), LK_ERR_INVALID, "query options must be a JSON object");
       if (const Json* p = j.get("path"); p && p->text()) {
-        LK_CHECK(p->str == "auto" || p->str == "dense" || p->str == "hash", LK_ERR_INVALID, "path must be auto|dense|hash");
+        LK_CHECK(p->str == "auto" || p->str == "dense" || p->str == "hash" || p->str == "records", LK_ERR_INVALID, "path must be auto|dense|hash|records");
         h->q.path_opt = p->str;
       }
       if (const Json* e = j.get("exact_sums")) h->q.exact_sums = e->as_bool();

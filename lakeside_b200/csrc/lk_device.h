@@ -116,7 +116,7 @@ struct ScanParams {
   uint64_t n_groups;
   int notnull_pcol;        // chart-field filter `field$type IS NOT NULL` (BaseExpr.scala:407-426), or -1
   int is_metrics;          // metrics: GROUP BY raw timestamp => (ts - base) % step must be one constant
-  int path;                // 0 dense, 1 hash
+  int path;                // 0 dense, 1 hash, 2 records (sort-based aggregation)
   int warp_agg;            // pre-reduce equal cells inside a warp before the global atomics
   int fits32;              // (endTs - base) and step are below 2^32: 32-bit bucket arithmetic
   int stop_after;          // profiling aid (LK_SCAN_STOP_AFTER=1..3): leave each tile after prologue / phase A / phase B; 0 = full
@@ -136,6 +136,10 @@ struct ScanParams {
   unsigned long long* rec_cell;
   unsigned long long* rec_seq;  // global row sequence number: segment order, then row order
   unsigned long long* rec_val[LK_MAX_AGGS];
+  // record path (path 2): rec_cell[i] = cell << rec_idx_bits | i and rec_vals[i * n_aggs + a], appended by the scan;
+  // finalize radix-sorts the keys on their cell bits and folds equal cells
+  unsigned long long* rec_vals;
+  uint32_t rec_idx_bits;
   uint32_t* counters;   // [0] status flags, [1] phase min, [2] phase max, [3] #claimed slots, [4] tile ticket, [5] #records
   unsigned long long* survivors;  // [0] rows that passed the WHERE clause
 };

@@ -168,6 +168,12 @@ struct Query::Device {
   size_t block_counts_cap = 0;
   uint8_t* dres = nullptr;
   size_t dres_cap = 0;
+  // record path: appended (cell, accumulator words) records + sort scratch
+  unsigned long long* rec_cell = nullptr;
+  unsigned long long* rec_vals = nullptr;
+  size_t rec_cap = 0;
+  uint8_t* sort_scratch = nullptr;
+  size_t sort_scratch_cap = 0;
   uint8_t* sparse_out = nullptr;  // partitioned copy of the claimed entries (sparse exchange)
   size_t sparse_cap = 0;
   int64_t n_rows = 0;
@@ -185,6 +191,7 @@ Query::~Query() {
     auto fr = [&](void* p) { if (p) cudaFreeAsync(p, d.st); };
     fr(d.arena); fr(d.tiles); fr(d.cursors); fr(d.runs); fr(d.chunks); fr(d.lut_cls); fr(d.lut_gcode); fr(d.pass_bits);
     fr(d.counters); fr(d.survivors); fr(d.planes); fr(d.block_counts); fr(d.dres); fr(d.sparse_out);
+    fr(d.rec_cell); fr(d.rec_vals); fr(d.sort_scratch);
     if (d.harena) {
       // an arena that was written but never emitted is dirty: clear it before handing it back
       if (d.executed && !d.finalized_device) cudaMemsetAsync(d.harena->entries, 0, d.harena->slots * d.harena->stride, d.st);
@@ -224,7 +231,8 @@ static void upload_group_tables(Query& q) {
   if (d.harena) { arena_release(d.harena); d.harena = nullptr; }
   if (q.n_cells > 0) {
     if (q.path == 0) CUDA_CHECK(cudaMallocAsync(&d.planes, (1 + q.aggs.size()) * q.n_cells * sizeof(unsigned long long), d.st));
-    else d.harena = arena_acquire(q.hash_slots, q.hash_stride, d.st);
+    else if (q.path == 1) d.harena = arena_acquire(q.hash_slots, q.hash_stride, d.st);
+    // path 2 (records) has no table: its record arrays are sized by the row count at the first execute
   }
   d.group_tables_stale = false;
 }
@@ -314,7 +322,8 @@ static void launch_scan(const Query& q, const ScanParams& P, bool emit) {
   const bool single = single_filter_ok(q);
   if (emit) launch_scan_table<0, true>(P, single, st);  // record pass of exact_sums: cells are written out, no table
   else if (P.path == 0) launch_scan_table<0, false>(P, single, st);
-  else launch_scan_table<1, false>(P, single, st);
+  else if (P.path == 1) launch_scan_table<1, false>(P, single, st);
+  else launch_scan_table<2, false>(P, single, st);
 }
 
 void device_execute(Query& q) {
@@ -346,11 +355,25 @@ void device_execute(Query& q) {
       CUDA_CHECK(cudaMemsetAsync(d.planes, 0, (1 + q.aggs.size()) * q.n_cells * sizeof(unsigned long long), d.st));
       P.rowcnt = d.planes;
       for (size_t a = 0; a < q.aggs.size(); a++) P.acc[a] = d.planes + (1 + a) * q.n_cells;
-    } else {
+    } else if (q.path == 1) {
       P.h_entries = d.harena->entries;
       P.h_occ = d.harena->occ;
       P.h_bkt = d.harena->occ_bkt;
       P.h_occ_cap = (uint32_t)std::min<uint64_t>(d.harena->slots, 0xffffffffu);
+    } else {
+      // one record per survivor at most: sized by the row count, so the scan can never overflow it
+      const size_t cap = (size_t)std::max<int64_t>(q.total_rows, 1);
+      if (d.rec_cap < cap) {
+        if (d.rec_cell) CUDA_CHECK(cudaFreeAsync(d.rec_cell, d.st));
+        if (d.rec_vals) CUDA_CHECK(cudaFreeAsync(d.rec_vals, d.st));
+        d.rec_cell = d.rec_vals = nullptr;
+        CUDA_CHECK(cudaMallocAsync(&d.rec_cell, cap * 8, d.st));
+        CUDA_CHECK(cudaMallocAsync(&d.rec_vals, cap * 8 * q.aggs.size(), d.st));
+        d.rec_cap = cap;
+      }
+      P.rec_cell = d.rec_cell;
+      P.rec_vals = d.rec_vals;
+      P.rec_cap = (uint32_t)std::min<size_t>(d.rec_cap, 0xffffffffu);
     }
     launch_scan(q, P, false);
     if (q.exact_sums) device_exact_sums(q, P);
@@ -611,6 +634,57 @@ __global__ void __launch_bounds__(HS_BLOCK) hash_emit_kernel(const uint32_t* __r
   emit_row(E, i, w[0] - 1, [&](int a) { return w[1 + a]; });
 }
 
+// ---- record path: the scan appended one (cell, accumulator words) record per survivor; sort the cells (radix sort over
+// the bits the cell space needs), fold equal neighbours, emit rows in cell order = timestamp-major (ORDER BY timestamp) ----
+constexpr int REC_BLOCK = 256;
+
+// number of distinct cells that START in each block of the sorted list
+__global__ void __launch_bounds__(REC_BLOCK) rec_count_kernel(const unsigned long long* __restrict__ sorted, uint32_t n, uint32_t idx_bits,
+                                                              uint32_t* __restrict__ block_counts) {
+  const uint32_t i = blockIdx.x * REC_BLOCK + threadIdx.x;
+  const bool head = i < n && (i == 0 || (sorted[i] >> idx_bits) != (sorted[i - 1] >> idx_bits));
+  const int c = __syncthreads_count(head);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)c;
+}
+
+// the thread at the first record of a cell folds the cell's records (usually one) and writes the row
+__global__ void __launch_bounds__(REC_BLOCK) rec_emit_kernel(const unsigned long long* __restrict__ sorted, uint32_t n, uint32_t idx_bits,
+                                                             const unsigned long long* __restrict__ vals, const uint32_t* __restrict__ block_offsets,
+                                                             const __grid_constant__ EmitParams E) {
+  __shared__ uint32_t warp_sums[REC_BLOCK / 32];
+  const uint32_t i = blockIdx.x * REC_BLOCK + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned long long idx_mask = (1ull << idx_bits) - 1;
+  unsigned long long key = i < n ? sorted[i] : 0ull;
+  const unsigned long long cell = key >> idx_bits;
+  const bool head = i < n && (i == 0 || cell != (sorted[i - 1] >> idx_bits));
+  const unsigned hm = __ballot_sync(0xffffffffu, head);
+  if (lane == 0) warp_sums[wid] = (uint32_t)__popc(hm);
+  __syncthreads();
+  if (!head) return;
+  uint32_t out = block_offsets[blockIdx.x] + (uint32_t)__popc(hm & ((1u << lane) - 1));
+  for (int w = 0; w < wid; w++) out += warp_sums[w];
+  unsigned long long acc[LK_MAX_AGGS];
+#pragma unroll
+  for (int a = 0; a < LK_MAX_AGGS; a++) acc[a] = 0;
+  uint32_t j = i;
+  do {
+    const unsigned long long* rec = vals + (size_t)(key & idx_mask) * E.n_aggs;
+#pragma unroll
+    for (int a = 0; a < LK_MAX_AGGS; a++) {
+      if (a >= E.n_aggs) break;
+      const unsigned long long w = rec[a];
+      if (E.ops[a] == AGG_SUM) acc[a] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)acc[a]) + __longlong_as_double((long long)w));
+      else if (E.ops[a] == AGG_COUNT) acc[a] += w;
+      else acc[a] = w > acc[a] ? w : acc[a];  // min (complemented key) and max (key): both stored as "max"
+    }
+    j++;
+    if (j >= n) break;
+    key = sorted[j];
+  } while ((key >> idx_bits) == cell);
+  emit_row(E, out, cell, [&](int a) { return acc[a]; });
+}
+
 // device result layout for n rows: ts[n] | val[a][n] | code[k][n] | nul[a][n]
 static size_t result_bytes(const Query& q, int64_t n) {
   return (size_t)n * (8 + 8 * q.aggs.size() + 4 * q.key_pcols.size() + q.aggs.size()) + 64;
@@ -673,12 +747,50 @@ void device_finalize_device(Query& q) {
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaMemcpyAsync(&d.h_counters[7], d.block_counts + nblocks, 4, cudaMemcpyDeviceToHost, d.st));
   }
+  const unsigned long long* rec_sorted = nullptr;
+  const uint32_t* rec_counts = nullptr;
+  uint32_t nrec = 0;
+  if (q.path == 2) {
+    CUDA_CHECK(cudaStreamSynchronize(d.st));  // the number of records is a launch parameter of the sort
+    nrec = d.h_counters[5];
+    d.h_counters[7] = 0;
+    if (nrec > 0 && !(d.h_counters[0] & ST_HASH_FULL)) {
+      // keys are (cell << idx_bits | record index): a stable LSD sort over the cell bits only -- equal cells keep
+      // their append order and the record index travels inside the key (8 bytes moved per record and pass)
+      const int begin_bit = (int)q.params.rec_idx_bits;
+      int end_bit = begin_bit + 1;
+      while (end_bit < 64 && (q.n_cells - 1) >> (end_bit - begin_bit)) end_bit++;
+      size_t tmp_bytes = 0;
+      CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)nrec,
+                                                begin_bit, end_bit, d.st));
+      nblocks = (nrec + REC_BLOCK - 1) / REC_BLOCK;
+      // scratch: sorted keys | block counts (+ total) | CUB temporary storage
+      const size_t need = (size_t)nrec * 8 + ((size_t)nblocks + 2) * 4 + tmp_bytes + 1024;
+      if (d.sort_scratch_cap < need) {
+        if (d.sort_scratch) CUDA_CHECK(cudaFreeAsync(d.sort_scratch, d.st));
+        d.sort_scratch = nullptr;
+        CUDA_CHECK(cudaMallocAsync(&d.sort_scratch, need, d.st));
+        d.sort_scratch_cap = need;
+      }
+      unsigned long long* sorted = reinterpret_cast<unsigned long long*>(d.sort_scratch);
+      uint32_t* counts = reinterpret_cast<uint32_t*>(sorted + nrec);
+      void* tmp = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(counts + nblocks + 2) + 255) & ~(uintptr_t)255);
+      CUDA_CHECK(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, (const unsigned long long*)d.rec_cell, sorted, (int)nrec, begin_bit, end_bit, d.st));
+      rec_count_kernel<<<nblocks, REC_BLOCK, 0, d.st>>>(sorted, nrec, (uint32_t)begin_bit, counts);
+      exclusive_scan_kernel<<<1, 1024, 0, d.st>>>(counts, nblocks, counts + nblocks);
+      CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaMemcpyAsync(&d.h_counters[7], counts + nblocks, 4, cudaMemcpyDeviceToHost, d.st));
+      rec_sorted = sorted;
+      rec_counts = counts;
+    }
+  }
   CUDA_CHECK(cudaStreamSynchronize(d.st));
   const uint32_t status = d.h_counters[0];
   if (status & ST_HASH_FULL) {
-    CUDA_CHECK(cudaMemsetAsync(d.harena->entries, 0, d.harena->slots * d.harena->stride, d.st));
+    if (d.harena) CUDA_CHECK(cudaMemsetAsync(d.harena->entries, 0, d.harena->slots * d.harena->stride, d.st));
     d.finalized_device = true;
-    fail(LK_ERR_NOMEM, strf("aggregate hash table of %llu slots overflowed; raise max_hash_slots in lk_init", (unsigned long long)q.hash_slots));
+    fail(LK_ERR_NOMEM, q.path == 2 ? std::string("record buffer overflowed (more survivors than rows?)")
+                                   : strf("aggregate hash table of %llu slots overflowed; raise max_hash_slots in lk_init", (unsigned long long)q.hash_slots));
   }
   LK_CHECK(!(status & ST_BAD_CODE), LK_ERR_IO, "corrupt segment: dictionary index out of range");
   if (q.is_metrics && d.h_counters[1] != 0xffffffffu) {
@@ -691,7 +803,7 @@ void device_finalize_device(Query& q) {
     }
     d.phase = d.h_counters[1];
   } else d.phase = 0;
-  const int64_t n = q.path == 0 ? (int64_t)d.h_counters[7] : (int64_t)d.h_counters[3];
+  const int64_t n = q.path == 1 ? (int64_t)d.h_counters[3] : (int64_t)d.h_counters[7];
   d.n_rows = n;
   if (n > 0) {
     ensure_dres(d, result_bytes(q, n));
@@ -699,6 +811,8 @@ void device_finalize_device(Query& q) {
     fill_emit_params(q, E, d.dres, n);
     if (q.path == 0) {
       dense_emit_kernel<<<nblocks, CMP_BLOCK, 0, d.st>>>(d.planes, q.n_cells, d.block_counts, E);
+    } else if (q.path == 2) {
+      rec_emit_kernel<<<nblocks, REC_BLOCK, 0, d.st>>>(rec_sorted, nrec, q.params.rec_idx_bits, d.rec_vals, rec_counts, E);
     } else {
       // scratch: hist/cursor[nbuckets + 1] | sorted[n]
       ensure_block_counts(d, (size_t)q.nbuckets + 1 + (size_t)n);

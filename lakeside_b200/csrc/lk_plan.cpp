@@ -518,6 +518,36 @@ void plan_query(Query& q) {
       if (t == T) q.pass_bits[c >> 5] |= 1u << (c & 31);
     }
   }
+  // Rough selectivity of the WHERE clause (only used to choose between the hash table and the record path): dictionary
+  // entries taken as equally likely, columns as independent, NULLs ignored; unknown (1.0) with numeric comparisons.
+  q.est_selectivity = 1.0;
+  {
+    bool ok = combos <= 65536;
+    for (auto& fc : q.fcols) ok = ok && !fc.numeric;
+    if (ok) {
+      std::vector<std::vector<double>> pc(q.fcols.size());
+      for (size_t f = 0; f < q.fcols.size(); f++) {
+        const FilterColPlan& fc = q.fcols[f];
+        pc[f].assign(fc.ncls, 0.0);
+        double tot = 0;
+        for (size_t i = 0; i < q.rgs.size(); i++) {
+          const ChunkInfo& ci = q.chunk_infos[i * np + fc.pcol];
+          for (uint32_t code = 0; code < ci.dict_n && ci.lut_cls + code < q.lut_cls.size(); code++) { pc[f][q.lut_cls[ci.lut_cls + code]] += 1; tot += 1; }
+        }
+        if (tot > 0) for (auto& x : pc[f]) x /= tot;
+        else pc[f][0] = 1.0;  // no dictionary at all: the column is absent / all NULL
+      }
+      double sel = 0;
+      for (uint64_t c = 0; c < combos; c++) {
+        if (!((q.pass_bits[c >> 5] >> (c & 31)) & 1)) continue;
+        double pr = 1;
+        uint64_t r = c;
+        for (size_t f = 0; f < q.fcols.size(); f++) { pr *= pc[f][r % q.fcols[f].ncls]; r /= q.fcols[f].ncls; }
+        sel += pr;
+      }
+      q.est_selectivity = q.fcols.empty() ? 1.0 : sel;
+    }
+  }
 
   trace.mark("predicate tables");
   // ---- ScanParams (device pointers are filled in by the device layer) ----
@@ -637,9 +667,21 @@ void rebuild_group_tables(Query& q) {
   bool dense;
   if (q.path_opt == "dense") dense = true;
   else if (q.path_opt == "hash") dense = false;
+  else if (q.path_opt == "records") dense = false;
   else dense = q.n_cells <= opt.dense_max_cells && (q.n_cells <= (1ull << 20) || q.n_cells <= 8ull * (uint64_t)std::max<int64_t>(q.total_rows, 1));
   if (dense) LK_CHECK(q.n_cells <= (1ull << 31), LK_ERR_UNSUPPORTED, "dense table too large; use path=hash");
   q.path = dense ? 0 : 1;
+  // Record path instead of the hash table when the filter is estimated to keep few rows: the survivors are appended
+  // as records and aggregated by a sort in finalize (no table to probe, nothing to clear).  Not with exact_sums (its
+  // fixed-order fold patches a table) and only while one record per row fits comfortably in HBM.
+  // the sort key packs (cell, record index) into 64 bits
+  uint32_t idx_bits = 1, cell_bits = 1;
+  while (idx_bits < 63 && ((uint64_t)std::max<int64_t>(q.total_rows, 1) - 1) >> idx_bits) idx_bits++;
+  while (cell_bits < 63 && (std::max<uint64_t>(q.n_cells, 1) - 1) >> cell_bits) cell_bits++;
+  P.rec_idx_bits = idx_bits;
+  const bool records_fit = (uint64_t)std::max<int64_t>(q.total_rows, 1) * 8 * (1 + q.aggs.size()) <= (16ull << 30) && q.total_rows < (1ll << 31) &&
+                           idx_bits + cell_bits <= 64;
+  if (!dense && !q.exact_sums && records_fit && (q.path_opt == "records" || (q.path_opt == "auto" && q.est_selectivity <= 0.25))) q.path = 2;
   P.path = q.path;
   // few cells => many rows per cell => warp-level pre-reduction pays
   P.warp_agg = dense && q.n_groups <= 4096;
@@ -656,7 +698,7 @@ void rebuild_group_tables(Query& q) {
 
 static void build_info_json(Query& q) {
   std::string s = "{";
-  s += strf("\"path\":\"%s\",\"tiles\":%zu,\"row_groups\":%zu,\"pcols\":%zu,\"total_rows\":%lld,\"touched_bytes\":%lld,", q.path ? "hash" : "dense",
+  s += strf("\"path\":\"%s\",\"tiles\":%zu,\"row_groups\":%zu,\"pcols\":%zu,\"total_rows\":%lld,\"touched_bytes\":%lld,", q.path == 0 ? "dense" : q.path == 1 ? "hash" : "records",
             q.tiles.size(), q.rgs.size(), q.pcols.size(), (long long)q.total_rows, (long long)q.touched_bytes);
   s += strf("\"n_groups\":%llu,\"n_buckets\":%u,\"n_cells\":%llu,\"hash_slots\":%llu,\"hash_stride\":%u,\"warp_agg\":%d,", (unsigned long long)q.n_groups,
             q.nbuckets, (unsigned long long)q.n_cells, (unsigned long long)q.hash_slots, q.hash_stride, q.params.warp_agg);

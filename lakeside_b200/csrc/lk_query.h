@@ -131,6 +131,7 @@ struct Query {
   int64_t touched_bytes = 0, total_rows = 0;
   uint64_t n_groups = 1;
   uint64_t n_cells = 0;
+  double est_selectivity = 1.0;  // rough fraction of rows the WHERE clause keeps (path choice only)
   int path = 0;  // 0 dense, 1 hash
   uint64_t hash_slots = 0;
   uint32_t hash_stride = 0;

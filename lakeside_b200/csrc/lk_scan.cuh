@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
           for (int a = 0; a < NA; a++)
             if (a < P.n_aggs && vvalid[a]) acc_update(P.acc[a] + cell, P.aggs[a].op, vbits[a], 1ull);
         }
-      } else {
+      } else if constexpr (PATH == 1) {
         // open addressing with linear probing; entry = {key = cell + 1, acc[n_aggs]}.  A plain load first: an atomic on a
         // line that is not yet in L2 measured slower than load + CAS (B200, r1).
         bool claimed = false;
@@ -607,6 +607,28 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
             const uint32_t o = base + __popc(cm & lt_mask);
             if (o < P.h_occ_cap) { P.h_occ[o] = claimed_slot; P.h_bkt[o] = bucket32; }
             else my_status |= ST_HASH_FULL;
+          }
+        }
+      } else {
+        // record path (selective filter, high-cardinality result): nothing is aggregated here.  Every survivor appends
+        // its cell to rec_cell[] and its n_aggs accumulator words (same encodings as the tables: all-zero = no value) to
+        // one row of rec_vals[]; finalize sorts the cells and folds equal ones.  Appends are sequential, coalesced writes:
+        // no 8 GB table, no random sector per survivor, nothing to clear afterwards.
+        const unsigned am = __ballot_sync(0xffffffffu, active);
+        if (am) {
+          const int leader = __ffs(am) - 1;
+          uint32_t base = 0;
+          if (lane == leader) base = atomicAdd(P.counters + 5, (uint32_t)__popc(am));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          const uint32_t o = base + __popc(am & lt_mask);
+          if (active) {
+            if (o < P.rec_cap) {
+              P.rec_cell[o] = (cell << P.rec_idx_bits) | o;  // sort key: the record index rides in the low bits
+              unsigned long long* rec = P.rec_vals + (size_t)o * P.n_aggs;
+#pragma unroll
+              for (int a = 0; a < NA; a++)
+                if (a < P.n_aggs) rec[a] = !vvalid[a] ? 0ull : P.aggs[a].op == AGG_COUNT ? 1ull : vbits[a];
+            } else my_status |= ST_HASH_FULL;
           }
         }
       }

@@ -41,7 +41,7 @@ def _rows_and_eval(rq, paths, aggs, combos, path="auto"):
     return n, vals, got
 
 
-@pytest.mark.parametrize("path", ["dense", "hash"])
+@pytest.mark.parametrize("path", ["dense", "hash", "records"])
 def test_eval_metrics_all_transforms(path):
     spec = synth.SynthSpec(dataset="metrics", rows=60000, n_names=3, cards=(8, 4, 4, 2))
     _, paths = H.dataset("eval_metrics", spec, 2)

@@ -40,7 +40,7 @@ def test_c1_int_values_bit_exact_sum():
         assert got["rows"][k][0] == v[0]  # integer-valued doubles: exact in any order
 
 
-@pytest.mark.parametrize("path", ["hash"])
+@pytest.mark.parametrize("path", ["hash", "records"])
 def test_c2_four_aggregates(path):
     spec = synth.SynthSpec(dataset="metrics", rows=200000)
     _, paths = H.dataset("c2_m200k", spec, 3)
@@ -52,7 +52,7 @@ def test_c2_four_aggregates(path):
     assert got["survivors"] >= len(want["rows"])
 
 
-@pytest.mark.parametrize("path", ["dense", "hash"])
+@pytest.mark.parametrize("path", ["dense", "hash", "records"])
 def test_small_group_space_dense_and_hash(path):
     spec = synth.SynthSpec(dataset="metrics", rows=150000, n_names=4, cards=(16, 4, 4, 2))
     _, paths = H.dataset("small_groups", spec, 2)

@@ -219,9 +219,9 @@ def main():
             f.readinto((ctypes.c_char * n).from_address(ptr))
         host.append((ptr, n))
 
-    # one GPU: the planner chooses (records for this selective, high-cardinality query); sharded: the hash table, whose
-    # occupied cells are what the sparse exchange partitions
-    table_path = "auto" if world == 1 else "hash"
+    # the planner chooses (records for this selective, high-cardinality query); sharded, the appended records (or the hash
+    # table's occupied cells) are what the sparse exchange partitions; LK_BENCH_PATH overrides (diagnosis)
+    table_path = os.environ.get("LK_BENCH_PATH", "auto")
 
     def new_query():
         q = api.Query(rq, aggregates=aggs, path=table_path)
@@ -438,9 +438,9 @@ def main():
                     "what": "lk_query_create + add_segment_buffer(pinned host bytes) + prepare (host index + H2D) + execute + finalize (D2H)"},
             # this library's own kernels per step (CUB's radix-sort kernels of the record path are library code and not counted):
             # records: scan, rec_count, exclusive_scan, rec_emit; hash: scan, hist, exclusive_scan, scatter, emit
-            # (+ sparse_hist, sparse_scatter, sparse_merge when sharded); dense: scan, count, exclusive_scan, emit
-            "gpu_launches": args.steps * ({"records": 4, "hash": 5, "dense": 4}[info["path"]] + (3 if world > 1 and info["path"] == "hash" else 0)),
-            "exchange": None if world == 1 else {"kind": "NCCL reduce of dense planes" if info["path"] == "dense" else "NCCL all-to-all of hash-partitioned occupied cells",
+            # (+ sparse_hist, sparse_scatter, sparse_merge / rec_part_hist, rec_part_scatter, rec_unpack when sharded); dense: scan, count, exclusive_scan, emit
+            "gpu_launches": args.steps * ({"records": 4, "hash": 5, "dense": 4}[info["path"]] + (3 if world > 1 and info["path"] != "dense" else 0)),
+            "exchange": None if world == 1 else {"kind": "NCCL reduce of dense planes" if info["path"] == "dense" else "NCCL all-to-all of hash-partitioned " + ("survivor records" if info["path"] == "records" else "occupied cells"),
                                                  "bytes_sent_per_rank_per_step": exchange_bytes[0]},
             "clocks": clocks,
         }

@@ -67,8 +67,23 @@ struct ChunkInfo {
   uint32_t lut_gcode;  // offset into the group-code pool (key columns)
   uint32_t phys_type;  // parquet physical type
   uint64_t seq_base;   // global sequence number of the row group's first row (fixed-order sums)
-  uint64_t pad;        // 48 bytes: three 16-byte cp.async transfers
+  uint32_t defbm_word0; // first 32-bit word of the chunk's expanded definition bitmap (bit r = row r is non-null)
+  uint32_t pad;        // 48 bytes
 };
+
+// One column chunk whose definition levels the device expands into a flat bitmap before the scan (def_expand_kernel):
+// its definition-level runs in the run pool and where its bitmap starts.  One CTA expands LK_DEF_BLOCK_RUNS consecutive
+// runs of one chunk; `cum` = number of CTAs of all earlier entries (a CTA finds its chunk by a binary search over it).
+constexpr uint32_t LK_DEF_BLOCK_RUNS = 1024;
+struct DefChunk {
+  uint64_t base_off;  // arena offset of the chunk's first byte
+  uint32_t run_lo, run_n;
+  uint32_t word0;     // first word of the chunk's bitmap
+  uint32_t num_rows;
+  uint32_t cum;
+  uint32_t pad;
+};
+static_assert(sizeof(DefChunk) == 32, "DefChunk must be 32 bytes");
 static_assert(sizeof(ChunkInfo) == 48, "ChunkInfo must be 48 bytes");
 
 struct FilterCol {
@@ -100,6 +115,7 @@ struct ScanParams {
   const ColCursor* cursors;
   const Run* runs;
   const ChunkInfo* chunks;
+  const uint32_t* defbm;      // expanded definition bitmaps of the nullable chunks (ChunkInfo::defbm_word0)
   const uint8_t* lut_cls;
   const uint32_t* lut_gcode;
   const uint32_t* pass_bits;  // bit i set <=> class combination i satisfies the WHERE clause
@@ -214,6 +230,49 @@ LK_HD uint32_t lk_def_word(const uint8_t* arena, const Run* runs, const ColCurso
     ri++;
   }
   return w;
+}
+
+// 32 bits starting at byte address p (arbitrary alignment); the arena is padded so the second word is always readable
+LK_HD uint32_t lk_load_u32_unaligned(const uint8_t* p) {
+  const uint64_t a = reinterpret_cast<uint64_t>(p);
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~3ull);
+  const unsigned sh = (unsigned)(a & 3) * 8;
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(__ldg(q), __ldg(q + 1), sh);
+#else
+  return sh ? (q[0] >> sh) | (q[1] << (32 - sh)) : q[0];
+#endif
+}
+
+// Expansion of ONE definition-level run (rows [r.start, next) of its chunk) into the chunk's flat bitmap (bit r = row r
+// is non-null).  Bit-packed levels of width 1 already are the bitmap bits; an RLE run of 1 is a range of ones.  Words
+// shared with neighbouring runs go through or_word(word, mask) (atomicOr on the device); the whole words inside a long
+// RLE run belong to it alone and go through fill(first, last_exclusive).  Shared by def_expand_kernel (lk_engine.cu) and
+// the CPU emulator of the tests.
+template <class OrWord, class Fill>
+LK_HD void lk_def_expand_run(const uint8_t* arena, uint64_t base_off, Run r, uint32_t next, OrWord or_word, Fill fill) {
+  if (next <= r.start) return;
+  if (r.kind_value >> 31) {
+    if (!(r.kind_value & 1)) return;
+    const uint32_t b0 = r.start, b1 = next;
+    const uint32_t w0 = b0 >> 5, w1 = (b1 - 1) >> 5;
+    const uint32_t m0 = 0xffffffffu << (b0 & 31), m1 = 0xffffffffu >> (31 - ((b1 - 1) & 31));
+    if (w0 == w1) { or_word(w0, m0 & m1); return; }
+    or_word(w0, m0);
+    or_word(w1, m1);
+    if (w1 - w0 > 1) fill(w0 + 1, w1);
+    return;
+  }
+  const uint8_t* src = arena + base_off + r.kind_value;
+  const uint32_t n = next - r.start;
+  for (uint32_t o = 0; o < n; o += 32) {
+    const uint32_t c = n - o < 32 ? n - o : 32;
+    uint32_t x = lk_load_u32_unaligned(src + (o >> 3));
+    if (c < 32) x &= (1u << c) - 1;
+    const uint32_t pos = r.start + o, sh = pos & 31;
+    if (x << sh) or_word(pos >> 5, x << sh);
+    if (sh && (x >> (32 - sh))) or_word((pos >> 5) + 1, x >> (32 - sh));
+  }
 }
 
 // dictionary index of chunk-level value `vidx`

@@ -149,12 +149,14 @@ void device_shutdown() {
 // ------------------------------------------------------------------------------------------------------------
 struct Query::Device {
   cudaStream_t st = nullptr;
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[10] = {};
   uint8_t* arena = nullptr;
   TileDesc* tiles = nullptr;
   ColCursor* cursors = nullptr;
   Run* runs = nullptr;
   ChunkInfo* chunks = nullptr;
+  DefChunk* def_chunks = nullptr;
+  uint32_t* defbm = nullptr;  // expanded definition bitmaps (rewritten by every execute)
   uint8_t* lut_cls = nullptr;
   uint32_t* lut_gcode = nullptr;
   uint32_t* pass_bits = nullptr;
@@ -189,7 +191,7 @@ Query::~Query() {
     Device& d = *dev;
     if (d.st) cudaStreamSynchronize(d.st);
     auto fr = [&](void* p) { if (p) cudaFreeAsync(p, d.st); };
-    fr(d.arena); fr(d.tiles); fr(d.cursors); fr(d.runs); fr(d.chunks); fr(d.lut_cls); fr(d.lut_gcode); fr(d.pass_bits);
+    fr(d.arena); fr(d.tiles); fr(d.cursors); fr(d.runs); fr(d.chunks); fr(d.def_chunks); fr(d.defbm); fr(d.lut_cls); fr(d.lut_gcode); fr(d.pass_bits);
     fr(d.counters); fr(d.survivors); fr(d.planes); fr(d.block_counts); fr(d.dres); fr(d.sparse_out);
     fr(d.rec_cell); fr(d.rec_vals); fr(d.sort_scratch);
     if (d.harena) {
@@ -262,6 +264,9 @@ void device_upload(Query& q) {
   upload_vec(d.tiles, q.tiles, d.st);
   upload_vec(d.cursors, q.cursors, d.st);
   upload_vec(d.runs, q.runs, d.st);
+  upload_vec(d.def_chunks, q.def_chunks, d.st);
+  if (d.defbm) { CUDA_CHECK(cudaFreeAsync(d.defbm, d.st)); d.defbm = nullptr; }
+  CUDA_CHECK(cudaMallocAsync(&d.defbm, std::max<size_t>(q.defbm_words * 4, 16), d.st));
   upload_vec(d.lut_cls, q.lut_cls, d.st);
   upload_vec(d.pass_bits, q.pass_bits, d.st);
   CUDA_CHECK(cudaMallocAsync(&d.counters, 8 * sizeof(uint32_t), d.st));
@@ -317,6 +322,100 @@ static void launch_scan_table(const ScanParams& P, bool single, cudaStream_t st)
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// definition levels: hybrid RLE / bit-packed stream -> one bit per row
+// ------------------------------------------------------------------------------------------------------------
+// A nullable column's definition levels alternate between short bit-packed groups (the 8 rows around a NULL) and RLE
+// runs of "valid": ~20 runs per 512-row tile at 5 % NULLs.  Walking them inside the scan costs every tile a run search and
+// 2-3 dependent loads per column; instead the runs are expanded into a flat bitmap first (bit-packed, width 1: the payload
+// bits are the bitmap bits; RLE of 1: a range of ones) and the scan reads 16 bits per lane.
+// One CTA takes LK_DEF_BLOCK_RUNS consecutive runs of one chunk: they cover one contiguous row range, whose words are
+// assembled in shared memory (shared-memory atomics) and stored once; only the first and last word of the range are
+// shared with the neighbouring CTAs and go through a global atomicOr.  Runs reaching beyond the shared window (long
+// stretches without NULLs) are written to global memory directly.
+constexpr int DX_BLOCK = 256;
+constexpr uint32_t DX_WIN = 2048;  // window words: 65536 rows
+struct DxOrShared {
+  uint32_t* win;
+  uint32_t wbase;
+  __device__ __forceinline__ void operator()(uint32_t word, uint32_t mask) const { atomicOr(win + (word - wbase), mask); }
+};
+struct DxFillShared {
+  uint32_t* win;
+  uint32_t wbase;
+  __device__ __forceinline__ void operator()(uint32_t a, uint32_t b) const { for (uint32_t i = a; i < b; i++) win[i - wbase] = 0xffffffffu; }
+};
+struct DxOr {
+  uint32_t* w;
+  __device__ __forceinline__ void operator()(uint32_t word, uint32_t mask) const { atomicOr(w + word, mask); }
+};
+struct DxFill {  // the whole words inside a long run are left to the warp
+  uint32_t* lo;
+  uint32_t* hi;
+  __device__ __forceinline__ void operator()(uint32_t a, uint32_t b) const { *lo = a; *hi = b; }
+};
+__global__ void __launch_bounds__(DX_BLOCK) def_expand_kernel(const uint8_t* __restrict__ arena, const Run* __restrict__ runs, const DefChunk* __restrict__ dcs,
+                                                              uint32_t ndc, uint32_t* __restrict__ bm) {
+  __shared__ uint32_t win[DX_WIN];
+  __shared__ uint32_t direct;  // some run of this CTA bypassed the window
+  const int lane = threadIdx.x & 31;
+  uint32_t lo = 0, hi = ndc;  // last chunk with cum <= blockIdx.x
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(&dcs[mid].cum) <= blockIdx.x) lo = mid; else hi = mid;
+  }
+  const DefChunk dc = dcs[lo];
+  const Run* __restrict__ r0 = runs + dc.run_lo;
+  const uint32_t k0 = (blockIdx.x - dc.cum) * LK_DEF_BLOCK_RUNS, k1 = min(dc.run_n, k0 + LK_DEF_BLOCK_RUNS);
+  const uint32_t row_lo = r0[k0].start, row_hi = k1 < dc.run_n ? r0[k1].start : dc.num_rows;
+  const uint32_t wbase = row_lo >> 5;
+  uint32_t* __restrict__ w = bm + dc.word0;
+  for (uint32_t i = threadIdx.x; i < DX_WIN; i += DX_BLOCK) win[i] = 0;
+  if (threadIdx.x == 0) direct = 0;
+  __syncthreads();
+  for (uint32_t kb = k0; kb < k1; kb += DX_BLOCK) {
+    const uint32_t k = kb + threadIdx.x;
+    uint32_t fill_lo = 0, fill_hi = 0;
+    if (k < k1) {
+      const Run r = r0[k];
+      const uint32_t next = k + 1 < dc.run_n ? r0[k + 1].start : dc.num_rows;
+      if (next > r.start) {
+        if (((next - 1) >> 5) - wbase < DX_WIN) {
+          lk_def_expand_run(arena, dc.base_off, r, next, DxOrShared{win, wbase}, DxFillShared{win, wbase});
+        } else {
+          direct = 1;
+          lk_def_expand_run(arena, dc.base_off, r, next, DxOr{w}, DxFill{&fill_lo, &fill_hi});
+        }
+      }
+    }
+    unsigned pending = __ballot_sync(0xffffffffu, fill_hi > fill_lo);
+    while (pending) {
+      const int src = __ffs(pending) - 1;
+      pending &= pending - 1;
+      const uint32_t a = __shfl_sync(0xffffffffu, fill_lo, src), b = __shfl_sync(0xffffffffu, fill_hi, src);
+      for (uint32_t i = a + lane; i < b; i += 32) w[i] = 0xffffffffu;
+    }
+  }
+  __syncthreads();
+  if (row_hi <= row_lo) return;
+  const uint32_t nw = min(DX_WIN, ((row_hi - 1) >> 5) - wbase + 1);
+  const bool all_atomic = direct != 0;
+  for (uint32_t i = threadIdx.x; i < nw; i += DX_BLOCK) {
+    const uint32_t v = win[i];
+    if (i == 0 || i + 1 == nw || all_atomic) { if (v) atomicOr(w + wbase + i, v); }
+    else w[wbase + i] = v;
+  }
+}
+
+static void launch_def_expand(const Query& q, const ScanParams& P) {
+  const Query::Device& d = *q.dev;
+  if (!q.def_blocks_total) return;
+  CUDA_CHECK(cudaMemsetAsync(d.defbm, 0, q.defbm_words * 4, d.st));
+  def_expand_kernel<<<(unsigned)q.def_blocks_total, DX_BLOCK, 0, d.st>>>(P.arena, P.runs, d.def_chunks, (uint32_t)q.def_chunks.size(), d.defbm);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 static void launch_scan(const Query& q, const ScanParams& P, bool emit) {
   cudaStream_t st = q.dev->st;
   const bool single = single_filter_ok(q);
@@ -339,12 +438,15 @@ void device_execute(Query& q) {
   P.cursors = d.cursors;
   P.runs = d.runs;
   P.chunks = d.chunks;
+  P.defbm = d.defbm;
   P.lut_cls = d.lut_cls;
   P.lut_gcode = d.lut_gcode;
   P.pass_bits = d.pass_bits;
   P.counters = d.counters;
   P.survivors = d.survivors;
-  CUDA_CHECK(cudaEventRecord(d.ev[2], d.st));
+  CUDA_CHECK(cudaEventRecord(d.ev[8], d.st));
+  launch_def_expand(q, P);  // part of every execute: the definition levels are decoded on the device, inside the timed step
+  CUDA_CHECK(cudaEventRecord(d.ev[9], d.st));
   static const uint32_t init_counters[8] = {0, 0xffffffffu, 0, 0, 0, 0, 0, 0};
   CUDA_CHECK(cudaMemcpyAsync(d.counters, init_counters, sizeof init_counters, cudaMemcpyHostToDevice, d.st));
   CUDA_CHECK(cudaMemsetAsync(d.survivors, 0, sizeof(unsigned long long), d.st));
@@ -375,10 +477,14 @@ void device_execute(Query& q) {
       P.rec_vals = d.rec_vals;
       P.rec_cap = (uint32_t)std::min<size_t>(d.rec_cap, 0xffffffffu);
     }
+    CUDA_CHECK(cudaEventRecord(d.ev[2], d.st));
     launch_scan(q, P, false);
+    CUDA_CHECK(cudaEventRecord(d.ev[3], d.st));
     if (q.exact_sums) device_exact_sums(q, P);
+  } else {
+    CUDA_CHECK(cudaEventRecord(d.ev[2], d.st));
+    CUDA_CHECK(cudaEventRecord(d.ev[3], d.st));
   }
-  CUDA_CHECK(cudaEventRecord(d.ev[3], d.st));
 }
 
 void device_sync(Query& q) {
@@ -921,6 +1027,7 @@ HostResult* device_fetch(Query& q) {
   CUDA_CHECK(cudaStreamSynchronize(d.st));
   float ms = 0;
   CUDA_CHECK(cudaEventElapsedTime(&ms, d.ev[2], d.ev[3])); q.t_ms[1] = ms;
+  CUDA_CHECK(cudaEventElapsedTime(&ms, d.ev[8], d.ev[9])); q.t_ms[5] = ms;
   CUDA_CHECK(cudaEventElapsedTime(&ms, d.ev[4], d.ev[5])); q.t_ms[2] = ms;
   CUDA_CHECK(cudaEventElapsedTime(&ms, d.ev[6], d.ev[7])); q.t_ms[3] = ms;
   return r.release();
@@ -930,6 +1037,7 @@ void device_timings(Query& q) {
   Query::Device& d = *q.dev;
   float ms = 0;
   if (d.executed && cudaEventElapsedTime(&ms, d.ev[2], d.ev[3]) == cudaSuccess) q.t_ms[1] = ms;
+  if (d.executed && cudaEventElapsedTime(&ms, d.ev[8], d.ev[9]) == cudaSuccess) q.t_ms[5] = ms;
   if (d.finalized_device && cudaEventElapsedTime(&ms, d.ev[4], d.ev[5]) == cudaSuccess) q.t_ms[2] = ms;
   cudaGetLastError();
 }
@@ -1057,9 +1165,154 @@ __global__ void __launch_bounds__(HS_BLOCK) sparse_merge_kernel(const uint8_t* _
   if (status) atomicOr(counters + 0, status);
 }
 
+// ---- record path: the same exchange over the appended records.  An exchanged record is {cell, acc[n_aggs]} (8 (1 + A)
+// bytes); the receiver re-keys what it gets (cell << idx_bits | position) and finalizes it like its own records: equal
+// cells of different ranks become neighbours in the sort and are folded there -- no merge pass.
+__global__ void __launch_bounds__(HS_BLOCK) rec_part_hist_kernel(const unsigned long long* __restrict__ keys, uint32_t n, uint32_t idx_bits, uint32_t nparts,
+                                                                 uint32_t* __restrict__ part_of, uint32_t* __restrict__ hist) {
+  __shared__ uint32_t h[SP_MAXPARTS];
+  if (threadIdx.x < SP_MAXPARTS) h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t lo = blockIdx.x * HS_CHUNK, hi = min(n, lo + HS_CHUNK);
+  for (uint32_t i0 = lo; i0 < hi; i0 += HS_BLOCK) {
+    const uint32_t i = i0 + threadIdx.x;
+    const bool valid = i < hi;
+    uint32_t p = 0;
+    if (valid) {
+      p = cell_partition(keys[i] >> idx_bits, nparts);
+      part_of[i] = p;
+    }
+    warp_agg_inc(h, p, valid);
+  }
+  __syncthreads();
+  if (threadIdx.x < nparts && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(HS_BLOCK) rec_part_scatter_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ vals,
+                                                                    const uint32_t* __restrict__ part_of, uint32_t n, uint32_t idx_bits, int n_aggs,
+                                                                    uint32_t nparts, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ out) {
+  __shared__ uint32_t cnt[SP_MAXPARTS];
+  __shared__ uint32_t base[SP_MAXPARTS];
+  if (threadIdx.x < SP_MAXPARTS) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t lo = blockIdx.x * HS_CHUNK, hi = min(n, lo + HS_CHUNK);
+  for (uint32_t i0 = lo; i0 < hi; i0 += HS_BLOCK) {
+    const uint32_t i = i0 + threadIdx.x;
+    const bool valid = i < hi;
+    warp_agg_inc(cnt, valid ? part_of[i] : 0u, valid);
+  }
+  __syncthreads();
+  if (threadIdx.x < nparts) {
+    const uint32_t c = cnt[threadIdx.x];
+    if (c) base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], c);
+    cnt[threadIdx.x] = 0;
+  }
+  __syncthreads();
+  const int w = 1 + n_aggs;
+  for (uint32_t i0 = lo; i0 < hi; i0 += HS_BLOCK) {
+    const uint32_t i = i0 + threadIdx.x;
+    const bool valid = i < hi;
+    const uint32_t p = valid ? part_of[i] : 0u;
+    const uint32_t pos = base[p] + warp_agg_inc(cnt, p, valid);
+    if (!valid) continue;
+    const unsigned long long key = keys[i];
+    const unsigned long long* src = vals + (size_t)(key & ((1ull << idx_bits) - 1)) * n_aggs;
+    unsigned long long* dst = out + (size_t)pos * w;
+    unsigned long long v[LK_MAX_AGGS];  // all loads, then all stores: the record's sectors reach L2 together
+#pragma unroll
+    for (int a = 0; a < LK_MAX_AGGS; a++) v[a] = a < n_aggs ? src[a] : 0ull;
+    dst[0] = key >> idx_bits;
+#pragma unroll
+    for (int a = 0; a < LK_MAX_AGGS; a++) if (a < n_aggs) dst[1 + a] = v[a];
+  }
+}
+
+__global__ void __launch_bounds__(HS_BLOCK) rec_unpack_kernel(const unsigned long long* __restrict__ in, uint32_t n, uint32_t at, int n_aggs, uint32_t idx_bits,
+                                                              unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
+  const uint32_t i = blockIdx.x * HS_BLOCK + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long* src = in + (size_t)i * (1 + n_aggs);
+  unsigned long long v[LK_MAX_AGGS];
+  const unsigned long long cell = src[0];
+#pragma unroll
+  for (int a = 0; a < LK_MAX_AGGS; a++) v[a] = a < n_aggs ? src[1 + a] : 0ull;
+  const uint32_t o = at + i;  // appended after the records of earlier calls
+  keys[o] = (cell << idx_bits) | o;
+#pragma unroll
+  for (int a = 0; a < LK_MAX_AGGS; a++) if (a < n_aggs) vals[(size_t)o * n_aggs + a] = v[a];
+}
+
+static void device_partial_records(Query& q, int nparts, void** entries_out, int64_t* counts, int* stride_out) {
+  Query::Device& d = *q.dev;
+  CUDA_CHECK(cudaMemcpyAsync(d.h_counters, d.counters, sizeof d.h_counters, cudaMemcpyDeviceToHost, d.st));
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  LK_CHECK(!(d.h_counters[0] & ST_HASH_FULL), LK_ERR_NOMEM, "record buffer overflowed");
+  LK_CHECK(!(d.h_counters[0] & ST_BAD_CODE), LK_ERR_IO, "corrupt segment: dictionary index out of range");
+  const uint32_t n = q.n_cells ? d.h_counters[5] : 0;
+  const int na = (int)q.aggs.size();
+  const uint32_t stride = 8u * (1 + na);
+  for (int p = 0; p < nparts; p++) counts[p] = 0;
+  *stride_out = (int)stride;
+  *entries_out = nullptr;
+  if (n == 0) return;
+  ensure_block_counts(d, 128 + (size_t)n);  // hist[64] | cursor[64] | part_of[n]
+  uint32_t* hist = d.block_counts;
+  uint32_t* cursor = hist + 64;
+  uint32_t* part_of = hist + 128;
+  if (d.sparse_cap < (size_t)n * stride) {
+    if (d.sparse_out) CUDA_CHECK(cudaFreeAsync(d.sparse_out, d.st));
+    d.sparse_out = nullptr;
+    CUDA_CHECK(cudaMallocAsync(&d.sparse_out, (size_t)n * stride, d.st));
+    d.sparse_cap = (size_t)n * stride;
+  }
+  CUDA_CHECK(cudaMemsetAsync(hist, 0, 128 * 4, d.st));
+  const int grid = (int)((n + HS_CHUNK - 1) / HS_CHUNK);
+  const uint32_t ib = q.params.rec_idx_bits;
+  rec_part_hist_kernel<<<grid, HS_BLOCK, 0, d.st>>>(d.rec_cell, n, ib, (uint32_t)nparts, part_of, hist);
+  uint32_t h[64];
+  CUDA_CHECK(cudaMemcpyAsync(h, hist, 64 * 4, cudaMemcpyDeviceToHost, d.st));
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  uint32_t starts[64] = {0};
+  uint32_t run = 0;
+  for (int p = 0; p < nparts; p++) { counts[p] = h[p]; starts[p] = run; run += h[p]; }
+  CUDA_CHECK(cudaMemcpyAsync(cursor, starts, 64 * 4, cudaMemcpyHostToDevice, d.st));
+  rec_part_scatter_kernel<<<grid, HS_BLOCK, 0, d.st>>>(d.rec_cell, d.rec_vals, part_of, n, ib, na, (uint32_t)nparts, cursor,
+                                                       reinterpret_cast<unsigned long long*>(d.sparse_out));
+  // the local record list is consumed: own + foreign records come back through lk_query_merge_sparse
+  CUDA_CHECK(cudaMemsetAsync(d.counters + 5, 0, 4, d.st));
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  *entries_out = d.sparse_out;
+}
+
+static void device_merge_records(Query& q, const void* dev_entries, int64_t n) {
+  Query::Device& d = *q.dev;
+  const int na = (int)q.aggs.size();
+  const uint32_t ib = q.params.rec_idx_bits;
+  // records are appended after those already merged (several calls allowed)
+  CUDA_CHECK(cudaMemcpyAsync(d.h_counters, d.counters, sizeof d.h_counters, cudaMemcpyDeviceToHost, d.st));
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  const uint64_t have = d.h_counters[5];
+  LK_CHECK(have + (uint64_t)n <= d.rec_cap && have + (uint64_t)n <= (1ull << ib), LK_ERR_NOMEM,
+           "record path: this rank received more records than it has rows; use path=hash for this query");
+  rec_unpack_kernel<<<(int)((n + HS_BLOCK - 1) / HS_BLOCK), HS_BLOCK, 0, d.st>>>(reinterpret_cast<const unsigned long long*>(dev_entries), (uint32_t)n, (uint32_t)have, na,
+                                                                               ib, d.rec_cell, d.rec_vals);
+  const uint32_t n32 = (uint32_t)(have + (uint64_t)n);
+  CUDA_CHECK(cudaMemcpyAsync(d.counters + 5, &n32, 4, cudaMemcpyHostToDevice, d.st));
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(d.st));  // n32 is on this frame
+}
+
 void device_partial_sparse(Query& q, int nparts, void** entries_out, int64_t* counts, int* stride_out) {
   LK_CHECK(q.dev && q.dev->executed, LK_ERR_INVALID, "lk_query_partial_sparse before lk_query_execute");
-  LK_CHECK(q.path == 1, LK_ERR_INVALID, "query uses the dense path; use lk_query_partial_dense");
+  LK_CHECK(q.path != 0, LK_ERR_INVALID, "query uses the dense path; use lk_query_partial_dense");
+  if (q.path == 2) {
+    LK_CHECK(nparts >= 1 && nparts <= SP_MAXPARTS, LK_ERR_INVALID, "nparts must be in [1, 64]");
+    LK_CHECK(!q.dev->finalized_device, LK_ERR_INVALID, "lk_query_partial_sparse after finalize");
+    CUDA_CHECK(cudaSetDevice(global_options().device));
+    device_partial_records(q, nparts, entries_out, counts, stride_out);
+    return;
+  }
   LK_CHECK(nparts >= 1 && nparts <= SP_MAXPARTS, LK_ERR_INVALID, "nparts must be in [1, 64]");
   Query::Device& d = *q.dev;
   LK_CHECK(!d.finalized_device, LK_ERR_INVALID, "lk_query_partial_sparse after finalize");
@@ -1109,11 +1362,12 @@ void device_partial_sparse(Query& q, int nparts, void** entries_out, int64_t* co
 
 void device_merge_sparse(Query& q, const void* dev_entries, int64_t n) {
   LK_CHECK(q.dev && q.dev->executed && !q.dev->finalized_device, LK_ERR_INVALID, "lk_query_merge_sparse needs an executed, not yet finalized query");
-  LK_CHECK(q.path == 1, LK_ERR_INVALID, "query uses the dense path");
+  LK_CHECK(q.path != 0, LK_ERR_INVALID, "query uses the dense path");
   LK_CHECK(n >= 0 && n < (int64_t)0xffffffffu, LK_ERR_INVALID, "bad entry count");
   if (n == 0) return;
   Query::Device& d = *q.dev;
   CUDA_CHECK(cudaSetDevice(global_options().device));
+  if (q.path == 2) { device_merge_records(q, dev_entries, n); return; }
   AggSlot4 ops;
   memset(&ops, 0, sizeof ops);
   for (size_t a = 0; a < q.aggs.size(); a++) ops.op[a] = q.aggs[a].op;

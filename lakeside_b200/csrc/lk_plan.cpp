@@ -350,6 +350,7 @@ void plan_query(Query& q) {
   q.chunk_infos.assign(q.rgs.size() * np, ChunkInfo{});
   uint32_t def_mask = 0;
   std::vector<uint32_t> def_masks(q.rgs.size(), 0);
+  std::vector<DefChunk> def_tmp(q.rgs.size() * np, DefChunk{});  // run_n > 0 <=> some tile of the chunk mixes NULLs and values
   parallel_for((int)q.rgs.size(), opt.host_threads, [&](int i) {
     const RowGroupPlan& rp = q.rgs[i];
     const uint8_t* file = q.segs[rp.seg].data;
@@ -414,6 +415,11 @@ void plan_query(Query& q) {
           c.drun_lo = dbase[p] + d0;
           c.drun_n = (uint16_t)(d1 - d0 + 1);
           def_masks[i] |= 1u << p;
+          DefChunk& dc = def_tmp[(size_t)i * np + p];
+          dc.base_off = rp.arena_base[p];
+          dc.run_lo = dbase[p];
+          dc.run_n = (uint32_t)nd;
+          dc.num_rows = rp.num_rows;
         }
         if (c.nvals > 0) {
           while (pi + 1 < npg && ci.pages[pi + 1].first_row <= r0) pi++;
@@ -441,6 +447,22 @@ void plan_query(Query& q) {
     }
   });
   for (auto m : def_masks) def_mask |= m;
+  // definition bitmaps: one bit per row for every chunk that has a tile mixing NULLs and values; the device expands
+  // the chunk's hybrid RLE/bit-packed definition levels into it (def_expand_kernel) and the scan reads 16 bits per lane
+  q.def_chunks.clear();
+  q.defbm_words = 0;
+  q.def_blocks_total = 0;
+  for (size_t k = 0; k < def_tmp.size(); k++) {
+    DefChunk dc = def_tmp[k];
+    if (!dc.run_n) continue;
+    dc.word0 = (uint32_t)q.defbm_words;
+    dc.cum = (uint32_t)q.def_blocks_total;
+    q.chunk_infos[k].defbm_word0 = dc.word0;
+    q.defbm_words += (dc.num_rows + 31) / 32 + 2;  // + 2: the scan's funnel-shifted reads touch one word past the last
+    q.def_blocks_total += (dc.run_n + LK_DEF_BLOCK_RUNS - 1) / LK_DEF_BLOCK_RUNS;
+    q.def_chunks.push_back(dc);
+  }
+  LK_CHECK(q.defbm_words < 0xffffffffull && q.def_blocks_total < 0x7fffffffull, LK_ERR_UNSUPPORTED, "glob too large for 32-bit definition bitmaps");
 
   trace.mark("tiles/cursors/runs");
   // ---- predicate: per-column classes over dictionary entries, then the pass bitmap over class combinations ----

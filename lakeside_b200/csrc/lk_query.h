@@ -141,6 +141,9 @@ struct Query {
   RawVec<ColCursor> cursors;
   RawVec<Run> runs;
   std::vector<ChunkInfo> chunk_infos;
+  std::vector<DefChunk> def_chunks;  // chunks whose definition levels are expanded on the device before every scan
+  uint64_t defbm_words = 0;          // size of the bitmap pool (32-bit words)
+  uint64_t def_blocks_total = 0;     // CTAs of def_expand_kernel
   std::vector<uint8_t> lut_cls;
   std::vector<uint32_t> lut_gcode;
   std::vector<uint32_t> pass_bits;

@@ -7,9 +7,8 @@
 // descriptors, the per-code pass bits of phase B) is reloaded only when the row group changes.
 // The kernel is latency bound with an instruction budget (profiles/README.md): the SM's instruction cache makes ~3 k SASS
 // instructions per instantiation the ceiling, hence the compile-time specialisation and the rolled column loops.
-//   A  definition levels: the lane finds the def run that holds its first row with a shuffle search over the run
-//      starts (both sequences are sorted), walks the 1-3 runs that cover its 16 rows (RLE: mask, bit-packed: one
-//      funnel shift) and a warp scan of the popcounts gives every lane its first value index
+//   A  definition levels: 16 bits per lane from the flat bitmap def_expand_kernel (lk_engine.cu) decoded the hybrid
+//      RLE/bit-packed levels into; a warp scan of the popcounts gives every lane its first value index
 //   B  WHERE: the lane slides a 64-bit window over the bit-packed dictionary indices of its rows (one funnel shift
 //      per value, run changes are rare); with one filter column the class table and the pass bitmap are folded into
 //      one bit per dictionary code per row group; with several, every row's class index is accumulated in shared
@@ -65,6 +64,15 @@ __device__ __forceinline__ uint32_t load_bits32(const uint8_t* __restrict__ p, u
   const uint32_t* q = reinterpret_cast<const uint32_t*>(a & ~3ull);
   const uint32_t sh = (uint32_t)(a & 3) * 8 + (bit & 7);
   return __funnelshift_r(__ldg(q), __ldg(q + 1), sh);
+}
+
+// request a line the tile will read a few hundred instructions from now (tuning builds: make EXTRA=-DSCAN_PREFETCH_L1)
+__device__ __forceinline__ void prefetch_line(const void* p) {
+#ifdef SCAN_PREFETCH_L1
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
 }
 
 // (valid, value index) of row r of column p
@@ -229,7 +237,15 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
         s.cur[lane] = c;
         if (td.rg != cached_rg) s.ci[lane] = P.chunks[(size_t)td.rg * P.npcols + lane];
         mine = !(c.flags & (CUR_ALL_VALID | CUR_ALL_NULL));
+        // the tile's 512 definition bits of this column (phase A reads them lane by lane): on their way while the
+        // run descriptors below are fetched
+        if (mine) {
+          const uint32_t* dw = P.defbm + s.ci[lane].defbm_word0 + (td.row0 >> 5);
+          prefetch_line(dw);
+          prefetch_line(dw + 16);
+        }
         if ((c.flags & CUR_DICT) && c.nvals) {
+          Run r0v;
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             Run r;
@@ -238,6 +254,14 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
             if (j < (int)c.vrun_n) r = runs[c.vrun_lo + j];
             s.vrs[lane][j] = r.start;
             s.vrk[lane][j] = r.kind_value;
+            if (j == 0) r0v = r;
+          }
+          // every line of a dictionary-coded column's indices is needed by phase B / C (0.5-1 byte per row): request the
+          // tile's lines now, one column per lane, instead of one dependent DRAM round trip per column later
+          if (!(r0v.kind_value >> 31)) {
+            const uint8_t* cb = arena + s.ci[lane].base_off + r0v.kind_value + (((c.vidx0 - r0v.start) * (uint32_t)c.width) >> 3);
+            const uint32_t nbytes = (c.nvals * (uint32_t)c.width + 7) >> 3;
+            for (uint32_t o = 0; o < nbytes + 127; o += 128) prefetch_line(cb + o);
           }
         }
       }
@@ -256,45 +280,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
     while (need) {
       const int p = __ffs(need) - 1;
       need &= need - 1;
-      const ColCursor& c = s.cur[p];
-      const uint32_t n = c.drun_n;
-      const Run* __restrict__ r0 = runs + c.drun_lo;
-      const uint8_t* __restrict__ chunk = arena + s.ci[p].base_off;
-      const uint32_t target = row0 + lrow0;  // my first row (chunk-level)
-      // first = index of the last run with start <= target.  Runs and targets are both sorted: every chunk of 32 runs
-      // is searched with shuffles (lower bound over the lanes' run starts).
-      uint32_t first = 0;
-      for (uint32_t base = 0; base < n; base += 32) {
-        const uint32_t st = base + lane < n ? r0[base + lane].start : 0xffffffffu;
-        uint32_t lo = 0;  // number of runs of this chunk with start <= target (starts ascending)
-#pragma unroll
-        for (int step = 16; step; step >>= 1) {
-          const uint32_t v = __shfl_sync(0xffffffffu, st, (lo + step - 1) & 31);
-          if (v <= target) lo += step;
-        }
-        if (__shfl_sync(0xffffffffu, st, 31) <= target) lo = 32;  // the search above tops out at 31
-        if (lo) first = base + lo - 1;
-        if (__all_sync(0xffffffffu, lo < 32)) break;
-      }
+      // the chunk's definition levels were expanded into a flat bitmap by def_expand_kernel: 16 bits per lane
       uint32_t bits = 0;
-      if (lrows) {
-        uint32_t filled = 0, ri = first;
-        Run run = r0[ri];
-        while (true) {
-          const uint32_t next = ri + 1 < n ? r0[ri + 1].start : 0xffffffffu;
-          uint32_t avail = next - (target + filled);
-          if (avail > lrows - filled) avail = lrows - filled;
-          const uint32_t m = (1u << avail) - 1;  // avail <= 16
-          if (run.kind_value >> 31) {
-            if (run.kind_value & 1) bits |= m << filled;
-          } else {
-            bits |= (load_bits32(chunk + run.kind_value, target + filled - run.start) & m) << filled;
-          }
-          filled += avail;
-          if (filled >= lrows) break;
-          run = r0[++ri];
-        }
-      }
+      if (lrows) bits = load_bits32(reinterpret_cast<const uint8_t*>(P.defbm + s.ci[p].defbm_word0), row0 + lrow0) & rowmask;
       uint32_t cnt = __popc(bits), incl = cnt;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {

@@ -53,6 +53,17 @@ static void run(Query& q, EmulResult& out) {
   for (auto& u : q.uploads) memcpy(A + u.arena_off, q.segs[u.seg].data + u.file_off, u.len);
   const ScanParams& P = q.params;
   const int np = (int)P.npcols;
+  // definition bitmaps the way def_expand_kernel builds them: one run at a time, every chunk of q.def_chunks
+  std::vector<uint32_t> defbm(q.defbm_words + 2, 0);
+  for (const DefChunk& dc : q.def_chunks) {
+    uint32_t* w = defbm.data() + dc.word0;
+    for (uint32_t k = 0; k < dc.run_n; k++) {
+      const Run r = q.runs[dc.run_lo + k];
+      const uint32_t next = k + 1 < dc.run_n ? q.runs[dc.run_lo + k + 1].start : dc.num_rows;
+      lk_def_expand_run(A, dc.base_off, r, next, [&](uint32_t word, uint32_t m) { w[word] |= m; },
+                        [&](uint32_t a, uint32_t b) { for (uint32_t i = a; i < b; i++) { LK_CHECK(w[i] == 0, LK_ERR_INVALID, "def bitmap: whole word written twice"); w[i] = 0xffffffffu; } });
+    }
+  }
   std::map<uint64_t, Cell> table;  // ordered by cell = bucket * n_groups + gid => sorted by timestamp
   uint32_t phase_min = 0xffffffffu, phase_max = 0;
   for (uint32_t t = 0; t < P.ntiles; t++) {
@@ -69,6 +80,13 @@ static void run(Query& q, EmulResult& out) {
       for (uint32_t w = 0; w < nwords; w++) {
         uint32_t nb = std::min(32u, td.nrows - 32 * w);
         bits[p][w] = lk_def_word(A, q.runs.data(), cur[p], ci[p], td.row0 + 32 * w, nb);
+        {  // the scan kernel reads the expanded bitmap instead of walking the runs: both must agree
+          const uint32_t bit = td.row0 + 32 * w;
+          const uint32_t* bw = defbm.data() + ci[p].defbm_word0 + (bit >> 5);
+          uint32_t x = (bit & 31) ? (bw[0] >> (bit & 31)) | (bw[1] << (32 - (bit & 31))) : bw[0];
+          if (nb < 32) x &= (1u << nb) - 1;
+          LK_CHECK(x == bits[p][w], LK_ERR_INVALID, "expanded definition bitmap differs from the run walk");
+        }
         pref[p][w] = (uint16_t)running;
         running += (uint32_t)__builtin_popcount(bits[p][w]);
       }

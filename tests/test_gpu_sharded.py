@@ -80,11 +80,12 @@ def test_dense_partials_reduce_like_nccl():
         q.close()
 
 
-def test_sparse_partials_partitioned_exchange():
+@pytest.mark.parametrize("table", ["hash", "records"])
+def test_sparse_partials_partitioned_exchange(table):
     be = synth.c2_base_expr()
     sa = synth.SynthSpec(dataset="metrics", rows=80000, cards=(16, 20, 32, 16))
     sb = synth.SynthSpec(dataset="metrics", rows=80000, cards=(16, 32, 24, 16))
-    qs, rq, paths = _shards("shard_sparse", sa, sb, 2, be, synth.C2_AGGREGATES, "hash")
+    qs, rq, paths = _shards("shard_sparse", sa, sb, 2, be, synth.C2_AGGREGATES, table)
     for q in qs:
         q.execute()
     parts = [q.partial_sparse(2) for q in qs]

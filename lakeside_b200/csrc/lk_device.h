@@ -74,7 +74,7 @@ struct ChunkInfo {
 // One column chunk whose definition levels the device expands into a flat bitmap before the scan (def_expand_kernel):
 // its definition-level runs in the run pool and where its bitmap starts.  One CTA expands LK_DEF_BLOCK_RUNS consecutive
 // runs of one chunk; `cum` = number of CTAs of all earlier entries (a CTA finds its chunk by a binary search over it).
-constexpr uint32_t LK_DEF_BLOCK_RUNS = 1024;
+constexpr uint32_t LK_DEF_BLOCK_RUNS = 2048;
 struct DefChunk {
   uint64_t base_off;  // arena offset of the chunk's first byte
   uint32_t run_lo, run_n;
@@ -249,8 +249,10 @@ LK_HD uint32_t lk_load_u32_unaligned(const uint8_t* p) {
 // shared with neighbouring runs go through or_word(word, mask) (atomicOr on the device); the whole words inside a long
 // RLE run belong to it alone and go through fill(first, last_exclusive).  Shared by def_expand_kernel (lk_engine.cu) and
 // the CPU emulator of the tests.
+// `first` = the first 32 payload bits of a bit-packed run when the caller has already loaded them (have_first).
 template <class OrWord, class Fill>
-LK_HD void lk_def_expand_run(const uint8_t* arena, uint64_t base_off, Run r, uint32_t next, OrWord or_word, Fill fill) {
+LK_HD void lk_def_expand_run(const uint8_t* arena, uint64_t base_off, Run r, uint32_t next, OrWord or_word, Fill fill, bool have_first = false,
+                             uint32_t first = 0) {
   if (next <= r.start) return;
   if (r.kind_value >> 31) {
     if (!(r.kind_value & 1)) return;
@@ -267,7 +269,7 @@ LK_HD void lk_def_expand_run(const uint8_t* arena, uint64_t base_off, Run r, uin
   const uint32_t n = next - r.start;
   for (uint32_t o = 0; o < n; o += 32) {
     const uint32_t c = n - o < 32 ? n - o : 32;
-    uint32_t x = lk_load_u32_unaligned(src + (o >> 3));
+    uint32_t x = (o == 0 && have_first) ? first : lk_load_u32_unaligned(src + (o >> 3));
     if (c < 32) x &= (1u << c) - 1;
     const uint32_t pos = r.start + o, sh = pos & 31;
     if (x << sh) or_word(pos >> 5, x << sh);

@@ -330,10 +330,12 @@ static void launch_scan_table(const ScanParams& P, bool single, cudaStream_t st)
 // runs of "valid": ~20 runs per 512-row tile at 5 % NULLs.  Walking them inside the scan costs every tile a run search and
 // 2-3 dependent loads per column; instead the runs are expanded into a flat bitmap first (bit-packed, width 1: the payload
 // bits are the bitmap bits; RLE of 1: a range of ones) and the scan reads 16 bits per lane.
-// One CTA takes LK_DEF_BLOCK_RUNS consecutive runs of one chunk: they cover one contiguous row range, whose words are
-// assembled in shared memory (shared-memory atomics) and stored once; only the first and last word of the range are
-// shared with the neighbouring CTAs and go through a global atomicOr.  Runs reaching beyond the shared window (long
-// stretches without NULLs) are written to global memory directly.
+// One CTA takes LK_DEF_BLOCK_RUNS consecutive runs of one chunk, DX_PER_THREAD consecutive runs per thread: they cover
+// one contiguous row range, whose words are assembled in shared memory (shared-memory atomics) and stored once; only the
+// first and last word of the range are shared with the neighbouring CTAs and go through a global atomicOr.  Runs reaching
+// beyond the shared window (long stretches without NULLs) are written to global memory directly.  The kernel is a chain of
+// three dependent memory round trips per CTA (chunk descriptor, run descriptors, payload bits): all of a thread's loads
+// of one stage are issued together.
 constexpr int DX_BLOCK = 256;
 constexpr uint32_t DX_WIN = 2048;  // window words: 65536 rows
 struct DxOrShared {
@@ -355,38 +357,58 @@ struct DxFill {  // the whole words inside a long run are left to the warp
   uint32_t* hi;
   __device__ __forceinline__ void operator()(uint32_t a, uint32_t b) const { *lo = a; *hi = b; }
 };
+constexpr int DX_PER_THREAD = LK_DEF_BLOCK_RUNS / DX_BLOCK;
 __global__ void __launch_bounds__(DX_BLOCK) def_expand_kernel(const uint8_t* __restrict__ arena, const Run* __restrict__ runs, const DefChunk* __restrict__ dcs,
-                                                              uint32_t ndc, uint32_t* __restrict__ bm) {
+                                                              uint32_t dc0, uint32_t* __restrict__ bm) {
   __shared__ uint32_t win[DX_WIN];
-  __shared__ uint32_t direct;  // some run of this CTA bypassed the window
+  __shared__ uint32_t sh_row_lo, sh_row_hi, direct;  // direct: some run of this CTA bypassed the window
   const int lane = threadIdx.x & 31;
-  uint32_t lo = 0, hi = ndc;  // last chunk with cum <= blockIdx.x
-  while (hi - lo > 1) {
-    const uint32_t mid = (lo + hi) >> 1;
-    if (__ldg(&dcs[mid].cum) <= blockIdx.x) lo = mid; else hi = mid;
-  }
-  const DefChunk dc = dcs[lo];
+  const DefChunk dc = dcs[dc0 + blockIdx.y];
+  const uint32_t k0 = blockIdx.x * LK_DEF_BLOCK_RUNS;
+  if (k0 >= dc.run_n) return;  // the grid is as wide as the chunk with the most runs
+  const uint32_t k1 = min(dc.run_n, k0 + LK_DEF_BLOCK_RUNS);
   const Run* __restrict__ r0 = runs + dc.run_lo;
-  const uint32_t k0 = (blockIdx.x - dc.cum) * LK_DEF_BLOCK_RUNS, k1 = min(dc.run_n, k0 + LK_DEF_BLOCK_RUNS);
-  const uint32_t row_lo = r0[k0].start, row_hi = k1 < dc.run_n ? r0[k1].start : dc.num_rows;
-  const uint32_t wbase = row_lo >> 5;
   uint32_t* __restrict__ w = bm + dc.word0;
+  // stage 1: my DX_PER_THREAD consecutive runs and the start of the one after them
+  const uint32_t kt = k0 + threadIdx.x * DX_PER_THREAD;
+  uint32_t start[DX_PER_THREAD + 1], kv[DX_PER_THREAD];
+#pragma unroll
+  for (int j = 0; j < DX_PER_THREAD; j++) {
+    Run r;
+    r.start = dc.num_rows;
+    r.kind_value = 0x80000000u;  // beyond the chunk: an empty RLE run of 0
+    if (kt + j < dc.run_n) r = r0[kt + j];
+    start[j] = r.start;
+    kv[j] = r.kind_value;
+  }
+  start[DX_PER_THREAD] = kt + DX_PER_THREAD < dc.run_n ? r0[kt + DX_PER_THREAD].start : dc.num_rows;
   for (uint32_t i = threadIdx.x; i < DX_WIN; i += DX_BLOCK) win[i] = 0;
-  if (threadIdx.x == 0) direct = 0;
+  if (threadIdx.x == 0) { sh_row_lo = start[0]; direct = 0; }
+#pragma unroll
+  for (int j = 0; j < DX_PER_THREAD; j++)
+    if (kt + j + 1 == k1) sh_row_hi = start[j + 1];  // the thread holding the CTA's last run
+  // stage 2: first payload word of my bit-packed runs
+  uint32_t first[DX_PER_THREAD];
+#pragma unroll
+  for (int j = 0; j < DX_PER_THREAD; j++) {
+    first[j] = 0;
+    if (!(kv[j] >> 31) && start[j + 1] > start[j]) first[j] = lk_load_u32_unaligned(arena + dc.base_off + kv[j]);
+  }
   __syncthreads();
-  for (uint32_t kb = k0; kb < k1; kb += DX_BLOCK) {
-    const uint32_t k = kb + threadIdx.x;
+  const uint32_t row_lo = sh_row_lo, row_hi = sh_row_hi;
+  const uint32_t wbase = row_lo >> 5;
+#pragma unroll
+  for (int j = 0; j < DX_PER_THREAD; j++) {
     uint32_t fill_lo = 0, fill_hi = 0;
-    if (k < k1) {
-      const Run r = r0[k];
-      const uint32_t next = k + 1 < dc.run_n ? r0[k + 1].start : dc.num_rows;
-      if (next > r.start) {
-        if (((next - 1) >> 5) - wbase < DX_WIN) {
-          lk_def_expand_run(arena, dc.base_off, r, next, DxOrShared{win, wbase}, DxFillShared{win, wbase});
-        } else {
-          direct = 1;
-          lk_def_expand_run(arena, dc.base_off, r, next, DxOr{w}, DxFill{&fill_lo, &fill_hi});
-        }
+    if (kt + j < k1 && start[j + 1] > start[j]) {
+      Run r;
+      r.start = start[j];
+      r.kind_value = kv[j];
+      if (((start[j + 1] - 1) >> 5) - wbase < DX_WIN) {
+        lk_def_expand_run(arena, dc.base_off, r, start[j + 1], DxOrShared{win, wbase}, DxFillShared{win, wbase}, true, first[j]);
+      } else {
+        direct = 1;
+        lk_def_expand_run(arena, dc.base_off, r, start[j + 1], DxOr{w}, DxFill{&fill_lo, &fill_hi}, true, first[j]);
       }
     }
     unsigned pending = __ballot_sync(0xffffffffu, fill_hi > fill_lo);
@@ -410,9 +432,15 @@ __global__ void __launch_bounds__(DX_BLOCK) def_expand_kernel(const uint8_t* __r
 
 static void launch_def_expand(const Query& q, const ScanParams& P) {
   const Query::Device& d = *q.dev;
-  if (!q.def_blocks_total) return;
+  if (q.def_chunks.empty()) return;
   CUDA_CHECK(cudaMemsetAsync(d.defbm, 0, q.defbm_words * 4, d.st));
-  def_expand_kernel<<<(unsigned)q.def_blocks_total, DX_BLOCK, 0, d.st>>>(P.arena, P.runs, d.def_chunks, (uint32_t)q.def_chunks.size(), d.defbm);
+  uint32_t max_runs = 0;
+  for (auto& dc : q.def_chunks) max_runs = std::max(max_runs, dc.run_n);
+  const uint32_t gx = (max_runs + LK_DEF_BLOCK_RUNS - 1) / LK_DEF_BLOCK_RUNS;
+  for (size_t c0 = 0; c0 < q.def_chunks.size(); c0 += 65535) {  // grid.y = chunk
+    const uint32_t gy = (uint32_t)std::min<size_t>(65535, q.def_chunks.size() - c0);
+    def_expand_kernel<<<dim3(gx, gy), DX_BLOCK, 0, d.st>>>(P.arena, P.runs, d.def_chunks, (uint32_t)c0, d.defbm);
+  }
   CUDA_CHECK(cudaGetLastError());
 }
 

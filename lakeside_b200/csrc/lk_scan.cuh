@@ -40,6 +40,9 @@ constexpr uint32_t SCAN_CHUNK_TILES = 4;  // consecutive tiles per ticket
 // gather addresses ahead of the dependent loads (+7 %: the extra address arithmetic costs more issue slots than the
 // latency it hides); batched branch-free gathers in registers (3400 SASS instructions: +16 %, instruction fetch);
 // cp.async staging of the seek index one tile ahead (long-scoreboard stalls 7.7 -> 2.2 per issue but +50 % instructions).
+// After the definition bitmaps (r1i, 0.84 ms): a rolled software pipeline over the key columns (index words of key k + 1
+// requested before the group-code lookup of key k: +3 %, spills) and prefetch.L2 of a survivor's PLAIN value sectors at
+// the top of phase C (+-0); prefetch.global.L1 instead of .L2 for the per-tile requests (+10 %).
 
 struct WarpSmem {
   ColCursor cur[LK_MAX_PCOLS];
@@ -212,9 +215,17 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
     if (lane == 0) t = atomicAdd(P.counters + 4, SCAN_CHUNK_TILES);
     return t;
   };
+  // descriptors and cursors of a chunk's tiles are consecutive: requested when the chunk starts
+  auto prefetch_chunk = [&](uint32_t t0, uint32_t t1) {
+    const uint8_t* c0 = reinterpret_cast<const uint8_t*>(P.cursors + (size_t)t0 * P.npcols);
+    const uint32_t nb = (t1 - t0) * P.npcols * (uint32_t)sizeof(ColCursor);
+    if ((uint32_t)lane * 128 < nb + 127) prefetch_line(c0 + lane * 128);
+    if (lane == 31) prefetch_line(P.tiles + t0);
+  };
   uint32_t pending = ticket();
   uint32_t tile = __shfl_sync(0xffffffffu, pending, 0);
   uint32_t chunk_end = min(tile + SCAN_CHUNK_TILES, P.ntiles);
+  if (tile < P.ntiles) prefetch_chunk(tile, chunk_end);
   pending = ticket();
   uint32_t cached_rg = 0xffffffffu;
 
@@ -223,6 +234,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
       tile = __shfl_sync(0xffffffffu, pending, 0);
       if (tile >= P.ntiles) break;
       chunk_end = min(tile + SCAN_CHUNK_TILES, P.ntiles);
+      prefetch_chunk(tile, chunk_end);
       pending = ticket();
     }
     const TileDesc td = P.tiles[tile];
@@ -277,12 +289,17 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
     const uint32_t rowmask = (1u << lrows) - 1;
 
     // ---- phase A: definition bits of my 16 rows + value-index prefix, one nullable column at a time ----
+    // (the load of the NEXT column's bits is issued before this column's warp scan: the L2 round trips overlap the shuffles)
+    auto def_bits = [&](int p) -> uint32_t {
+      return load_bits32(reinterpret_cast<const uint8_t*>(P.defbm + s.ci[p].defbm_word0), row0 + lrow0);
+    };
+    uint32_t bits_next = need ? def_bits(__ffs(need) - 1) : 0u;
     while (need) {
       const int p = __ffs(need) - 1;
       need &= need - 1;
       // the chunk's definition levels were expanded into a flat bitmap by def_expand_kernel: 16 bits per lane
-      uint32_t bits = 0;
-      if (lrows) bits = load_bits32(reinterpret_cast<const uint8_t*>(P.defbm + s.ci[p].defbm_word0), row0 + lrow0) & rowmask;
+      const uint32_t bits = bits_next & rowmask;
+      if (need) bits_next = def_bits(__ffs(need) - 1);
       uint32_t cnt = __popc(bits), incl = cnt;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {

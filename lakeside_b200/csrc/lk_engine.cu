@@ -42,6 +42,13 @@ void device_init() {
   cudaDeviceProp prop;
   CUDA_CHECK(cudaGetDeviceProperties(&prop, global_options().device));
   g_num_sms = prop.multiProcessorCount;
+  if (const char* g = getenv("LK_L2_FETCH")) {  // tuning aid: L2 fetch granularity hint (32 / 64 / 128 bytes)
+    size_t got = 0;
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+    cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+    fprintf(stderr, "[lk] cudaLimitMaxL2FetchGranularity = %zu\n", got);
+    cudaGetLastError();
+  }
   cudaMemPool_t pool;
   CUDA_CHECK(cudaDeviceGetDefaultMemPool(&pool, global_options().device));
   uint64_t thresh = ~0ull;  // keep freed blocks cached: repeated queries re-use them without cudaMalloc
@@ -330,48 +337,50 @@ static void launch_scan_table(const ScanParams& P, bool single, cudaStream_t st)
 // runs of "valid": ~20 runs per 512-row tile at 5 % NULLs.  Walking them inside the scan costs every tile a run search and
 // 2-3 dependent loads per column; instead the runs are expanded into a flat bitmap first (bit-packed, width 1: the payload
 // bits are the bitmap bits; RLE of 1: a range of ones) and the scan reads 16 bits per lane.
-// One CTA takes LK_DEF_BLOCK_RUNS consecutive runs of one chunk, DX_PER_THREAD consecutive runs per thread: they cover
-// one contiguous row range, whose words are assembled in shared memory (shared-memory atomics) and stored once; only the
-// first and last word of the range are shared with the neighbouring CTAs and go through a global atomicOr.  Runs reaching
-// beyond the shared window (long stretches without NULLs) are written to global memory directly.  The kernel is a chain of
-// three dependent memory round trips per CTA (chunk descriptor, run descriptors, payload bits): all of a thread's loads
-// of one stage are issued together.
+// One CTA takes LK_DEF_BLOCK_RUNS consecutive runs of one chunk, every thread DX_PER_THREAD consecutive ones: a thread's
+// runs cover one contiguous row range, so it assembles the bitmap words sequentially in a register (RLE and bit-packed
+// runs share one code path: the pattern is the payload bits, all ones or all zeros) and hands every finished word to the
+// CTA's window in shared memory; the window is stored once, and only its first and last word -- shared with the
+// neighbouring CTAs -- go through a global atomicOr.  Runs reaching beyond the window (long stretches without NULLs)
+// are written to global memory directly: edge words by atomicOr, whole words by the CTA together.
 constexpr int DX_BLOCK = 256;
-constexpr uint32_t DX_WIN = 2048;  // window words: 65536 rows
-struct DxOrShared {
-  uint32_t* win;
-  uint32_t wbase;
-  __device__ __forceinline__ void operator()(uint32_t word, uint32_t mask) const { atomicOr(win + (word - wbase), mask); }
-};
-struct DxFillShared {
-  uint32_t* win;
-  uint32_t wbase;
-  __device__ __forceinline__ void operator()(uint32_t a, uint32_t b) const { for (uint32_t i = a; i < b; i++) win[i - wbase] = 0xffffffffu; }
-};
+constexpr uint32_t DX_WIN = 1024;  // window words: 32768 rows (1024 runs at 5 % NULLs cover ~12 k)
+constexpr int DX_PER_THREAD = LK_DEF_BLOCK_RUNS / DX_BLOCK;
+constexpr uint32_t DX_QUEUE = 128;
 struct DxOr {
   uint32_t* w;
   __device__ __forceinline__ void operator()(uint32_t word, uint32_t mask) const { atomicOr(w + word, mask); }
 };
-struct DxFill {  // the whole words inside a long run are left to the warp
-  uint32_t* lo;
-  uint32_t* hi;
-  __device__ __forceinline__ void operator()(uint32_t a, uint32_t b) const { *lo = a; *hi = b; }
+struct DxFillQueue {  // the whole words inside a long run: short stretches by the thread, long ones queued for the CTA
+  uint32_t* w;
+  uint2* q;
+  uint32_t* n;
+  __device__ __forceinline__ void operator()(uint32_t a, uint32_t b) const {
+    if (b - a > 64) {
+      const uint32_t slot = atomicAdd(n, 1u);
+      if (slot < DX_QUEUE) { q[slot] = make_uint2(a, b); return; }
+    }
+    for (uint32_t i = a; i < b; i++) w[i] = 0xffffffffu;
+  }
 };
-constexpr int DX_PER_THREAD = LK_DEF_BLOCK_RUNS / DX_BLOCK;
+// a run that does not fit the shared window (rare): one out-of-line copy
+__device__ __noinline__ void def_expand_direct(const uint8_t* arena, uint64_t base_off, Run r, uint32_t next, uint32_t* w, uint2* q, uint32_t* nq) {
+  lk_def_expand_run(arena, base_off, r, next, DxOr{w}, DxFillQueue{w, q, nq});
+}
 __global__ void __launch_bounds__(DX_BLOCK) def_expand_kernel(const uint8_t* __restrict__ arena, const Run* __restrict__ runs, const DefChunk* __restrict__ dcs,
                                                               uint32_t dc0, uint32_t* __restrict__ bm) {
   __shared__ uint32_t win[DX_WIN];
-  __shared__ uint32_t sh_row_lo, sh_row_hi, direct;  // direct: some run of this CTA bypassed the window
-  const int lane = threadIdx.x & 31;
+  __shared__ uint2 fillq[DX_QUEUE];
+  __shared__ uint32_t sh_row_lo, sh_row_hi, nfill, ndirect;
   const DefChunk dc = dcs[dc0 + blockIdx.y];
   const uint32_t k0 = blockIdx.x * LK_DEF_BLOCK_RUNS;
   if (k0 >= dc.run_n) return;  // the grid is as wide as the chunk with the most runs
   const uint32_t k1 = min(dc.run_n, k0 + LK_DEF_BLOCK_RUNS);
   const Run* __restrict__ r0 = runs + dc.run_lo;
   uint32_t* __restrict__ w = bm + dc.word0;
-  // stage 1: my DX_PER_THREAD consecutive runs and the start of the one after them
+  // my DX_PER_THREAD consecutive runs, the start of the one after them, and the first payload word of the bit-packed ones
   const uint32_t kt = k0 + threadIdx.x * DX_PER_THREAD;
-  uint32_t start[DX_PER_THREAD + 1], kv[DX_PER_THREAD];
+  uint32_t start[DX_PER_THREAD + 1], kv[DX_PER_THREAD], first[DX_PER_THREAD];
 #pragma unroll
   for (int j = 0; j < DX_PER_THREAD; j++) {
     Run r;
@@ -383,12 +392,10 @@ __global__ void __launch_bounds__(DX_BLOCK) def_expand_kernel(const uint8_t* __r
   }
   start[DX_PER_THREAD] = kt + DX_PER_THREAD < dc.run_n ? r0[kt + DX_PER_THREAD].start : dc.num_rows;
   for (uint32_t i = threadIdx.x; i < DX_WIN; i += DX_BLOCK) win[i] = 0;
-  if (threadIdx.x == 0) { sh_row_lo = start[0]; direct = 0; }
+  if (threadIdx.x == 0) { sh_row_lo = start[0]; nfill = 0; ndirect = 0; }
 #pragma unroll
   for (int j = 0; j < DX_PER_THREAD; j++)
     if (kt + j + 1 == k1) sh_row_hi = start[j + 1];  // the thread holding the CTA's last run
-  // stage 2: first payload word of my bit-packed runs
-  uint32_t first[DX_PER_THREAD];
 #pragma unroll
   for (int j = 0; j < DX_PER_THREAD; j++) {
     first[j] = 0;
@@ -397,36 +404,70 @@ __global__ void __launch_bounds__(DX_BLOCK) def_expand_kernel(const uint8_t* __r
   __syncthreads();
   const uint32_t row_lo = sh_row_lo, row_hi = sh_row_hi;
   const uint32_t wbase = row_lo >> 5;
+  // sequential assembly: `acc` holds my bits of word (cur >> 5) below bit (cur & 31)
+  uint32_t acc = 0, cur = start[0];
+  auto emit = [&]() {  // hand the word under the cursor to the window
+    if (acc) atomicOr(win + ((cur >> 5) - wbase), acc);
+    acc = 0;
+  };
 #pragma unroll
   for (int j = 0; j < DX_PER_THREAD; j++) {
-    uint32_t fill_lo = 0, fill_hi = 0;
-    if (kt + j < k1 && start[j + 1] > start[j]) {
+    if (kt + j >= k1 || start[j + 1] <= start[j]) continue;
+    const uint32_t n = start[j + 1] - start[j];
+    if (((start[j + 1] - 1) >> 5) - wbase >= DX_WIN) {  // does not fit the window
+      if (((cur >> 5) - wbase) < DX_WIN) emit(); else acc = 0;
+      ndirect = 1;
       Run r;
       r.start = start[j];
       r.kind_value = kv[j];
-      if (((start[j + 1] - 1) >> 5) - wbase < DX_WIN) {
-        lk_def_expand_run(arena, dc.base_off, r, start[j + 1], DxOrShared{win, wbase}, DxFillShared{win, wbase}, true, first[j]);
-      } else {
-        direct = 1;
-        lk_def_expand_run(arena, dc.base_off, r, start[j + 1], DxOr{w}, DxFill{&fill_lo, &fill_hi}, true, first[j]);
-      }
+      def_expand_direct(arena, dc.base_off, r, start[j + 1], w, fillq, &nfill);
+      cur = start[j + 1];
+      continue;
     }
-    unsigned pending = __ballot_sync(0xffffffffu, fill_hi > fill_lo);
-    while (pending) {
-      const int src = __ffs(pending) - 1;
-      pending &= pending - 1;
-      const uint32_t a = __shfl_sync(0xffffffffu, fill_lo, src), b = __shfl_sync(0xffffffffu, fill_hi, src);
-      for (uint32_t i = a + lane; i < b; i += 32) w[i] = 0xffffffffu;
+    const uint32_t sh = cur & 31;
+    if (kv[j] >> 31) {
+      // RLE: n equal bits in constant time -- the rest of the word under the cursor, whole words (no one else writes
+      // them: plain stores), and the low bits of the last word stay in the accumulator
+      const uint32_t ones = (kv[j] & 1) ? 0xffffffffu : 0u;
+      if (sh + n < 32) acc |= (ones & ((1u << n) - 1)) << sh;
+      else {
+        acc |= ones << sh;
+        emit();
+        const uint32_t wi = (cur >> 5) - wbase, full = ((sh + n) >> 5) - 1;
+        if (ones) for (uint32_t i = 1; i <= full; i++) win[wi + i] = 0xffffffffu;
+        const uint32_t rem = (sh + n) & 31;
+        acc = rem ? (ones & ((1u << rem) - 1)) : 0u;
+      }
+      cur += n;
+      continue;
+    }
+    for (uint32_t o = 0; o < n; o += 32) {  // bit-packed: one trip unless the run is longer than 32 rows
+      uint32_t pat = o == 0 ? first[j] : lk_load_u32_unaligned(arena + dc.base_off + kv[j] + (o >> 3));
+      const uint32_t c = min(n - o, 32u);
+      if (c < 32) pat &= (1u << c) - 1;
+      const uint32_t s2 = cur & 31;
+      acc |= pat << s2;
+      if (s2 + c >= 32) {  // the word is complete
+        emit();
+        acc = s2 ? pat >> (32 - s2) : 0u;
+      }
+      cur += c;
     }
   }
+  if ((cur & 31) && ((cur >> 5) - wbase) < DX_WIN) emit();
   __syncthreads();
   if (row_hi <= row_lo) return;
+  const uint32_t nq = min(nfill, DX_QUEUE);
+  const bool all_atomic = ndirect != 0;  // a direct run may own words of this range
   const uint32_t nw = min(DX_WIN, ((row_hi - 1) >> 5) - wbase + 1);
-  const bool all_atomic = direct != 0;
   for (uint32_t i = threadIdx.x; i < nw; i += DX_BLOCK) {
     const uint32_t v = win[i];
     if (i == 0 || i + 1 == nw || all_atomic) { if (v) atomicOr(w + wbase + i, v); }
     else w[wbase + i] = v;
+  }
+  for (uint32_t e = 0; e < nq; e++) {
+    const uint2 f = fillq[e];
+    for (uint32_t i = f.x + threadIdx.x; i < f.y; i += DX_BLOCK) w[i] = 0xffffffffu;
   }
 }
 

@@ -42,15 +42,19 @@ constexpr uint32_t SCAN_CHUNK_TILES = 4;  // consecutive tiles per ticket
 // cp.async staging of the seek index one tile ahead (long-scoreboard stalls 7.7 -> 2.2 per issue but +50 % instructions).
 // After the definition bitmaps (r1i, 0.84 ms): a rolled software pipeline over the key columns (index words of key k + 1
 // requested before the group-code lookup of key k: +3 %, spills) and prefetch.L2 of a survivor's PLAIN value sectors at
-// the top of phase C (+-0); prefetch.global.L1 instead of .L2 for the per-tile requests (+10 %).
+// the top of phase C (+-0); prefetch.global.L1 instead of .L2 for the per-tile requests (+10 %); the first four key
+// columns as one unrolled batch (all index words requested before the first use: +14 %, 3.0 k instructions and spills);
+// cudaLimitMaxL2FetchGranularity 32 / 128 (+-0).
 
 struct WarpSmem {
   ColCursor cur[LK_MAX_PCOLS];
   ChunkInfo ci[LK_MAX_PCOLS];
-  uint16_t defb[LK_MAX_PCOLS][32];  // definition bits of the 16 rows of every lane
+  uint16_t defb[LK_MAX_PCOLS][32];  // definition bits of the 16 rows of every lane (every column: all-valid tiles hold ones)
   uint16_t vpre[LK_MAX_PCOLS][32];  // non-null values of the tile before the lane's first row
-  uint32_t vrs[LK_MAX_PCOLS][4];    // start index of the tile's first 4 dictionary-index runs (0xffffffff = none)
-  uint32_t vrk[LK_MAX_PCOLS][4];    // their kind_value words
+  alignas(16) uint32_t vrs[LK_MAX_PCOLS][4];  // start index of the tile's first 4 dictionary-index runs (0xffffffff = none)
+  uint32_t vrk[LK_MAX_PCOLS][4];    // RLE run: the repeated index; bit-packed run: 8 * byte offset - start * width, so that
+                                    // index v of the run sits vrk + v * width bits after the chunk's first byte
+  uint8_t vrle[LK_MAX_PCOLS];       // bit j set <=> run j is an RLE run
   uint32_t codepass[SCAN_CODEPASS_MAX / 32];  // single filter column: bit c set <=> dictionary code c passes the WHERE
   uint16_t surv[LK_TILE_ROWS_MAX];
 };
@@ -80,18 +84,17 @@ __device__ __forceinline__ void prefetch_line(const void* p) {
 
 // (valid, value index) of row r of column p
 __device__ __forceinline__ bool col_pos(const WarpSmem& s, int p, uint32_t r, uint32_t& vidx) {
-  const ColCursor& c = s.cur[p];
-  if (c.flags & CUR_ALL_VALID) { vidx = c.vidx0 + r; return true; }
-  if (c.flags & CUR_ALL_NULL) return false;
+  // branch-free: phase A leaves defb / vpre filled for every column (all-valid tiles: ones and 16 * lane)
   const uint32_t db = s.defb[p][r >> 4];
   const uint32_t j = r & 15;
-  vidx = c.vidx0 + s.vpre[p][r >> 4] + __popc(db & ((1u << j) - 1));
+  vidx = s.cur[p].vidx0 + s.vpre[p][r >> 4] + __popc(db & ((1u << j) - 1));
   return (db >> j) & 1;
 }
 
 // index (0..3) of the dictionary-index run holding value `vidx`, for columns with at most 4 runs in the tile
 __device__ __forceinline__ uint32_t fast_run(const WarpSmem& s, int p, uint32_t vidx) {
-  return (uint32_t)(vidx >= s.vrs[p][1]) + (uint32_t)(vidx >= s.vrs[p][2]) + (uint32_t)(vidx >= s.vrs[p][3]);
+  const uint4 st = *reinterpret_cast<const uint4*>(s.vrs[p]);  // one 16-byte shared load
+  return (uint32_t)(vidx >= st.y) + (uint32_t)(vidx >= st.z) + (uint32_t)(vidx >= st.w);
 }
 
 // more than 4 runs of the column in the tile (rare): binary search in the global run pool; one out-of-line copy
@@ -105,9 +108,11 @@ __device__ __forceinline__ uint32_t dict_code(const WarpSmem& s, int p, const ui
   if (c.vrun_n > 4) return dict_code_slow(arena, runs, &c, &s.ci[p], vidx);
   const uint32_t ri = fast_run(s, p, vidx);
   const uint32_t kv = s.vrk[p][ri];
-  if (kv >> 31) return kv & 0x7fffffffu;
+  if ((s.vrle[p] >> ri) & 1) return kv;
   const uint32_t w = c.width;
-  return load_bits32(arena + s.ci[p].base_off + kv, (vidx - s.vrs[p][ri]) * w) & ((1u << w) - 1);
+  const uint32_t bit = kv + vidx * w;  // from the chunk's first byte, which is 256-byte aligned
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(arena + s.ci[p].base_off) + (bit >> 5);
+  return __funnelshift_r(__ldg(q), __ldg(q + 1), bit) & ((1u << w) - 1);
 }
 
 __device__ __forceinline__ uint64_t value_bits(const WarpSmem& s, int p, const uint8_t* __restrict__ arena, const Run* __restrict__ runs, uint32_t vidx,
@@ -147,25 +152,26 @@ struct SeqReader {
   const uint32_t* fk;
   const uint8_t* chunk;
   const uint32_t* wp;
-  uint32_t ri, n, next_start, rle, cur, nxt, sh, width, mask;
+  uint32_t ri, n, next_start, rle, cur, nxt, sh, width, mask, frle;
   bool is_rle;
   __device__ __forceinline__ void open_run(uint32_t vidx) {
-    Run r;
+    uint32_t bitpos;  // of index vidx, from the chunk's first byte (4-byte aligned)
     if (fs) {
-      r.start = fs[ri];
-      r.kind_value = fk[ri];
+      rle = fk[ri];
+      is_rle = (frle >> ri) & 1;
+      bitpos = rle + vidx * width;
       next_start = ri < 3 ? fs[ri + 1] : 0xffffffffu;
     } else {
-      r = r0[ri];
+      const Run r = r0[ri];
       next_start = ri + 1 < n ? r0[ri + 1].start : 0xffffffffu;
+      is_rle = r.kind_value >> 31;
+      rle = r.kind_value & 0x7fffffffu;
+      bitpos = r.kind_value * 8 + (vidx - r.start) * width;
     }
-    is_rle = r.kind_value >> 31;
-    rle = r.kind_value & 0x7fffffffu;
+    sh = 0;
     if (!is_rle) {
-      const uint32_t bitpos = (vidx - r.start) * width;
-      const uint64_t a = reinterpret_cast<uint64_t>(chunk + r.kind_value + (bitpos >> 3));
-      wp = reinterpret_cast<const uint32_t*>(a & ~3ull);
-      sh = (uint32_t)(a & 3) * 8 + (bitpos & 7);
+      wp = reinterpret_cast<const uint32_t*>(chunk) + (bitpos >> 5);
+      sh = bitpos & 31;
       cur = __ldg(wp);
       nxt = __ldg(wp + 1);
     }
@@ -177,18 +183,23 @@ struct SeqReader {
     const bool fast = n <= 4;
     fs = fast ? s.vrs[p] : nullptr;
     fk = s.vrk[p];
+    frle = s.vrle[p];
     chunk = arena + s.ci[p].base_off;
     width = c.width;
     mask = (1u << width) - 1;  // width <= 31 (checked by the host index)
     ri = fast ? fast_run(s, p, vidx) : lk_find_run(r0, n, vidx);
     open_run(vidx);
   }
+  // the index under the cursor / step over it (take = false: stay, for a NULL row)
+  __device__ __forceinline__ uint32_t peek() const { return is_rle ? rle : (__funnelshift_r(cur, nxt, sh) & mask); }
+  __device__ __forceinline__ void advance(bool take) {
+    sh += (take && !is_rle) ? width : 0u;
+    if (sh >= 32) { sh -= 32; cur = nxt; nxt = __ldg(++wp + 1); }
+  }
   __device__ __forceinline__ uint32_t next(uint32_t vidx) {
     if (vidx >= next_start) { ri++; open_run(vidx); }
-    if (is_rle) return rle;
-    const uint32_t code = __funnelshift_r(cur, nxt, sh) & mask;
-    sh += width;
-    if (sh >= 32) { sh -= 32; cur = nxt; nxt = __ldg(++wp + 1); }
+    const uint32_t code = peek();
+    advance(true);
     return code;
   }
 };
@@ -258,16 +269,20 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
         }
         if ((c.flags & CUR_DICT) && c.nvals) {
           Run r0v;
+          uint32_t rle_mask = 0;
 #pragma unroll
           for (int j = 0; j < 4; j++) {
             Run r;
             r.start = 0xffffffffu;
             r.kind_value = 0;
             if (j < (int)c.vrun_n) r = runs[c.vrun_lo + j];
+            const uint32_t rl = r.kind_value >> 31;
             s.vrs[lane][j] = r.start;
-            s.vrk[lane][j] = r.kind_value;
+            s.vrk[lane][j] = rl ? (r.kind_value & 0x7fffffffu) : r.kind_value * 8u - r.start * (uint32_t)c.width;
+            rle_mask |= rl << j;
             if (j == 0) r0v = r;
           }
+          s.vrle[lane] = (uint8_t)rle_mask;
           // every line of a dictionary-coded column's indices is needed by phase B / C (0.5-1 byte per row): request the
           // tile's lines now, one column per lane, instead of one dependent DRAM round trip per column later
           if (!(r0v.kind_value >> 31)) {
@@ -293,6 +308,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
     auto def_bits = [&](int p) -> uint32_t {
       return load_bits32(reinterpret_cast<const uint8_t*>(P.defbm + s.ci[p].defbm_word0), row0 + lrow0);
     };
+    const uint32_t need_all = need;
     uint32_t bits_next = need ? def_bits(__ffs(need) - 1) : 0u;
     while (need) {
       const int p = __ffs(need) - 1;
@@ -309,6 +325,14 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
       s.defb[p][lane] = (uint16_t)bits;
       s.vpre[p][lane] = (uint16_t)(incl - cnt);
     }
+    // the other columns get the same shape (all valid: ones and 16 * lane; all NULL: zeros), so that nothing downstream
+    // branches on the cursor flags
+    for (uint32_t rest = ((1u << P.npcols) - 1) & ~need_all; rest; rest &= rest - 1) {
+      const int p = __ffs(rest) - 1;
+      const bool av = s.cur[p].flags & CUR_ALL_VALID;
+      s.defb[p][lane] = (uint16_t)(av ? rowmask : 0u);
+      s.vpre[p][lane] = (uint16_t)(av ? lrow0 : 0u);
+    }
     __syncwarp();
     if (P.stop_after == 2) continue;
 
@@ -316,10 +340,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
     uint32_t passmask = 0;
     // definition bits and first value index of this lane's rows in column p
     auto lane_def = [&](int p, uint32_t& defbits, uint32_t& vidx) {
-      const ColCursor& c = s.cur[p];
-      if (c.flags & CUR_ALL_VALID) { defbits = rowmask; vidx = c.vidx0 + lrow0; }
-      else if (c.flags & CUR_ALL_NULL) { defbits = 0; vidx = 0; }
-      else { defbits = s.defb[p][lane]; vidx = c.vidx0 + s.vpre[p][lane]; }
+      defbits = s.defb[p][lane];
+      vidx = s.cur[p].vidx0 + s.vpre[p][lane];
     };
     // SINGLE: one string filter column whose dictionaries all have <= SCAN_CODEPASS_MAX entries (checked by the host)
     if constexpr (SINGLE) {
@@ -348,11 +370,21 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
         if (defbits) {
           SeqReader rd;
           rd.seek(s, p, arena, runs, vidx);
-          for (uint32_t m = defbits; m; m &= m - 1) {
-            const uint32_t code = rd.next(vidx++);
-            if (code < dict_n) passmask |= ((s.codepass[code >> 5] >> (code & 31)) & 1u) << (__ffs(m) - 1);
-            else my_status |= ST_BAD_CODE;
+          // one iteration per ROW slot (no find-first-set walk over the valid rows, no divergence between lanes); a NULL
+          // row looks at the index under the cursor, ignores it and does not step over it
+          uint32_t maxcode = 0;
+#pragma unroll 4
+          for (int j = 0; j < SCAN_ROWS_PER_LANE; j++) {
+            const bool v = (defbits >> j) & 1;
+            if (v && vidx >= rd.next_start) { rd.ri++; rd.open_run(vidx); }
+            const uint32_t code = v ? rd.peek() : 0u;
+            maxcode = max(maxcode, code);
+            const uint32_t cb = min(code, SCAN_CODEPASS_MAX - 1);
+            passmask |= ((s.codepass[cb >> 5] >> (cb & 31)) & (uint32_t)v) << j;
+            vidx += v;
+            rd.advance(v);
           }
+          if (maxcode >= dict_n) my_status |= ST_BAD_CODE;
         }
       }
     } else if (lrows) {
@@ -405,11 +437,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
       }
     }
     passmask &= rowmask;
-    if (passmask && P.notnull_pcol >= 0) {
-      const ColCursor& c = s.cur[P.notnull_pcol];
-      if (c.flags & CUR_ALL_NULL) passmask = 0;
-      else if (!(c.flags & CUR_ALL_VALID)) passmask &= s.defb[P.notnull_pcol][lane];
-    }
+    if (P.notnull_pcol >= 0) passmask &= s.defb[P.notnull_pcol][lane];
     // compaction: warp exclusive scan of the per-lane survivor counts
     uint32_t nsurv;
     {

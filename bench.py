@@ -340,11 +340,13 @@ def main():
         print("exchange trace (ms):", [(b[0], round((b[1] - a[1]) * 1e3, 3)) for a, b in zip(last, last[1:])], file=sys.stderr)
     # per-kernel duration of the dominant kernel (CUDA events recorded by the library around each scan launch, on its
     # launching stream); measured in a separate loop so that reading them never serialises the timed region
-    per_scan = []
+    per_scan, per_defx = [], []
     for _ in range(args.steps):
         q.execute()
         q.finalize_device()
-        per_scan.append(q.timings["scan_ms"])
+        tm = q.timings
+        per_scan.append(tm["scan_ms"])
+        per_defx.append(tm["def_expand_ms"])
     clocks = sampler.stop(t_region0, t_region1)
     if world > 1:
         t = torch.tensor([dev_ms], device="cuda")
@@ -424,7 +426,8 @@ def main():
                        "aggregate_table": info["path"], "n_groups": info["n_groups"], "n_buckets": info["n_buckets"],
                        "survivor_rows_per_gpu": survivors, "result_rows": result_rows,
                        "l2": f"inputs ({touched / 1e9:.2f} GB of encoded column chunks per GPU) are larger than the 126 MB L2; no explicit flush",
-                       "timed_region": "scan kernel + on-device compaction of the aggregate table (inputs HBM-resident)",
+                       "timed_region": "definition-level expansion + scan kernel + on-device aggregation/compaction of the result rows (inputs HBM-resident)",
+                       "def_expand_ms": sum(per_defx) / len(per_defx),
                        "GBps_algorithmic": touched * world / (ms_per_step / 1e3) / 1e9,
                        "GBps_logical_36B_per_row": 36.0 * rows_per_rank * world / (ms_per_step / 1e3) / 1e9},
             "roofline": {"bound": "hbm", "kernel": "lk::scan_kernel (fused decode+filter+bucket+group-by aggregate)",
@@ -437,9 +440,10 @@ def main():
                     "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps,
                     "what": "lk_query_create + add_segment_buffer(pinned host bytes) + prepare (host index + H2D) + execute + finalize (D2H)"},
             # this library's own kernels per step (CUB's radix-sort kernels of the record path are library code and not counted):
+            # def_expand (when a touched column has NULLs) +
             # records: scan, rec_count, exclusive_scan, rec_emit; hash: scan, hist, exclusive_scan, scatter, emit
             # (+ sparse_hist, sparse_scatter, sparse_merge / rec_part_hist, rec_part_scatter, rec_unpack when sharded); dense: scan, count, exclusive_scan, emit
-            "gpu_launches": args.steps * ({"records": 4, "hash": 5, "dense": 4}[info["path"]] + (3 if world > 1 and info["path"] != "dense" else 0)),
+            "gpu_launches": args.steps * ((1 if info.get("def_chunks", 1) else 0) + {"records": 4, "hash": 5, "dense": 4}[info["path"]] + (3 if world > 1 and info["path"] != "dense" else 0)),
             "exchange": None if world == 1 else {"kind": "NCCL reduce of dense planes" if info["path"] == "dense" else "NCCL all-to-all of hash-partitioned " + ("survivor records" if info["path"] == "records" else "occupied cells"),
                                                  "bytes_sent_per_rank_per_step": exchange_bytes[0]},
             "clocks": clocks,

@@ -724,8 +724,9 @@ static void build_info_json(Query& q) {
             q.tiles.size(), q.rgs.size(), q.pcols.size(), (long long)q.total_rows, (long long)q.touched_bytes);
   s += strf("\"n_groups\":%llu,\"n_buckets\":%u,\"n_cells\":%llu,\"hash_slots\":%llu,\"hash_stride\":%u,\"warp_agg\":%d,", (unsigned long long)q.n_groups,
             q.nbuckets, (unsigned long long)q.n_cells, (unsigned long long)q.hash_slots, q.hash_stride, q.params.warp_agg);
-  s += strf("\"ts_lo\":%lld,\"ts_hi\":%lld,\"step\":%lld,\"base\":%lld,\"is_metrics\":%d,\"arena_bytes\":%llu,\"runs\":%zu,", (long long)q.ts_lo,
-            (long long)q.ts_hi, (long long)q.step, (long long)q.base, (int)q.is_metrics, (unsigned long long)q.arena_bytes, q.runs.size());
+  s += strf("\"ts_lo\":%lld,\"ts_hi\":%lld,\"step\":%lld,\"base\":%lld,\"is_metrics\":%d,\"arena_bytes\":%llu,\"runs\":%zu,\"def_chunks\":%zu,\"def_bitmap_bytes\":%llu,", (long long)q.ts_lo,
+            (long long)q.ts_hi, (long long)q.step, (long long)q.base, (int)q.is_metrics, (unsigned long long)q.arena_bytes, q.runs.size(),
+            q.def_chunks.size(), (unsigned long long)q.defbm_words * 4);
   s += "\"columns\":[";
   for (size_t i = 0; i < q.pcols.size(); i++) {
     if (i) s += ",";

@@ -68,8 +68,8 @@ int lk_eval(const char* pushdown_request_json, const char* const* parquet_paths,
  *                                                              filter and grouping (QueryEngineV2.scala:280-296 issues them
  *                                                              as separate requests); default = the request's own chart
  *    "path": "auto"|"dense"|"hash"|"records",                   aggregate layout (records: survivors are appended and
- *                                                               aggregated by a sort in finalize; auto picks it for
- *                                                               selective filters over large group spaces)
+ *                                                               aggregated by a sort in finalize; auto picks it when
+ *                                                               the group space is too large for dense planes)
  *    "exact_sums": false}                                       fixed-order (row order) bit-exact double sums */
 int lk_query_create(const char* pushdown_request_json, const char* options_json, lk_query** out);
 int lk_query_add_segment_file(lk_query* q, const char* path);

@@ -35,6 +35,7 @@ namespace lk {
 
 constexpr int MG_TILE = 2048;
 constexpr int MG_BLOCK = 256;
+constexpr uint32_t MG_COARSE = 64;  // tiles per coarse split boundary
 
 struct MergeElem {
   unsigned long long key;  // order-mapped timestamp
@@ -66,18 +67,41 @@ __device__ __forceinline__ uint32_t bound(const long long* __restrict__ ts, uint
   return lo;
 }
 
-// kernel 1: per-stream split of output rank r = blockIdx.x * MG_TILE.  splits[p * K + j] = elements of stream j before r.
+// kernel 1: per-stream split of output rank r = blockIdx.x * rank_stride.  splits[p * K + j] = elements of stream j before r.
+// Two passes: a COARSE one (rank_stride = MG_COARSE tiles, whole streams, the whole key domain; it also records the key
+// under every boundary) and the FINE one (every tile boundary), which searches only the windows between its two
+// neighbouring coarse boundaries -- a few hundred elements per stream and a key range that is usually a single value --
+// instead of bisecting the whole key domain over whole streams for each of the thousands of tiles.
 __global__ void __launch_bounds__(MG_BLOCK) merge_split_kernel(const long long* __restrict__ ts, const uint32_t* __restrict__ offs, int K,
                                                                uint64_t total, unsigned long long kmin, unsigned long long kmax, int reverse,
-                                                               uint32_t* __restrict__ splits) {
+                                                               uint32_t* __restrict__ splits, uint64_t rank_stride,
+                                                               const uint32_t* __restrict__ coarse, const unsigned long long* __restrict__ ckey,
+                                                               uint32_t per_coarse, unsigned long long* __restrict__ key_out) {
   __shared__ unsigned long long red[MG_BLOCK / 32];
   __shared__ unsigned long long bcast;
-  const uint64_t r = (uint64_t)blockIdx.x * MG_TILE;
+  uint64_t r = (uint64_t)blockIdx.x * rank_stride;
   uint32_t* out = splits + (size_t)blockIdx.x * K;
   if (r >= total) {  // the sentinel boundary after the last tile
     for (int j = threadIdx.x; j < K; j += MG_BLOCK) out[j] = offs[j + 1] - offs[j];
+    if (key_out && threadIdx.x == 0) key_out[blockIdx.x] = kmax;
     return;
   }
+  const uint32_t* c0 = nullptr;  // fine pass: splits of the coarse boundaries either side
+  const uint32_t* c1 = nullptr;
+  if (coarse) {
+    const uint32_t c = blockIdx.x / per_coarse;
+    c0 = coarse + (size_t)c * K;
+    c1 = c0 + K;
+    if (blockIdx.x % per_coarse == 0) {  // this boundary IS a coarse one
+      for (int j = threadIdx.x; j < K; j += MG_BLOCK) out[j] = c0[j];
+      return;
+    }
+    r -= (uint64_t)c * per_coarse * rank_stride;  // rank inside the windows
+    kmin = ckey[c];
+    kmax = ckey[c + 1];
+  }
+  auto win_lo = [&](int j) -> uint32_t { return offs[j] + (c0 ? c0[j] : 0u); };
+  auto win_hi = [&](int j) -> uint32_t { return c1 ? offs[j] + c1[j] : offs[j + 1]; };
   auto block_sum = [&](unsigned long long v) -> unsigned long long {
 #pragma unroll
     for (int d = 16; d; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -97,13 +121,14 @@ __global__ void __launch_bounds__(MG_BLOCK) merge_split_kernel(const long long* 
   while (lo < hi) {
     const unsigned long long mid = lo + ((hi - lo) >> 1);
     unsigned long long c = 0;
-    for (int j = threadIdx.x; j < K; j += MG_BLOCK) c += bound(ts, offs[j], offs[j + 1], mid, reverse, true) - offs[j];
+    for (int j = threadIdx.x; j < K; j += MG_BLOCK) { const uint32_t wl = win_lo(j); c += bound(ts, wl, win_hi(j), mid, reverse, true) - wl; }
     c = block_sum(c);
     if (c > r) hi = mid; else lo = mid + 1;
   }
   const unsigned long long tstar = lo;
+  if (key_out && threadIdx.x == 0) key_out[blockIdx.x] = tstar;
   unsigned long long less = 0;
-  for (int j = threadIdx.x; j < K; j += MG_BLOCK) less += bound(ts, offs[j], offs[j + 1], tstar, reverse, false) - offs[j];
+  for (int j = threadIdx.x; j < K; j += MG_BLOCK) { const uint32_t wl = win_lo(j); less += bound(ts, wl, win_hi(j), tstar, reverse, false) - wl; }
   less = block_sum(less);
   // ties at tstar are consumed from the highest stream index downwards
   unsigned long long rem = r - less;
@@ -114,8 +139,9 @@ __global__ void __launch_bounds__(MG_BLOCK) merge_split_kernel(const long long* 
     const int j = jb + (MG_BLOCK - 1 - (int)threadIdx.x);  // thread 0 handles the highest stream of the chunk
     uint32_t lb = 0, cnt = 0;
     if (j < K) {
-      lb = bound(ts, offs[j], offs[j + 1], tstar, reverse, false);
-      cnt = bound(ts, lb, offs[j + 1], tstar, reverse, true) - lb;
+      const uint32_t wh = win_hi(j);
+      lb = bound(ts, win_lo(j), wh, tstar, reverse, false);
+      cnt = bound(ts, lb, wh, tstar, reverse, true) - lb;
     }
     // inclusive scan of cnt in thread order (descending stream index)
     __shared__ uint32_t warp_tot[MG_BLOCK / 32];
@@ -153,31 +179,41 @@ __global__ void __launch_bounds__(MG_BLOCK) merge_tile_kernel(const long long* _
   MergeElem* bufB = bufA + MG_TILE;
   uint32_t* rb = reinterpret_cast<uint32_t*>(bufB + MG_TILE);  // run boundaries, K + 1 entries (ping)
   uint32_t* rb2 = rb + (K + 1);                                 // (pong)
+  uint32_t* rid = rb2 + (K + 1);                                // stream of every non-empty run
+  __shared__ int nruns_s;
   const uint32_t* s0 = splits + (size_t)blockIdx.x * K;
   const uint32_t* s1 = s0 + K;
   const uint64_t tile_base = (uint64_t)blockIdx.x * MG_TILE;
   const uint32_t n = (uint32_t)min((uint64_t)MG_TILE, total - tile_base);
-  // run boundaries = exclusive prefix of the sub-range lengths (single-warp scan over K)
+  // run boundaries = exclusive prefix of the sub-range lengths (single-warp scan over K); streams that contribute
+  // nothing to this tile are dropped here (with heavy timestamp ties a tile draws from a dozen of the K streams, so the
+  // merge tree below has 4 levels instead of log2 K)
   if (threadIdx.x < 32) {
-    uint32_t carry = 0;
+    uint32_t carry = 0, nr = 0;
     for (int jb = 0; jb < K; jb += 32) {
       const int j = jb + threadIdx.x;
       uint32_t c = j < K ? s1[j] - s0[j] : 0, incl = c;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if ((int)threadIdx.x >= d) incl += o; }
-      if (j < K) rb[j] = carry + incl - c;
+      const unsigned ne = __ballot_sync(0xffffffffu, c > 0);
+      if (c > 0) {
+        const uint32_t slot = nr + __popc(ne & ((1u << threadIdx.x) - 1));
+        rb[slot] = carry + incl - c;
+        rid[slot] = (uint32_t)j;
+      }
+      nr += __popc(ne);
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (threadIdx.x == 0) rb[K] = carry;
+    if (threadIdx.x == 0) { rb[nr] = carry; nruns_s = (int)nr; }
   }
   __syncthreads();
+  const int nruns0 = nruns_s;
   // load: slot s belongs to the stream j with rb[j] <= s < rb[j + 1]
   for (uint32_t s = threadIdx.x; s < n; s += MG_BLOCK) {
-    int lo = 0, hi = K;
+    int lo = 0, hi = nruns0;
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (rb[mid] <= s) lo = mid; else hi = mid; }
-    // skip empty streams that share the same boundary: take the LAST j with rb[j] <= s
-    const int j = lo;
-    const uint32_t gi = offs[j] + s0[j] + (s - rb[j]);
+    const int j = (int)rid[lo];
+    const uint32_t gi = offs[j] + s0[j] + (s - rb[lo]);
     MergeElem e;
     e.key = ts_key(ts[gi], reverse);
     e.tag = (uint32_t)(K - 1 - j) * MG_TILE + s;
@@ -188,7 +224,7 @@ __global__ void __launch_bounds__(MG_BLOCK) merge_tile_kernel(const long long* _
   // pairwise merge tree over runs
   MergeElem* src = bufA;
   MergeElem* dst = bufB;
-  int nruns = K;
+  int nruns = nruns0;
   while (nruns > 1) {
     const int nnew = (nruns + 1) >> 1;
     for (uint32_t s = threadIdx.x; s < n; s += MG_BLOCK) {
@@ -292,6 +328,8 @@ struct lk_merge {
   double* d_val = nullptr;
   uint32_t* d_offs = nullptr;
   uint32_t* d_splits = nullptr;
+  uint32_t* d_coarse = nullptr;         // splits of every MG_COARSE-th tile boundary
+  unsigned long long* d_ckey = nullptr;  // and the key under each of them
   long long* o_ts = nullptr;
   int* o_gid = nullptr;
   double* o_val = nullptr;
@@ -348,6 +386,9 @@ lk_merge* merge_create(int k, const int64_t* const* ts, const int32_t* const* gi
     CUDA_CHECK(cudaMallocAsync(&m->o_src, n * 4, m->st));
     m->ntiles = (uint32_t)((total + MG_TILE - 1) / MG_TILE);
     CUDA_CHECK(cudaMallocAsync(&m->d_splits, ((size_t)m->ntiles + 1) * std::max(k, 1) * 4, m->st));
+    const size_t ncoarse = (m->ntiles + MG_COARSE - 1) / MG_COARSE;
+    CUDA_CHECK(cudaMallocAsync(&m->d_coarse, (ncoarse + 1) * std::max(k, 1) * 4, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->d_ckey, (ncoarse + 1) * 8, m->st));
     CUDA_CHECK(cudaMemcpyAsync(m->d_offs, offs.data(), (k + 1) * 4, cudaMemcpyHostToDevice, m->st));
     for (int j = 0; j < k; j++) {
       if (!lens[j]) continue;
@@ -363,7 +404,7 @@ lk_merge* merge_create(int k, const int64_t* const* ts, const int32_t* const* gi
     CUDA_CHECK(cudaEventElapsedTime(&f, m->ev[0], m->ev[1]));
     m->ms[0] = f;
     static bool attr_set = false;
-    size_t smem = 2 * MG_TILE * sizeof(MergeElem) + 2 * (size_t)(k + 1) * 4 + 16;
+    size_t smem = 2 * MG_TILE * sizeof(MergeElem) + 3 * (size_t)(k + 1) * 4 + 16;
     LK_CHECK(smem <= 200 * 1024, LK_ERR_UNSUPPORTED, "merge: too many streams for one shared-memory tile");
     (void)attr_set;
     CUDA_CHECK(cudaFuncSetAttribute(merge_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -378,8 +419,12 @@ void merge_run(lk_merge* m) {
   CUDA_CHECK(cudaSetDevice(global_options().device));
   CUDA_CHECK(cudaEventRecord(m->ev[2], m->st));
   if (m->total > 0) {
-    size_t smem = 2 * MG_TILE * sizeof(MergeElem) + 2 * (size_t)(m->K + 1) * 4 + 16;
-    merge_split_kernel<<<m->ntiles + 1, MG_BLOCK, 0, m->st>>>(m->d_ts, m->d_offs, m->K, m->total, m->kmin, m->kmax, m->reverse ? 1 : 0, m->d_splits);
+    size_t smem = 2 * MG_TILE * sizeof(MergeElem) + 3 * (size_t)(m->K + 1) * 4 + 16;
+    const uint32_t ncoarse = (m->ntiles + MG_COARSE - 1) / MG_COARSE;  // coarse boundaries 0..ncoarse (the last one is the sentinel)
+    merge_split_kernel<<<ncoarse + 1, MG_BLOCK, 0, m->st>>>(m->d_ts, m->d_offs, m->K, m->total, m->kmin, m->kmax, m->reverse ? 1 : 0, m->d_coarse,
+                                                            (uint64_t)MG_COARSE * MG_TILE, nullptr, nullptr, 1, m->d_ckey);
+    merge_split_kernel<<<m->ntiles + 1, MG_BLOCK, 0, m->st>>>(m->d_ts, m->d_offs, m->K, m->total, m->kmin, m->kmax, m->reverse ? 1 : 0, m->d_splits,
+                                                              (uint64_t)MG_TILE, m->d_coarse, m->d_ckey, MG_COARSE, nullptr);
     merge_tile_kernel<<<m->ntiles, MG_BLOCK, smem, m->st>>>(m->d_ts, m->d_gid, m->d_val, m->d_offs, m->K, m->total, m->reverse ? 1 : 0, m->d_splits,
                                                             m->o_ts, m->o_gid, m->o_val, m->o_src);
     CUDA_CHECK(cudaGetLastError());
@@ -464,7 +509,7 @@ void merge_destroy(lk_merge* m) {
   if (!m) return;
   if (m->st) {
     cudaStreamSynchronize(m->st);
-    void* ptrs[] = {m->d_ts, m->d_gid, m->d_val, m->d_offs, m->d_splits, m->o_ts, m->o_gid, m->o_val, m->o_src};
+    void* ptrs[] = {m->d_ts, m->d_gid, m->d_val, m->d_offs, m->d_splits, m->d_coarse, m->d_ckey, m->o_ts, m->o_gid, m->o_val, m->o_src};
     for (void* p : ptrs) if (p) cudaFreeAsync(p, m->st);
     cudaStreamSynchronize(m->st);
     cudaStreamDestroy(m->st);

@@ -50,7 +50,7 @@ segs = int(os.environ.get("C4_SEGMENTS", "100"))
 spec = synth.c4_spec(1 << 20)
 paths = synth.write_dataset("/tmp/lk_probe/c4_1048576", spec, segs)
 rq = json.dumps(synth.push_down_request(synth.c4_base_expr(), list(range(segs)), 10000))
-q = api.Query(rq, aggregates=synth.C2_AGGREGATES)
+q = api.Query(rq, aggregates=synth.C2_AGGREGATES, path=os.environ.get("C4_PATH", "auto"))
 for p in paths:
     q.add_segment_file(p)
 q.prepare()

@@ -71,3 +71,16 @@ def test_single_aggregate_requests(agg, rollup):
     got = H.gpu_eval_single(rq, paths)
     want = H.oracle_single(rq, paths)
     H.assert_same(got, want, [agg], f"{agg}({rollup})")
+
+
+@pytest.mark.parametrize("null_frac", [2e-5, 1e-3, 0.5, 0.97])
+def test_definition_level_shapes(null_frac):
+    """def_expand_kernel over very different run structures: a handful of NULLs per chunk (RLE runs of 10^5 rows: written
+    to global memory directly, whole words queued for the CTA), one NULL per ~1000 rows (runs longer than a thread's fill
+    budget but inside the window), every other row NULL (bit-packed runs of hundreds of rows), almost only NULLs."""
+    spec = synth.SynthSpec(dataset="metrics", rows=300000, null_frac=null_frac, cards=(16, 8, 8, 4), n_names=4)
+    _, paths = H.dataset(f"defshape_{null_frac}", spec, 2)
+    rq = H.request_json(synth.c2_base_expr(), [0, 1], 10000)
+    got = H.gpu_eval_multi(rq, paths, synth.C2_AGGREGATES)
+    want = H.oracle_multi(rq, paths, synth.C2_AGGREGATES)
+    H.assert_same(got, want, ["sum", "sum", "min", "max"], f"defshape/{null_frac}")

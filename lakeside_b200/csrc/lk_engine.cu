@@ -311,8 +311,7 @@ static void launch_scan_variant(const ScanParams& P, cudaStream_t st) {
     CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, scan_kernel<PATH, SINGLE, EMIT, NA>, SCAN_BLOCK, 0));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
-  const uint32_t chunks = (P.ntiles + SCAN_CHUNK_TILES - 1) / SCAN_CHUNK_TILES;  // one ticket = SCAN_CHUNK_TILES tiles
-  const int grid = (int)std::min<uint32_t>((chunks + SCAN_WARPS - 1) / SCAN_WARPS, (uint32_t)(num_sms() * ctas_per_sm));
+  const int grid = (int)std::min<uint32_t>((P.ntiles + SCAN_WARPS - 1) / SCAN_WARPS, (uint32_t)(num_sms() * ctas_per_sm));
   scan_kernel<PATH, SINGLE, EMIT, NA><<<grid, SCAN_BLOCK, 0, st>>>(P);
   CUDA_CHECK(cudaGetLastError());
 }

@@ -2,8 +2,8 @@
 //
 // Work unit: one WARP owns one tile (<= 512 consecutive rows of one row group; a tile never crosses a page of any
 // touched column, so every (tile, column) pair is one contiguous piece of one page).  Warps are fully independent --
-// no block-level barrier anywhere -- and pull chunks of SCAN_CHUNK_TILES consecutive tiles from a global ticket counter
-// (the next ticket is requested a chunk ahead).  Lane l owns rows [16 l, 16 l + 16).  What is per row group (chunk
+// no block-level barrier anywhere -- and pull one tile at a time from a global ticket counter (the ticket after the
+// next is requested a tile ahead).  Lane l owns rows [16 l, 16 l + 16).  What is per row group (chunk
 // descriptors, the per-code pass bits of phase B) is reloaded only when the row group changes.
 // The kernel is latency bound with an instruction budget (profiles/README.md): the SM's instruction cache makes ~3 k SASS
 // instructions per instantiation the ceiling, hence the compile-time specialisation and the rolled column loops.
@@ -30,7 +30,6 @@ constexpr int SCAN_BLOCK = SCAN_WARPS * 32;
 constexpr int SCAN_ROWS_PER_LANE = LK_TILE_ROWS_MAX / 32;  // 16
 static_assert(SCAN_ROWS_PER_LANE == 16, "the kernel is written for 512-row tiles");
 constexpr uint32_t SCAN_CODEPASS_MAX = 1024;
-constexpr uint32_t SCAN_CHUNK_TILES = 4;  // consecutive tiles per ticket
 #ifndef SCAN_MIN_CTAS
 // resident CTAs per SM the register allocation is held to: 9 x 4 warps at 56 registers measured 4 % faster than 8 x 4 at
 // 64 and 8 % faster than 10 x 4 at 48 (spills); tuning builds: make EXTRA=-DSCAN_MIN_CTAS=n
@@ -219,36 +218,32 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
   uint32_t my_phase_min = 0xffffffffu, my_phase_max = 0, my_status = 0;
   unsigned long long my_surv = 0;
 
-  // tiles are handed out in chunks of SCAN_CHUNK_TILES consecutive tiles; the ticket of the NEXT chunk is requested a
-  // chunk ahead (lane 0 holds it, nobody waits for it until the boundary), so the atomic is off the critical path
+  // tiles are handed out one at a time by a global ticket counter (B200, C2: 8 tiles per ticket 0.885 ms, 4: 0.834, 2: 0.814,
+  // 1: 0.797 -- a tile is ~20 us of a warp's time, so coarser tickets leave a visible tail).  The ticket after the next is
+  // requested a tile ahead (lane 0 holds it, nobody waits for it), and the next tile's descriptor and cursors are
+  // prefetched while this one is processed.
   auto ticket = [&]() -> uint32_t {
     uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(P.counters + 4, SCAN_CHUNK_TILES);
+    if (lane == 0) t = atomicAdd(P.counters + 4, 1u);
     return t;
-  };
-  // descriptors and cursors of a chunk's tiles are consecutive: requested when the chunk starts
-  auto prefetch_chunk = [&](uint32_t t0, uint32_t t1) {
-    const uint8_t* c0 = reinterpret_cast<const uint8_t*>(P.cursors + (size_t)t0 * P.npcols);
-    const uint32_t nb = (t1 - t0) * P.npcols * (uint32_t)sizeof(ColCursor);
-    if ((uint32_t)lane * 128 < nb + 127) prefetch_line(c0 + lane * 128);
-    if (lane == 31) prefetch_line(P.tiles + t0);
   };
   uint32_t pending = ticket();
   uint32_t tile = __shfl_sync(0xffffffffu, pending, 0);
-  uint32_t chunk_end = min(tile + SCAN_CHUNK_TILES, P.ntiles);
-  if (tile < P.ntiles) prefetch_chunk(tile, chunk_end);
   pending = ticket();
   uint32_t cached_rg = 0xffffffffu;
 
-  for (;; tile++) {
-    if (tile >= chunk_end) {
-      tile = __shfl_sync(0xffffffffu, pending, 0);
-      if (tile >= P.ntiles) break;
-      chunk_end = min(tile + SCAN_CHUNK_TILES, P.ntiles);
-      prefetch_chunk(tile, chunk_end);
-      pending = ticket();
+  for (;;) {
+    if (tile >= P.ntiles) break;
+    const uint32_t tile_next = __shfl_sync(0xffffffffu, pending, 0);  // requested one tile ago
+    pending = ticket();
+    if (tile_next < P.ntiles) {
+      const uint8_t* c0 = reinterpret_cast<const uint8_t*>(P.cursors + (size_t)tile_next * P.npcols);
+      if ((uint32_t)lane * 128 < P.npcols * (uint32_t)sizeof(ColCursor) + 127) prefetch_line(c0 + lane * 128);
+      if (lane == 31) prefetch_line(P.tiles + tile_next);
     }
-    const TileDesc td = P.tiles[tile];
+    const uint32_t tile_cur = tile;
+    tile = tile_next;  // (`continue` below moves on to it)
+    const TileDesc td = P.tiles[tile_cur];
     const uint32_t nrows = td.nrows;
     const uint32_t row0 = td.row0;
     __syncwarp();  // every lane is done with the previous tile's shared state
@@ -256,7 +251,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
     {
       bool mine = false;
       if (lane < (int)P.npcols) {
-        const ColCursor c = P.cursors[(size_t)tile * P.npcols + lane];  // == td.cursor0 + lane: no wait for td
+        const ColCursor c = P.cursors[(size_t)tile_cur * P.npcols + lane];  // == td.cursor0 + lane: no wait for td
         s.cur[lane] = c;
         if (td.rg != cached_rg) s.ci[lane] = P.chunks[(size_t)td.rg * P.npcols + lane];
         mine = !(c.flags & (CUR_ALL_VALID | CUR_ALL_NULL));

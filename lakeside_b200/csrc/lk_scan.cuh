@@ -43,7 +43,8 @@ constexpr uint32_t SCAN_CODEPASS_MAX = 1024;
 // requested before the group-code lookup of key k: +3 %, spills) and prefetch.L2 of a survivor's PLAIN value sectors at
 // the top of phase C (+-0); prefetch.global.L1 instead of .L2 for the per-tile requests (+10 %); the first four key
 // columns as one unrolled batch (all index words requested before the first use: +14 %, 3.0 k instructions and spills);
-// cudaLimitMaxL2FetchGranularity 32 / 128 (+-0).
+// cudaLimitMaxL2FetchGranularity 32 / 128 (+-0); r1x (0.80 ms): two key columns at a time, branch-free, both columns'
+// index words requested before either is used (+5 %); 10 / 8 CTAs per SM (+4 % / +5 %).
 
 struct WarpSmem {
   ColCursor cur[LK_MAX_PCOLS];

@@ -152,10 +152,12 @@ struct SeqReader {
   const uint32_t* fk;
   const uint8_t* chunk;
   const uint32_t* wp;
-  uint32_t ri, n, next_start, rle, cur, nxt, sh, width, mask, frle;
-  bool is_rle;
+  uint32_t ri, n, next_start, cur, nxt, sh, width, mask, frle;
+  uint32_t adv;  // bits one index occupies: `width` in a bit-packed run, 0 in an RLE run (whose window holds the value)
   __device__ __forceinline__ void open_run(uint32_t vidx) {
     uint32_t bitpos;  // of index vidx, from the chunk's first byte (4-byte aligned)
+    uint32_t rle;
+    bool is_rle;
     if (fs) {
       rle = fk[ri];
       is_rle = (frle >> ri) & 1;
@@ -168,10 +170,15 @@ struct SeqReader {
       rle = r.kind_value & 0x7fffffffu;
       bitpos = r.kind_value * 8 + (vidx - r.start) * width;
     }
+    // an RLE run is a window that never moves: the repeated index sits in `cur`, every step advances by 0 bits
     sh = 0;
+    adv = 0;
+    cur = rle;
+    nxt = 0;
     if (!is_rle) {
       wp = reinterpret_cast<const uint32_t*>(chunk) + (bitpos >> 5);
       sh = bitpos & 31;
+      adv = width;
       cur = __ldg(wp);
       nxt = __ldg(wp + 1);
     }
@@ -191,9 +198,9 @@ struct SeqReader {
     open_run(vidx);
   }
   // the index under the cursor / step over it (take = false: stay, for a NULL row)
-  __device__ __forceinline__ uint32_t peek() const { return is_rle ? rle : (__funnelshift_r(cur, nxt, sh) & mask); }
+  __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(cur, nxt, sh) & mask; }
   __device__ __forceinline__ void advance(bool take) {
-    sh += (take && !is_rle) ? width : 0u;
+    sh += take ? adv : 0u;
     if (sh >= 32) { sh -= 32; cur = nxt; nxt = __ldg(++wp + 1); }
   }
   __device__ __forceinline__ uint32_t next(uint32_t vidx) {
@@ -232,6 +239,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
   uint32_t tile = __shfl_sync(0xffffffffu, pending, 0);
   pending = ticket();
   uint32_t cached_rg = 0xffffffffu;
+  uint32_t filled_valid = 0, filled_null = 0;  // columns whose defb / vpre rows hold the all-valid / all-NULL pattern
 
   for (;;) {
     if (tile >= P.ntiles) break;
@@ -248,14 +256,16 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
     const uint32_t nrows = td.nrows;
     const uint32_t row0 = td.row0;
     __syncwarp();  // every lane is done with the previous tile's shared state
-    uint32_t need = 0;  // columns with some (not all) NULLs in this tile
+    uint32_t need = 0;      // columns with some (not all) NULLs in this tile
+    uint32_t allvalid = 0;  // columns without NULLs in this tile
     {
-      bool mine = false;
+      bool mine = false, mine_valid = false;
       if (lane < (int)P.npcols) {
         const ColCursor c = P.cursors[(size_t)tile_cur * P.npcols + lane];  // == td.cursor0 + lane: no wait for td
         s.cur[lane] = c;
         if (td.rg != cached_rg) s.ci[lane] = P.chunks[(size_t)td.rg * P.npcols + lane];
         mine = !(c.flags & (CUR_ALL_VALID | CUR_ALL_NULL));
+        mine_valid = c.flags & CUR_ALL_VALID;
         // the tile's 512 definition bits of this column (phase A reads them lane by lane): on their way while the
         // run descriptors below are fetched
         if (mine) {
@@ -289,6 +299,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
         }
       }
       need = __ballot_sync(0xffffffffu, mine);
+      allvalid = __ballot_sync(0xffffffffu, mine_valid);
     }
     const bool new_rg = td.rg != cached_rg;  // chunk descriptors (and the per-code pass bits) are per row group
     cached_rg = td.rg;
@@ -323,11 +334,22 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
     }
     // the other columns get the same shape (all valid: ones and 16 * lane; all NULL: zeros), so that nothing downstream
     // branches on the cursor flags
-    for (uint32_t rest = ((1u << P.npcols) - 1) & ~need_all; rest; rest &= rest - 1) {
-      const int p = __ffs(rest) - 1;
-      const bool av = s.cur[p].flags & CUR_ALL_VALID;
-      s.defb[p][lane] = (uint16_t)(av ? rowmask : 0u);
-      s.vpre[p][lane] = (uint16_t)(av ? lrow0 : 0u);
+    // (their patterns do not depend on the tile -- rows beyond the tile are masked where it matters -- so a column is
+    // only rewritten when its kind changes: filled_valid / filled_null remember what the warp's rows hold)
+    {
+      const uint32_t allnull = ((1u << P.npcols) - 1) & ~need_all & ~allvalid;
+      for (uint32_t m = allvalid & ~filled_valid; m; m &= m - 1) {
+        const int p = __ffs(m) - 1;
+        s.defb[p][lane] = 0xffffu;
+        s.vpre[p][lane] = (uint16_t)lrow0;
+      }
+      for (uint32_t m = allnull & ~filled_null; m; m &= m - 1) {
+        const int p = __ffs(m) - 1;
+        s.defb[p][lane] = 0;
+        s.vpre[p][lane] = 0;
+      }
+      filled_valid = allvalid;
+      filled_null = allnull;
     }
     __syncwarp();
     if (P.stop_after == 2) continue;
@@ -336,7 +358,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
     uint32_t passmask = 0;
     // definition bits and first value index of this lane's rows in column p
     auto lane_def = [&](int p, uint32_t& defbits, uint32_t& vidx) {
-      defbits = s.defb[p][lane];
+      defbits = s.defb[p][lane] & rowmask;
       vidx = s.cur[p].vidx0 + s.vpre[p][lane];
     };
     // SINGLE: one string filter column whose dictionaries all have <= SCAN_CODEPASS_MAX entries (checked by the host)

@@ -135,7 +135,7 @@ struct ScanParams {
   int path;                // 0 dense, 1 hash, 2 records (sort-based aggregation)
   int warp_agg;            // pre-reduce equal cells inside a warp before the global atomics
   int fits32;              // (endTs - base) and step are below 2^32: 32-bit bucket arithmetic
-  int stop_after;          // profiling aid (LK_SCAN_STOP_AFTER=1..3): leave each tile after prologue / phase A / phase B; 0 = full
+  int stop_after;          // profiling aid (LK_SCAN_STOP_AFTER=1..5, builds with -DLK_SCAN_PROFILING only): leave each tile after prologue / phase A / phase B; 0 = full
   // dense path: cell = bucket * n_groups + group
   unsigned long long* rowcnt;
   unsigned long long* acc[LK_MAX_AGGS];

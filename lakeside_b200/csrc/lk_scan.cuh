@@ -215,6 +215,13 @@ struct SeqReader {
 // mode of exact_sums: every instantiation carries only its own code (the generic kernel overflowed the instruction
 // cache: ncu showed 4.2 no-instruction stall cycles per issue).
 // NA bounds the unrolled aggregate slots (4 or LK_MAX_AGGS): each slot is a full copy of the value decode.
+// LK_SCAN_STOP_AFTER (profiling aid: leave each tile after the prologue / phase A / phase B, skip the table update) is
+// only compiled into tuning builds (make EXTRA=-DLK_SCAN_PROFILING): the checks cost ~1 % of the instructions
+#ifdef LK_SCAN_PROFILING
+#define STOP_AFTER P.stop_after
+#else
+#define STOP_AFTER 0
+#endif
 template <int PATH, bool SINGLE, bool EMIT, int NA>
 __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const __grid_constant__ ScanParams P) {
   __shared__ WarpSmemT<!SINGLE> smem[SCAN_WARPS];
@@ -304,7 +311,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
     const bool new_rg = td.rg != cached_rg;  // chunk descriptors (and the per-code pass bits) are per row group
     cached_rg = td.rg;
     __syncwarp();
-    if (P.stop_after == 1) continue;
+    if (STOP_AFTER == 1) continue;
 
     const uint32_t lrow0 = (uint32_t)lane * SCAN_ROWS_PER_LANE;
     const uint32_t lrows = lrow0 >= nrows ? 0u : min((uint32_t)SCAN_ROWS_PER_LANE, nrows - lrow0);
@@ -352,7 +359,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
       filled_null = allnull;
     }
     __syncwarp();
-    if (P.stop_after == 2) continue;
+    if (STOP_AFTER == 2) continue;
 
     // ---- phase B: WHERE on dictionary codes ----
     uint32_t passmask = 0;
@@ -470,7 +477,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
       for (uint32_t m = passmask; m; m &= m - 1) s.surv[o++] = (uint16_t)(lrow0 + __ffs(m) - 1);
     }
     __syncwarp();
-    if (P.stop_after == 3) { my_surv += (lane == 0) ? nsurv : 0; continue; }
+    if (STOP_AFTER == 3) { my_surv += (lane == 0) ? nsurv : 0; continue; }
 
     // ---- phase C: one lane per survivor ----
     for (uint32_t i0 = 0; i0 < nsurv; i0 += 32) {
@@ -528,11 +535,11 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
             if constexpr (PATH == 1 && !EMIT) {
               // first probe of the hash table: in flight while the values are gathered
               slot = lk_hash64(cell) & P.h_mask;
-              if (P.stop_after < 4) probe_key = *reinterpret_cast<volatile unsigned long long*>(P.h_entries + slot * P.h_stride);
+              if (STOP_AFTER < 4) probe_key = *reinterpret_cast<volatile unsigned long long*>(P.h_entries + slot * P.h_stride);
             }
 #pragma unroll
             for (int a = 0; a < NA; a++) {
-              if (a < P.n_aggs && P.stop_after != 5) {
+              if (a < P.n_aggs && STOP_AFTER != 5) {
                 const int p = P.aggs[a].pcol;
                 vvalid[a] = col_pos(s, p, r, vidx);
                 if (vvalid[a]) {
@@ -570,7 +577,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
         }
         continue;
       }
-      if (P.stop_after >= 4) {  // profiling aid: no table update
+      if (STOP_AFTER >= 4) {  // profiling aid: no table update
         unsigned long long x = cell;
 #pragma unroll
         for (int a = 0; a < NA; a++) x ^= vbits[a];

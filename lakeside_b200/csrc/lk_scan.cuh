@@ -317,27 +317,41 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
     const uint32_t lrows = lrow0 >= nrows ? 0u : min((uint32_t)SCAN_ROWS_PER_LANE, nrows - lrow0);
     const uint32_t rowmask = (1u << lrows) - 1;
 
-    // ---- phase A: definition bits of my 16 rows + value-index prefix, one nullable column at a time ----
-    // (the load of the NEXT column's bits is issued before this column's warp scan: the L2 round trips overlap the shuffles)
+    // ---- phase A: definition bits of my 16 rows + value-index prefix of every nullable column ----
     auto def_bits = [&](int p) -> uint32_t {
       return load_bits32(reinterpret_cast<const uint8_t*>(P.defbm + s.ci[p].defbm_word0), row0 + lrow0);
     };
     const uint32_t need_all = need;
-    uint32_t bits_next = need ? def_bits(__ffs(need) - 1) : 0u;
+    // three columns per warp scan: the lanes' popcounts (<= 16, prefix <= 512) ride in 10-bit fields of one word, and the
+    // three columns' loads are in flight together
     while (need) {
-      const int p = __ffs(need) - 1;
+      const int p0 = __ffs(need) - 1;
       need &= need - 1;
-      // the chunk's definition levels were expanded into a flat bitmap by def_expand_kernel: 16 bits per lane
-      const uint32_t bits = bits_next & rowmask;
-      if (need) bits_next = def_bits(__ffs(need) - 1);
-      uint32_t cnt = __popc(bits), incl = cnt;
+      const int p1 = need ? __ffs(need) - 1 : -1;
+      need &= need - 1;  // (0 stays 0)
+      const int p2 = need ? __ffs(need) - 1 : -1;
+      need &= need - 1;
+      const uint32_t b0 = def_bits(p0) & rowmask;
+      const uint32_t b1 = p1 >= 0 ? def_bits(p1) & rowmask : 0u;
+      const uint32_t b2 = p2 >= 0 ? def_bits(p2) & rowmask : 0u;
+      const uint32_t cnt = __popc(b0) | (__popc(b1) << 10) | (__popc(b2) << 20);
+      uint32_t incl = cnt;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d);
         if (lane >= d) incl += o;
       }
-      s.defb[p][lane] = (uint16_t)bits;
-      s.vpre[p][lane] = (uint16_t)(incl - cnt);
+      const uint32_t excl = incl - cnt;
+      s.defb[p0][lane] = (uint16_t)b0;
+      s.vpre[p0][lane] = (uint16_t)(excl & 1023u);
+      if (p1 >= 0) {
+        s.defb[p1][lane] = (uint16_t)b1;
+        s.vpre[p1][lane] = (uint16_t)((excl >> 10) & 1023u);
+      }
+      if (p2 >= 0) {
+        s.defb[p2][lane] = (uint16_t)b2;
+        s.vpre[p2][lane] = (uint16_t)(excl >> 20);
+      }
     }
     // the other columns get the same shape (all valid: ones and 16 * lane; all NULL: zeros), so that nothing downstream
     // branches on the cursor flags

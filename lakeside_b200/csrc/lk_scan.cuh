@@ -151,7 +151,8 @@ struct SeqReader {
   const uint32_t* fs;  // or: starts / kind words of its <= 4 runs in shared memory (absent runs start at 0xffffffff)
   const uint32_t* fk;
   const uint8_t* chunk;
-  const uint32_t* wp;
+  const uint32_t* wbase;  // the chunk's first word; `cur` is word widx of it
+  uint32_t widx;
   uint32_t ri, n, next_start, cur, nxt, sh, width, mask, frle;
   uint32_t adv;  // bits one index occupies: `width` in a bit-packed run, 0 in an RLE run (whose window holds the value)
   __device__ __forceinline__ void open_run(uint32_t vidx) {
@@ -176,11 +177,12 @@ struct SeqReader {
     cur = rle;
     nxt = 0;
     if (!is_rle) {
-      wp = reinterpret_cast<const uint32_t*>(chunk) + (bitpos >> 5);
+      wbase = reinterpret_cast<const uint32_t*>(chunk);
+      widx = bitpos >> 5;
       sh = bitpos & 31;
       adv = width;
-      cur = __ldg(wp);
-      nxt = __ldg(wp + 1);
+      cur = __ldg(wbase + widx);
+      nxt = __ldg(wbase + widx + 1);
     }
   }
   __device__ __forceinline__ void seek(const WarpSmem& s, int p, const uint8_t* arena, const Run* runs, uint32_t vidx) {
@@ -201,7 +203,7 @@ struct SeqReader {
   __device__ __forceinline__ uint32_t peek() const { return __funnelshift_r(cur, nxt, sh) & mask; }
   __device__ __forceinline__ void advance(bool take) {
     sh += take ? adv : 0u;
-    if (sh >= 32) { sh -= 32; cur = nxt; nxt = __ldg(++wp + 1); }
+    if (sh >= 32) { sh -= 32; cur = nxt; nxt = __ldg(wbase + (++widx) + 1); }
   }
   __device__ __forceinline__ uint32_t next(uint32_t vidx) {
     if (vidx >= next_start) { ri++; open_run(vidx); }
@@ -409,20 +411,22 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
         if (defbits) {
           SeqReader rd;
           rd.seek(s, p, arena, runs, vidx);
+          rd.mask &= SCAN_CODEPASS_MAX - 1;  // (the host admits only dictionaries of <= SCAN_CODEPASS_MAX entries here)
           // one iteration per ROW slot (no find-first-set walk over the valid rows, no divergence between lanes); a NULL
-          // row looks at the index under the cursor, ignores it and does not step over it
-          uint32_t maxcode = 0;
+          // row looks at the index under the cursor, ignores it and does not step over it.  The pass bits are shifted in
+          // from the top: after 16 slots they sit in bits 16..31.
+          uint32_t maxcode = 0, acc = 0;
 #pragma unroll 4
           for (int j = 0; j < SCAN_ROWS_PER_LANE; j++) {
-            const bool v = (defbits >> j) & 1;
+            const uint32_t v = (defbits >> j) & 1u;
             if (v && vidx >= rd.next_start) { rd.ri++; rd.open_run(vidx); }
-            const uint32_t code = v ? rd.peek() : 0u;
-            maxcode = max(maxcode, code);
-            const uint32_t cb = min(code, SCAN_CODEPASS_MAX - 1);
-            passmask |= ((s.codepass[cb >> 5] >> (cb & 31)) & (uint32_t)v) << j;
+            const uint32_t code = rd.peek();
+            maxcode = max(maxcode, v ? code : 0u);
+            acc = __funnelshift_r(acc, (s.codepass[code >> 5] >> (code & 31)) & v, 1);
             vidx += v;
             rd.advance(v);
           }
+          passmask |= acc >> 16;
           if (maxcode >= dict_n) my_status |= ST_BAD_CODE;
         }
       }

@@ -44,7 +44,9 @@ constexpr uint32_t SCAN_CODEPASS_MAX = 1024;
 // the top of phase C (+-0); prefetch.global.L1 instead of .L2 for the per-tile requests (+10 %); the first four key
 // columns as one unrolled batch (all index words requested before the first use: +14 %, 3.0 k instructions and spills);
 // cudaLimitMaxL2FetchGranularity 32 / 128 (+-0); r1x (0.80 ms): two key columns at a time, branch-free, both columns'
-// index words requested before either is used (+5 %); 10 / 8 CTAs per SM (+4 % / +5 %).
+// index words requested before either is used (+5 %); 10 / 8 CTAs per SM (+4 % / +5 %); r2c (0.72 ms): record slots
+// reserved right after the timestamp check so that the counter's round trip overlaps the key / value decode (+2 %:
+// the reservation's three values live across the whole decode and spill).
 
 struct WarpSmem {
   ColCursor cur[LK_MAX_PCOLS];

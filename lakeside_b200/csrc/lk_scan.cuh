@@ -241,21 +241,18 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
   // 1: 0.797 -- a tile is ~20 us of a warp's time, so coarser tickets leave a visible tail).  The ticket after the next is
   // requested a tile ahead (lane 0 holds it, nobody waits for it), and the next tile's descriptor and cursors are
   // prefetched while this one is processed.
-  auto ticket = [&]() -> uint32_t {
-    uint32_t t = 0;
-    if (lane == 0) t = atomicAdd(P.counters + 4, 1u);
-    return t;
-  };
-  uint32_t pending = ticket();
+  // (the atomic's result goes straight into lane 0's `pending`: nothing merges it with another value, so nothing waits)
+  uint32_t pending = 0;
+  if (lane == 0) pending = atomicAdd(P.counters + 4, 1u);
   uint32_t tile = __shfl_sync(0xffffffffu, pending, 0);
-  pending = ticket();
+  if (lane == 0) pending = atomicAdd(P.counters + 4, 1u);
   uint32_t cached_rg = 0xffffffffu;
   uint32_t filled_valid = 0, filled_null = 0;  // columns whose defb / vpre rows hold the all-valid / all-NULL pattern
 
   for (;;) {
     if (tile >= P.ntiles) break;
     const uint32_t tile_next = __shfl_sync(0xffffffffu, pending, 0);  // requested one tile ago
-    pending = ticket();
+    if (lane == 0) pending = atomicAdd(P.counters + 4, 1u);
     if (tile_next < P.ntiles) {
       const uint8_t* c0 = reinterpret_cast<const uint8_t*>(P.cursors + (size_t)tile_next * P.npcols);
       if ((uint32_t)lane * 128 < P.npcols * (uint32_t)sizeof(ColCursor) + 127) prefetch_line(c0 + lane * 128);

@@ -389,8 +389,6 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
   ci.num_rows = (uint32_t)rg_rows;
   LK_CHECK(cm.num_values == rg_rows, LK_ERR_UNSUPPORTED, "column '" + leaf.name + "': repeated values are not supported");
   chunk_byte_range(cm, len, leaf.name, ci.file_start, ci.file_len);
-  // the kernels address a chunk's bit-packed indices by a 32-bit BIT offset from the chunk's first byte
-  LK_CHECK(ci.file_len < (1ull << 28), LK_ERR_UNSUPPORTED, "column chunk of '" + leaf.name + "' is larger than 256 MB");
   const uint64_t cend = ci.file_start + ci.file_len;
   uint64_t p = ci.file_start;
   uint32_t row = 0, vidx = 0;
@@ -505,6 +503,9 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
     p = pend;
   }
   LK_CHECK(row == ci.num_rows, LK_ERR_IO, "parquet: pages do not cover the row group");
+  // the kernels address a chunk's bit-packed dictionary indices by a 32-bit BIT offset from the chunk's first byte
+  LK_CHECK(ci.val_runs.empty() || ci.file_len < (1ull << 29), LK_ERR_UNSUPPORTED,
+           "dictionary-coded column chunk of '" + leaf.name + "' is larger than 512 MB");
   return ci;
 }
 

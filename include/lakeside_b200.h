@@ -120,7 +120,8 @@ int64_t lk_query_survivors(lk_query* q);
  * the order of lk_result_*.  Returns the number of rows written, -1 on error. */
 int64_t lk_query_eval(lk_query* q, const char* aggregation, const char* chart_type, const char* metric_type, double* out, int64_t cap);
 /* Timings of the last execute/finalize in milliseconds (CUDA events on the query's stream):
- * [0] H2D upload, [1] scan kernel(s), [2] finalize kernels, [3] D2H, [4] host planning. */
+ * [0] H2D upload, [1] scan kernel, [2] finalize kernels, [3] D2H, [4] host planning, [5] definition-level expansion
+ * (def_expand_kernel + the clear of its bitmaps, at the start of every execute). */
 int lk_query_timings(lk_query* q, double* ms /*[8]*/);
 /* Algorithmic bytes: sum of total_compressed_size of the touched column chunks. */
 int64_t lk_query_touched_bytes(lk_query* q);

@@ -462,6 +462,8 @@ void plan_query(Query& q) {
     q.def_blocks_total += (dc.run_n + LK_DEF_BLOCK_RUNS - 1) / LK_DEF_BLOCK_RUNS;
     q.def_chunks.push_back(dc);
   }
+  // lanes beyond a short last tile still read "their" 16 bits (and mask them away): up to 512 rows past the chunk's end
+  if (q.defbm_words) q.defbm_words += 32;
   LK_CHECK(q.defbm_words < 0xffffffffull && q.def_blocks_total < 0x7fffffffull, LK_ERR_UNSUPPORTED, "glob too large for 32-bit definition bitmaps");
 
   trace.mark("tiles/cursors/runs");

@@ -152,10 +152,11 @@ struct ScanParams {
   unsigned long long* rec_cell;
   unsigned long long* rec_seq;  // global row sequence number: segment order, then row order
   unsigned long long* rec_val[LK_MAX_AGGS];
-  // record path (path 2): rec_cell[i] = cell << rec_idx_bits | i and rec_vals[i * n_aggs + a], appended by the scan;
-  // finalize radix-sorts the keys on their cell bits and folds equal cells
+  // record path (path 2): rec_cell[i] = ((bucket << rec_gid_bits | group) << rec_idx_bits) | i and rec_vals[i * n_aggs + a],
+  // appended by the scan; finalize partitions the keys into (bucket, hash slice) bins and folds each bin in shared memory
   unsigned long long* rec_vals;
   uint32_t rec_idx_bits;
+  uint32_t rec_gid_bits;
   uint32_t* counters;   // [0] status flags, [1] phase min, [2] phase max, [3] #claimed slots, [4] tile ticket, [5] #records
   unsigned long long* survivors;  // [0] rows that passed the WHERE clause
 };
@@ -330,6 +331,15 @@ LK_HD uint32_t lk_numeric_class(const FilterCol& f, double x) {
     cls |= (uint32_t)t << l;
   }
   return cls;
+}
+
+// ---- record path finalize ----
+LK_HD uint32_t lk_rf_mix(uint64_t gid) {  // 32 well-mixed bits of a group id: the slot inside its bucket's region of the key table
+  uint32_t h = (uint32_t)gid ^ (uint32_t)(gid >> 32) * 0x9E3779B1u;
+  h *= 0x9E3779B1u; h ^= h >> 16;
+  h *= 0x85EBCA6Bu; h ^= h >> 13;
+  h *= 0xC2B2AE35u; h ^= h >> 16;
+  return h;
 }
 
 LK_HD uint64_t lk_hash64(uint64_t x) {  // splitmix64 finaliser

@@ -9,11 +9,12 @@
 #include "lk_engine.h"
 #include "lk_scan.cuh"
 
-#include <cub/device/device_radix_sort.cuh>  // exact_sums (optional fixed-order pass) only
+#include <cub/device/device_radix_sort.cuh>  // exact_sums (the optional fixed-order pass) only; nothing on the default path
 
 namespace lk {
 
 static void device_exact_sums(Query& q, const ScanParams& base);
+void device_resolve(Query& q);
 
 #define CUDA_CHECK(x)                                                                                        \
   do {                                                                                                       \
@@ -181,8 +182,15 @@ struct Query::Device {
   unsigned long long* rec_cell = nullptr;
   unsigned long long* rec_vals = nullptr;
   size_t rec_cap = 0;
-  uint8_t* sort_scratch = nullptr;
-  size_t sort_scratch_cap = 0;
+  // record path finalize: key table (two slots per record) + per-bucket counters (capacity learned from the first finalize,
+  // checked on the device)
+  unsigned long long* rf_sorted = nullptr;
+  uint32_t* rf_tables = nullptr;
+  struct RecFin* fin = nullptr;
+  uint32_t* fin_host = nullptr;  // pinned: [0..7] RecFin, [8..15] the scan's counters, copied back at the end of finalize
+  size_t fin_cap = 0;            // records the finalize scratch and the result buffer hold
+  bool fin_pending = false;      // finalize kernels enqueued, row count / status not yet read back
+  size_t dres_stride = 0;        // rows per result column in dres
   uint8_t* sparse_out = nullptr;  // partitioned copy of the claimed entries (sparse exchange)
   size_t sparse_cap = 0;
   int64_t n_rows = 0;
@@ -200,7 +208,8 @@ Query::~Query() {
     auto fr = [&](void* p) { if (p) cudaFreeAsync(p, d.st); };
     fr(d.arena); fr(d.tiles); fr(d.cursors); fr(d.runs); fr(d.chunks); fr(d.def_chunks); fr(d.defbm); fr(d.lut_cls); fr(d.lut_gcode); fr(d.pass_bits);
     fr(d.counters); fr(d.survivors); fr(d.planes); fr(d.block_counts); fr(d.dres); fr(d.sparse_out);
-    fr(d.rec_cell); fr(d.rec_vals); fr(d.sort_scratch);
+    fr(d.rec_cell); fr(d.rec_vals); fr(d.rf_sorted); fr(d.rf_tables); fr(d.fin);
+    if (d.fin_host) pinned_free(d.fin_host);
     if (d.harena) {
       // an arena that was written but never emitted is dirty: clear it before handing it back
       if (d.executed && !d.finalized_device) cudaMemsetAsync(d.harena->entries, 0, d.harena->slots * d.harena->stride, d.st);
@@ -519,6 +528,7 @@ void device_execute(Query& q) {
   CUDA_CHECK(cudaMemcpyAsync(d.counters, init_counters, sizeof init_counters, cudaMemcpyHostToDevice, d.st));
   CUDA_CHECK(cudaMemsetAsync(d.survivors, 0, sizeof(unsigned long long), d.st));
   d.finalized_device = false;
+  d.fin_pending = false;  // a finalize nobody waited for is superseded by this execute
   d.executed = true;
   if (q.n_cells > 0 && P.ntiles > 0) {
     if (q.path == 0) {
@@ -558,6 +568,7 @@ void device_execute(Query& q) {
 void device_sync(Query& q) {
   LK_CHECK(q.dev && q.dev->st, LK_ERR_INVALID, "query has no device state");
   CUDA_CHECK(cudaStreamSynchronize(q.dev->st));
+  device_resolve(q);  // a pending record-path finalize reports its row count / errors here
 }
 
 void* device_stream(Query& q) { return q.dev ? (void*)q.dev->st : nullptr; }
@@ -584,10 +595,12 @@ struct EmitParams {
   double divisor[LK_MAX_AGGS];
   uint64_t key_stride[LK_MAX_KEYS];
   uint32_t key_null[LK_MAX_KEYS];
+  uint64_t magic_stride[LK_MAX_KEYS], magic_radix[LK_MAX_KEYS];  // floor(2^64 / d) + 1 (0: d == 1): n / d = umul64hi(n, magic) for n, d < 2^32
   int64_t base, step;
   uint32_t phase;
+  const uint32_t* phase_ptr;  // record path: the scan's phase counter, read on the device (nothing waits for the host); else null
   uint64_t n_groups;
-  int cells32;
+  int cells32, groups32;
   int64_t* ts;
   double* val[LK_MAX_AGGS];
   uint8_t* nul[LK_MAX_AGGS];
@@ -597,17 +610,10 @@ struct EmitParams {
 // `acc(a)` returns the accumulator word of aggregate a; the loop over aggregates is unrolled so that a caller holding
 // the words in registers (hash path) indexes them statically
 template <class AccFn>
-__device__ __forceinline__ void emit_row(const EmitParams& E, uint64_t out, uint64_t cell, AccFn acc) {
-  uint64_t bucket, gid;
-  if (E.cells32) {  // the whole (group x bucket) space fits 32 bits: 32-bit divisions (a 64-bit one costs ~100 instructions)
-    const uint32_t b32 = (uint32_t)cell / (uint32_t)E.n_groups;
-    gid = (uint32_t)cell - b32 * (uint32_t)E.n_groups;
-    bucket = b32;
-  } else {
-    bucket = cell / E.n_groups;
-    gid = cell - bucket * E.n_groups;
-  }
-  E.ts[out] = E.base + (int64_t)bucket * E.step + (int64_t)E.phase;
+__device__ __forceinline__ void emit_row_bg(const EmitParams& E, uint64_t out, uint64_t bucket, uint64_t gid, AccFn acc) {
+  uint32_t phase = E.phase;
+  if (E.phase_ptr) { phase = *E.phase_ptr; if (phase == 0xffffffffu) phase = 0; }
+  E.ts[out] = E.base + (int64_t)bucket * E.step + (int64_t)phase;
 #pragma unroll
   for (int a = 0; a < LK_MAX_AGGS; a++) {
     if (a >= E.n_aggs) break;
@@ -626,10 +632,27 @@ __device__ __forceinline__ void emit_row(const EmitParams& E, uint64_t out, uint
   }
   for (int k = 0; k < E.n_keys; k++) {
     uint32_t g;
-    if (E.cells32) g = ((uint32_t)gid / (uint32_t)E.key_stride[k]) % (E.key_null[k] + 1);
-    else g = (uint32_t)((gid / E.key_stride[k]) % ((uint64_t)E.key_null[k] + 1));
+    if (E.groups32) {  // division by the invariant stride / radix as a 64 x 64 -> high 64 multiply (a 32-bit division costs ~25 instructions)
+      const uint64_t q = E.magic_stride[k] ? __umul64hi(gid, E.magic_stride[k]) : gid;
+      const uint64_t qq = E.magic_radix[k] ? __umul64hi(q, E.magic_radix[k]) : q;  // (radix 1: q / 1)
+      g = (uint32_t)(q - qq * ((uint64_t)E.key_null[k] + 1));
+    } else g = (uint32_t)((gid / E.key_stride[k]) % ((uint64_t)E.key_null[k] + 1));
     E.code[k][out] = g == E.key_null[k] ? -1 : (int32_t)g;
   }
+}
+
+template <class AccFn>
+__device__ __forceinline__ void emit_row(const EmitParams& E, uint64_t out, uint64_t cell, AccFn acc) {
+  uint64_t bucket, gid;
+  if (E.cells32) {  // the whole (group x bucket) space fits 32 bits: 32-bit divisions (a 64-bit one costs ~100 instructions)
+    const uint32_t b32 = (uint32_t)cell / (uint32_t)E.n_groups;
+    gid = (uint32_t)cell - b32 * (uint32_t)E.n_groups;
+    bucket = b32;
+  } else {
+    bucket = cell / E.n_groups;
+    gid = cell - bucket * E.n_groups;
+  }
+  emit_row_bg(E, out, bucket, gid, acc);
 }
 
 constexpr int CMP_BLOCK = 256;
@@ -808,58 +831,224 @@ __global__ void __launch_bounds__(HS_BLOCK) hash_emit_kernel(const uint32_t* __r
   emit_row(E, i, w[0] - 1, [&](int a) { return w[1 + a]; });
 }
 
-// ---- record path: the scan appended one (cell, accumulator words) record per survivor; sort the cells (radix sort over
-// the bits the cell space needs), fold equal neighbours, emit rows in cell order = timestamp-major (ORDER BY timestamp) ----
-constexpr int REC_BLOCK = 256;
+// ---- record path: the scan appended one (key, accumulator words) record per survivor, key = (bucket, group id, record
+// index).  Finalize groups equal (bucket, group) keys through a global table of 8-byte entries and writes the rows:
+//   rec_bhist    records per bucket (warp-aggregated counters: neighbouring records share their bucket)
+//   rec_regions  prefix over the buckets: bucket b owns table slots [2 start_b, 2 start_b + 2 n_b) -- load factor 0.5 in
+//                every bucket whatever the skew, and a region never overflows into its neighbour
+//   rec_group    every record inserts its key into its bucket's region (CAS, linear probing inside the region).  The first
+//                record of a cell becomes its OWNER; a later one folds its accumulator words into the owner's row of
+//                rec_vals[] (add / add / max on the table encodings) and marks itself consumed.  Records arrive clustered
+//                by time, so the regions being probed at any moment are a few hundred KB that stay in L2.
+//   rec_rowscan  prefix over the owners per bucket = first row of every bucket
+//   rec_emit     owners copy their row out: bucket-major = timestamp order (ORDER BY timestamp: BaseExpr.scala:394, 403;
+//                the order inside a bucket is unspecified there too), positions from one warp-aggregated cursor per bucket
+// No library call and no host round trip: every size the kernels need is computed on the device.
+constexpr int RF_BLOCK = 256;
+struct RecFin {  // device-resident bookkeeping of one finalize
+  uint32_t nrec, nrows, status, pad;
+};
+enum : uint32_t { RF_ST_CAP = 1, RF_ST_TABLE = 2 };
+constexpr unsigned long long RF_CONSUMED = ~0ull;  // key of a record folded into its owner (real keys use at most 63 bits)
+struct RecGeom {
+  uint32_t idx_bits, gid_bits, nbuckets;
+  uint32_t rec_cap;  // capacity of the record arrays
+  uint32_t fin_cap;  // records the key table (2 slots each) and the result columns hold
+  uint32_t fp_shift; // key table entry = fingerprint << fp_shift | (record index + 1); 32 = no room for a fingerprint
+  uint32_t cstride;  // words between the per-bucket counters that are bumped atomically: with few buckets every counter
+                     // gets its own 128-byte line (atomics on one line serialise at ~7 ns each on B200: 360 counters packed
+                     // into 12 lines kept ONE L2 slice 97 % busy and cost 120 us per pass over 6.2 M records)
+};
 
-// number of distinct cells that START in each block of the sorted list
-__global__ void __launch_bounds__(REC_BLOCK) rec_count_kernel(const unsigned long long* __restrict__ sorted, uint32_t n, uint32_t idx_bits,
-                                                              uint32_t* __restrict__ block_counts) {
-  const uint32_t i = blockIdx.x * REC_BLOCK + threadIdx.x;
-  const bool head = i < n && (i == 0 || (sorted[i] >> idx_bits) != (sorted[i - 1] >> idx_bits));
-  const int c = __syncthreads_count(head);
-  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)c;
+// Per-bucket counters are bumped once per warp and distinct bucket: the lanes of a warp that hold the same bucket elect a
+// leader (__match_any_sync) who adds their count.  (A 32-record stretch of the list holds ~2.5 buckets: the scan appends up to
+// 32 survivors of one tile at a time, and neighbouring appends come from tiles anywhere in the time range.)
+// Returns the lane's rank among its peers; *base receives what the leader's atomicAdd returned (when want_base).
+template <bool WANT_BASE>
+__device__ __forceinline__ uint32_t warp_bucket_bump(uint32_t* ctr, uint32_t cs, uint32_t bucket, bool valid, uint32_t* base) {
+  const int lane = threadIdx.x & 31;
+  const unsigned peers = __match_any_sync(0xffffffffu, valid ? bucket : 0xffffffffu);
+  const int leader = __ffs(peers) - 1;
+  uint32_t b = 0;
+  if (valid && lane == leader) {
+    if (WANT_BASE) b = atomicAdd(&ctr[(size_t)bucket * cs], (uint32_t)__popc(peers));
+    else atomicAdd(&ctr[(size_t)bucket * cs], (uint32_t)__popc(peers));
+  }
+  if (WANT_BASE) *base = __shfl_sync(0xffffffffu, b, leader);
+  return __popc(peers & ((1u << lane) - 1));
 }
 
-// the thread at the first record of a cell folds the cell's records (usually one) and writes the row
-__global__ void __launch_bounds__(REC_BLOCK) rec_emit_kernel(const unsigned long long* __restrict__ sorted, uint32_t n, uint32_t idx_bits,
-                                                             const unsigned long long* __restrict__ vals, const uint32_t* __restrict__ block_offsets,
-                                                             const __grid_constant__ EmitParams E) {
-  __shared__ uint32_t warp_sums[REC_BLOCK / 32];
-  const uint32_t i = blockIdx.x * REC_BLOCK + threadIdx.x;
+__global__ void __launch_bounds__(RF_BLOCK) rec_bhist_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ counters,
+                                                             const __grid_constant__ RecGeom G, uint32_t* __restrict__ bkt_recs) {
+  const uint32_t nrec = min(counters[5], G.rec_cap);
+  if (nrec > G.fin_cap) return;  // rec_regions_kernel raises RF_ST_CAP; the host grows the scratch and finalizes again
+  const uint32_t sh = G.idx_bits + G.gid_bits;
+  const uint32_t n32 = (nrec + 31u) & ~31u;  // whole warps
+  for (uint32_t i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n32; i += gridDim.x * RF_BLOCK) {
+    const bool valid = i < nrec;
+    warp_bucket_bump<false>(bkt_recs, G.cstride, valid ? (uint32_t)(keys[i] >> sh) : 0u, valid, nullptr);
+  }
+}
+
+// one block: out[b] = sum of in[0..b) (`in` strided), out[n] = total; optionally zeroes the strided `zero[0..n)` on the way
+constexpr int BS_BLOCK = 1024;
+constexpr int BS_PER = 8;
+__device__ __forceinline__ uint32_t block_exclusive_scan_u32(const uint32_t* __restrict__ in, uint32_t in_stride, uint32_t n, uint32_t* __restrict__ out,
+                                                             uint32_t* __restrict__ zero, uint32_t zero_stride) {
+  __shared__ uint32_t warp_tot[BS_BLOCK / 32];
+  __shared__ uint32_t carry_s;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned long long idx_mask = (1ull << idx_bits) - 1;
-  unsigned long long key = i < n ? sorted[i] : 0ull;
-  const unsigned long long cell = key >> idx_bits;
-  const bool head = i < n && (i == 0 || cell != (sorted[i - 1] >> idx_bits));
-  const unsigned hm = __ballot_sync(0xffffffffu, head);
-  if (lane == 0) warp_sums[wid] = (uint32_t)__popc(hm);
+  if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
-  if (!head) return;
-  uint32_t out = block_offsets[blockIdx.x] + (uint32_t)__popc(hm & ((1u << lane) - 1));
-  for (int w = 0; w < wid; w++) out += warp_sums[w];
-  unsigned long long acc[LK_MAX_AGGS];
+  for (uint32_t base = 0; base < n; base += BS_BLOCK * BS_PER) {
+    const uint32_t first = base + threadIdx.x * BS_PER;
+    uint32_t c[BS_PER], local = 0;
 #pragma unroll
-  for (int a = 0; a < LK_MAX_AGGS; a++) acc[a] = 0;
-  uint32_t j = i;
-  do {
-    const unsigned long long* rec = vals + (size_t)(key & idx_mask) * E.n_aggs;
+    for (int k = 0; k < BS_PER; k++) { c[k] = first + k < n ? in[(size_t)(first + k) * in_stride] : 0u; local += c[k]; }
+    uint32_t incl = local;
 #pragma unroll
-    for (int a = 0; a < LK_MAX_AGGS; a++) {
-      if (a >= E.n_aggs) break;
-      const unsigned long long w = rec[a];
-      if (E.ops[a] == AGG_SUM) acc[a] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)acc[a]) + __longlong_as_double((long long)w));
-      else if (E.ops[a] == AGG_COUNT) acc[a] += w;
-      else acc[a] = w > acc[a] ? w : acc[a];  // min (complemented key) and max (key): both stored as "max"
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const uint32_t t = warp_tot[lane];
+      uint32_t ti = t;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= d) ti += o; }
+      warp_tot[lane] = ti - t;
     }
-    j++;
-    if (j >= n) break;
-    key = sorted[j];
-  } while ((key >> idx_bits) == cell);
-  emit_row(E, out, cell, [&](int a) { return acc[a]; });
+    __syncthreads();
+    uint32_t run = carry_s + warp_tot[wid] + incl - local;
+#pragma unroll
+    for (int k = 0; k < BS_PER; k++) {
+      if (first + k < n) { out[first + k] = run; if (zero) zero[(size_t)(first + k) * zero_stride] = 0; }
+      run += c[k];
+    }
+    __syncthreads();
+    if (threadIdx.x == BS_BLOCK - 1) carry_s = run;
+    __syncthreads();
+  }
+  const uint32_t total = carry_s;
+  if (threadIdx.x == 0) out[n] = total;
+  return total;
 }
 
-// device result layout for n rows: ts[n] | val[a][n] | code[k][n] | nul[a][n]
+__global__ void __launch_bounds__(BS_BLOCK) rec_regions_kernel(const uint32_t* __restrict__ counters, const __grid_constant__ RecGeom G,
+                                                               const uint32_t* __restrict__ bkt_recs, uint32_t* __restrict__ rec_start,
+                                                               uint32_t* __restrict__ bkt_rows, RecFin* __restrict__ fin) {
+  const uint32_t nrec = min(counters[5], G.rec_cap);
+  if (nrec > G.fin_cap) {
+    if (threadIdx.x == 0) { fin->nrec = nrec; fin->status = RF_ST_CAP; fin->nrows = 0; }
+    return;
+  }
+  block_exclusive_scan_u32(bkt_recs, G.cstride, G.nbuckets, rec_start, bkt_rows, G.cstride);
+  if (threadIdx.x == 0) { fin->nrec = nrec; fin->nrows = 0; }
+}
+
+// The key table holds 32-bit entries: (fingerprint of the group id) << fp_shift | (record index + 1) of the cell's owner.  At
+// two slots per record it is 8 bytes per record, so table and key list together stay inside the 126 MB L2 for lists of ~7 M
+// records.  A probe that meets an occupied slot with another fingerprint moves on without touching memory; an equal
+// fingerprint is confirmed against the owner's key in keys[] (an owner's key is never rewritten).
+// One record per thread and iteration, small code, full occupancy: the batched variants of this pass (8 records per lane in
+// flight, 120 registers, 5-14 k SASS instructions) measured 330-400 us per 6.2 M records on B200, stalled on instruction fetch
+// and on the longest probe chain of every 8 x 32 batch.
+__global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals,
+                                                             const uint32_t* __restrict__ rec_start, uint32_t* __restrict__ table,
+                                                             uint32_t* __restrict__ bkt_rows, RecFin* __restrict__ fin, const __grid_constant__ RecGeom G,
+                                                             const __grid_constant__ EmitParams E) {
+  if (fin->status & RF_ST_CAP) return;
+  const uint32_t nrec = fin->nrec;
+  const uint32_t n32 = (nrec + 31u) & ~31u;
+  const unsigned long long gid_mask = (1ull << G.gid_bits) - 1;
+  const uint32_t fp_shift = G.fp_shift, idx_field = fp_shift < 32 ? (1u << fp_shift) - 1 : 0xffffffffu;  // fp_shift == 32: no fingerprint bits
+  uint32_t my_status = 0;
+  for (uint32_t i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n32; i += gridDim.x * RF_BLOCK) {
+    const bool valid = i < nrec;
+    bool owner = false;
+    uint32_t bucket = 0;
+    if (valid) {
+      const unsigned long long key = keys[i];
+      const unsigned long long cellx = key >> G.idx_bits;
+      bucket = (uint32_t)(cellx >> G.gid_bits);
+      const uint32_t s0 = __ldg(rec_start + bucket), s1 = __ldg(rec_start + bucket + 1);
+      const uint32_t width = 2u * (s1 - s0);  // >= 2: this record is one of the bucket's
+      uint32_t* const region = table + 2ull * s0;
+      const uint32_t h = lk_rf_mix(cellx & gid_mask);
+      const uint32_t entry = (fp_shift < 32 ? (h * 0x2545F491u) >> fp_shift << fp_shift : 0u) | (i + 1);
+      uint32_t slot = __umulhi(h, width), probe = 0;
+      for (; probe < width; probe++) {
+        const uint32_t prev = atomicCAS(region + slot, 0u, entry);
+        if (prev == 0u) { owner = true; break; }
+        if (((prev ^ entry) & ~idx_field) == 0u) {  // same fingerprint: look at the owner's key
+          const uint32_t oi = (prev & idx_field) - 1;
+          if ((keys[oi] >> G.idx_bits) == cellx) {
+            // a later record of the cell: fold into the owner's row, leave the list
+            const unsigned long long* mine = vals + (size_t)i * E.n_aggs;
+            unsigned long long* own = vals + (size_t)oi * E.n_aggs;
+            for (int a = 0; a < E.n_aggs; a++) {
+              const unsigned long long x = mine[a];
+              if (E.ops[a] == AGG_SUM) atomicAdd(reinterpret_cast<double*>(own + a), __longlong_as_double((long long)x));
+              else if (E.ops[a] == AGG_COUNT) atomicAdd(own + a, x);
+              else if (x) atomicMax(own + a, x);  // min (complemented key) and max (key)
+            }
+            keys[i] = RF_CONSUMED;
+            break;
+          }
+        }
+        slot = slot + 1 == width ? 0u : slot + 1;  // another cell's slot: linear probing inside the region
+      }
+      if (probe == width) my_status |= RF_ST_TABLE;  // cannot happen: the region has two slots per record of its bucket
+    }
+    warp_bucket_bump<false>(bkt_rows, G.cstride, bucket, owner, nullptr);
+  }
+  if (my_status) atomicOr(&fin->status, my_status);
+}
+
+__global__ void __launch_bounds__(BS_BLOCK) rec_rowscan_kernel(const uint32_t* __restrict__ bkt_rows, uint32_t nbuckets, uint32_t cstride,
+                                                               uint32_t* __restrict__ row_start, uint32_t* __restrict__ row_cursor, RecFin* __restrict__ fin) {
+  if (fin->status & RF_ST_CAP) return;
+  const uint32_t total = block_exclusive_scan_u32(bkt_rows, cstride, nbuckets, row_start, row_cursor, cstride);
+  if (threadIdx.x == 0) fin->nrows = total;
+}
+
+// rows: every owner copies its record out at (first row of its bucket) + (cursor of the bucket, bumped once per warp and bucket)
+__global__ void __launch_bounds__(RF_BLOCK) rec_emit_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ vals,
+                                                            const uint32_t* __restrict__ row_start, uint32_t* __restrict__ row_cursor,
+                                                            const RecFin* __restrict__ fin, const __grid_constant__ RecGeom G,
+                                                            const __grid_constant__ EmitParams E) {
+  if (fin->status & RF_ST_CAP) return;
+  const uint32_t nrec = fin->nrec;
+  const uint32_t n32 = (nrec + 31u) & ~31u;
+  const unsigned long long gid_mask = (1ull << G.gid_bits) - 1;
+  for (uint32_t i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n32; i += gridDim.x * RF_BLOCK) {
+    unsigned long long key = RF_CONSUMED;
+    if (i < nrec) key = keys[i];
+    const bool owner = key != RF_CONSUMED;
+    const unsigned long long cellx = key >> G.idx_bits;
+    const uint32_t bucket = owner ? (uint32_t)(cellx >> G.gid_bits) : 0u;
+    // the accumulator row is requested before the cursor's round trip
+    unsigned long long w[LK_MAX_AGGS];
+    if (owner) {
+      const unsigned long long* rec = vals + (size_t)i * E.n_aggs;
+      if (E.n_aggs == 4) {  // one 32-byte sector
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(rec), b2 = *(reinterpret_cast<const ulonglong2*>(rec) + 1);
+        w[0] = a.x; w[1] = a.y; w[2] = b2.x; w[3] = b2.y;
+        w[4] = w[5] = w[6] = 0;
+      } else {
+#pragma unroll
+        for (int a = 0; a < LK_MAX_AGGS; a++) w[a] = a < E.n_aggs ? rec[a] : 0ull;
+      }
+    }
+    uint32_t base = 0;
+    const uint32_t rank = warp_bucket_bump<true>(row_cursor, G.cstride, bucket, owner, &base);
+    if (owner) {
+      const uint32_t out = __ldg(row_start + bucket) + base + rank;
+      if (out < G.fin_cap) emit_row_bg(E, out, bucket, cellx & gid_mask, [&](int a) { return w[a]; });
+    }
+  }
+}
+
+// device result layout for `stride` rows per column: ts[stride] | val[a][stride] | code[k][stride] | nul[a][stride]
 static size_t result_bytes(const Query& q, int64_t n) {
   return (size_t)n * (8 + 8 * q.aggs.size() + 4 * q.key_pcols.size() + q.aggs.size()) + 64;
 }
@@ -869,12 +1058,20 @@ static void fill_emit_params(const Query& q, EmitParams& E, uint8_t* basep, int6
   E.n_aggs = (int)q.aggs.size();
   E.n_keys = (int)q.key_pcols.size();
   for (int a = 0; a < E.n_aggs; a++) { E.ops[a] = q.aggs[a].op; E.divisor[a] = q.aggs[a].divisor; }
-  for (int k = 0; k < E.n_keys; k++) { E.key_stride[k] = q.params.keys[k].stride; E.key_null[k] = q.params.keys[k].null_code; }
+  auto magic = [](uint64_t dv) -> uint64_t { return dv <= 1 ? 0ull : (uint64_t)((((unsigned __int128)1) << 64) / dv) + 1; };
+  for (int k = 0; k < E.n_keys; k++) {
+    E.key_stride[k] = q.params.keys[k].stride;
+    E.key_null[k] = q.params.keys[k].null_code;
+    E.magic_stride[k] = magic(E.key_stride[k]);
+    E.magic_radix[k] = magic((uint64_t)E.key_null[k] + 1);  // radix >= 2 unless the dictionary is empty (radix 1: q % 1 = 0 = the NULL code)
+  }
   E.base = q.base;
   E.step = q.step;
   E.phase = q.dev->phase;
+  E.phase_ptr = nullptr;
   E.n_groups = q.n_groups;
   E.cells32 = q.n_cells < (1ull << 32);
+  E.groups32 = q.n_groups < (1ull << 32);
   uint8_t* p = basep;
   E.ts = (int64_t*)p; p += 8 * n;
   for (int a = 0; a < E.n_aggs; a++) { E.val[a] = (double*)p; p += 8 * n; }
@@ -898,20 +1095,142 @@ static void ensure_block_counts(Query::Device& d, size_t n) {
   d.block_counts_cap = n;
 }
 
+static void clear_arena_if_any(Query::Device& d) {
+  if (d.harena) CUDA_CHECK(cudaMemsetAsync(d.harena->entries, 0, d.harena->slots * d.harena->stride, d.st));
+}
+
+// status flags / timestamp phase of the scan, common to all paths (host copies of the counters in h)
+static void check_scan_status(Query& q, const uint32_t* h) {
+  Query::Device& d = *q.dev;
+  if (h[0] & ST_HASH_FULL) {
+    clear_arena_if_any(d);
+    d.finalized_device = true;
+    fail(LK_ERR_NOMEM, q.path == 2 ? std::string("record buffer overflowed: this shard received more records than its buffer holds")
+                                   : strf("aggregate hash table of %llu slots overflowed; raise max_hash_slots in lk_init", (unsigned long long)q.hash_slots));
+  }
+  LK_CHECK(!(h[0] & ST_BAD_CODE), LK_ERR_IO, "corrupt segment: dictionary index out of range");
+  if (q.is_metrics && h[1] != 0xffffffffu) {
+    // GROUP BY "_cardinalhq.timestamp": metric segments are pre-rolled to the step grid (QueryEngineV2.scala:746-752);
+    // every timestamp must sit at one offset from startTs modulo step, otherwise buckets would merge distinct rows.
+    if (h[1] != h[2]) {
+      clear_arena_if_any(d);
+      d.finalized_device = true;
+      fail(LK_ERR_UNSUPPORTED, "metric timestamps are not on one step-aligned grid; cannot bucket GROUP BY timestamp densely");
+    }
+    d.phase = h[1];
+  } else d.phase = 0;
+}
+
+// ---- record path: sizes the scratch (from the record count of the first finalize; later finalizes re-use it and the
+// kernels verify that it still fits) and enqueues the kernels; nothing here waits for the device once sized ----
+static size_t rec_counter_stride(const Query& q) { return q.nbuckets <= 8192 ? 32 : 1; }
+
+static void rec_finalize_size(Query& q, uint32_t nrec) {
+  Query::Device& d = *q.dev;
+  const size_t cap = std::min<size_t>(std::max<size_t>(d.rec_cap, 1), (size_t)nrec + nrec / 8 + 4096);
+  if (d.rf_sorted) CUDA_CHECK(cudaFreeAsync(d.rf_sorted, d.st));
+  if (d.rf_tables) CUDA_CHECK(cudaFreeAsync(d.rf_tables, d.st));
+  d.rf_sorted = nullptr;
+  d.rf_tables = nullptr;
+  CUDA_CHECK(cudaMallocAsync(&d.rf_sorted, 2 * cap * 4 + 64, d.st));  // the key table: two 32-bit slots per record
+  // u32 words: bkt_recs[nb * cs] | bkt_rows[nb * cs] | row_cursor[nb * cs] | rec_start[nb] | row_start[nb]
+  const size_t nb = (size_t)q.nbuckets + 1, cs = rec_counter_stride(q);
+  CUDA_CHECK(cudaMallocAsync(&d.rf_tables, (3 * nb * cs + 2 * nb) * 4 + 64, d.st));
+  if (!d.fin) CUDA_CHECK(cudaMallocAsync(&d.fin, sizeof(RecFin), d.st));
+  if (!d.fin_host) d.fin_host = static_cast<uint32_t*>(pinned_alloc(64));
+  d.fin_cap = cap;
+  ensure_dres(d, result_bytes(q, (int64_t)cap));
+}
+
+static void rec_finalize_launch(Query& q) {
+  Query::Device& d = *q.dev;
+  RecGeom G;
+  G.idx_bits = q.params.rec_idx_bits;
+  G.gid_bits = q.params.rec_gid_bits;
+  G.nbuckets = q.nbuckets;
+  G.rec_cap = (uint32_t)std::min<size_t>(d.rec_cap, 0xffffffffu);
+  G.fin_cap = (uint32_t)std::min<size_t>(d.fin_cap, 0xffffffffu);
+  G.fp_shift = 1;
+  while (G.fp_shift < 32 && ((uint64_t)d.fin_cap + 1) >> G.fp_shift) G.fp_shift++;  // bits of (largest record index + 1)
+  const size_t nb = (size_t)q.nbuckets + 1, cs = rec_counter_stride(q);
+  G.cstride = (uint32_t)cs;
+  uint32_t* bkt_recs = d.rf_tables;
+  uint32_t* bkt_rows = bkt_recs + nb * cs;
+  uint32_t* row_cursor = bkt_rows + nb * cs;
+  uint32_t* rec_start = row_cursor + nb * cs;
+  uint32_t* row_start = rec_start + nb;
+  CUDA_CHECK(cudaMemsetAsync(bkt_recs, 0, nb * cs * 4, d.st));
+  CUDA_CHECK(cudaMemsetAsync(d.rf_sorted, 0, 2 * d.fin_cap * 4, d.st));
+  CUDA_CHECK(cudaMemsetAsync(d.fin, 0, sizeof(RecFin), d.st));
+  EmitParams E;
+  fill_emit_params(q, E, d.dres, (int64_t)d.fin_cap);
+  E.phase_ptr = d.counters + 1;  // the scan's timestamp phase (metrics), read on the device: nothing waits for the host
+  d.dres_stride = d.fin_cap;
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((d.fin_cap + RF_BLOCK * 16 - 1) / (RF_BLOCK * 16), (size_t)num_sms() * 8));
+  rec_bhist_kernel<<<grid, RF_BLOCK, 0, d.st>>>(d.rec_cell, d.counters, G, bkt_recs);
+  rec_regions_kernel<<<1, BS_BLOCK, 0, d.st>>>(d.counters, G, bkt_recs, rec_start, bkt_rows, d.fin);
+  rec_group_kernel<<<grid, RF_BLOCK, 0, d.st>>>(d.rec_cell, d.rec_vals, rec_start, reinterpret_cast<uint32_t*>(d.rf_sorted), bkt_rows, d.fin, G, E);
+  rec_rowscan_kernel<<<1, BS_BLOCK, 0, d.st>>>(bkt_rows, q.nbuckets, G.cstride, row_start, row_cursor, d.fin);
+  rec_emit_kernel<<<grid, RF_BLOCK, 0, d.st>>>(d.rec_cell, d.rec_vals, row_start, row_cursor, d.fin, G, E);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaMemcpyAsync(d.fin_host, d.fin, sizeof(RecFin), cudaMemcpyDeviceToHost, d.st));
+  CUDA_CHECK(cudaMemcpyAsync(d.fin_host + 8, d.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.st));
+  d.fin_pending = true;
+}
+
+// Waits for a pending record-path finalize and reads back what it left for the host: the row count, the scan's status
+// flags and timestamp phase.  A finalize whose scratch turned out too small (more records than the capacity learned from
+// an earlier run) is repeated once with the right size: the appended records are still in place.
+void device_resolve(Query& q) {
+  if (!q.dev || !q.dev->fin_pending) return;
+  Query::Device& d = *q.dev;
+  CUDA_CHECK(cudaSetDevice(global_options().device));
+  for (int attempt = 0;; attempt++) {
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    d.fin_pending = false;
+    const RecFin* f = reinterpret_cast<const RecFin*>(d.fin_host);
+    check_scan_status(q, d.fin_host + 8);
+    if (f->status & RF_ST_CAP) {
+      LK_CHECK(attempt == 0, LK_ERR_NOMEM, "record finalize: scratch still too small after regrowing");
+      rec_finalize_size(q, f->nrec);
+      rec_finalize_launch(q);
+      CUDA_CHECK(cudaEventRecord(d.ev[5], d.st));
+      continue;
+    }
+    LK_CHECK(!(f->status & RF_ST_TABLE), LK_ERR_CUDA, "record finalize: key table region overflowed (internal error)");
+    d.n_rows = f->nrows;
+    return;
+  }
+}
+
 void device_finalize_device(Query& q) {
   LK_CHECK(q.dev && q.dev->executed, LK_ERR_INVALID, "lk_query_finalize before lk_query_execute");
   Query::Device& d = *q.dev;
   CUDA_CHECK(cudaSetDevice(global_options().device));
   if (d.finalized_device) return;
   CUDA_CHECK(cudaEventRecord(d.ev[4], d.st));
-  CUDA_CHECK(cudaMemcpyAsync(d.h_counters, d.counters, sizeof d.h_counters, cudaMemcpyDeviceToHost, d.st));
   d.n_rows = 0;
-  if (q.n_cells == 0 || q.tiles.empty()) {
+  d.fin_pending = false;
+  if (q.n_cells == 0 || (q.path != 2 && q.tiles.empty()) || (q.path == 2 && d.rec_cap == 0)) {
     CUDA_CHECK(cudaStreamSynchronize(d.st));
     d.finalized_device = true;
     CUDA_CHECK(cudaEventRecord(d.ev[5], d.st));
     return;
   }
+  if (q.path == 2) {
+    if (d.fin_cap == 0) {
+      // first finalize of this query: one read-back of the record count sizes the scratch and the result buffer
+      CUDA_CHECK(cudaMemcpyAsync(d.h_counters, d.counters, sizeof d.h_counters, cudaMemcpyDeviceToHost, d.st));
+      CUDA_CHECK(cudaStreamSynchronize(d.st));
+      check_scan_status(q, d.h_counters);
+      rec_finalize_size(q, d.h_counters[5]);
+    }
+    rec_finalize_launch(q);
+    d.finalized_device = true;
+    CUDA_CHECK(cudaEventRecord(d.ev[5], d.st));
+    return;
+  }
+  CUDA_CHECK(cudaMemcpyAsync(d.h_counters, d.counters, sizeof d.h_counters, cudaMemcpyDeviceToHost, d.st));
   uint32_t nblocks = 0;
   if (q.path == 0) {
     nblocks = (uint32_t)((q.n_cells + CMP_CHUNK - 1) / CMP_CHUNK);
@@ -921,72 +1240,17 @@ void device_finalize_device(Query& q) {
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaMemcpyAsync(&d.h_counters[7], d.block_counts + nblocks, 4, cudaMemcpyDeviceToHost, d.st));
   }
-  const unsigned long long* rec_sorted = nullptr;
-  const uint32_t* rec_counts = nullptr;
-  uint32_t nrec = 0;
-  if (q.path == 2) {
-    CUDA_CHECK(cudaStreamSynchronize(d.st));  // the number of records is a launch parameter of the sort
-    nrec = d.h_counters[5];
-    d.h_counters[7] = 0;
-    if (nrec > 0 && !(d.h_counters[0] & ST_HASH_FULL)) {
-      // keys are (cell << idx_bits | record index): a stable LSD sort over the cell bits only -- equal cells keep
-      // their append order and the record index travels inside the key (8 bytes moved per record and pass)
-      const int begin_bit = (int)q.params.rec_idx_bits;
-      int end_bit = begin_bit + 1;
-      while (end_bit < 64 && (q.n_cells - 1) >> (end_bit - begin_bit)) end_bit++;
-      size_t tmp_bytes = 0;
-      CUDA_CHECK(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (int)nrec,
-                                                begin_bit, end_bit, d.st));
-      nblocks = (nrec + REC_BLOCK - 1) / REC_BLOCK;
-      // scratch: sorted keys | block counts (+ total) | CUB temporary storage
-      const size_t need = (size_t)nrec * 8 + ((size_t)nblocks + 2) * 4 + tmp_bytes + 1024;
-      if (d.sort_scratch_cap < need) {
-        if (d.sort_scratch) CUDA_CHECK(cudaFreeAsync(d.sort_scratch, d.st));
-        d.sort_scratch = nullptr;
-        CUDA_CHECK(cudaMallocAsync(&d.sort_scratch, need, d.st));
-        d.sort_scratch_cap = need;
-      }
-      unsigned long long* sorted = reinterpret_cast<unsigned long long*>(d.sort_scratch);
-      uint32_t* counts = reinterpret_cast<uint32_t*>(sorted + nrec);
-      void* tmp = reinterpret_cast<void*>((reinterpret_cast<uintptr_t>(counts + nblocks + 2) + 255) & ~(uintptr_t)255);
-      CUDA_CHECK(cub::DeviceRadixSort::SortKeys(tmp, tmp_bytes, (const unsigned long long*)d.rec_cell, sorted, (int)nrec, begin_bit, end_bit, d.st));
-      rec_count_kernel<<<nblocks, REC_BLOCK, 0, d.st>>>(sorted, nrec, (uint32_t)begin_bit, counts);
-      exclusive_scan_kernel<<<1, 1024, 0, d.st>>>(counts, nblocks, counts + nblocks);
-      CUDA_CHECK(cudaGetLastError());
-      CUDA_CHECK(cudaMemcpyAsync(&d.h_counters[7], counts + nblocks, 4, cudaMemcpyDeviceToHost, d.st));
-      rec_sorted = sorted;
-      rec_counts = counts;
-    }
-  }
   CUDA_CHECK(cudaStreamSynchronize(d.st));
-  const uint32_t status = d.h_counters[0];
-  if (status & ST_HASH_FULL) {
-    if (d.harena) CUDA_CHECK(cudaMemsetAsync(d.harena->entries, 0, d.harena->slots * d.harena->stride, d.st));
-    d.finalized_device = true;
-    fail(LK_ERR_NOMEM, q.path == 2 ? std::string("record buffer overflowed (more survivors than rows?)")
-                                   : strf("aggregate hash table of %llu slots overflowed; raise max_hash_slots in lk_init", (unsigned long long)q.hash_slots));
-  }
-  LK_CHECK(!(status & ST_BAD_CODE), LK_ERR_IO, "corrupt segment: dictionary index out of range");
-  if (q.is_metrics && d.h_counters[1] != 0xffffffffu) {
-    // GROUP BY "_cardinalhq.timestamp": metric segments are pre-rolled to the step grid (QueryEngineV2.scala:746-752);
-    // every timestamp must sit at one offset from startTs modulo step, otherwise buckets would merge distinct rows.
-    if (d.h_counters[1] != d.h_counters[2]) {
-      if (d.harena) CUDA_CHECK(cudaMemsetAsync(d.harena->entries, 0, d.harena->slots * d.harena->stride, d.st));
-      d.finalized_device = true;
-      fail(LK_ERR_UNSUPPORTED, "metric timestamps are not on one step-aligned grid; cannot bucket GROUP BY timestamp densely");
-    }
-    d.phase = d.h_counters[1];
-  } else d.phase = 0;
+  check_scan_status(q, d.h_counters);
   const int64_t n = q.path == 1 ? (int64_t)d.h_counters[3] : (int64_t)d.h_counters[7];
   d.n_rows = n;
+  d.dres_stride = (size_t)n;
   if (n > 0) {
     ensure_dres(d, result_bytes(q, n));
     EmitParams E;
     fill_emit_params(q, E, d.dres, n);
     if (q.path == 0) {
       dense_emit_kernel<<<nblocks, CMP_BLOCK, 0, d.st>>>(d.planes, q.n_cells, d.block_counts, E);
-    } else if (q.path == 2) {
-      rec_emit_kernel<<<nblocks, REC_BLOCK, 0, d.st>>>(rec_sorted, nrec, q.params.rec_idx_bits, d.rec_vals, rec_counts, E);
     } else {
       // scratch: hist/cursor[nbuckets + 1] | sorted[n]
       ensure_block_counts(d, (size_t)q.nbuckets + 1 + (size_t)n);
@@ -1023,13 +1287,14 @@ __global__ void __launch_bounds__(256) eval_transform_kernel(const double* __res
 
 int64_t device_eval(Query& q, const std::string& aggregation, const std::string& chart_type, const std::string& metric_type, double* out, int64_t cap) {
   LK_CHECK(q.dev && q.dev->finalized_device, LK_ERR_INVALID, "lk_query_eval needs a finalized query");
+  device_resolve(q);
   Query::Device& d = *q.dev;
   const int64_t n = d.n_rows;
   LK_CHECK(out && cap >= n, LK_ERR_INVALID, "lk_query_eval: output buffer too small");
   if (n == 0) return 0;
   CUDA_CHECK(cudaSetDevice(global_options().device));
   EmitParams E;
-  fill_emit_params(q, E, d.dres, n);
+  fill_emit_params(q, E, d.dres, (int64_t)d.dres_stride);
   // map-sketch key -> aggregate slot.  Metrics are pre-rolled: the slot over `rollup_<key>` is the key's value
   // (count = sum(rollup_count)); otherwise the first slot whose aggregation has that name.
   auto column = [&](const char* name) -> const double* {
@@ -1063,6 +1328,7 @@ int64_t device_eval(Query& q, const std::string& aggregation, const std::string&
 HostResult* device_fetch(Query& q) {
   Query::Device& d = *q.dev;
   LK_CHECK(d.finalized_device, LK_ERR_INVALID, "fetch before finalize");
+  device_resolve(q);
   auto r = std::make_unique<HostResult>();
   const int64_t n = d.n_rows;
   r->n = n;
@@ -1081,12 +1347,24 @@ HostResult* device_fetch(Query& q) {
   if (n > 0) {
     size_t bytes = result_bytes(q, n);
     r->pinned = (uint8_t*)pinned_alloc(bytes);
-    CUDA_CHECK(cudaMemcpyAsync(r->pinned, d.dres, bytes, cudaMemcpyDeviceToHost, d.st));
     uint8_t* p = r->pinned;
     r->ts = (int64_t*)p; p += 8 * n;
     for (size_t a = 0; a < q.aggs.size(); a++) { r->values.push_back((double*)p); p += 8 * n; }
     for (size_t k = 0; k < q.key_pcols.size(); k++) { r->codes.push_back((int32_t*)p); p += 4 * n; }
     for (size_t a = 0; a < q.aggs.size(); a++) { r->nulls.push_back(p); p += n; }
+    if (d.dres_stride == (size_t)n) {
+      CUDA_CHECK(cudaMemcpyAsync(r->pinned, d.dres, bytes - 64, cudaMemcpyDeviceToHost, d.st));
+    } else {
+      // the device columns are `dres_stride` rows apart (record path: capacity, not the row count): one copy per column
+      EmitParams E;
+      fill_emit_params(q, E, d.dres, (int64_t)d.dres_stride);
+      CUDA_CHECK(cudaMemcpyAsync(r->ts, E.ts, 8 * n, cudaMemcpyDeviceToHost, d.st));
+      for (size_t a = 0; a < q.aggs.size(); a++) {
+        CUDA_CHECK(cudaMemcpyAsync(r->values[a], E.val[a], 8 * n, cudaMemcpyDeviceToHost, d.st));
+        CUDA_CHECK(cudaMemcpyAsync(r->nulls[a], E.nul[a], n, cudaMemcpyDeviceToHost, d.st));
+      }
+      for (size_t k = 0; k < q.key_pcols.size(); k++) CUDA_CHECK(cudaMemcpyAsync(r->codes[k], E.code[k], 4 * n, cudaMemcpyDeviceToHost, d.st));
+    }
   } else {
     for (size_t a = 0; a < q.aggs.size(); a++) { r->values.push_back(nullptr); r->nulls.push_back(nullptr); }
     for (size_t k = 0; k < q.key_pcols.size(); k++) r->codes.push_back(nullptr);

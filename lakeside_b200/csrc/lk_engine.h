@@ -22,6 +22,7 @@ void device_partial_dense(Query& q, int64_t* n_cells, int* n_planes, void** ptrs
 void device_partial_sparse(Query& q, int nparts, void** entries_out, int64_t* counts, int* stride_out);
 void device_merge_sparse(Query& q, const void* dev_entries, int64_t n);
 void device_finalize_device(Query& q);     // compaction into result rows in HBM
+void device_resolve(Query& q);             // waits for a pending (asynchronous) finalize: row count, deferred errors
 HostResult* device_fetch(Query& q);        // D2H
 void device_timings(Query& q);
 int64_t device_survivors(Query& q);

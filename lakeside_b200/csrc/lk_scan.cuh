@@ -546,7 +546,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
               }
               gid += (uint64_t)gcode * P.keys[k].stride;
             }
-            cell = bucket * P.n_groups + gid;
+            // record path: the key keeps bucket and group id in separate bit fields (finalize bins on them without a division)
+            if constexpr (PATH == 2 && !EMIT) cell = (bucket << P.rec_gid_bits) | gid;
+            else cell = bucket * P.n_groups + gid;
             bucket32 = (uint32_t)bucket;
             seq = s.ci[P.ts_pcol].seq_base + row0 + r;
             if constexpr (PATH == 1 && !EMIT) {
@@ -686,8 +688,8 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
         }
       } else {
         // record path (selective filter, high-cardinality result): nothing is aggregated here.  Every survivor appends
-        // its cell to rec_cell[] and its n_aggs accumulator words (same encodings as the tables: all-zero = no value) to
-        // one row of rec_vals[]; finalize sorts the cells and folds equal ones.  Appends are sequential, coalesced writes:
+        // its (bucket, group) key to rec_cell[] and its n_aggs accumulator words (same encodings as the tables: all-zero = no value)
+        // to one row of rec_vals[]; finalize bins the keys and folds equal ones.  Appends are sequential, coalesced writes:
         // no 8 GB table, no random sector per survivor, nothing to clear afterwards.
         const unsigned am = __ballot_sync(0xffffffffu, active);
         if (am) {
@@ -698,7 +700,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
           const uint32_t o = base + __popc(am & lt_mask);
           if (active) {
             if (o < P.rec_cap) {
-              P.rec_cell[o] = (cell << P.rec_idx_bits) | o;  // sort key: the record index rides in the low bits
+              P.rec_cell[o] = (cell << P.rec_idx_bits) | o;  // the record index rides in the low bits
               unsigned long long* rec = P.rec_vals + (size_t)o * P.n_aggs;
 #pragma unroll
               for (int a = 0; a < NA; a++)

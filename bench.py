@@ -250,18 +250,13 @@ def main():
 
     trace = [] if os.environ.get("LK_BENCH_TRACE") else None  # per-phase wall clock of the exchange (adds syncs: diagnosis only)
 
-    def mark(name):
-        if trace is not None:
-            q.sync()
-            torch.cuda.synchronize()
-            trace.append((name, time.perf_counter()))
-
     def exchange(qq, path):
-        """The ONE exchange step of the sharded path (no collective touches the scan).
+        """Host-mediated exchange of the paths that still need one (the record path -- what the planner picks for this
+        workload -- exchanges INSIDE the scan through the lk_comm attached to the query: nothing to do here).
         dense : NCCL reduce of every (group x bucket) plane to rank 0 (sum f64 / sum u64 / max on order-preserving keys)
         hash  : cells are hash-partitioned over the ranks; NCCL all-to-all of the occupied 32/64-byte entries, each rank
                 merges and finalises its own partition."""
-        if world == 1:
+        if world == 1 or path == "records":
             return
         if path == "dense":
             n_cells, planes = qq.partial_dense()
@@ -279,24 +274,30 @@ def main():
             exchange_bytes[0] = n_cells * 8 * len(planes)
             torch.cuda.synchronize()
         else:
-            mark("execute")
             ptr, counts, stride = qq.partial_sparse(world)
-            mark("partition")
             send_counts = torch.tensor(counts, dtype=torch.int64, device="cuda")
             recv_counts = torch.empty_like(send_counts)
             dist.all_to_all_single(recv_counts, send_counts)
             rc = recv_counts.tolist()
-            mark("counts")
             n_send = sum(counts)
             send = _as_tensor(ptr, n_send * stride, "|u1", torch.uint8) if n_send else torch.empty(0, dtype=torch.uint8, device="cuda")
             recv = torch.empty(sum(rc) * stride, dtype=torch.uint8, device="cuda")
             dist.all_to_all_single(recv, send, [c * stride for c in rc], [c * stride for c in counts])
             torch.cuda.synchronize()
-            mark("all_to_all")
             qq.merge_sparse(recv.data_ptr(), sum(rc))
-            mark("merge")
             qq._keep.append(recv)
             exchange_bytes[0] = (n_send - counts[rank]) * stride
+
+    # the communicator of the record path: every rank's receive pools, mapped by its peers (CUDA IPC); the handles travel
+    # over torch.distributed once, at setup -- the data path never touches NCCL or the host
+    comm = None
+    if world > 1 and table_path in ("auto", "records"):
+        pool_records = int(os.environ.get("LK_BENCH_POOL_RECORDS", str(max(1 << 20, N_SEGMENTS * ROWS // 8))))
+        comm = api.Comm(rank, world, pool_records, max_aggs=len(aggs))
+        handles = [None] * world
+        dist.all_gather_object(handles, comm.handle())
+        comm.connect(handles)
+        dist.barrier()
 
     # ---------------- resident ("kernel-only") arm ----------------
     sampler = ClockSampler(local_rank)  # started here: nvidia-smi needs a few 100 ms before its first sample
@@ -305,8 +306,15 @@ def main():
     if world > 1:
         q.plan()
         agree_on_dictionaries(q)
+    if comm is not None:
+        q.set_comm(comm)
     q.prepare()
     info = q.info
+    if world > 1:  # every rank must have chosen the same aggregate layout: the exchange depends on it
+        paths_all = [None] * world
+        dist.all_gather_object(paths_all, info["path"])
+        assert len(set(paths_all)) == 1, f"ranks disagree on the aggregate layout: {paths_all}"
+        assert comm is None or info["path"] == "records", info["path"]
     rows_per_rank = q.total_rows
     touched = q.touched_bytes
 
@@ -314,7 +322,6 @@ def main():
         q.execute()
         exchange(q, info["path"])
         q.finalize_device()
-        mark("finalize")
         q._keep.clear()
 
     for _ in range(max(3, args.warmup)):
@@ -335,14 +342,12 @@ def main():
     torch.cuda.synchronize()
     t_region1 = time.perf_counter()
     dev_ms = e0.elapsed_time(e1)
-    if trace and rank == 0:
-        last = trace[-1 - 6:]
-        print("exchange trace (ms):", [(b[0], round((b[1] - a[1]) * 1e3, 3)) for a, b in zip(last, last[1:])], file=sys.stderr)
     # per-kernel duration of the dominant kernel (CUDA events recorded by the library around each scan launch, on its
     # launching stream); measured in a separate loop so that reading them never serialises the timed region
     per_scan, per_defx = [], []
     for _ in range(args.steps):
         q.execute()
+        exchange(q, info["path"])
         q.finalize_device()
         tm = q.timings
         per_scan.append(tm["scan_ms"])
@@ -370,6 +375,8 @@ def main():
         if world > 1:  # the column chunks start moving during plan(); they overlap the index build and the agreement
             qq.plan()
             agree_on_dictionaries(qq)
+        if comm is not None:
+            qq.set_comm(comm)
         qq.prepare()
         t.append(time.perf_counter())
         qq.execute()
@@ -443,9 +450,15 @@ def main():
             # def_expand (when a touched column has NULLs) +
             # records: scan, rec_count, exclusive_scan, rec_emit; hash: scan, hist, exclusive_scan, scatter, emit
             # (+ sparse_hist, sparse_scatter, sparse_merge / rec_part_hist, rec_part_scatter, rec_unpack when sharded); dense: scan, count, exclusive_scan, emit
-            "gpu_launches": args.steps * ((1 if info.get("def_chunks", 1) else 0) + {"records": 4, "hash": 5, "dense": 4}[info["path"]] + (3 if world > 1 and info["path"] != "dense" else 0)),
-            "exchange": None if world == 1 else {"kind": "NCCL reduce of dense planes" if info["path"] == "dense" else "NCCL all-to-all of hash-partitioned " + ("survivor records" if info["path"] == "records" else "occupied cells"),
-                                                 "bytes_sent_per_rank_per_step": exchange_bytes[0]},
+            # records: def_expand, scan, rec_bhist, rec_regions, rec_group, rec_rowscan, rec_emit (+ comm_begin, comm_seal_publish, comm_wait
+            # when sharded); hash: scan, hist, exclusive_scan, scatter, emit (+ sparse_hist, sparse_scatter, sparse_merge); dense: scan, count, exclusive_scan, emit
+            "gpu_launches": args.steps * ((1 if info.get("def_chunks", 1) else 0) + {"records": 6, "hash": 5, "dense": 4}[info["path"]] + (3 if world > 1 and info["path"] != "dense" else 0)),
+            "exchange": None if world == 1 else {
+                "kind": ("NCCL reduce of dense planes" if info["path"] == "dense" else
+                         "survivor records stored into the owner rank's receive pool over NVLink during the scan (lk_comm: CUDA IPC peer pools, "
+                         "one remote atomic per 256 records, device-side completion flags; no NCCL call or host round trip on the data path)"
+                         if info["path"] == "records" else "NCCL all-to-all of hash-partitioned occupied cells"),
+                "bytes_sent_per_rank_per_step": (int(survivors * (world - 1) / world) * 8 * (1 + len(aggs)) if info["path"] == "records" else exchange_bytes[0])},
             "clocks": clocks,
         }
         print(json.dumps(line))

@@ -38,6 +38,7 @@ extern "C" {
 typedef struct lk_query lk_query;   /* one glob evaluation: request + segments + device state */
 typedef struct lk_result lk_result; /* host-resident result rows, sorted by timestamp ascending */
 typedef struct lk_merge lk_merge;   /* K-way merge job */
+typedef struct lk_comm lk_comm;     /* sharded evaluation: this rank's receive pools + its peers' (one GPU per rank, one NVLink node) */
 
 /* ---- library ------------------------------------------------------------------------------------------ */
 /* options_json (may be NULL): {"device": 0, "max_hash_slots": 134217728, "dense_max_cells": 33554432,
@@ -104,8 +105,30 @@ int lk_query_partial_dense(lk_query* q, int64_t* n_cells, int* n_planes, void** 
  * finalizes: every rank then holds the final rows of its partition. */
 int lk_query_partial_sparse(lk_query* q, int nparts, void** entries, int64_t* counts /*[nparts]*/, int* stride_bytes);
 int lk_query_merge_sparse(lk_query* q, const void* device_entries, int64_t n);
-/* Compacts the non-empty cells into result rows sorted by timestamp, still in HBM (asynchronous apart from one
- * scalar read-back).  Idempotent until the next execute.  The hash path also returns its table to the clean state. */
+/* ---- sharded evaluation of the record path: the exchange runs INSIDE the scan, over NVLink / NVSwitch -----------------
+ * Replaces, for partial results of one query on several GPUs, the reference's fan-out / fan-in over HTTP + SSE
+ * (SegmentSequencer.scala:137-158, WorkerManager.scala:150-156) and the re-aggregation by (timestamp, tags) that follows it
+ * (TimeGroupedSketchAggregator.scala:157-177).  One rank per GPU; the (group x bucket) cells are hash-partitioned over the
+ * ranks; while a rank scans its segments every survivor record is stored straight into the receive pool of the rank that
+ * owns its cell (peer memory mapped with CUDA IPC -- or plain pointers when the ranks are threads of one process); finalize
+ * waits ON THE DEVICE for all sources and each rank then holds the final rows of its partition.  No host round trip and no
+ * collective call on the data path.  Setup is in two steps because the host owns the out-of-band channel (the reference's
+ * is HTTP): every rank creates its half and exports a handle blob, the host all-gathers the blobs, every rank connects.
+ * pool_records: capacity of this rank's receive pool (records of all sources that hash to this rank, per query; a query
+ * that overflows it fails with LK_ERR_NOMEM); max_aggs: most aggregates of one fused pass.  Every rank must execute the
+ * same sequence of queries on a communicator (one epoch per lk_query_execute).  Group-by dictionaries are agreed on
+ * beforehand with lk_query_export_dictionaries / lk_query_import_dictionaries, as for the dense path. */
+int lk_comm_create(int rank, int world, int64_t pool_records, int max_aggs, lk_comm** out);
+int lk_comm_handle(lk_comm* c, const void** blob, size_t* len);
+int lk_comm_connect(lk_comm* c, const void* blobs /* world blobs in rank order */, size_t len_each);
+void lk_comm_destroy(lk_comm* c);
+/* Attach before the first lk_query_execute (NULL detaches).  With a communicator attached the query must take the record
+ * path ("path":"records" or what auto picks for a large group space); execute + finalize then include the exchange. */
+int lk_query_set_comm(lk_query* q, lk_comm* c);
+/* Compacts the non-empty cells into result rows sorted by timestamp, still in HBM.  Idempotent until the next execute.
+ * The hash path also returns its table to the clean state.  Dense and hash paths read one scalar back; the record path is
+ * fully asynchronous once its scratch has been sized by the query's first finalize: the row count and any error of the
+ * scan / finalize kernels are then reported by the next lk_query_sync, lk_query_finalize or lk_query_eval. */
 int lk_query_finalize_device(lk_query* q);
 /* lk_query_finalize_device + copy of the rows to (pinned) host memory. */
 int lk_query_finalize(lk_query* q, lk_result** out);

@@ -86,6 +86,11 @@ _SIGNATURES = {
     "lk_merge_download": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "lk_merge_reduce": (c_int, [c_void_p, c_int, POINTER(c_int64), c_void_p, c_void_p, c_void_p]),
     "lk_merge_destroy": (None, [c_void_p]),
+    "lk_comm_create": (c_int, [c_int, c_int, c_int64, c_int, POINTER(c_void_p)]),
+    "lk_comm_handle": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t)]),
+    "lk_comm_connect": (c_int, [c_void_p, c_char_p, c_size_t]),
+    "lk_comm_destroy": (None, [c_void_p]),
+    "lk_query_set_comm": (c_int, [c_void_p, c_void_p]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

@@ -131,6 +131,38 @@ class GlobResult:
         return out
 
 
+class Comm:
+    """Communicator of the sharded record path (``lk_comm``): this rank's receive pools and its peers', one GPU per rank.
+    ``handle()`` is all-gathered by the host (any channel), ``connect(handles)`` maps the peers' pools (CUDA IPC, or plain
+    pointers inside one process).  With a Comm attached (``Query.set_comm``) survivor records travel to the rank that owns
+    their (group x bucket) cell DURING the scan, over NVLink; ``finalize`` waits on the device for all sources."""
+
+    def __init__(self, rank: int, world: int, pool_records: int, max_aggs: int = 4):
+        self._h = ctypes.c_void_p()
+        self.rank, self.world = rank, world
+        _lib.check(_lib.load().lk_comm_create(rank, world, int(pool_records), max_aggs, ctypes.byref(self._h)))
+
+    def handle(self) -> bytes:
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        _lib.check(_lib.load().lk_comm_handle(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return ctypes.string_at(p.value, n.value)
+
+    def connect(self, handles: Sequence[bytes]):
+        assert len(handles) == self.world and len({len(h) for h in handles}) == 1
+        _lib.check(_lib.load().lk_comm_connect(self._h, b"".join(handles), len(handles[0])))
+
+    def close(self):
+        if self._h:
+            _lib.load().lk_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class Query:
     """Staged evaluation of one glob: create -> add segments -> prepare (HBM resident) -> execute -> finalize."""
 
@@ -155,6 +187,11 @@ class Query:
     def add_segment_bytes(self, data: bytes):
         buf = ctypes.create_string_buffer(data, len(data))
         self.add_segment_buffer(ctypes.addressof(buf), len(data), keepalive=buf)
+
+    def set_comm(self, comm: Optional["Comm"]):
+        """Sharded evaluation: attach the communicator before the first execute (record path)."""
+        _lib.check(_lib.load().lk_query_set_comm(self._h, comm._h if comm is not None else None))
+        self._comm = comm  # keep it alive
 
     def plan(self):
         """Host half of prepare (no CUDA): usable on a CPU-only box for the sharding/dictionary logic."""

@@ -18,6 +18,7 @@ using namespace lk;
 
 struct lk_query { Query q; };
 struct lk_result { HostResult* r; };
+struct lk_comm { Comm* c; };
 
 static thread_local std::string tl_error;
 
@@ -288,6 +289,32 @@ int64_t lk_query_eval(lk_query* q, const char* aggregation, const char* chart_ty
     n = device_eval(q->q, aggregation, chart_type, metric_type, out, cap);
   });
   return n;
+}
+
+int lk_comm_create(int rank, int world, int64_t pool_records, int max_aggs, lk_comm** out) {
+  return guard([&] {
+    LK_CHECK(out, LK_ERR_INVALID, "null argument");
+    auto h = std::make_unique<lk_comm>();
+    h->c = comm_create(rank, world, pool_records, max_aggs);
+    *out = h.release();
+  });
+}
+int lk_comm_handle(lk_comm* c, const void** blob, size_t* len) {
+  return guard([&] { LK_CHECK(c && blob && len, LK_ERR_INVALID, "null argument"); comm_handle(c->c, blob, len); });
+}
+int lk_comm_connect(lk_comm* c, const void* blobs, size_t len_each) {
+  return guard([&] { LK_CHECK(c && blobs, LK_ERR_INVALID, "null argument"); comm_connect(c->c, blobs, len_each); });
+}
+void lk_comm_destroy(lk_comm* c) {
+  if (!c) return;
+  comm_destroy(c->c);
+  delete c;
+}
+int lk_query_set_comm(lk_query* q, lk_comm* c) {
+  return guard([&] {
+    LK_CHECK(q, LK_ERR_INVALID, "null argument");
+    q->q.comm = c ? c->c : nullptr;
+  });
 }
 
 int lk_query_stream(lk_query* q, void** cuda_stream) {

@@ -107,7 +107,31 @@ struct AggSlot {
   uint8_t pcol;  // value column
 };
 
-enum : uint32_t { ST_HASH_FULL = 1, ST_BAD_CODE = 2 };
+enum : uint32_t { ST_HASH_FULL = 1, ST_BAD_CODE = 2, ST_XCHG_TIMEOUT = 8, ST_XCHG_PHASE = 16 };
+
+// ---- sharded evaluation: the exchange of the record path (one process / GPU per rank, all on one NVLink / NVSwitch node) ----
+// Every rank owns two receive pools (even / odd epochs) of LK_XCHG_CHUNK-record chunks in one cudaMalloc'ed block that its
+// peers map (CUDA IPC).  During the scan a survivor record goes straight into the pool of the rank that owns its cell
+// (stores over NVLink); a sender takes the chunks it fills from the owner's pool with one remote atomic per chunk and
+// allocates inside its current chunk with a local atomic.  See lk_scan.cuh (append) and lk_engine.cu (seal / publish / wait).
+constexpr int LK_MAX_RANKS = 16;
+constexpr uint32_t LK_XCHG_CHUNK = 256;
+struct CommCtrl {  // control words at the start of a rank's exchange block; peers write into it
+  uint32_t pool_next[2];          // chunks handed out of receive pool 0 / 1 (bumped by the senders' remote atomics)
+  uint32_t pad[30];               // (the counters the senders bump sit in their own 128-byte line)
+  uint32_t flag[LK_MAX_RANKS];    // epoch whose records source s has delivered completely
+  uint32_t status[LK_MAX_RANKS];  // scan status flags of source s in that epoch
+  uint32_t phase_min[LK_MAX_RANKS], phase_max[LK_MAX_RANKS];  // its timestamp phase range (metrics)
+};
+struct XchgParams {
+  uint32_t world, rank;
+  uint32_t pool_chunks;                    // chunks per pool
+  unsigned long long* keys[LK_MAX_RANKS];  // this epoch's receive pool of rank d: keys[chunk * LK_XCHG_CHUNK + slot]
+  unsigned long long* vals[LK_MAX_RANKS];  // ... and its accumulator rows (n_aggs words each)
+  uint32_t* next[LK_MAX_RANKS];            // &ctrl(d).pool_next[epoch & 1]
+  CommCtrl* ctrl[LK_MAX_RANKS];            // control words of rank d
+  unsigned long long* state;               // local, per destination: current chunk << 32 | records placed in it
+};
 
 struct ScanParams {
   const uint8_t* arena;
@@ -157,6 +181,7 @@ struct ScanParams {
   unsigned long long* rec_vals;
   uint32_t rec_idx_bits;
   uint32_t rec_gid_bits;
+  XchgParams x;         // path 3 (sharded record path): records are appended to the owner rank's pool instead
   uint32_t* counters;   // [0] status flags, [1] phase min, [2] phase max, [3] #claimed slots, [4] tile ticket, [5] #records
   unsigned long long* survivors;  // [0] rows that passed the WHERE clause
 };

@@ -1,5 +1,6 @@
 // Device layer of liblakeside_b200: HBM residency of a prepared query, kernel launches, result compaction.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -182,6 +183,7 @@ struct Query::Device {
   unsigned long long* rec_cell = nullptr;
   unsigned long long* rec_vals = nullptr;
   size_t rec_cap = 0;
+  bool rec_borrowed = false;  // rec_cell / rec_vals point into the communicator's receive pool
   // record path finalize: key table (two slots per record) + per-bucket counters (capacity learned from the first finalize,
   // checked on the device)
   unsigned long long* rf_sorted = nullptr;
@@ -208,7 +210,8 @@ Query::~Query() {
     auto fr = [&](void* p) { if (p) cudaFreeAsync(p, d.st); };
     fr(d.arena); fr(d.tiles); fr(d.cursors); fr(d.runs); fr(d.chunks); fr(d.def_chunks); fr(d.defbm); fr(d.lut_cls); fr(d.lut_gcode); fr(d.pass_bits);
     fr(d.counters); fr(d.survivors); fr(d.planes); fr(d.block_counts); fr(d.dres); fr(d.sparse_out);
-    fr(d.rec_cell); fr(d.rec_vals); fr(d.rf_sorted); fr(d.rf_tables); fr(d.fin);
+    if (!d.rec_borrowed) { fr(d.rec_cell); fr(d.rec_vals); }
+    fr(d.rf_sorted); fr(d.rf_tables); fr(d.fin);
     if (d.fin_host) pinned_free(d.fin_host);
     if (d.harena) {
       // an arena that was written but never emitted is dirty: clear it before handing it back
@@ -493,13 +496,203 @@ static void launch_def_expand(const Query& q, const ScanParams& P) {
   CUDA_CHECK(cudaGetLastError());
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// communicator of the sharded record path (replaces the HTTP/SSE fan-in of SegmentSequencer.scala:137-158 +
+// the re-aggregation of TimeGroupedSketchAggregator.scala:157-177 for partial results of the same query on several GPUs)
+// ------------------------------------------------------------------------------------------------------------
+// block of rank r: CommCtrl (4 KB) | keys pool 0 | keys pool 1 | vals pool 0 | vals pool 1, `cap` = pool_chunks * LK_XCHG_CHUNK records each
+struct Comm {
+  int rank = 0, world = 1, max_aggs = 4, device = 0;
+  size_t pool_chunks = 0;
+  uint8_t* block = nullptr;
+  size_t block_bytes = 0;
+  uint8_t* peer[LK_MAX_RANKS] = {};
+  bool peer_ipc[LK_MAX_RANKS] = {};
+  unsigned long long* send_state = nullptr;
+  uint32_t epoch = 0;
+  bool connected = false;
+  std::string blob;
+  size_t cap() const { return pool_chunks * LK_XCHG_CHUNK; }
+  CommCtrl* ctrl(int r) const { return reinterpret_cast<CommCtrl*>(peer[r]); }
+  unsigned long long* keys(int r, uint32_t pool) const { return reinterpret_cast<unsigned long long*>(peer[r] + 4096) + (size_t)pool * cap(); }
+  unsigned long long* vals(int r, uint32_t pool) const {
+    return reinterpret_cast<unsigned long long*>(peer[r] + 4096) + 2 * cap() + (size_t)pool * cap() * max_aggs;
+  }
+};
+struct CommBlob {
+  uint32_t magic;
+  int32_t rank, world, device, max_aggs;
+  int64_t pid;
+  uint64_t raw_ptr, pool_chunks;
+  cudaIpcMemHandle_t handle;
+};
+constexpr uint32_t COMM_MAGIC = 0x6c6b636du;
+
+int comm_world(const Comm* c) { return c ? c->world : 1; }
+
+Comm* comm_create(int rank, int world, int64_t pool_records, int max_aggs) {
+  device_init();
+  LK_CHECK(world >= 1 && world <= LK_MAX_RANKS && rank >= 0 && rank < world, LK_ERR_INVALID, "lk_comm_create: bad rank / world");
+  LK_CHECK(max_aggs >= 1 && max_aggs <= LK_MAX_AGGS, LK_ERR_INVALID, "lk_comm_create: bad max_aggs");
+  LK_CHECK(pool_records > 0 && pool_records < (1ll << 31), LK_ERR_INVALID, "lk_comm_create: pool_records out of range");
+  auto c = std::make_unique<Comm>();
+  c->rank = rank;
+  c->world = world;
+  c->max_aggs = max_aggs;
+  c->device = global_options().device;
+  // every sender may hold one partly filled chunk per destination: world chunks of slack
+  c->pool_chunks = ((size_t)pool_records + LK_XCHG_CHUNK - 1) / LK_XCHG_CHUNK + (size_t)world + 1;
+  c->block_bytes = 4096 + 2 * c->cap() * 8 * (size_t)(1 + max_aggs);
+  cudaError_t e = cudaMalloc(&c->block, c->block_bytes);  // (not from the stream-ordered pool: IPC handles need a plain allocation)
+  if (e != cudaSuccess) { cudaGetLastError(); fail(LK_ERR_NOMEM, strf("lk_comm_create: %zu bytes of receive pools: %s", c->block_bytes, cudaGetErrorString(e))); }
+  CUDA_CHECK(cudaMemset(c->block, 0, 4096));
+  CUDA_CHECK(cudaMalloc(&c->send_state, LK_MAX_RANKS * sizeof(unsigned long long)));
+  CommBlob b;
+  memset(&b, 0, sizeof b);
+  b.magic = COMM_MAGIC;
+  b.rank = rank;
+  b.world = world;
+  b.device = c->device;
+  b.max_aggs = max_aggs;
+  b.pid = (int64_t)getpid();
+  b.raw_ptr = (uint64_t)(uintptr_t)c->block;
+  b.pool_chunks = c->pool_chunks;
+  CUDA_CHECK(cudaIpcGetMemHandle(&b.handle, c->block));
+  c->blob.assign(reinterpret_cast<const char*>(&b), sizeof b);
+  c->peer[rank] = c->block;
+  CUDA_CHECK(cudaDeviceSynchronize());
+  return c.release();
+}
+
+void comm_handle(Comm* c, const void** blob, size_t* len) {
+  *blob = c->blob.data();
+  *len = c->blob.size();
+}
+
+void comm_connect(Comm* c, const void* blobs, size_t len_each) {
+  LK_CHECK(len_each == sizeof(CommBlob), LK_ERR_INVALID, "lk_comm_connect: handle blobs of the wrong size");
+  CUDA_CHECK(cudaSetDevice(c->device));
+  for (int r = 0; r < c->world; r++) {
+    CommBlob b;
+    memcpy(&b, static_cast<const uint8_t*>(blobs) + (size_t)r * len_each, sizeof b);
+    LK_CHECK(b.magic == COMM_MAGIC && b.rank == r && b.world == c->world, LK_ERR_INVALID, strf("lk_comm_connect: blob %d is not rank %d of %d", r, r, c->world));
+    LK_CHECK(b.pool_chunks == c->pool_chunks && b.max_aggs == c->max_aggs, LK_ERR_INVALID, "lk_comm_connect: ranks created their pools with different sizes");
+    if (r == c->rank) continue;
+    if (b.pid == (int64_t)getpid()) {
+      // same process (one thread per GPU, or the single-GPU tests): the allocation is addressable as it is
+      if (b.device != c->device) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) fail(LK_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e));
+        cudaGetLastError();
+      }
+      c->peer[r] = reinterpret_cast<uint8_t*>((uintptr_t)b.raw_ptr);
+    } else {
+      void* p = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&p, b.handle, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess) { cudaGetLastError(); fail(LK_ERR_CUDA, strf("cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e))); }
+      c->peer[r] = static_cast<uint8_t*>(p);
+      c->peer_ipc[r] = true;
+    }
+  }
+  c->connected = true;
+}
+
+void comm_destroy(Comm* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  for (int r = 0; r < c->world; r++)
+    if (c->peer_ipc[r]) cudaIpcCloseMemHandle(c->peer[r]);
+  if (c->send_state) cudaFree(c->send_state);
+  if (c->block) cudaFree(c->block);
+  cudaGetLastError();
+  delete c;
+}
+
+// start of an epoch: recycle the pool of the NEXT epoch (nobody can be writing to it: a peer reaches that epoch only after it
+// has seen this rank's flag of the current one, published after this kernel) and take a first chunk of every owner's pool
+__global__ void comm_begin_kernel(CommCtrl* mine, uint32_t next_pool, const __grid_constant__ XchgParams X) {
+  if (threadIdx.x == 0) mine->pool_next[next_pool] = 0;
+  if (threadIdx.x < X.world) {
+    const uint32_t cid = atomicAdd(X.next[threadIdx.x], 1u);
+    X.state[threadIdx.x] = (unsigned long long)cid << 32;
+  }
+}
+
+constexpr unsigned long long RF_CONSUMED_KEY = ~0ull;  // == RF_CONSUMED of the finalize passes
+// end of the scan: block d voids the unused tail of the chunk this rank was filling in rank d's pool, then tells rank d that
+// everything this rank had for it has been written (status flags and timestamp phase of the local scan ride along)
+__global__ void __launch_bounds__(LK_XCHG_CHUNK) comm_seal_publish_kernel(const __grid_constant__ XchgParams X, uint32_t epoch, const uint32_t* __restrict__ counters) {
+  const uint32_t d = blockIdx.x;
+  const unsigned long long st = X.state[d];
+  const uint32_t cid = (uint32_t)(st >> 32), fill = min((uint32_t)st, LK_XCHG_CHUNK);
+  if (cid < X.pool_chunks && threadIdx.x >= fill) X.keys[d][(size_t)cid * LK_XCHG_CHUNK + threadIdx.x] = RF_CONSUMED_KEY;
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    CommCtrl* c = X.ctrl[d];
+    c->status[X.rank] = counters[0] | (cid >= X.pool_chunks ? (uint32_t)ST_HASH_FULL : 0u);
+    c->phase_min[X.rank] = counters[1];
+    c->phase_max[X.rank] = counters[2];
+    __threadfence_system();
+    *reinterpret_cast<volatile uint32_t*>(&c->flag[X.rank]) = epoch;
+  }
+}
+
+// before finalize: wait until every source has delivered this epoch (device-side, no host in the loop), then fold the sources'
+// status flags and timestamp phases into the local counters and publish how many record slots of the pool are in use
+__global__ void comm_wait_kernel(CommCtrl* mine, uint32_t world, uint32_t epoch, uint32_t pool, uint32_t pool_chunks, uint32_t* counters) {
+  const uint32_t lane = threadIdx.x;
+  uint32_t status = 0, pmin = 0xffffffffu, pmax = 0;
+  if (lane < world) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while ((int32_t)(*reinterpret_cast<volatile uint32_t*>(&mine->flag[lane]) - epoch) < 0) {
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > 20000000000ull) { status |= ST_XCHG_TIMEOUT; break; }  // 20 s: a peer died or never ran this query
+      __nanosleep(200);
+    }
+    __threadfence_system();
+    status |= *reinterpret_cast<volatile uint32_t*>(&mine->status[lane]);
+    pmin = *reinterpret_cast<volatile uint32_t*>(&mine->phase_min[lane]);
+    pmax = *reinterpret_cast<volatile uint32_t*>(&mine->phase_max[lane]);
+  }
+#pragma unroll
+  for (int dd = 16; dd; dd >>= 1) {
+    status |= __shfl_xor_sync(0xffffffffu, status, dd);
+    pmin = min(pmin, __shfl_xor_sync(0xffffffffu, pmin, dd));
+    pmax = max(pmax, __shfl_xor_sync(0xffffffffu, pmax, dd));
+  }
+  if (lane == 0) {
+    counters[0] = status;
+    counters[1] = pmin;
+    counters[2] = pmax;
+    counters[5] = min(*reinterpret_cast<volatile uint32_t*>(&mine->pool_next[pool]), pool_chunks) * LK_XCHG_CHUNK;
+  }
+}
+
+static void comm_fill_params(const Comm& c, XchgParams& X, uint32_t pool) {
+  memset(&X, 0, sizeof X);
+  X.world = (uint32_t)c.world;
+  X.rank = (uint32_t)c.rank;
+  X.pool_chunks = (uint32_t)c.pool_chunks;
+  for (int r = 0; r < c.world; r++) {
+    X.keys[r] = c.keys(r, pool);
+    X.vals[r] = c.vals(r, pool);
+    X.ctrl[r] = c.ctrl(r);
+    X.next[r] = &c.ctrl(r)->pool_next[pool];
+  }
+  X.state = c.send_state;
+}
+
 static void launch_scan(const Query& q, const ScanParams& P, bool emit) {
   cudaStream_t st = q.dev->st;
   const bool single = single_filter_ok(q);
   if (emit) launch_scan_table<0, true>(P, single, st);  // record pass of exact_sums: cells are written out, no table
   else if (P.path == 0) launch_scan_table<0, false>(P, single, st);
   else if (P.path == 1) launch_scan_table<1, false>(P, single, st);
-  else launch_scan_table<2, false>(P, single, st);
+  else if (P.path == 2) launch_scan_table<2, false>(P, single, st);
+  else launch_scan_table<3, false>(P, single, st);  // record path, sharded: appends go to the owner ranks' pools
 }
 
 void device_execute(Query& q) {
@@ -530,6 +723,25 @@ void device_execute(Query& q) {
   d.finalized_device = false;
   d.fin_pending = false;  // a finalize nobody waited for is superseded by this execute
   d.executed = true;
+  const bool sharded = q.comm != nullptr;
+  if (sharded) {
+    // every rank runs the same sequence of queries on a communicator: one epoch per execute, pools alternate
+    Comm& c = *q.comm;
+    LK_CHECK(c.connected || c.world == 1, LK_ERR_INVALID, "lk_query_execute: the attached lk_comm is not connected");
+    LK_CHECK(q.path == 2, LK_ERR_UNSUPPORTED, "an attached lk_comm exchanges the record path only (dense planes: lk_query_partial_dense + reduce)");
+    LK_CHECK((int)q.aggs.size() <= c.max_aggs, LK_ERR_INVALID, "the lk_comm was created for fewer aggregates than this query has");
+    LK_CHECK(!d.rec_cell || d.rec_borrowed, LK_ERR_INVALID, "lk_query_set_comm after an unsharded execute");
+    c.epoch++;
+    const uint32_t pool = c.epoch & 1;
+    comm_fill_params(c, P.x, pool);
+    P.path = 3;
+    d.rec_cell = c.keys(c.rank, pool);
+    d.rec_vals = c.vals(c.rank, pool);
+    d.rec_cap = c.cap();
+    d.rec_borrowed = true;
+    comm_begin_kernel<<<1, 32, 0, d.st>>>(c.ctrl(c.rank), pool ^ 1, P.x);
+    CUDA_CHECK(cudaGetLastError());
+  }
   if (q.n_cells > 0 && P.ntiles > 0) {
     if (q.path == 0) {
       CUDA_CHECK(cudaMemsetAsync(d.planes, 0, (1 + q.aggs.size()) * q.n_cells * sizeof(unsigned long long), d.st));
@@ -540,7 +752,7 @@ void device_execute(Query& q) {
       P.h_occ = d.harena->occ;
       P.h_bkt = d.harena->occ_bkt;
       P.h_occ_cap = (uint32_t)std::min<uint64_t>(d.harena->slots, 0xffffffffu);
-    } else {
+    } else if (!q.comm) {
       // one record per survivor at most: sized by the row count, so the scan can never overflow it
       const size_t cap = (size_t)std::max<int64_t>(q.total_rows, 1);
       if (d.rec_cap < cap) {
@@ -562,6 +774,10 @@ void device_execute(Query& q) {
   } else {
     CUDA_CHECK(cudaEventRecord(d.ev[2], d.st));
     CUDA_CHECK(cudaEventRecord(d.ev[3], d.st));
+  }
+  if (sharded) {  // (also for a shard without tiles: its peers wait for its flag)
+    comm_seal_publish_kernel<<<q.comm->world, LK_XCHG_CHUNK, 0, d.st>>>(P.x, q.comm->epoch, d.counters);
+    CUDA_CHECK(cudaGetLastError());
   }
 }
 
@@ -885,8 +1101,9 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_bhist_kernel(const unsigned long
   const uint32_t sh = G.idx_bits + G.gid_bits;
   const uint32_t n32 = (nrec + 31u) & ~31u;  // whole warps
   for (uint32_t i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n32; i += gridDim.x * RF_BLOCK) {
-    const bool valid = i < nrec;
-    warp_bucket_bump<false>(bkt_recs, G.cstride, valid ? (uint32_t)(keys[i] >> sh) : 0u, valid, nullptr);
+    const unsigned long long key = i < nrec ? keys[i] : RF_CONSUMED;
+    const bool valid = key != RF_CONSUMED;  // (a sharded pool has void slots at the end of partly filled chunks)
+    warp_bucket_bump<false>(bkt_recs, G.cstride, valid ? (uint32_t)(key >> sh) : 0u, valid, nullptr);
   }
 }
 
@@ -963,11 +1180,11 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long*
   const uint32_t fp_shift = G.fp_shift, idx_field = fp_shift < 32 ? (1u << fp_shift) - 1 : 0xffffffffu;  // fp_shift == 32: no fingerprint bits
   uint32_t my_status = 0;
   for (uint32_t i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n32; i += gridDim.x * RF_BLOCK) {
-    const bool valid = i < nrec;
+    const unsigned long long key = i < nrec ? keys[i] : RF_CONSUMED;
+    const bool valid = key != RF_CONSUMED;
     bool owner = false;
     uint32_t bucket = 0;
     if (valid) {
-      const unsigned long long key = keys[i];
       const unsigned long long cellx = key >> G.idx_bits;
       bucket = (uint32_t)(cellx >> G.gid_bits);
       const uint32_t s0 = __ldg(rec_start + bucket), s1 = __ldg(rec_start + bucket + 1);
@@ -1102,6 +1319,7 @@ static void clear_arena_if_any(Query::Device& d) {
 // status flags / timestamp phase of the scan, common to all paths (host copies of the counters in h)
 static void check_scan_status(Query& q, const uint32_t* h) {
   Query::Device& d = *q.dev;
+  LK_CHECK(!(h[0] & ST_XCHG_TIMEOUT), LK_ERR_CUDA, "sharded exchange: a peer rank did not deliver its records within 20 s");
   if (h[0] & ST_HASH_FULL) {
     clear_arena_if_any(d);
     d.finalized_device = true;
@@ -1211,13 +1429,18 @@ void device_finalize_device(Query& q) {
   CUDA_CHECK(cudaEventRecord(d.ev[4], d.st));
   d.n_rows = 0;
   d.fin_pending = false;
-  if (q.n_cells == 0 || (q.path != 2 && q.tiles.empty()) || (q.path == 2 && d.rec_cap == 0)) {
+  if ((q.n_cells == 0 && !q.comm) || (q.path != 2 && q.tiles.empty()) || (q.path == 2 && d.rec_cap == 0)) {
     CUDA_CHECK(cudaStreamSynchronize(d.st));
     d.finalized_device = true;
     CUDA_CHECK(cudaEventRecord(d.ev[5], d.st));
     return;
   }
   if (q.path == 2) {
+    if (q.comm) {
+      const Comm& c = *q.comm;
+      comm_wait_kernel<<<1, 32, 0, d.st>>>(c.ctrl(c.rank), (uint32_t)c.world, c.epoch, c.epoch & 1, (uint32_t)c.pool_chunks, d.counters);
+      CUDA_CHECK(cudaGetLastError());
+    }
     if (d.fin_cap == 0) {
       // first finalize of this query: one read-back of the record count sizes the scratch and the result buffer
       CUDA_CHECK(cudaMemcpyAsync(d.h_counters, d.counters, sizeof d.h_counters, cudaMemcpyDeviceToHost, d.st));
@@ -1511,154 +1734,10 @@ __global__ void __launch_bounds__(HS_BLOCK) sparse_merge_kernel(const uint8_t* _
   if (status) atomicOr(counters + 0, status);
 }
 
-// ---- record path: the same exchange over the appended records.  An exchanged record is {cell, acc[n_aggs]} (8 (1 + A)
-// bytes); the receiver re-keys what it gets (cell << idx_bits | position) and finalizes it like its own records: equal
-// cells of different ranks become neighbours in the sort and are folded there -- no merge pass.
-__global__ void __launch_bounds__(HS_BLOCK) rec_part_hist_kernel(const unsigned long long* __restrict__ keys, uint32_t n, uint32_t idx_bits, uint32_t nparts,
-                                                                 uint32_t* __restrict__ part_of, uint32_t* __restrict__ hist) {
-  __shared__ uint32_t h[SP_MAXPARTS];
-  if (threadIdx.x < SP_MAXPARTS) h[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t lo = blockIdx.x * HS_CHUNK, hi = min(n, lo + HS_CHUNK);
-  for (uint32_t i0 = lo; i0 < hi; i0 += HS_BLOCK) {
-    const uint32_t i = i0 + threadIdx.x;
-    const bool valid = i < hi;
-    uint32_t p = 0;
-    if (valid) {
-      p = cell_partition(keys[i] >> idx_bits, nparts);
-      part_of[i] = p;
-    }
-    warp_agg_inc(h, p, valid);
-  }
-  __syncthreads();
-  if (threadIdx.x < nparts && h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], h[threadIdx.x]);
-}
-
-__global__ void __launch_bounds__(HS_BLOCK) rec_part_scatter_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ vals,
-                                                                    const uint32_t* __restrict__ part_of, uint32_t n, uint32_t idx_bits, int n_aggs,
-                                                                    uint32_t nparts, uint32_t* __restrict__ cursor, unsigned long long* __restrict__ out) {
-  __shared__ uint32_t cnt[SP_MAXPARTS];
-  __shared__ uint32_t base[SP_MAXPARTS];
-  if (threadIdx.x < SP_MAXPARTS) cnt[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t lo = blockIdx.x * HS_CHUNK, hi = min(n, lo + HS_CHUNK);
-  for (uint32_t i0 = lo; i0 < hi; i0 += HS_BLOCK) {
-    const uint32_t i = i0 + threadIdx.x;
-    const bool valid = i < hi;
-    warp_agg_inc(cnt, valid ? part_of[i] : 0u, valid);
-  }
-  __syncthreads();
-  if (threadIdx.x < nparts) {
-    const uint32_t c = cnt[threadIdx.x];
-    if (c) base[threadIdx.x] = atomicAdd(&cursor[threadIdx.x], c);
-    cnt[threadIdx.x] = 0;
-  }
-  __syncthreads();
-  const int w = 1 + n_aggs;
-  for (uint32_t i0 = lo; i0 < hi; i0 += HS_BLOCK) {
-    const uint32_t i = i0 + threadIdx.x;
-    const bool valid = i < hi;
-    const uint32_t p = valid ? part_of[i] : 0u;
-    const uint32_t pos = base[p] + warp_agg_inc(cnt, p, valid);
-    if (!valid) continue;
-    const unsigned long long key = keys[i];
-    const unsigned long long* src = vals + (size_t)(key & ((1ull << idx_bits) - 1)) * n_aggs;
-    unsigned long long* dst = out + (size_t)pos * w;
-    unsigned long long v[LK_MAX_AGGS];  // all loads, then all stores: the record's sectors reach L2 together
-#pragma unroll
-    for (int a = 0; a < LK_MAX_AGGS; a++) v[a] = a < n_aggs ? src[a] : 0ull;
-    dst[0] = key >> idx_bits;
-#pragma unroll
-    for (int a = 0; a < LK_MAX_AGGS; a++) if (a < n_aggs) dst[1 + a] = v[a];
-  }
-}
-
-__global__ void __launch_bounds__(HS_BLOCK) rec_unpack_kernel(const unsigned long long* __restrict__ in, uint32_t n, uint32_t at, int n_aggs, uint32_t idx_bits,
-                                                              unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals) {
-  const uint32_t i = blockIdx.x * HS_BLOCK + threadIdx.x;
-  if (i >= n) return;
-  const unsigned long long* src = in + (size_t)i * (1 + n_aggs);
-  unsigned long long v[LK_MAX_AGGS];
-  const unsigned long long cell = src[0];
-#pragma unroll
-  for (int a = 0; a < LK_MAX_AGGS; a++) v[a] = a < n_aggs ? src[1 + a] : 0ull;
-  const uint32_t o = at + i;  // appended after the records of earlier calls
-  keys[o] = (cell << idx_bits) | o;
-#pragma unroll
-  for (int a = 0; a < LK_MAX_AGGS; a++) if (a < n_aggs) vals[(size_t)o * n_aggs + a] = v[a];
-}
-
-static void device_partial_records(Query& q, int nparts, void** entries_out, int64_t* counts, int* stride_out) {
-  Query::Device& d = *q.dev;
-  CUDA_CHECK(cudaMemcpyAsync(d.h_counters, d.counters, sizeof d.h_counters, cudaMemcpyDeviceToHost, d.st));
-  CUDA_CHECK(cudaStreamSynchronize(d.st));
-  LK_CHECK(!(d.h_counters[0] & ST_HASH_FULL), LK_ERR_NOMEM, "record buffer overflowed");
-  LK_CHECK(!(d.h_counters[0] & ST_BAD_CODE), LK_ERR_IO, "corrupt segment: dictionary index out of range");
-  const uint32_t n = q.n_cells ? d.h_counters[5] : 0;
-  const int na = (int)q.aggs.size();
-  const uint32_t stride = 8u * (1 + na);
-  for (int p = 0; p < nparts; p++) counts[p] = 0;
-  *stride_out = (int)stride;
-  *entries_out = nullptr;
-  if (n == 0) return;
-  ensure_block_counts(d, 128 + (size_t)n);  // hist[64] | cursor[64] | part_of[n]
-  uint32_t* hist = d.block_counts;
-  uint32_t* cursor = hist + 64;
-  uint32_t* part_of = hist + 128;
-  if (d.sparse_cap < (size_t)n * stride) {
-    if (d.sparse_out) CUDA_CHECK(cudaFreeAsync(d.sparse_out, d.st));
-    d.sparse_out = nullptr;
-    CUDA_CHECK(cudaMallocAsync(&d.sparse_out, (size_t)n * stride, d.st));
-    d.sparse_cap = (size_t)n * stride;
-  }
-  CUDA_CHECK(cudaMemsetAsync(hist, 0, 128 * 4, d.st));
-  const int grid = (int)((n + HS_CHUNK - 1) / HS_CHUNK);
-  const uint32_t ib = q.params.rec_idx_bits;
-  rec_part_hist_kernel<<<grid, HS_BLOCK, 0, d.st>>>(d.rec_cell, n, ib, (uint32_t)nparts, part_of, hist);
-  uint32_t h[64];
-  CUDA_CHECK(cudaMemcpyAsync(h, hist, 64 * 4, cudaMemcpyDeviceToHost, d.st));
-  CUDA_CHECK(cudaStreamSynchronize(d.st));
-  uint32_t starts[64] = {0};
-  uint32_t run = 0;
-  for (int p = 0; p < nparts; p++) { counts[p] = h[p]; starts[p] = run; run += h[p]; }
-  CUDA_CHECK(cudaMemcpyAsync(cursor, starts, 64 * 4, cudaMemcpyHostToDevice, d.st));
-  rec_part_scatter_kernel<<<grid, HS_BLOCK, 0, d.st>>>(d.rec_cell, d.rec_vals, part_of, n, ib, na, (uint32_t)nparts, cursor,
-                                                       reinterpret_cast<unsigned long long*>(d.sparse_out));
-  // the local record list is consumed: own + foreign records come back through lk_query_merge_sparse
-  CUDA_CHECK(cudaMemsetAsync(d.counters + 5, 0, 4, d.st));
-  CUDA_CHECK(cudaGetLastError());
-  CUDA_CHECK(cudaStreamSynchronize(d.st));
-  *entries_out = d.sparse_out;
-}
-
-static void device_merge_records(Query& q, const void* dev_entries, int64_t n) {
-  Query::Device& d = *q.dev;
-  const int na = (int)q.aggs.size();
-  const uint32_t ib = q.params.rec_idx_bits;
-  // records are appended after those already merged (several calls allowed)
-  CUDA_CHECK(cudaMemcpyAsync(d.h_counters, d.counters, sizeof d.h_counters, cudaMemcpyDeviceToHost, d.st));
-  CUDA_CHECK(cudaStreamSynchronize(d.st));
-  const uint64_t have = d.h_counters[5];
-  LK_CHECK(have + (uint64_t)n <= d.rec_cap && have + (uint64_t)n <= (1ull << ib), LK_ERR_NOMEM,
-           "record path: this rank received more records than it has rows; use path=hash for this query");
-  rec_unpack_kernel<<<(int)((n + HS_BLOCK - 1) / HS_BLOCK), HS_BLOCK, 0, d.st>>>(reinterpret_cast<const unsigned long long*>(dev_entries), (uint32_t)n, (uint32_t)have, na,
-                                                                               ib, d.rec_cell, d.rec_vals);
-  const uint32_t n32 = (uint32_t)(have + (uint64_t)n);
-  CUDA_CHECK(cudaMemcpyAsync(d.counters + 5, &n32, 4, cudaMemcpyHostToDevice, d.st));
-  CUDA_CHECK(cudaGetLastError());
-  CUDA_CHECK(cudaStreamSynchronize(d.st));  // n32 is on this frame
-}
-
 void device_partial_sparse(Query& q, int nparts, void** entries_out, int64_t* counts, int* stride_out) {
   LK_CHECK(q.dev && q.dev->executed, LK_ERR_INVALID, "lk_query_partial_sparse before lk_query_execute");
   LK_CHECK(q.path != 0, LK_ERR_INVALID, "query uses the dense path; use lk_query_partial_dense");
-  if (q.path == 2) {
-    LK_CHECK(nparts >= 1 && nparts <= SP_MAXPARTS, LK_ERR_INVALID, "nparts must be in [1, 64]");
-    LK_CHECK(!q.dev->finalized_device, LK_ERR_INVALID, "lk_query_partial_sparse after finalize");
-    CUDA_CHECK(cudaSetDevice(global_options().device));
-    device_partial_records(q, nparts, entries_out, counts, stride_out);
-    return;
-  }
+  LK_CHECK(q.path != 2, LK_ERR_INVALID, "the record path exchanges its records during the scan: attach an lk_comm (lk_query_set_comm)");
   LK_CHECK(nparts >= 1 && nparts <= SP_MAXPARTS, LK_ERR_INVALID, "nparts must be in [1, 64]");
   Query::Device& d = *q.dev;
   LK_CHECK(!d.finalized_device, LK_ERR_INVALID, "lk_query_partial_sparse after finalize");
@@ -1713,7 +1792,7 @@ void device_merge_sparse(Query& q, const void* dev_entries, int64_t n) {
   if (n == 0) return;
   Query::Device& d = *q.dev;
   CUDA_CHECK(cudaSetDevice(global_options().device));
-  if (q.path == 2) { device_merge_records(q, dev_entries, n); return; }
+  LK_CHECK(q.path != 2, LK_ERR_INVALID, "the record path exchanges its records during the scan: attach an lk_comm (lk_query_set_comm)");
   AggSlot4 ops;
   memset(&ops, 0, sizeof ops);
   for (size_t a = 0; a < q.aggs.size(); a++) ops.op[a] = q.aggs[a].op;

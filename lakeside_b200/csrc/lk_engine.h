@@ -26,6 +26,13 @@ void device_resolve(Query& q);             // waits for a pending (asynchronous)
 HostResult* device_fetch(Query& q);        // D2H
 void device_timings(Query& q);
 int64_t device_survivors(Query& q);
+// sharded evaluation: communicator over the peers' receive pools (CUDA IPC on one NVLink / NVSwitch node)
+Comm* comm_create(int rank, int world, int64_t pool_records, int max_aggs);
+void comm_handle(Comm* c, const void** blob, size_t* len);
+void comm_connect(Comm* c, const void* blobs, size_t len_each);
+void comm_destroy(Comm* c);
+int comm_world(const Comm* c);
+
 int64_t device_eval(Query& q, const std::string& aggregation, const std::string& chart_type, const std::string& metric_type, double* out, int64_t cap);  // BaseExpr.eval on the reduced rows
 
 }  // namespace lk

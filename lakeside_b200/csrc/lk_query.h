@@ -102,12 +102,14 @@ struct RowGroupPlan {
 };
 
 struct HostResult;
+struct Comm;  // sharded evaluation: peer receive pools (lk_engine.cu)
 
 struct Query {
   PushDownRequest req;
   std::vector<AggSpec> aggs;
   std::string path_opt = "auto";
   bool exact_sums = false;
+  Comm* comm = nullptr;  // attached communicator: the record path exchanges its records through it during the scan
   std::vector<SegmentInput> segs;
 
   // ---- plan ----

@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
               gid += (uint64_t)gcode * P.keys[k].stride;
             }
             // record path: the key keeps bucket and group id in separate bit fields (finalize bins on them without a division)
-            if constexpr (PATH == 2 && !EMIT) cell = (bucket << P.rec_gid_bits) | gid;
+            if constexpr (PATH >= 2 && !EMIT) cell = (bucket << P.rec_gid_bits) | gid;
             else cell = bucket * P.n_groups + gid;
             bucket32 = (uint32_t)bucket;
             seq = s.ci[P.ts_pcol].seq_base + row0 + r;
@@ -686,10 +686,10 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
             else my_status |= ST_HASH_FULL;
           }
         }
-      } else {
+      } else if constexpr (PATH == 2) {
         // record path (selective filter, high-cardinality result): nothing is aggregated here.  Every survivor appends
         // its (bucket, group) key to rec_cell[] and its n_aggs accumulator words (same encodings as the tables: all-zero = no value)
-        // to one row of rec_vals[]; finalize bins the keys and folds equal ones.  Appends are sequential, coalesced writes:
+        // to one row of rec_vals[]; finalize groups equal keys and writes the rows.  Appends are sequential, coalesced writes:
         // no 8 GB table, no random sector per survivor, nothing to clear afterwards.
         const unsigned am = __ballot_sync(0xffffffffu, active);
         if (am) {
@@ -700,12 +700,57 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
           const uint32_t o = base + __popc(am & lt_mask);
           if (active) {
             if (o < P.rec_cap) {
-              P.rec_cell[o] = (cell << P.rec_idx_bits) | o;  // the record index rides in the low bits
+              P.rec_cell[o] = cell << P.rec_idx_bits;
               unsigned long long* rec = P.rec_vals + (size_t)o * P.n_aggs;
 #pragma unroll
               for (int a = 0; a < NA; a++)
                 if (a < P.n_aggs) rec[a] = !vvalid[a] ? 0ull : P.aggs[a].op == AGG_COUNT ? 1ull : vbits[a];
             } else my_status |= ST_HASH_FULL;
+          }
+        }
+      } else {
+        // sharded record path: the record goes straight into the receive pool of the rank that owns its cell (stores over
+        // NVLink / NVSwitch, fire and forget: the transfer overlaps the scan).  The lanes of one destination elect a leader that
+        // allocates their slots: a LOCAL atomic on (current chunk << 32 | fill) of that destination; the batch that reaches
+        // the end of the chunk fetches the next one from the owner's pool (one REMOTE atomic per LK_XCHG_CHUNK records)
+        // and installs it; batches that arrive at a full chunk in between wait for that and try again.
+        const XchgParams& X = P.x;
+        uint32_t dest = 0xffffffffu;
+        if (active) dest = X.world > 1 ? __umulhi((uint32_t)(lk_hash64(cell) >> 32), X.world) : 0u;  // (independent of the key table's hash)
+        const unsigned peers = __match_any_sync(0xffffffffu, dest);
+        if (__any_sync(0xffffffffu, active)) {
+          const int leader = __ffs(peers) - 1;
+          const uint32_t n = (uint32_t)__popc(peers);
+          uint32_t cid = 0, pos = 0, ncid = 0;
+          if (active && lane == leader) {
+            unsigned long long* st = X.state + dest;
+            for (;;) {
+              const unsigned long long old = atomicAdd(st, (unsigned long long)n);
+              cid = (uint32_t)(old >> 32);
+              pos = (uint32_t)old;
+              if (pos + n < LK_XCHG_CHUNK) { ncid = cid; break; }
+              if (pos < LK_XCHG_CHUNK) {  // this batch reaches the end of the chunk: it brings the next one
+                ncid = atomicAdd(X.next[dest], 1u);
+                atomicExch(st, ((unsigned long long)ncid << 32) | (unsigned long long)(pos + n - LK_XCHG_CHUNK));
+                break;
+              }
+              while ((uint32_t)(*reinterpret_cast<volatile unsigned long long*>(st) >> 32) == cid) {}
+            }
+          }
+          cid = __shfl_sync(0xffffffffu, cid, leader);
+          pos = __shfl_sync(0xffffffffu, pos, leader);
+          ncid = __shfl_sync(0xffffffffu, ncid, leader);
+          if (active) {
+            const uint32_t p = pos + (uint32_t)__popc(peers & lt_mask);
+            const uint32_t chunk = p < LK_XCHG_CHUNK ? cid : ncid;
+            if (chunk < X.pool_chunks) {
+              const size_t o = (size_t)chunk * LK_XCHG_CHUNK + (p < LK_XCHG_CHUNK ? p : p - LK_XCHG_CHUNK);
+              X.keys[dest][o] = cell;
+              unsigned long long* rec = X.vals[dest] + o * P.n_aggs;
+#pragma unroll
+              for (int a = 0; a < NA; a++)
+                if (a < P.n_aggs) rec[a] = !vvalid[a] ? 0ull : P.aggs[a].op == AGG_COUNT ? 1ull : vbits[a];
+            } else my_status |= ST_HASH_FULL;  // the owner's pool is exhausted: reported, the query fails
           }
         }
       }

@@ -80,12 +80,11 @@ def test_dense_partials_reduce_like_nccl():
         q.close()
 
 
-@pytest.mark.parametrize("table", ["hash", "records"])
-def test_sparse_partials_partitioned_exchange(table):
+def test_hash_partials_partitioned_exchange():
     be = synth.c2_base_expr()
     sa = synth.SynthSpec(dataset="metrics", rows=80000, cards=(16, 20, 32, 16))
     sb = synth.SynthSpec(dataset="metrics", rows=80000, cards=(16, 32, 24, 16))
-    qs, rq, paths = _shards("shard_sparse", sa, sb, 2, be, synth.C2_AGGREGATES, table)
+    qs, rq, paths = _shards("shard_sparse", sa, sb, 2, be, synth.C2_AGGREGATES, "hash")
     for q in qs:
         q.execute()
     parts = [q.partial_sparse(2) for q in qs]
@@ -103,11 +102,127 @@ def test_sparse_partials_partitioned_exchange(table):
         got_rows.update(g["rows"])
         assert g["ts_order"] == sorted(g["ts_order"])
         order += g["ts_order"]
-    assert all(len(q.export_dictionaries()) > 0 for q in qs)
     want = H.oracle_multi(rq, paths, synth.C2_AGGREGATES)
     got = {"cols": want["cols"], "rows": got_rows, "ts_order": sorted(order)}
-    H.assert_same(got, want, ["sum", "sum", "min", "max"], "sharded/sparse")
-    # both partitions are populated
+    H.assert_same(got, want, ["sum", "sum", "min", "max"], "sharded/hash")
     assert all(sum(c) > 0 for _, c, _ in parts) and all(parts[0][1][p] + parts[1][1][p] > 0 for p in range(2))
     for q in qs:
         q.close()
+
+
+def _comm_ranks(world, pool_records, max_aggs=4):
+    """`world` ranks of one communicator inside this process, all on cuda:0 (the ranks' blocks are addressed directly: same
+    protocol, same kernels as the one-process-per-GPU layout, where the blocks are mapped with CUDA IPC)."""
+    from lakeside_b200 import api
+
+    comms = [api.Comm(r, world, pool_records, max_aggs) for r in range(world)]
+    handles = [c.handle() for c in comms]
+    for c in comms:
+        c.connect(handles)
+    return comms
+
+
+def _run_sharded_records(qs, comms, steps=1):
+    """All ranks execute (scan + exchange: records land in the owners' pools), THEN all finalize -- on one GPU a rank's wait
+    kernel must not be launched before its sources' scans (kernels that wait on one another cannot share a GPU)."""
+    out = None
+    for _ in range(steps):
+        for q in qs:
+            q.execute()
+        for q in qs:
+            q.sync()
+        got_rows, order, parts = {}, [], []
+        for q in qs:
+            res = q.finalize()
+            g = H.canon_from_gpu(res)
+            res.close()
+            assert not (set(g["rows"]) & set(got_rows)), "partitions overlap"
+            got_rows.update(g["rows"])
+            assert g["ts_order"] == sorted(g["ts_order"])
+            order += g["ts_order"]
+            parts.append(len(g["rows"]))
+        out = (got_rows, order, parts)
+    return out
+
+
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_records_exchange_through_comm(world):
+    """The record path's exchange inside the scan: `world` rank-shards with different tag dictionaries, cells hash-partitioned
+    over the ranks' receive pools; the union of the ranks' rows equals the oracle over all segments.  Two steps: the pools
+    alternate between epochs."""
+    from lakeside_b200 import api
+
+    api.init()
+    be = synth.c2_base_expr()
+    specs = [synth.SynthSpec(dataset="metrics", rows=80000, cards=(16, 20 + 4 * r, 32 - 3 * r, 16)) for r in range(world)]
+    paths = []
+    for r, sp in enumerate(specs):
+        paths += H.dataset(f"shard_comm_{r}", sp, 2, first_index=100 * r)[1]
+    idx = [100 * r + i for r in range(world) for i in range(2)]
+    full = synth.push_down_request(be, idx, 10000)
+    comms = _comm_ranks(world, pool_records=200000)
+    qs = []
+    for rank in range(world):
+        sub = dict(full, segmentRequests=full["segmentRequests"][2 * rank:2 * rank + 2])
+        q = api.Query(json.dumps(sub), aggregates=synth.C2_AGGREGATES, path="records")
+        for p in paths[2 * rank:2 * rank + 2]:
+            q.add_segment_file(p)
+        q.plan()
+        qs.append(q)
+    blob = api.union_dictionaries([q.export_dictionaries() for q in qs])
+    for q, c in zip(qs, comms):
+        q.import_dictionaries(blob)
+        q.set_comm(c)
+        q.prepare()
+    got_rows, order, parts = _run_sharded_records(qs, comms, steps=3)
+    want = H.oracle_multi(json.dumps(full), paths, synth.C2_AGGREGATES)
+    got = {"cols": want["cols"], "rows": got_rows, "ts_order": sorted(order)}
+    H.assert_same(got, want, ["sum", "sum", "min", "max"], f"sharded/records/world{world}")
+    assert all(n > 0 for n in parts), parts  # every rank owns part of the cells
+    if world > 1:
+        assert max(parts) < 0.75 * sum(parts), parts
+    for q in qs:
+        q.close()
+    for c in comms:
+        c.close()
+
+
+def test_records_exchange_phase_and_empty_source():
+    """an unaligned startTs gives the metric timestamps a phase; a rank whose filter keeps nothing must still
+    stamp the rows it OWNS with the phase its peers saw (phase min / max travel with the exchange), and ranks that saw
+    different phases are detected."""
+    from lakeside_b200 import api
+
+    api.init()
+    be = synth.c2_base_expr()
+    sa = synth.SynthSpec(dataset="metrics", rows=50000, cards=(16, 8, 8, 4))
+    # rank 1's segments have no svc-03 at all (one service value): its scan finds no survivor
+    sb = synth.SynthSpec(dataset="metrics", rows=50000, cards=(1, 8, 8, 4))
+    pa = H.dataset("phase_a", sa, 1)[1]
+    pb = H.dataset("phase_b", sb, 1, first_index=100)[1]
+    paths = pa + pb
+    start = synth.T0 - 3000  # timestamps sit at phase 3000 of the 10 s grid counted from startTs
+    full = synth.push_down_request(be, [0, 100], 10000, start_ts=start, end_ts=synth.T0 + synth.HOUR_MS)
+    comms = _comm_ranks(2, pool_records=100000)
+    qs = []
+    for rank in range(2):
+        sub = dict(full, segmentRequests=[full["segmentRequests"][rank]])
+        q = api.Query(json.dumps(sub), aggregates=synth.C2_AGGREGATES, path="records")
+        q.add_segment_file(paths[rank])
+        q.plan()
+        qs.append(q)
+    blob = api.union_dictionaries([q.export_dictionaries() for q in qs])
+    for q, c in zip(qs, comms):
+        q.import_dictionaries(blob)
+        q.set_comm(c)
+        q.prepare()
+    got_rows, order, parts = _run_sharded_records(qs, comms)
+    assert qs[1].survivors == 0 and parts[1] > 0  # rank 1 scanned nothing useful but owns half of the cells
+    want = H.oracle_multi(json.dumps(full), paths, synth.C2_AGGREGATES)
+    got = {"cols": want["cols"], "rows": got_rows, "ts_order": sorted(order)}
+    H.assert_same(got, want, ["sum", "sum", "min", "max"], "sharded/records/phase")
+    assert all((ts - start) % 10000 == 3000 for ts in order)
+    for q in qs:
+        q.close()
+    for c in comms:
+        c.close()

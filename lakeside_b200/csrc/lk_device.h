@@ -110,27 +110,28 @@ struct AggSlot {
 enum : uint32_t { ST_HASH_FULL = 1, ST_BAD_CODE = 2, ST_XCHG_TIMEOUT = 8, ST_XCHG_PHASE = 16 };
 
 // ---- sharded evaluation: the exchange of the record path (one process / GPU per rank, all on one NVLink / NVSwitch node) ----
-// Every rank owns two receive pools (even / odd epochs) of LK_XCHG_CHUNK-record chunks in one cudaMalloc'ed block that its
-// peers map (CUDA IPC).  During the scan a survivor record goes straight into the pool of the rank that owns its cell
-// (stores over NVLink); a sender takes the chunks it fills from the owner's pool with one remote atomic per chunk and
-// allocates inside its current chunk with a local atomic.  See lk_scan.cuh (append) and lk_engine.cu (seal / publish / wait).
+// Every rank owns two receive pools (even / odd epochs) in one cudaMalloc'ed block that its peers map (CUDA IPC).  A pool is
+// divided into one REGION per source rank.  During the scan a survivor record goes straight into the sender's region of the
+// pool of the rank that owns its cell (stores over NVLink, fire and forget); the slot comes from a LOCAL counter per
+// destination -- nothing on the data path waits for a peer.  At the end the sender publishes how many records it wrote.
+// (A first version handed out 256-record chunks of a shared pool with one remote atomic per chunk: at 4 G records/s per
+// destination a chunk lasts 60 ns and every sender sat in the remote atomic's round trip -- 121 ms per step at N = 2.)
+// See lk_scan.cuh (append) and lk_engine.cu (publish / wait).
 constexpr int LK_MAX_RANKS = 16;
-constexpr uint32_t LK_XCHG_CHUNK = 256;
 struct CommCtrl {  // control words at the start of a rank's exchange block; peers write into it
-  uint32_t pool_next[2];          // chunks handed out of receive pool 0 / 1 (bumped by the senders' remote atomics)
-  uint32_t pad[30];               // (the counters the senders bump sit in their own 128-byte line)
-  uint32_t flag[LK_MAX_RANKS];    // epoch whose records source s has delivered completely
-  uint32_t status[LK_MAX_RANKS];  // scan status flags of source s in that epoch
+  uint32_t flag[LK_MAX_RANKS];      // epoch whose records source s has delivered completely
+  uint32_t count[2][LK_MAX_RANKS];  // records source s wrote into its region of pool 0 / 1
+  uint32_t status[LK_MAX_RANKS];    // scan status flags of source s in that epoch
   uint32_t phase_min[LK_MAX_RANKS], phase_max[LK_MAX_RANKS];  // its timestamp phase range (metrics)
+  uint32_t prefix[LK_MAX_RANKS + 1];  // local: records of sources 0..s-1 (written by the wait kernel for the finalize passes)
 };
 struct XchgParams {
   uint32_t world, rank;
-  uint32_t pool_chunks;                    // chunks per pool
-  unsigned long long* keys[LK_MAX_RANKS];  // this epoch's receive pool of rank d: keys[chunk * LK_XCHG_CHUNK + slot]
+  uint32_t region_cap;                     // records per (source, pool) region
+  unsigned long long* keys[LK_MAX_RANKS];  // this rank's region in this epoch's pool of rank d
   unsigned long long* vals[LK_MAX_RANKS];  // ... and its accumulator rows (n_aggs words each)
-  uint32_t* next[LK_MAX_RANKS];            // &ctrl(d).pool_next[epoch & 1]
   CommCtrl* ctrl[LK_MAX_RANKS];            // control words of rank d
-  unsigned long long* state;               // local, per destination: current chunk << 32 | records placed in it
+  uint32_t* count;                         // local, per destination: records written so far
 };
 
 struct ScanParams {

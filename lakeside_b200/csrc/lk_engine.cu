@@ -500,19 +500,20 @@ static void launch_def_expand(const Query& q, const ScanParams& P) {
 // communicator of the sharded record path (replaces the HTTP/SSE fan-in of SegmentSequencer.scala:137-158 +
 // the re-aggregation of TimeGroupedSketchAggregator.scala:157-177 for partial results of the same query on several GPUs)
 // ------------------------------------------------------------------------------------------------------------
-// block of rank r: CommCtrl (4 KB) | keys pool 0 | keys pool 1 | vals pool 0 | vals pool 1, `cap` = pool_chunks * LK_XCHG_CHUNK records each
+// block of rank r: CommCtrl (4 KB) | keys pool 0 | keys pool 1 | vals pool 0 | vals pool 1; a pool = world regions of
+// `region_cap` records, region s written by source s only
 struct Comm {
   int rank = 0, world = 1, max_aggs = 4, device = 0;
-  size_t pool_chunks = 0;
+  size_t region_cap = 0;
   uint8_t* block = nullptr;
   size_t block_bytes = 0;
   uint8_t* peer[LK_MAX_RANKS] = {};
   bool peer_ipc[LK_MAX_RANKS] = {};
-  unsigned long long* send_state = nullptr;
+  uint32_t* send_count = nullptr;  // local: records written per destination in the current epoch
   uint32_t epoch = 0;
   bool connected = false;
   std::string blob;
-  size_t cap() const { return pool_chunks * LK_XCHG_CHUNK; }
+  size_t cap() const { return region_cap * (size_t)world; }
   CommCtrl* ctrl(int r) const { return reinterpret_cast<CommCtrl*>(peer[r]); }
   unsigned long long* keys(int r, uint32_t pool) const { return reinterpret_cast<unsigned long long*>(peer[r] + 4096) + (size_t)pool * cap(); }
   unsigned long long* vals(int r, uint32_t pool) const {
@@ -523,7 +524,7 @@ struct CommBlob {
   uint32_t magic;
   int32_t rank, world, device, max_aggs;
   int64_t pid;
-  uint64_t raw_ptr, pool_chunks;
+  uint64_t raw_ptr, region_cap;
   cudaIpcMemHandle_t handle;
 };
 constexpr uint32_t COMM_MAGIC = 0x6c6b636du;
@@ -540,13 +541,13 @@ Comm* comm_create(int rank, int world, int64_t pool_records, int max_aggs) {
   c->world = world;
   c->max_aggs = max_aggs;
   c->device = global_options().device;
-  // every sender may hold one partly filled chunk per destination: world chunks of slack
-  c->pool_chunks = ((size_t)pool_records + LK_XCHG_CHUNK - 1) / LK_XCHG_CHUNK + (size_t)world + 1;
+  static_assert(sizeof(CommCtrl) <= 4096, "control block");
+  c->region_cap = (((size_t)pool_records + world - 1) / world + 63) & ~(size_t)63;  // every source may send this many records to one owner
   c->block_bytes = 4096 + 2 * c->cap() * 8 * (size_t)(1 + max_aggs);
   cudaError_t e = cudaMalloc(&c->block, c->block_bytes);  // (not from the stream-ordered pool: IPC handles need a plain allocation)
   if (e != cudaSuccess) { cudaGetLastError(); fail(LK_ERR_NOMEM, strf("lk_comm_create: %zu bytes of receive pools: %s", c->block_bytes, cudaGetErrorString(e))); }
   CUDA_CHECK(cudaMemset(c->block, 0, 4096));
-  CUDA_CHECK(cudaMalloc(&c->send_state, LK_MAX_RANKS * sizeof(unsigned long long)));
+  CUDA_CHECK(cudaMalloc(&c->send_count, LK_MAX_RANKS * sizeof(uint32_t)));
   CommBlob b;
   memset(&b, 0, sizeof b);
   b.magic = COMM_MAGIC;
@@ -556,7 +557,7 @@ Comm* comm_create(int rank, int world, int64_t pool_records, int max_aggs) {
   b.max_aggs = max_aggs;
   b.pid = (int64_t)getpid();
   b.raw_ptr = (uint64_t)(uintptr_t)c->block;
-  b.pool_chunks = c->pool_chunks;
+  b.region_cap = c->region_cap;
   CUDA_CHECK(cudaIpcGetMemHandle(&b.handle, c->block));
   c->blob.assign(reinterpret_cast<const char*>(&b), sizeof b);
   c->peer[rank] = c->block;
@@ -576,7 +577,7 @@ void comm_connect(Comm* c, const void* blobs, size_t len_each) {
     CommBlob b;
     memcpy(&b, static_cast<const uint8_t*>(blobs) + (size_t)r * len_each, sizeof b);
     LK_CHECK(b.magic == COMM_MAGIC && b.rank == r && b.world == c->world, LK_ERR_INVALID, strf("lk_comm_connect: blob %d is not rank %d of %d", r, r, c->world));
-    LK_CHECK(b.pool_chunks == c->pool_chunks && b.max_aggs == c->max_aggs, LK_ERR_INVALID, "lk_comm_connect: ranks created their pools with different sizes");
+    LK_CHECK(b.region_cap == c->region_cap && b.max_aggs == c->max_aggs, LK_ERR_INVALID, "lk_comm_connect: ranks created their pools with different sizes");
     if (r == c->rank) continue;
     if (b.pid == (int64_t)getpid()) {
       // same process (one thread per GPU, or the single-GPU tests): the allocation is addressable as it is
@@ -603,86 +604,76 @@ void comm_destroy(Comm* c) {
   cudaDeviceSynchronize();
   for (int r = 0; r < c->world; r++)
     if (c->peer_ipc[r]) cudaIpcCloseMemHandle(c->peer[r]);
-  if (c->send_state) cudaFree(c->send_state);
+  if (c->send_count) cudaFree(c->send_count);
   if (c->block) cudaFree(c->block);
   cudaGetLastError();
   delete c;
 }
 
-// start of an epoch: recycle the pool of the NEXT epoch (nobody can be writing to it: a peer reaches that epoch only after it
-// has seen this rank's flag of the current one, published after this kernel) and take a first chunk of every owner's pool
-__global__ void comm_begin_kernel(CommCtrl* mine, uint32_t next_pool, const __grid_constant__ XchgParams X) {
-  if (threadIdx.x == 0) mine->pool_next[next_pool] = 0;
-  if (threadIdx.x < X.world) {
-    const uint32_t cid = atomicAdd(X.next[threadIdx.x], 1u);
-    X.state[threadIdx.x] = (unsigned long long)cid << 32;
-  }
-}
-
-constexpr unsigned long long RF_CONSUMED_KEY = ~0ull;  // == RF_CONSUMED of the finalize passes
-// end of the scan: block d voids the unused tail of the chunk this rank was filling in rank d's pool, then tells rank d that
-// everything this rank had for it has been written (status flags and timestamp phase of the local scan ride along)
-__global__ void __launch_bounds__(LK_XCHG_CHUNK) comm_seal_publish_kernel(const __grid_constant__ XchgParams X, uint32_t epoch, const uint32_t* __restrict__ counters) {
-  const uint32_t d = blockIdx.x;
-  const unsigned long long st = X.state[d];
-  const uint32_t cid = (uint32_t)(st >> 32), fill = min((uint32_t)st, LK_XCHG_CHUNK);
-  if (cid < X.pool_chunks && threadIdx.x >= fill) X.keys[d][(size_t)cid * LK_XCHG_CHUNK + threadIdx.x] = RF_CONSUMED_KEY;
+// end of the scan: tell every owner how many records this rank wrote into its region of the owner's pool (the status flags
+// and the timestamp phase of the local scan ride along), then raise this rank's flag there.  The stores of the scan kernel
+// are complete when this kernel starts (stream order); the fences order count / status before the flag.
+__global__ void comm_publish_kernel(const __grid_constant__ XchgParams X, uint32_t epoch, const uint32_t* __restrict__ counters) {
+  const uint32_t d = threadIdx.x;
+  if (d >= X.world) return;
+  CommCtrl* c = X.ctrl[d];
+  const uint32_t n = X.count[d];
+  c->count[epoch & 1][X.rank] = min(n, X.region_cap);
+  c->status[X.rank] = counters[0] | (n > X.region_cap ? (uint32_t)ST_HASH_FULL : 0u);
+  c->phase_min[X.rank] = counters[1];
+  c->phase_max[X.rank] = counters[2];
   __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    CommCtrl* c = X.ctrl[d];
-    c->status[X.rank] = counters[0] | (cid >= X.pool_chunks ? (uint32_t)ST_HASH_FULL : 0u);
-    c->phase_min[X.rank] = counters[1];
-    c->phase_max[X.rank] = counters[2];
-    __threadfence_system();
-    *reinterpret_cast<volatile uint32_t*>(&c->flag[X.rank]) = epoch;
-  }
+  *reinterpret_cast<volatile uint32_t*>(&c->flag[X.rank]) = epoch;
 }
 
 // before finalize: wait until every source has delivered this epoch (device-side, no host in the loop), then fold the sources'
-// status flags and timestamp phases into the local counters and publish how many record slots of the pool are in use
-__global__ void comm_wait_kernel(CommCtrl* mine, uint32_t world, uint32_t epoch, uint32_t pool, uint32_t pool_chunks, uint32_t* counters) {
+// status flags and timestamp phases into the local counters and lay the sources' record counts out as one list
+__global__ void comm_wait_kernel(CommCtrl* mine, uint32_t world, uint32_t epoch, uint32_t* counters) {
   const uint32_t lane = threadIdx.x;
-  uint32_t status = 0, pmin = 0xffffffffu, pmax = 0;
+  uint32_t status = 0, pmin = 0xffffffffu, pmax = 0, cnt = 0;
   if (lane < world) {
     unsigned long long t0, t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     while ((int32_t)(*reinterpret_cast<volatile uint32_t*>(&mine->flag[lane]) - epoch) < 0) {
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
       if (t - t0 > 20000000000ull) { status |= ST_XCHG_TIMEOUT; break; }  // 20 s: a peer died or never ran this query
-      __nanosleep(200);
+      __nanosleep(100);
     }
     __threadfence_system();
     status |= *reinterpret_cast<volatile uint32_t*>(&mine->status[lane]);
     pmin = *reinterpret_cast<volatile uint32_t*>(&mine->phase_min[lane]);
     pmax = *reinterpret_cast<volatile uint32_t*>(&mine->phase_max[lane]);
+    cnt = *reinterpret_cast<volatile uint32_t*>(&mine->count[epoch & 1][lane]);
   }
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, dd); if (lane >= (uint32_t)dd) incl += o; }
+  if (lane <= LK_MAX_RANKS) mine->prefix[lane] = incl - cnt;  // (lanes >= world hold the total)
 #pragma unroll
   for (int dd = 16; dd; dd >>= 1) {
     status |= __shfl_xor_sync(0xffffffffu, status, dd);
     pmin = min(pmin, __shfl_xor_sync(0xffffffffu, pmin, dd));
     pmax = max(pmax, __shfl_xor_sync(0xffffffffu, pmax, dd));
   }
-  if (lane == 0) {
+  if (lane == 31) {
     counters[0] = status;
     counters[1] = pmin;
     counters[2] = pmax;
-    counters[5] = min(*reinterpret_cast<volatile uint32_t*>(&mine->pool_next[pool]), pool_chunks) * LK_XCHG_CHUNK;
+    counters[5] = incl;  // records of all sources
   }
 }
 
-static void comm_fill_params(const Comm& c, XchgParams& X, uint32_t pool) {
+static void comm_fill_params(const Comm& c, XchgParams& X, uint32_t pool, size_t n_aggs) {
   memset(&X, 0, sizeof X);
   X.world = (uint32_t)c.world;
   X.rank = (uint32_t)c.rank;
-  X.pool_chunks = (uint32_t)c.pool_chunks;
+  X.region_cap = (uint32_t)c.region_cap;
   for (int r = 0; r < c.world; r++) {
-    X.keys[r] = c.keys(r, pool);
-    X.vals[r] = c.vals(r, pool);
+    X.keys[r] = c.keys(r, pool) + (size_t)c.rank * c.region_cap;
+    X.vals[r] = c.vals(r, pool) + (size_t)c.rank * c.region_cap * n_aggs;  // rows of n_aggs words: row of record p = vals + p * n_aggs
     X.ctrl[r] = c.ctrl(r);
-    X.next[r] = &c.ctrl(r)->pool_next[pool];
   }
-  X.state = c.send_state;
+  X.count = c.send_count;
 }
 
 static void launch_scan(const Query& q, const ScanParams& P, bool emit) {
@@ -733,14 +724,13 @@ void device_execute(Query& q) {
     LK_CHECK(!d.rec_cell || d.rec_borrowed, LK_ERR_INVALID, "lk_query_set_comm after an unsharded execute");
     c.epoch++;
     const uint32_t pool = c.epoch & 1;
-    comm_fill_params(c, P.x, pool);
+    comm_fill_params(c, P.x, pool, q.aggs.size());
     P.path = 3;
     d.rec_cell = c.keys(c.rank, pool);
     d.rec_vals = c.vals(c.rank, pool);
     d.rec_cap = c.cap();
     d.rec_borrowed = true;
-    comm_begin_kernel<<<1, 32, 0, d.st>>>(c.ctrl(c.rank), pool ^ 1, P.x);
-    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemsetAsync(c.send_count, 0, LK_MAX_RANKS * sizeof(uint32_t), d.st));
   }
   if (q.n_cells > 0 && P.ntiles > 0) {
     if (q.path == 0) {
@@ -776,7 +766,7 @@ void device_execute(Query& q) {
     CUDA_CHECK(cudaEventRecord(d.ev[3], d.st));
   }
   if (sharded) {  // (also for a shard without tiles: its peers wait for its flag)
-    comm_seal_publish_kernel<<<q.comm->world, LK_XCHG_CHUNK, 0, d.st>>>(P.x, q.comm->epoch, d.counters);
+    comm_publish_kernel<<<1, 32, 0, d.st>>>(P.x, q.comm->epoch, d.counters);
     CUDA_CHECK(cudaGetLastError());
   }
 }
@@ -1070,11 +1060,21 @@ struct RecGeom {
   uint32_t idx_bits, gid_bits, nbuckets;
   uint32_t rec_cap;  // capacity of the record arrays
   uint32_t fin_cap;  // records the key table (2 slots each) and the result columns hold
+  uint32_t world, region_cap;  // sharded: the list is the concatenation of one region per source rank (world <= 1: one plain list)
+  const uint32_t* prefix;      // ... prefix[s] = records of sources 0..s-1 (CommCtrl::prefix)
   uint32_t fp_shift; // key table entry = fingerprint << fp_shift | (record index + 1); 32 = no room for a fingerprint
   uint32_t cstride;  // words between the per-bucket counters that are bumped atomically: with few buckets every counter
                      // gets its own 128-byte line (atomics on one line serialise at ~7 ns each on B200: 360 counters packed
                      // into 12 lines kept ONE L2 slice 97 % busy and cost 120 us per pass over 6.2 M records)
 };
+
+// position of record i of the list in the record arrays
+__device__ __forceinline__ uint32_t rec_phys(uint32_t i, const RecGeom& G) {
+  if (G.world <= 1) return i;
+  uint32_t s = 0;
+  while (s + 1 < G.world && i >= __ldg(G.prefix + s + 1)) s++;
+  return s * G.region_cap + (i - __ldg(G.prefix + s));
+}
 
 // Per-bucket counters are bumped once per warp and distinct bucket: the lanes of a warp that hold the same bucket elect a
 // leader (__match_any_sync) who adds their count.  (A 32-record stretch of the list holds ~2.5 buckets: the scan appends up to
@@ -1101,8 +1101,8 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_bhist_kernel(const unsigned long
   const uint32_t sh = G.idx_bits + G.gid_bits;
   const uint32_t n32 = (nrec + 31u) & ~31u;  // whole warps
   for (uint32_t i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n32; i += gridDim.x * RF_BLOCK) {
-    const unsigned long long key = i < nrec ? keys[i] : RF_CONSUMED;
-    const bool valid = key != RF_CONSUMED;  // (a sharded pool has void slots at the end of partly filled chunks)
+    const unsigned long long key = i < nrec ? keys[rec_phys(i, G)] : RF_CONSUMED;
+    const bool valid = key != RF_CONSUMED;
     warp_bucket_bump<false>(bkt_recs, G.cstride, valid ? (uint32_t)(key >> sh) : 0u, valid, nullptr);
   }
 }
@@ -1180,7 +1180,8 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long*
   const uint32_t fp_shift = G.fp_shift, idx_field = fp_shift < 32 ? (1u << fp_shift) - 1 : 0xffffffffu;  // fp_shift == 32: no fingerprint bits
   uint32_t my_status = 0;
   for (uint32_t i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n32; i += gridDim.x * RF_BLOCK) {
-    const unsigned long long key = i < nrec ? keys[i] : RF_CONSUMED;
+    const uint32_t pi = i < nrec ? rec_phys(i, G) : 0u;
+    const unsigned long long key = i < nrec ? keys[pi] : RF_CONSUMED;
     const bool valid = key != RF_CONSUMED;
     bool owner = false;
     uint32_t bucket = 0;
@@ -1191,7 +1192,7 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long*
       const uint32_t width = 2u * (s1 - s0);  // >= 2: this record is one of the bucket's
       uint32_t* const region = table + 2ull * s0;
       const uint32_t h = lk_rf_mix(cellx & gid_mask);
-      const uint32_t entry = (fp_shift < 32 ? (h * 0x2545F491u) >> fp_shift << fp_shift : 0u) | (i + 1);
+      const uint32_t entry = (fp_shift < 32 ? (h * 0x2545F491u) >> fp_shift << fp_shift : 0u) | (pi + 1);
       uint32_t slot = __umulhi(h, width), probe = 0;
       for (; probe < width; probe++) {
         const uint32_t prev = atomicCAS(region + slot, 0u, entry);
@@ -1200,7 +1201,7 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long*
           const uint32_t oi = (prev & idx_field) - 1;
           if ((keys[oi] >> G.idx_bits) == cellx) {
             // a later record of the cell: fold into the owner's row, leave the list
-            const unsigned long long* mine = vals + (size_t)i * E.n_aggs;
+            const unsigned long long* mine = vals + (size_t)pi * E.n_aggs;
             unsigned long long* own = vals + (size_t)oi * E.n_aggs;
             for (int a = 0; a < E.n_aggs; a++) {
               const unsigned long long x = mine[a];
@@ -1208,7 +1209,7 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long*
               else if (E.ops[a] == AGG_COUNT) atomicAdd(own + a, x);
               else if (x) atomicMax(own + a, x);  // min (complemented key) and max (key)
             }
-            keys[i] = RF_CONSUMED;
+            keys[pi] = RF_CONSUMED;
             break;
           }
         }
@@ -1239,14 +1240,15 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_emit_kernel(const unsigned long 
   const unsigned long long gid_mask = (1ull << G.gid_bits) - 1;
   for (uint32_t i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n32; i += gridDim.x * RF_BLOCK) {
     unsigned long long key = RF_CONSUMED;
-    if (i < nrec) key = keys[i];
+    const uint32_t pi = i < nrec ? rec_phys(i, G) : 0u;
+    if (i < nrec) key = keys[pi];
     const bool owner = key != RF_CONSUMED;
     const unsigned long long cellx = key >> G.idx_bits;
     const uint32_t bucket = owner ? (uint32_t)(cellx >> G.gid_bits) : 0u;
     // the accumulator row is requested before the cursor's round trip
     unsigned long long w[LK_MAX_AGGS];
     if (owner) {
-      const unsigned long long* rec = vals + (size_t)i * E.n_aggs;
+      const unsigned long long* rec = vals + (size_t)pi * E.n_aggs;
       if (E.n_aggs == 4) {  // one 32-byte sector
         const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(rec), b2 = *(reinterpret_cast<const ulonglong2*>(rec) + 1);
         w[0] = a.x; w[1] = a.y; w[2] = b2.x; w[3] = b2.y;
@@ -1368,8 +1370,12 @@ static void rec_finalize_launch(Query& q) {
   G.nbuckets = q.nbuckets;
   G.rec_cap = (uint32_t)std::min<size_t>(d.rec_cap, 0xffffffffu);
   G.fin_cap = (uint32_t)std::min<size_t>(d.fin_cap, 0xffffffffu);
+  G.world = q.comm ? (uint32_t)q.comm->world : 1u;
+  G.region_cap = q.comm ? (uint32_t)q.comm->region_cap : 0u;
+  G.prefix = q.comm ? q.comm->ctrl(q.comm->rank)->prefix : nullptr;
   G.fp_shift = 1;
-  while (G.fp_shift < 32 && ((uint64_t)d.fin_cap + 1) >> G.fp_shift) G.fp_shift++;  // bits of (largest record index + 1)
+  const uint64_t max_index = G.world > 1 ? (uint64_t)d.rec_cap : (uint64_t)d.fin_cap;
+  while (G.fp_shift < 32 && (max_index + 1) >> G.fp_shift) G.fp_shift++;  // bits of (largest record position + 1)
   const size_t nb = (size_t)q.nbuckets + 1, cs = rec_counter_stride(q);
   G.cstride = (uint32_t)cs;
   uint32_t* bkt_recs = d.rf_tables;
@@ -1438,7 +1444,7 @@ void device_finalize_device(Query& q) {
   if (q.path == 2) {
     if (q.comm) {
       const Comm& c = *q.comm;
-      comm_wait_kernel<<<1, 32, 0, d.st>>>(c.ctrl(c.rank), (uint32_t)c.world, c.epoch, c.epoch & 1, (uint32_t)c.pool_chunks, d.counters);
+      comm_wait_kernel<<<1, 32, 0, d.st>>>(c.ctrl(c.rank), (uint32_t)c.world, c.epoch, d.counters);
       CUDA_CHECK(cudaGetLastError());
     }
     if (d.fin_cap == 0) {

@@ -709,48 +709,35 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
           }
         }
       } else {
-        // sharded record path: the record goes straight into the receive pool of the rank that owns its cell (stores over
-        // NVLink / NVSwitch, fire and forget: the transfer overlaps the scan).  The lanes of one destination elect a leader that
-        // allocates their slots: a LOCAL atomic on (current chunk << 32 | fill) of that destination; the batch that reaches
-        // the end of the chunk fetches the next one from the owner's pool (one REMOTE atomic per LK_XCHG_CHUNK records)
-        // and installs it; batches that arrive at a full chunk in between wait for that and try again.
+        // sharded record path: the record goes straight into this rank's region of the receive pool of the rank that owns its
+        // cell (stores over NVLink / NVSwitch, fire and forget: the transfer overlaps the scan).  The lanes of one
+        // destination elect a leader that takes their slots from a LOCAL counter; the accumulator row travels as one 32-byte
+        // store (a peer write is a link transaction of its own: four 8-byte stores per record quadrupled them).
         const XchgParams& X = P.x;
         uint32_t dest = 0xffffffffu;
         if (active) dest = X.world > 1 ? __umulhi((uint32_t)(lk_hash64(cell) >> 32), X.world) : 0u;  // (independent of the key table's hash)
         const unsigned peers = __match_any_sync(0xffffffffu, dest);
         if (__any_sync(0xffffffffu, active)) {
           const int leader = __ffs(peers) - 1;
-          const uint32_t n = (uint32_t)__popc(peers);
-          uint32_t cid = 0, pos = 0, ncid = 0;
-          if (active && lane == leader) {
-            unsigned long long* st = X.state + dest;
-            for (;;) {
-              const unsigned long long old = atomicAdd(st, (unsigned long long)n);
-              cid = (uint32_t)(old >> 32);
-              pos = (uint32_t)old;
-              if (pos + n < LK_XCHG_CHUNK) { ncid = cid; break; }
-              if (pos < LK_XCHG_CHUNK) {  // this batch reaches the end of the chunk: it brings the next one
-                ncid = atomicAdd(X.next[dest], 1u);
-                atomicExch(st, ((unsigned long long)ncid << 32) | (unsigned long long)(pos + n - LK_XCHG_CHUNK));
-                break;
-              }
-              while ((uint32_t)(*reinterpret_cast<volatile unsigned long long*>(st) >> 32) == cid) {}
-            }
-          }
-          cid = __shfl_sync(0xffffffffu, cid, leader);
+          uint32_t pos = 0;
+          if (active && lane == leader) pos = atomicAdd(X.count + dest, (uint32_t)__popc(peers));
           pos = __shfl_sync(0xffffffffu, pos, leader);
-          ncid = __shfl_sync(0xffffffffu, ncid, leader);
           if (active) {
-            const uint32_t p = pos + (uint32_t)__popc(peers & lt_mask);
-            const uint32_t chunk = p < LK_XCHG_CHUNK ? cid : ncid;
-            if (chunk < X.pool_chunks) {
-              const size_t o = (size_t)chunk * LK_XCHG_CHUNK + (p < LK_XCHG_CHUNK ? p : p - LK_XCHG_CHUNK);
+            const uint32_t o = pos + (uint32_t)__popc(peers & lt_mask);
+            if (o < X.region_cap) {
               X.keys[dest][o] = cell;
-              unsigned long long* rec = X.vals[dest] + o * P.n_aggs;
+              unsigned long long w[NA];
 #pragma unroll
-              for (int a = 0; a < NA; a++)
-                if (a < P.n_aggs) rec[a] = !vvalid[a] ? 0ull : P.aggs[a].op == AGG_COUNT ? 1ull : vbits[a];
-            } else my_status |= ST_HASH_FULL;  // the owner's pool is exhausted: reported, the query fails
+              for (int a = 0; a < NA; a++) w[a] = (a >= P.n_aggs || !vvalid[a]) ? 0ull : P.aggs[a].op == AGG_COUNT ? 1ull : vbits[a];
+              unsigned long long* rec = X.vals[dest] + (size_t)o * P.n_aggs;
+              if (NA == 4 && P.n_aggs == 4) {
+                asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec), "l"(w[0]), "l"(w[1]), "l"(w[2]), "l"(w[3]) : "memory");
+              } else {
+#pragma unroll
+                for (int a = 0; a < NA; a++)
+                  if (a < P.n_aggs) rec[a] = w[a];
+              }
+            } else my_status |= ST_HASH_FULL;  // this rank's region of the owner's pool is full: reported, the query fails
           }
         }
       }

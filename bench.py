@@ -1,19 +1,25 @@
 #!/usr/bin/env python
 """bench.py -- scan-filter-aggregate throughput of the per-segment DataExpr path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c3|c3dense|c4|c5]
 
-One "step" = one pass of the hot path over one batch of synthetic sealed segments.  Workload at N = 1 is
-BASELINE.json configs[1] (C2): 100 metric segments x 1 Mi rows, filter `resource.service.name eq svc-03`, group by
-3 tags (+ name, as the reference's SQL always does), count/sum/min/max = sum(rollup_sum), sum(rollup_count),
-min(rollup_min), max(rollup_max) fused in one pass, 10 s step.  At N > 1 every rank holds its own 100 segments (weak
-scaling, different seeds), evaluates them with no data-path collective and the partial aggregates meet in one NCCL
-exchange (dense tables: reduce; sparse tables: gather of the occupied cells) -- SURVEY.md §8e.
+One "step" = one pass of the hot path over one batch of synthetic sealed segments.  The default workload (the one the
+driver runs) is BASELINE.json configs[1] (C2): 100 metric segments x 1 Mi rows per GPU, filter `resource.service.name eq
+svc-03`, group by 3 tags (+ name, as the reference's SQL always does), count/sum/min/max = sum(rollup_sum),
+sum(rollup_count), min(rollup_min), max(rollup_max) fused in one pass, 10 s step.  At N > 1 every rank holds its own 100
+segments (weak scaling, different seeds) and evaluates them with no data-path collective: the survivor records reach the
+rank that owns their (group x bucket) cell DURING the scan, through the library's communicator (lk_comm: peer receive pools
+over NVLink) -- SURVEY.md §8e.  Other workloads (builder-run, lines kept under profiles/): c3 = configs[2] (64 x 15 625 000
+rows, strong-sharded over N), c3dense = the same segments with a name filter and one group-by tag (dense (group x bucket)
+planes, NCCL reduce), c4 = configs[3] (regex on the pod dictionary, 10^6 tag combinations), c5 = configs[4] (K-way merge).
 
-value : rows/s, inputs (encoded Parquet column chunks + seek index) already resident in HBM; the timed region is
-        scan kernel + on-device compaction of the aggregate table into result rows.
-e2e   : the same metric through the C ABI with HOST buffers: footer/page/run indexing on the host, H2D of the touched
-        column chunks from pinned memory, kernels, D2H of the result rows -- every step.
+value  : rows/s, inputs (encoded Parquet column chunks + seek index) already resident in HBM; the timed region is
+         definition-level expansion + scan kernel (+ exchange) + on-device aggregation of the result rows.
+e2e    : the same metric through the C ABI with HOST buffers: footer/page/run indexing on the host, H2D of the touched
+         column chunks from pinned memory, kernels, D2H of the result rows -- every step.
+parity : after the timed loop the result rows of all ranks are checked against an independent engine (Arrow C++ compute
+         over every rank's files): survivor rows, sum / min / max of the aggregates and a group-weighted checksum that moves
+         when a record is lost, duplicated or attributed to the wrong (timestamp, tags) group.
 """
 from __future__ import annotations
 
@@ -25,22 +31,85 @@ import subprocess
 import sys
 import threading
 import time
+import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path[:0] = [ROOT]
 
-METRIC = "rows/sec scan-filter-agg (C2: tag-equality filter + group-by 3 tags, count/sum/min/max, 10s step)"
 UNIT = "rows/s"
-N_SEGMENTS = int(os.environ.get("LK_BENCH_SEGMENTS", "100"))
-ROWS = int(os.environ.get("LK_BENCH_ROWS", str(1 << 20)))
 DATA_ROOT = os.environ.get("LK_BENCH_DATA", "/tmp/lakeside_b200_bench")
 STEP_MS = 10000
 
 
-def workload_name(n_gpus: int) -> str:
-    return (f"C2: {N_SEGMENTS} synthetic metric segments x {ROWS} rows per GPU ({N_SEGMENTS * ROWS / 1e6:.1f}M rows/GPU), "
-            "filter resource.service.name eq svc-03, group by name + 3 tags, sum(rollup_sum)/sum(rollup_count)/min(rollup_min)/max(rollup_max), "
-            "step 10 s")
+# ----------------------------------------------------------------------------------------------------------------------
+# workloads
+# ----------------------------------------------------------------------------------------------------------------------
+class Workload:
+    """Segments of this rank + the PushDownRequest over them."""
+
+    def __init__(self, name: str, rank: int, world: int):
+        from lakeside_b200 import synth
+
+        self.name = name
+        self.scaling = "weak"
+        self.aggs = synth.C2_AGGREGATES
+        self.group_cols = [synth.NAME] + list(synth.GROUP_TAGS)
+        self.filter = ("eq", synth.TAG_SERVICE, "svc-03")
+        self.path_opt = os.environ.get("LK_BENCH_PATH", "auto")
+        if name == "c2":
+            self.n_seg = int(os.environ.get("LK_BENCH_SEGMENTS", "100"))
+            self.rows = int(os.environ.get("LK_BENCH_ROWS", str(1 << 20)))
+            self.spec = synth.SynthSpec(dataset="metrics", rows=self.rows)
+            self.first = rank * self.n_seg
+            self.base_expr = synth.c2_base_expr()
+            self.metric = "rows/sec scan-filter-agg (C2: tag-equality filter + group-by 3 tags, count/sum/min/max, 10s step)"
+            self.desc = (f"C2: {self.n_seg} synthetic metric segments x {self.rows} rows per GPU ({self.n_seg * self.rows / 1e6:.1f}M rows/GPU), "
+                         "filter resource.service.name eq svc-03, group by name + 3 tags, sum(rollup_sum)/sum(rollup_count)/min(rollup_min)/max(rollup_max), step 10 s")
+        elif name in ("c3", "c3dense"):
+            total = int(os.environ.get("LK_BENCH_SEGMENTS", "64"))
+            self.rows = int(os.environ.get("LK_BENCH_ROWS", "15625000"))
+            assert total % world == 0, "C3 shards its segments evenly"
+            self.n_seg = total // world
+            self.spec = synth.SynthSpec(dataset="metrics", rows=self.rows)
+            self.first = rank * self.n_seg
+            self.scaling = "strong"
+            self.base_expr = synth.c2_base_expr()
+            if name == "c3":
+                self.metric = "rows/sec scan-filter-agg (C3: 1B rows / 64 sealed segments sharded over N GPUs, C2 query)"
+                self.desc = (f"C3: {total} segments x {self.rows} rows = {total * self.rows / 1e9:.2f} B rows, strong-sharded over {world} GPU(s) "
+                             f"({self.n_seg} segments each), C2 query (filter service eq svc-03, group by name + 3 tags, 4 aggregates, step 10 s)")
+            else:
+                self.base_expr["filter"] = {"k": synth.NAME, "v": ["metric_007"], "op": "eq", "dataType": "string", "extracted": False, "computed": False}
+                self.base_expr["chart"]["groupBys"] = [synth.TAG_ZONE]
+                self.group_cols = [synth.NAME, synth.TAG_ZONE]
+                self.filter = ("eq", synth.NAME, "metric_007")
+                self.metric = "rows/sec scan-filter-agg (C3 dense: name filter, group by 1 tag, dense (group x bucket) planes + NCCL reduce)"
+                self.desc = (f"C3-dense: {total} segments x {self.rows} rows sharded over {world} GPU(s), filter _cardinalhq.name eq metric_007, "
+                             "group by name + availability zone, 4 aggregates, step 10 s; partial (group x bucket) planes reduced with NCCL")
+        elif name == "c4":
+            self.n_seg = int(os.environ.get("LK_BENCH_SEGMENTS", "100"))
+            self.rows = int(os.environ.get("LK_BENCH_ROWS", str(1 << 20)))
+            self.spec = synth.c4_spec(self.rows)
+            self.first = rank * self.n_seg
+            self.base_expr = synth.c4_base_expr()
+            self.filter = ("regex", synth.TAG_POD, "^pod-[0-4].*")
+            self.metric = "rows/sec scan-filter-agg (C4: regex-on-dictionary predicate, 10^6 tag combinations)"
+            self.desc = (f"C4: {self.n_seg} segments x {self.rows} rows per GPU, 100 x 100 x 100 tag combinations, filter pod regex ^pod-[0-4].* "
+                         "(evaluated once per dictionary entry), group by name + 3 tags, 4 aggregates, step 10 s")
+        else:
+            raise SystemExit(f"unknown workload {name}")
+        self.root = os.path.join(DATA_ROOT, f"{'c4' if name == 'c4' else 'm'}_{self.rows}")
+
+    def generate(self, limit=None):
+        from lakeside_b200 import synth
+
+        n = self.n_seg if limit is None else min(limit, self.n_seg)
+        workers = int(os.environ.get("LK_BENCH_GEN_WORKERS", "0")) or None
+        if self.rows > (1 << 22):  # 15.6 M-row segments: ~3 GB of generator state each
+            workers = min(workers or 8, 8)
+        self.paths = synth.write_dataset(self.root, self.spec, n, first_index=self.first, workers=workers)
+        self.rq = json.dumps(synth.push_down_request(self.base_expr, list(range(self.first, self.first + n)), STEP_MS))
+        return self.paths
 
 
 def measured_peaks():
@@ -111,85 +180,309 @@ class ClockSampler:
                 "samples": len(sm), "window": window}
 
 
-def gen_dataset(rank: int):
+# ----------------------------------------------------------------------------------------------------------------------
+# independent check of the result (Arrow C++ compute; shares no code with the library or the oracle)
+# ----------------------------------------------------------------------------------------------------------------------
+_MUL = 1000003
+
+
+def _str_hash(s) -> int:
+    return 0x10000 if s is None else (zlib.crc32(s.encode() if isinstance(s, str) else bytes(s)) & 0xffff)
+
+
+def _group_weights(ts, hash_cols):
+    """One weight in [0, 1) per row from its (timestamp, tag values): the same arithmetic on both sides of the check."""
+    import numpy as np
+
+    k = ts.astype(np.uint64) // np.uint64(1000)
+    with np.errstate(over="ignore"):
+        for h in hash_cols:
+            k = k * np.uint64(_MUL) + h.astype(np.uint64)
+    return (k % np.uint64(65521)).astype(np.float64) / 65521.0
+
+
+def _arrow_filter(wl: Workload, t):
+    import pyarrow as pa
+    import pyarrow.compute as pc
+
+    op, col, val = wl.filter
+    c = t[col]
+    if pa.types.is_dictionary(c.type):
+        c = pc.cast(c, pa.string())
+    m = pc.equal(c, val) if op == "eq" else pc.match_substring_regex(c, val, ignore_case=True)
+    return pc.fill_null(m, False)
+
+
+def arrow_summary(wl: Workload, paths) -> dict:
+    """Survivor rows, aggregate totals and the group-weighted checksums of `paths`, computed by Arrow C++."""
+    import numpy as np
+    import pyarrow.compute as pc
+    import pyarrow.parquet as pq
+    from concurrent.futures import ThreadPoolExecutor
+
     from lakeside_b200 import synth
 
-    spec = synth.SynthSpec(dataset="metrics", rows=ROWS)
-    first = rank * N_SEGMENTS
-    root = os.path.join(DATA_ROOT, f"c2_{ROWS}")
-    paths = synth.write_dataset(root, spec, N_SEGMENTS, first_index=first)
-    rq = json.dumps(synth.push_down_request(synth.c2_base_expr(), list(range(first, first + N_SEGMENTS)), STEP_MS))
-    return paths, rq, synth.C2_AGGREGATES
+    vcols = ["rollup_sum", "rollup_count", "rollup_min", "rollup_max"]
+    cols = [synth.TIMESTAMP, wl.filter[1]] + [c for c in wl.group_cols if c != wl.filter[1]] + vcols
+
+    def one(p):
+        t = pq.read_table(p, columns=cols)
+        f = t.filter(_arrow_filter(wl, t))
+        n = f.num_rows
+        if n == 0:
+            return dict(n=0, s=0.0, c=0.0, mn=np.inf, mx=-np.inf, wc=0.0, ws=0.0)
+        ts = f[synth.TIMESTAMP].to_numpy()
+        hs = []
+        for c in wl.group_cols:
+            d = f[c].combine_chunks()
+            d = d if hasattr(d, "dictionary") else d.dictionary_encode()
+            dh = np.array([_str_hash(x) for x in d.dictionary.to_pylist()] + [_str_hash(None)], dtype=np.uint64)
+            idx = pc.fill_null(d.indices, len(dh) - 1).to_numpy(zero_copy_only=False)
+            hs.append(dh[idx])
+        w = _group_weights(ts, hs)
+        s, c = f["rollup_sum"].to_numpy(), f["rollup_count"].to_numpy()
+        return dict(n=n, s=float(s.sum()), c=float(c.sum()), mn=float(f["rollup_min"].to_numpy().min()), mx=float(f["rollup_max"].to_numpy().max()),
+                    wc=float(np.dot(w, c)), ws=float(np.dot(w, s)))
+
+    with ThreadPoolExecutor(max_workers=min(8 if wl.rows > (1 << 22) else 16, os.cpu_count() or 1)) as ex:
+        parts = list(ex.map(one, paths))
+    return dict(n=sum(p["n"] for p in parts), s=sum(p["s"] for p in parts), c=sum(p["c"] for p in parts), mn=min(p["mn"] for p in parts),
+                mx=max(p["mx"] for p in parts), wc=sum(p["wc"] for p in parts), ws=sum(p["ws"] for p in parts))
+
+
+def result_summary(res, survivors: int) -> dict:
+    import numpy as np
+
+    n = res.num_rows
+    if n == 0:
+        return dict(n=survivors, rows=0, s=0.0, c=0.0, mn=np.inf, mx=-np.inf, wc=0.0, ws=0.0, sorted=True)
+    hs = []
+    for t in range(res.num_tags):
+        dh = np.array([_str_hash(x) for x in res.tag_dicts[t]] + [_str_hash(None)], dtype=np.uint64)
+        codes = res.tag_codes[t]
+        hs.append(dh[np.where(codes < 0, len(dh) - 1, codes)])
+    w = _group_weights(res.ts, hs)
+    v = res.values
+    mnv = v[2][res.value_nulls[2] == 0]
+    mxv = v[3][res.value_nulls[3] == 0]
+    return dict(n=survivors, rows=n, s=float(v[0].sum()), c=float(v[1].sum()), mn=float(mnv.min()) if len(mnv) else np.inf,
+                mx=float(mxv.max()) if len(mxv) else -np.inf, wc=float(np.dot(w, v[1])), ws=float(np.dot(w, v[0])),
+                sorted=bool(np.all(np.diff(res.ts) >= 0)))
+
+
+def compare_summaries(got: dict, want: dict) -> dict:
+    def close(a, b, tol):
+        return abs(a - b) <= tol * max(abs(a), abs(b), 1e-300)
+
+    checks = {
+        "survivor_rows": got["n"] == want["n"],
+        "sum_rollup_count": got["c"] == want["c"],  # integer-valued doubles: exact in any order
+        "min_rollup_min": got["mn"] == want["mn"],
+        "max_rollup_max": got["mx"] == want["mx"],
+        "sum_rollup_sum_rel1e-9": close(got["s"], want["s"], 1e-9),
+        "group_weighted_count_checksum_rel1e-9": close(got["wc"], want["wc"], 1e-9),
+        "group_weighted_sum_checksum_rel1e-9": close(got["ws"], want["ws"], 1e-9),
+        "rows_sorted_by_timestamp": bool(got.get("sorted", True)),
+    }
+    return {"ok": all(checks.values()), "checks": checks, "survivor_rows": [got["n"], want["n"]], "result_rows": got["rows"],
+            "sum_rollup_sum": [got["s"], want["s"]], "group_weighted_count_checksum": [got["wc"], want["wc"]],
+            "against": "Arrow C++ compute (pyarrow) over the files of all ranks, all-reduced"}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's evaluator is Scala + DuckDB 1.3.2 over JDBC (Commons.scala:240); BASELINE.md §3
+# gives the probe order.  No JVM exists in this image; DuckDB is probed; else the multithreaded Arrow C++ (Acero) restatement.
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_engine():
+    try:
+        import duckdb  # noqa: F401
+
+        return "duckdb"
+    except Exception:
+        return "acero"
+
+
+def cpu_eval(wl: Workload, paths, engine: str):
+    """One evaluation of the workload's query over `paths` on the host cores; returns the number of result rows."""
+    from lakeside_b200 import synth
+
+    if engine == "duckdb":
+        import duckdb
+
+        if os.path.join(ROOT, "oracle") not in sys.path:
+            sys.path[:0] = [os.path.join(ROOT, "oracle")]
+        import lakeside_oracle as lo
+
+        con = duckdb.connect()
+        con.execute(f"PRAGMA threads={os.cpu_count()}")
+        table = "read_parquet([" + ",".join("'" + p + "'" for p in paths) + "], union_by_name=True)"
+        n = 0
+        # the reference issues one request per aggregation (QueryEngineV2.scala:280-296): four statements for this workload
+        for agg, rollup in wl.aggs:
+            be = dict(wl.base_expr, chart=dict(wl.base_expr["chart"], aggregation=agg, rollup=rollup))
+            rq = json.loads(wl.rq)
+            rq["baseExpr"] = be
+            req = lo.push_down_request_from_json(json.dumps(rq))
+            sql = lo.generate_sql(req.baseExpr, synth.T0, synth.T0 + synth.HOUR_MS, step_in_millis=STEP_MS, global_agg=agg).replace("{tableName}", table)
+            n = len(con.execute(sql).fetchall())
+        return n
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    import pyarrow.dataset as ds
+
+    op, col, val = wl.filter
+    f = pc.field(col) == val if op == "eq" else pc.match_substring_regex(pc.field(col).cast(pa.string()), val, ignore_case=True)
+    f = f & (pc.field(synth.TIMESTAMP) >= synth.T0) & (pc.field(synth.TIMESTAMP) < synth.T0 + synth.HOUR_MS)
+    vcols = ["rollup_sum", "rollup_count", "rollup_min", "rollup_max"]
+    keys = [synth.TIMESTAMP] + wl.group_cols
+    t = ds.dataset(paths, format="parquet").to_table(columns=keys + vcols, filter=f, use_threads=True)
+    out = pa.TableGroupBy(t, keys, use_threads=True).aggregate([("rollup_sum", "sum"), ("rollup_count", "sum"), ("rollup_min", "min"), ("rollup_max", "max")])
+    out = out.sort_by(synth.TIMESTAMP)
+    return out.num_rows
+
+
+def cpu_baseline(wl: Workload, steps: int, warmup: int, budget_s: float = 20.0):
+    import pyarrow as pa
+
+    engine = cpu_engine()
+    sample = int(os.environ.get("LK_BENCH_REF_SEGMENTS", "0")) or max(1, (16 << 20) // max(wl.rows, 1))
+    sample = max(1, min(len(wl.paths), sample))
+    paths = wl.paths[:sample]
+    pa.set_cpu_count(os.cpu_count() or 1)
+    one, rows_out = 1.0, 0
+    for _ in range(max(1, warmup)):
+        t0 = time.perf_counter()
+        rows_out = cpu_eval(wl, paths, engine)
+        one = time.perf_counter() - t0
+    steps = max(1, min(steps, int(budget_s / max(one, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_eval(wl, paths, engine)
+    dt = (time.perf_counter() - t0) / steps
+    what = ("DuckDB executing the reference's generated SQL (PRAGMA threads = all cores)" if engine == "duckdb" else
+            "Arrow C++ / Acero restatement (dataset scan with pushed-down filter + hash group-by, all cores; no JVM / DuckDB in this image)")
+    return {"value": sample * wl.rows / dt, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference" if engine == "duckdb" else "port",
+            "engine": engine, "sample": f"{sample} of {wl.n_seg} segments x {wl.rows} rows per step, {steps} step(s), page cache warm; {what}",
+            "ms_per_step": dt * 1e3, "result_rows": rows_out, "steps": steps}
 
 
 def run_reference(args):
-    """--impl reference: the reference's evaluator is Scala + DuckDB 1.3.2 over JDBC; neither a JVM nor DuckDB exists in this
-    image, so this arm times the oracle port of the same path (Arrow C++ Parquet decode + NumPy
-    filter / group-by, all host threads Arrow wants) on a bounded sample of the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
-    import lakeside_oracle as lo
-    from lakeside_b200 import synth
-
-    sample = max(1, min(N_SEGMENTS, int(os.environ.get("LK_BENCH_REF_SEGMENTS", "4"))))
-    spec = synth.SynthSpec(dataset="metrics", rows=ROWS)
-    paths = synth.write_dataset(os.path.join(DATA_ROOT, f"c2_{ROWS}"), spec, sample)
-    rq = lo.push_down_request_from_json(json.dumps(synth.push_down_request(synth.c2_base_expr(), list(range(sample)), STEP_MS)))
-    aggs = [(a, "rollup_" + r) for a, r in synth.C2_AGGREGATES]
-    for _ in range(max(1, args.warmup // 3)):
-        lo.evaluate_glob(rq, paths, aggs=aggs)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        lo.evaluate_glob(rq, paths, aggs=aggs)
-    dt = (time.perf_counter() - t0) / args.steps
-    rows = sample * ROWS
-    import pyarrow as pa
-
-    cores = pa.cpu_count()
-    v = rows / dt
+    if args.workload == "c5":
+        return run_c5(args, reference=True)
+    wl = Workload(args.workload, 0, 1)
+    sample = int(os.environ.get("LK_BENCH_REF_SEGMENTS", "0")) or max(1, min(wl.n_seg, (16 << 20) // max(wl.rows, 1)))
+    wl.generate(limit=sample)
+    cb = cpu_baseline(wl, args.steps, max(1, args.warmup // 3))
     line = {
-        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(1), "sample": f"{sample} of {N_SEGMENTS} segments per step"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{sample} segments x {ROWS} rows, oracle port (Arrow C++ decode + NumPy), page cache warm"},
-        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": wl.metric, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": cb["steps"], "warmup": args.warmup,
+        "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": wl.desc, "sample": cb["sample"]},
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "engine", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
-def cpu_baseline(paths, rq_json, aggs):
-    sys.path[:0] = [os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
-    import lakeside_oracle as lo
-    import pyarrow as pa
+# ----------------------------------------------------------------------------------------------------------------------
+# C5: K-way merge of sorted per-segment streams (BASELINE.json configs[4])
+# ----------------------------------------------------------------------------------------------------------------------
+def run_c5(args, reference=False):
+    import numpy as np
 
-    sample = max(1, min(len(paths), int(os.environ.get("LK_BENCH_REF_SEGMENTS", "4"))))
-    rq = lo.push_down_request_from_json(rq_json)
-    rq.segmentRequests = rq.segmentRequests[:sample]
-    ag = [(a, "rollup_" + r) for a, r in aggs]
-    lo.evaluate_glob(rq, paths[:sample], aggs=ag)
-    best = 1e30
-    for _ in range(2):
+    K, M, T0 = 256, 65536, 1699999200000
+    rng = np.random.Generator(np.random.PCG64(20240))
+    ts = [np.sort(T0 + 10000 * rng.integers(0, 360, M)).astype(np.int64) for _ in range(K)]
+    gid = [rng.integers(0, 16384, M).astype(np.int32) for _ in range(K)]
+    val = [rng.standard_normal(M) for _ in range(K)]
+    n = K * M
+    metric = "elements/sec K-way merge of 256 sorted per-segment streams (C5)"
+    desc = f"C5: {K} streams x {M} elements (ts int64, gid int32, value f64), 360 distinct timestamps (heavy ties), merged into one stream of {n} elements"
+
+    def cpu_merge():
+        # the reference's left-deep mergeSorted fold emits, on equal timestamps, the later-folded source first: a stable sort by
+        # (ts, source descending) is the same order; NumPy's lexsort over the concatenation (single thread)
+        allts = np.concatenate(ts)
+        src = np.repeat(np.arange(K, dtype=np.int32), M)
+        order = np.lexsort((-src, allts))
+        return allts[order], src[order]
+
+    t0 = time.perf_counter()
+    cpu_ts, cpu_src = cpu_merge()
+    cpu_dt = time.perf_counter() - t0
+    cpu = {"value": n / cpu_dt, "unit": "elements/s", "cores": 1, "kind": "port",
+           "sample": "the full C5 input, NumPy stable lexsort by (timestamp, source descending) = the left-deep mergeSorted order"}
+    if reference:
+        print(json.dumps({"impl": "reference", "metric": metric, "value": cpu["value"], "unit": "elements/s", "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+                          "ms_per_step": cpu_dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+                          "config": {"workload": desc}, "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "elements/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    from lakeside_b200 import _lib, api
+
+    api.init()
+    lib = _lib.load()
+    P = ctypes.c_void_p
+    lens = (ctypes.c_int64 * K)(*[M] * K)
+    h = P()
+    _lib.check(lib.lk_merge_create(K, (P * K)(*[t.ctypes.data for t in ts]), (P * K)(*[g.ctypes.data for g in gid]),
+                                   (P * K)(*[v.ctypes.data for v in val]), lens, 0, ctypes.byref(h)))
+    sampler = ClockSampler(0)
+    sampler.start()
+    times = []
+    nw = max(3, args.warmup)
+    t_region0 = time.perf_counter()
+    for i in range(nw + args.steps):
+        if i == nw:
+            t_region0 = time.perf_counter()
+        _lib.check(lib.lk_merge_run(h))
+        _lib.check(lib.lk_merge_sync(h))
+        ms = (ctypes.c_double * 4)()
+        _lib.check(lib.lk_merge_timings(h, ms))
+        times.append(ms[1])
+    t_region1 = time.perf_counter()
+    clocks = sampler.stop(t_region0, t_region1)
+    o_ts, o_gid, o_val, o_src = np.empty(n, np.int64), np.empty(n, np.int32), np.empty(n, np.float64), np.empty(n, np.int32)
+    _lib.check(lib.lk_merge_download(h, o_ts.ctypes.data, o_gid.ctypes.data, o_val.ctypes.data, o_src.ctypes.data))
+    lib.lk_merge_destroy(h)
+    ok = bool(np.array_equal(o_ts, cpu_ts)) and bool(np.array_equal(o_src, cpu_src))
+    # end to end: host streams in, merged stream out (H2D + kernels + D2H)
+    e2e_t = []
+    for _ in range(3):
         t0 = time.perf_counter()
-        lo.evaluate_glob(rq, paths[:sample], aggs=ag)
-        best = min(best, time.perf_counter() - t0)
-    return {"value": sample * ROWS / best, "unit": UNIT, "cores": pa.cpu_count(), "kind": "port",
-            "sample": f"{sample} of {len(paths)} segments x {ROWS} rows; oracle port (Arrow C++ Parquet decode + NumPy filter/group-by), "
-                      "page cache warm, best of 2"}
+        api.merge_streams_index(ts)
+        e2e_t.append(time.perf_counter() - t0)
+    tm = times[nw:]
+    k_ms = sum(tm) / len(tm)
+    peak, peak_src = measured_peaks()
+    achieved = 40.0 * n / (k_ms / 1e3) / 1e9
+    print(json.dumps({
+        "metric": metric, "value": n / (k_ms / 1e3), "unit": "elements/s", "n_gpus": 1, "steps": args.steps, "warmup": nw,
+        "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": desc, "l2": "671 MB of streams + output: larger than the 126 MB L2"},
+        "roofline": {"bound": "hbm", "kernel": "lk merge (split + merge-path tile kernels)", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": 40 * n, "kernel_ms": k_ms,
+                     "note": "algorithmic bytes = 2 x 20 B per element (SURVEY §8d)"},
+        "cpu_baseline": cpu, "parity": {"ok": ok, "checks": {"merged (timestamp, source) order == stable sort by (timestamp, source descending)": ok}},
+        "e2e": {"value": n / min(e2e_t), "unit": "elements/s", "h2d_bytes_per_step": 20 * n, "d2h_bytes_per_step": 24 * n, "ms_per_step": min(e2e_t) * 1e3},
+        "gpu_launches": args.steps * 3, "clocks": clocks}))
 
 
+# ----------------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native")
+    ap.add_argument("--workload", default=os.environ.get("LK_BENCH_WORKLOAD", "c2"), choices=["c2", "c3", "c3dense", "c4", "c5"])
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "c5":
+        return run_c5(args)
 
     import torch
     import torch.distributed as dist
@@ -207,7 +500,9 @@ def main():
     api.init(device=local_rank)
     lib = _lib.load()
 
-    paths, rq, aggs = gen_dataset(rank)
+    wl = Workload(args.workload, rank, world)
+    paths = wl.generate()
+    rq, aggs = wl.rq, wl.aggs
     # segment bytes in pinned host memory (what a worker's segment cache would hold)
     host = []
     for p in paths:
@@ -219,9 +514,9 @@ def main():
             f.readinto((ctypes.c_char * n).from_address(ptr))
         host.append((ptr, n))
 
-    # the planner chooses (records for this selective, high-cardinality query); sharded, the appended records (or the hash
-    # table's occupied cells) are what the sparse exchange partitions; LK_BENCH_PATH overrides (diagnosis)
-    table_path = os.environ.get("LK_BENCH_PATH", "auto")
+    # the planner chooses the aggregate layout (records for the selective, high-cardinality C2 / C3 / C4 queries; dense planes
+    # for c3dense); LK_BENCH_PATH overrides (diagnosis)
+    table_path = wl.path_opt
 
     def new_query():
         q = api.Query(rq, aggregates=aggs, path=table_path)
@@ -248,11 +543,9 @@ def main():
     SIGN = torch.iinfo(torch.int64).min
     exchange_bytes = [0]
 
-    trace = [] if os.environ.get("LK_BENCH_TRACE") else None  # per-phase wall clock of the exchange (adds syncs: diagnosis only)
-
     def exchange(qq, path):
-        """Host-mediated exchange of the paths that still need one (the record path -- what the planner picks for this
-        workload -- exchanges INSIDE the scan through the lk_comm attached to the query: nothing to do here).
+        """Host-mediated exchange of the paths that still need one (the record path -- what the planner picks for C2 / C3 / C4
+        -- exchanges INSIDE the scan through the lk_comm attached to the query: nothing to do here).
         dense : NCCL reduce of every (group x bucket) plane to rank 0 (sum f64 / sum u64 / max on order-preserving keys)
         hash  : cells are hash-partitioned over the ranks; NCCL all-to-all of the occupied 32/64-byte entries, each rank
                 merges and finalises its own partition."""
@@ -288,33 +581,33 @@ def main():
             qq._keep.append(recv)
             exchange_bytes[0] = (n_send - counts[rank]) * stride
 
-    # the communicator of the record path: every rank's receive pools, mapped by its peers (CUDA IPC); the handles travel
-    # over torch.distributed once, at setup -- the data path never touches NCCL or the host
-    comm = None
-    if world > 1 and table_path in ("auto", "records"):
-        pool_records = int(os.environ.get("LK_BENCH_POOL_RECORDS", str(max(1 << 20, N_SEGMENTS * ROWS // 8))))
-        comm = api.Comm(rank, world, pool_records, max_aggs=len(aggs))
-        handles = [None] * world
-        dist.all_gather_object(handles, comm.handle())
-        comm.connect(handles)
-        dist.barrier()
-
     # ---------------- resident ("kernel-only") arm ----------------
     sampler = ClockSampler(local_rank)  # started here: nvidia-smi needs a few 100 ms before its first sample
     sampler.start()
     q = new_query()
-    if world > 1:
-        q.plan()
-        agree_on_dictionaries(q)
-    if comm is not None:
-        q.set_comm(comm)
-    q.prepare()
+    q.plan()
+    agree_on_dictionaries(q)
     info = q.info
-    if world > 1:  # every rank must have chosen the same aggregate layout: the exchange depends on it
+    # the communicator of the record path: every rank's receive pools, mapped by its peers (CUDA IPC); the handles travel
+    # over torch.distributed once, at setup -- the data path never touches NCCL or the host
+    comm = None
+    if world > 1:
         paths_all = [None] * world
         dist.all_gather_object(paths_all, info["path"])
-        assert len(set(paths_all)) == 1, f"ranks disagree on the aggregate layout: {paths_all}"
-        assert comm is None or info["path"] == "records", info["path"]
+        assert len(set(paths_all)) == 1, f"ranks disagree on the aggregate layout: {paths_all}"  # the exchange depends on it
+        if info["path"] == "records":
+            rows_all = [None] * world
+            dist.all_gather_object(rows_all, q.total_rows)
+            # receive pool: a quarter of the average shard's rows for the 1/16-selective filters, three quarters for C4's regex
+            # (the cells are hash-partitioned evenly over the owners); LK_BENCH_POOL_RECORDS overrides
+            pool_records = int(os.environ.get("LK_BENCH_POOL_RECORDS", "0")) or max(1 << 20, (sum(rows_all) // world) * (3 if wl.name == "c4" else 1) // 4)
+            comm = api.Comm(rank, world, pool_records, max_aggs=len(aggs))
+            handles = [None] * world
+            dist.all_gather_object(handles, comm.handle())
+            comm.connect(handles)
+            dist.barrier()
+            q.set_comm(comm)
+    q.prepare()
     rows_per_rank = q.total_rows
     touched = q.touched_bytes
 
@@ -342,9 +635,12 @@ def main():
     torch.cuda.synchronize()
     t_region1 = time.perf_counter()
     dev_ms = e0.elapsed_time(e1)
+    wall_ms = (t_region1 - t_region0) * 1e3
+    if info["path"] != "records" and world > 1:
+        dev_ms = wall_ms  # NCCL runs on torch's stream and through the host: the query stream's events do not span it
     # per-kernel duration of the dominant kernel (CUDA events recorded by the library around each scan launch, on its
     # launching stream); measured in a separate loop so that reading them never serialises the timed region
-    per_scan, per_defx = [], []
+    per_scan, per_defx, per_fin = [], [], []
     for _ in range(args.steps):
         q.execute()
         exchange(q, info["path"])
@@ -352,29 +648,55 @@ def main():
         tm = q.timings
         per_scan.append(tm["scan_ms"])
         per_defx.append(tm["def_expand_ms"])
+        per_fin.append(tm["finalize_ms"])
     clocks = sampler.stop(t_region0, t_region1)
+    total_rows = rows_per_rank
     if world > 1:
-        t = torch.tensor([dev_ms], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms = float(t.item())
+        tmax = torch.tensor([dev_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = torch.tensor([float(rows_per_rank)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        dev_ms = float(tmax.item())
+        total_rows = int(tsum.item())
     ms_per_step = dev_ms / args.steps
-    value = rows_per_rank * world / (ms_per_step / 1e3)
+    value = total_rows / (ms_per_step / 1e3)
     survivors = q.survivors
-    result_rows = None
+
+    # ---------------- parity of the (sharded) result against an independent engine ----------------
+    parity = None
+    if os.environ.get("LK_BENCH_PARITY", "1") != "0":
+        q.execute()
+        exchange(q, info["path"])
+        res = q.finalize()
+        got = result_summary(res, survivors)
+        res.close()
+        want = arrow_summary(wl, paths)
+        if world > 1:
+            def allred(d, keys_sum, keys_min, keys_max):
+                for keys, op in ((keys_sum, dist.ReduceOp.SUM), (keys_min, dist.ReduceOp.MIN), (keys_max, dist.ReduceOp.MAX)):
+                    t = torch.tensor([float(d[k]) for k in keys], device="cuda", dtype=torch.float64)
+                    dist.all_reduce(t, op=op)
+                    for k, v in zip(keys, t.tolist()):
+                        d[k] = v
+            srt = torch.tensor([1.0 if got.get("sorted", True) else 0.0], device="cuda", dtype=torch.float64)
+            dist.all_reduce(srt, op=dist.ReduceOp.MIN)
+            got["sorted"] = bool(srt.item() > 0.5)
+            allred(got, ["n", "rows", "s", "c", "wc", "ws"], ["mn"], ["mx"])
+            allred(want, ["n", "s", "c", "wc", "ws"], ["mn"], ["mx"])
+            got["n"], got["rows"], want["n"] = int(got["n"]), int(got["rows"]), int(want["n"])
+        parity = compare_summaries(got, want)
 
     # ---------------- end-to-end arm: host buffers -> result rows on the host, every step ----------------
     q.close()
     e2e_steps = max(2, min(args.steps, 5))
-
     e2e_trace = []
 
     def e2e_step():
         t = [time.perf_counter()]
         qq = new_query()
         t.append(time.perf_counter())
-        if world > 1:  # the column chunks start moving during plan(); they overlap the index build and the agreement
-            qq.plan()
-            agree_on_dictionaries(qq)
+        qq.plan()  # the column chunks start moving here; they overlap the index build and the dictionary agreement
+        agree_on_dictionaries(qq)
         if comm is not None:
             qq.set_comm(comm)
         qq.prepare()
@@ -387,7 +709,6 @@ def main():
         d2h = n * (8 + 8 * res.num_values + 4 * res.num_tags + res.num_values)
         h2d = qq.touched_bytes
         res.close()
-        t.append(time.perf_counter())
         qq.close()
         t.append(time.perf_counter())
         e2e_trace.append([round((b - a) * 1e3, 2) for a, b in zip(t, t[1:])])
@@ -408,60 +729,72 @@ def main():
     e2e_dt = (time.perf_counter() - t0) / e2e_steps
     gc.enable()
     if world > 1:
-        t = torch.tensor([e2e_dt], device="cuda")
+        t = torch.tensor([e2e_dt], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
-    e2e_value = rows_per_rank * world / e2e_dt
-    if trace is not None and rank == 0:
-        print("e2e trace (ms) [create, plan+prepare, execute+exchange+finalize, result close, query close]:", e2e_trace[-e2e_steps:], file=sys.stderr)
+    e2e_value = total_rows / e2e_dt
+    if os.environ.get("LK_BENCH_TRACE") and rank == 0:
+        print("e2e trace (ms) [create, plan+prepare, execute+exchange+finalize, close]:", e2e_trace[-e2e_steps:], file=sys.stderr)
 
     if rank == 0:
         peak, peak_src = measured_peaks()
         k_ms = sum(per_scan) / len(per_scan)
         achieved = touched / (k_ms / 1e3) / 1e9
-        traffic = None
+        traffic, traffic_note = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
             tj = json.load(open(tp))
-            if tj.get("segments") == N_SEGMENTS and tj.get("rows") == ROWS:
+            if tj.get("workload", "c2") == wl.name and tj.get("segments") == wl.n_seg and tj.get("rows") == wl.rows:
                 traffic = tj.get("dram_bytes_per_launch")
+                traffic_note = ("static: dram__bytes_read.sum + dram__bytes_write.sum of one scan_kernel launch of this workload, from the committed ncu "
+                                "capture (profiles/traffic.json); not re-measured in this run")
+        n_launch = (1 if info.get("def_chunks", 1) else 0) + {"records": 6, "hash": 5, "dense": 4}[info["path"]] + \
+            ((2 if info["path"] == "records" else 3 if info["path"] == "hash" else 0) if world > 1 else 0)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "metric": wl.metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl.scaling, "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": workload_name(world), "segments_per_gpu": N_SEGMENTS, "rows_per_segment": ROWS,
+            "config": {"workload": wl.desc, "segments_per_gpu": wl.n_seg, "rows_per_segment": wl.rows,
                        "aggregate_table": info["path"], "n_groups": info["n_groups"], "n_buckets": info["n_buckets"],
                        "survivor_rows_per_gpu": survivors, "result_rows": result_rows,
                        "l2": f"inputs ({touched / 1e9:.2f} GB of encoded column chunks per GPU) are larger than the 126 MB L2; no explicit flush",
-                       "timed_region": "definition-level expansion + scan kernel + on-device aggregation/compaction of the result rows (inputs HBM-resident)",
-                       "def_expand_ms": sum(per_defx) / len(per_defx),
+                       "timed_region": "definition-level expansion + scan kernel (sharded: survivor records stored into the owner ranks' pools over NVLink while it "
+                                       "runs) + device-side wait for all sources + on-device grouping of the records into result rows (inputs HBM-resident)",
+                       "def_expand_ms": sum(per_defx) / len(per_defx), "finalize_ms": sum(per_fin) / len(per_fin),
+                       "step_wall_ms": wall_ms / args.steps,
                        "GBps_algorithmic": touched * world / (ms_per_step / 1e3) / 1e9,
-                       "GBps_logical_36B_per_row": 36.0 * rows_per_rank * world / (ms_per_step / 1e3) / 1e9},
-            "roofline": {"bound": "hbm", "kernel": "lk::scan_kernel (fused decode+filter+bucket+group-by aggregate)",
+                       "step_frac_of_measured_hbm_peak": touched / (ms_per_step / 1e3) / 1e9 / peak,
+                       "GBps_logical_36B_per_row": 36.0 * total_rows / (ms_per_step / 1e3) / 1e9},
+            "roofline": {"bound": "hbm",
+                         "kernel": ("lk::scan_kernel (fused Parquet decode + WHERE + step bucket + group id; appends one record per survivor, which the rec_* "
+                                    "finalize kernels group into rows)" if info["path"] == "records" else
+                                    "lk::scan_kernel (fused Parquet decode + WHERE + step bucket + group-by aggregate)"),
                          "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                         "frac_of_nominal_8TBps": achieved / 8000.0, "traffic": traffic,
+                         "frac_of_nominal_8TBps": achieved / 8000.0, "traffic": traffic, "traffic_note": traffic_note,
                          "algorithmic_bytes_per_launch": touched, "kernel_ms": k_ms,
                          "note": "algorithmic bytes = sum of ColumnMetaData.total_compressed_size of the touched column chunks (SURVEY §8d)"},
-            "cpu_baseline": cpu_baseline(paths, rq, aggs) if world == 1 else None,  # timed on rank 0 at N = 1 only
+            "cpu_baseline": cpu_baseline(wl, 3, 1) if world == 1 else None,  # timed on rank 0 at N = 1 only
+            "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
                     "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps,
                     "what": "lk_query_create + add_segment_buffer(pinned host bytes) + prepare (host index + H2D) + execute + finalize (D2H)"},
-            # this library's own kernels per step (CUB's radix-sort kernels of the record path are library code and not counted):
-            # def_expand (when a touched column has NULLs) +
-            # records: scan, rec_count, exclusive_scan, rec_emit; hash: scan, hist, exclusive_scan, scatter, emit
-            # (+ sparse_hist, sparse_scatter, sparse_merge / rec_part_hist, rec_part_scatter, rec_unpack when sharded); dense: scan, count, exclusive_scan, emit
-            # records: def_expand, scan, rec_bhist, rec_regions, rec_group, rec_rowscan, rec_emit (+ comm_begin, comm_seal_publish, comm_wait
-            # when sharded); hash: scan, hist, exclusive_scan, scatter, emit (+ sparse_hist, sparse_scatter, sparse_merge); dense: scan, count, exclusive_scan, emit
-            "gpu_launches": args.steps * ((1 if info.get("def_chunks", 1) else 0) + {"records": 6, "hash": 5, "dense": 4}[info["path"]] + (3 if world > 1 and info["path"] != "dense" else 0)),
+            # this library's own kernels per step -- records: def_expand, scan, rec_bhist, rec_regions, rec_group, rec_rowscan, rec_emit
+            # (+ comm_publish, comm_wait when sharded); hash: scan, hist, exclusive_scan, scatter, emit (+ sparse_hist, sparse_scatter,
+            # sparse_merge); dense: scan, count, exclusive_scan, emit.  No library (CUB / NCCL) kernel on the record path.
+            "gpu_launches": args.steps * n_launch,
             "exchange": None if world == 1 else {
                 "kind": ("NCCL reduce of dense planes" if info["path"] == "dense" else
-                         "survivor records stored into the owner rank's receive pool over NVLink during the scan (lk_comm: CUDA IPC peer pools, "
-                         "one remote atomic per 256 records, device-side completion flags; no NCCL call or host round trip on the data path)"
+                         "survivor records stored into the owner rank's receive pool over NVLink during the scan (lk_comm: CUDA IPC peer pools, local "
+                         "slot counters, device-side completion flags; no NCCL call or host round trip on the data path)"
                          if info["path"] == "records" else "NCCL all-to-all of hash-partitioned occupied cells"),
                 "bytes_sent_per_rank_per_step": (int(survivors * (world - 1) / world) * 8 * (1 + len(aggs)) if info["path"] == "records" else exchange_bytes[0])},
             "clocks": clocks,
         }
         print(json.dumps(line))
+    if comm is not None:
+        torch.cuda.synchronize()
+        dist.barrier()
+        comm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -640,7 +640,7 @@ def main():
         dev_ms = wall_ms  # NCCL runs on torch's stream and through the host: the query stream's events do not span it
     # per-kernel duration of the dominant kernel (CUDA events recorded by the library around each scan launch, on its
     # launching stream); measured in a separate loop so that reading them never serialises the timed region
-    per_scan, per_defx, per_fin = [], [], []
+    per_scan, per_defx, per_fin, per_wait = [], [], [], []
     for _ in range(args.steps):
         q.execute()
         exchange(q, info["path"])
@@ -649,6 +649,7 @@ def main():
         per_scan.append(tm["scan_ms"])
         per_defx.append(tm["def_expand_ms"])
         per_fin.append(tm["finalize_ms"])
+        per_wait.append(tm["exchange_wait_ms"])
     clocks = sampler.stop(t_region0, t_region1)
     total_rows = rows_per_rank
     if world > 1:
@@ -761,6 +762,7 @@ def main():
                        "timed_region": "definition-level expansion + scan kernel (sharded: survivor records stored into the owner ranks' pools over NVLink while it "
                                        "runs) + device-side wait for all sources + on-device grouping of the records into result rows (inputs HBM-resident)",
                        "def_expand_ms": sum(per_defx) / len(per_defx), "finalize_ms": sum(per_fin) / len(per_fin),
+                       "exchange_wait_ms_in_finalize": (sum(per_wait) / len(per_wait)) if world > 1 else None,
                        "step_wall_ms": wall_ms / args.steps,
                        "GBps_algorithmic": touched * world / (ms_per_step / 1e3) / 1e9,
                        "step_frac_of_measured_hbm_peak": touched / (ms_per_step / 1e3) / 1e9 / peak,

@@ -144,7 +144,8 @@ int64_t lk_query_survivors(lk_query* q);
 int64_t lk_query_eval(lk_query* q, const char* aggregation, const char* chart_type, const char* metric_type, double* out, int64_t cap);
 /* Timings of the last execute/finalize in milliseconds (CUDA events on the query's stream):
  * [0] H2D upload, [1] scan kernel, [2] finalize kernels, [3] D2H, [4] host planning, [5] definition-level expansion
- * (def_expand_kernel + the clear of its bitmaps, at the start of every execute). */
+ * (def_expand_kernel + the clear of its bitmaps, at the start of every execute), [6] sharded record path: the device-side wait
+ * for the other ranks' records at the start of finalize (included in [2]). */
 int lk_query_timings(lk_query* q, double* ms /*[8]*/);
 /* Algorithmic bytes: sum of total_compressed_size of the touched column chunks. */
 int64_t lk_query_touched_bytes(lk_query* q);

@@ -256,7 +256,7 @@ class Query:
     def timings(self) -> Dict[str, float]:
         ms = (ctypes.c_double * 8)()
         _lib.check(_lib.load().lk_query_timings(self._h, ms))
-        return {"h2d_ms": ms[0], "scan_ms": ms[1], "finalize_ms": ms[2], "d2h_ms": ms[3], "plan_ms": ms[4], "def_expand_ms": ms[5]}
+        return {"h2d_ms": ms[0], "scan_ms": ms[1], "finalize_ms": ms[2], "d2h_ms": ms[3], "plan_ms": ms[4], "def_expand_ms": ms[5], "exchange_wait_ms": ms[6]}
 
     @property
     def touched_bytes(self) -> int:

@@ -158,7 +158,7 @@ void device_shutdown() {
 // ------------------------------------------------------------------------------------------------------------
 struct Query::Device {
   cudaStream_t st = nullptr;
-  cudaEvent_t ev[10] = {};
+  cudaEvent_t ev[12] = {};
   uint8_t* arena = nullptr;
   TileDesc* tiles = nullptr;
   ColCursor* cursors = nullptr;
@@ -1444,8 +1444,10 @@ void device_finalize_device(Query& q) {
   if (q.path == 2) {
     if (q.comm) {
       const Comm& c = *q.comm;
+      CUDA_CHECK(cudaEventRecord(d.ev[10], d.st));
       comm_wait_kernel<<<1, 32, 0, d.st>>>(c.ctrl(c.rank), (uint32_t)c.world, c.epoch, d.counters);
       CUDA_CHECK(cudaGetLastError());
+      CUDA_CHECK(cudaEventRecord(d.ev[11], d.st));
     }
     if (d.fin_cap == 0) {
       // first finalize of this query: one read-back of the record count sizes the scratch and the result buffer
@@ -1614,6 +1616,7 @@ void device_timings(Query& q) {
   if (d.executed && cudaEventElapsedTime(&ms, d.ev[2], d.ev[3]) == cudaSuccess) q.t_ms[1] = ms;
   if (d.executed && cudaEventElapsedTime(&ms, d.ev[8], d.ev[9]) == cudaSuccess) q.t_ms[5] = ms;
   if (d.finalized_device && cudaEventElapsedTime(&ms, d.ev[4], d.ev[5]) == cudaSuccess) q.t_ms[2] = ms;
+  if (d.finalized_device && q.comm && q.path == 2 && cudaEventElapsedTime(&ms, d.ev[10], d.ev[11]) == cudaSuccess) q.t_ms[6] = ms;
   cudaGetLastError();
 }
 

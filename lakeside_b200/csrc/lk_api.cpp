@@ -180,7 +180,10 @@ int lk_query_plan(lk_query* q) {
     // With a GPU present the column chunks start moving to HBM as soon as the arena layout is known, exactly as in
     // lk_query_prepare; without one (host-logic tests, dictionary agreement on a CPU box) planning is host-only.
     Query* qp = &q->q;
-    if (device_count() > 0) q->q.on_layout = [qp] { device_begin_upload(*qp); };
+    if (device_count() > 0) {
+      q->q.on_layout = [qp] { device_begin_upload(*qp); };
+      q->q.device_index = !getenv("LK_HOST_INDEX");  // run headers and cursors are built on the device during prepare
+    }
     plan_query(q->q);
     q->q.on_layout = nullptr;
     q->q.t_ms[4] = now_ms() - t0;
@@ -195,7 +198,8 @@ int lk_query_prepare(lk_query* q) {
       double t0 = now_ms();
       device_init();  // fail before any host work when there is no GPU
       Query* qp = &q->q;
-      q->q.on_layout = [qp] { device_begin_upload(*qp); };  // column chunks start moving while the host builds the index
+      q->q.on_layout = [qp] { device_begin_upload(*qp); };  // column chunks start moving while the host walks the page headers
+      q->q.device_index = !getenv("LK_HOST_INDEX");          // run headers and cursors are built on the device (LK_HOST_INDEX: on the host)
       plan_query(q->q);
       q->q.on_layout = nullptr;
       q->q.t_ms[4] = now_ms() - t0;

@@ -359,6 +359,99 @@ LK_HD uint32_t lk_numeric_class(const FilterCol& f, double x) {
   return cls;
 }
 
+// ---- seek index built on the device (lk_engine.cu: idx_* kernels) ----
+// The host walks footers and PAGE headers only; the run headers of every hybrid stream (definition levels, dictionary
+// indices) are walked by the device once the column chunks are in HBM: one thread per page, a count pass and a fill pass,
+// then one thread per (tile, column) computes the cursor.  Replaces ~0.6 host core-seconds per 105 M rows.
+struct IdxPage {
+  uint64_t def_off, def_end;  // arena byte range of the definition-level stream (def_end == def_off: REQUIRED column, all rows valid)
+  uint64_t val_off, val_end;  // arena byte range of the values: PLAIN values, or hybrid dictionary indices (after the width byte)
+  uint32_t first_row, num_rows;
+  uint32_t chunk;             // index into IdxChunk[]
+  uint8_t dict_coded, bit_width, pad[2];
+  // filled by the device
+  uint32_t nn;                // non-null values of the page
+  uint32_t first_vidx;        // non-null values of the chunk before the page
+  uint32_t def_runs, val_runs;
+  uint32_t def_run0, val_run0;  // first run of the page in the run pool
+};
+struct IdxChunk {
+  uint64_t base_off;          // arena offset of the chunk's first byte
+  uint32_t page0, npages;
+  uint32_t present, max_def, esz, num_rows, dict_n, string_typed;
+  // filled by the device
+  uint32_t def_run0, def_runs, val_run0, val_runs;
+  uint32_t nn, mixed;         // non-null values; some tile of the chunk mixes NULLs and values (needs a definition bitmap)
+};
+enum : uint32_t { IDX_ST_TRUNCATED = 1, IDX_ST_BAD_RUN = 2, IDX_ST_BAD_CODE = 4, IDX_ST_PLAIN_STRING = 8 };
+
+struct HybridRun {
+  uint32_t n;        // elements the run contributes (clipped to what the page still needs)
+  uint32_t is_rle, value;
+  uint64_t payload;  // bit-packed: offset of the packed bytes
+  uint64_t next;     // offset of the next run header
+};
+// One run header of an RLE / bit-packed hybrid stream at `off` (< end); `remaining` elements are still expected.
+// Returns 0 or an IDX_ST_* flag.  The host's page walker and the device's index kernels share it.
+LK_HD uint32_t lk_hybrid_next(const uint8_t* base, uint64_t off, uint64_t end, uint32_t bit_width, uint32_t remaining, HybridRun& r) {
+  uint64_t h = 0;
+  uint32_t shift = 0;
+  for (;;) {
+    if (off >= end) return IDX_ST_TRUNCATED;
+    const uint32_t b = base[off++];
+    h |= (uint64_t)(b & 0x7f) << shift;
+    if (!(b & 0x80)) break;
+    shift += 7;
+    if (shift > 63) return IDX_ST_BAD_RUN;
+  }
+  if (h & 1) {
+    const uint64_t groups = h >> 1, n = groups * 8, bytes = groups * (uint64_t)bit_width;
+    if (groups == 0) return IDX_ST_BAD_RUN;
+    const uint32_t take = n < (uint64_t)remaining ? (uint32_t)n : remaining;
+    // a writer may truncate the padding of the final group; require the bytes that carry real values
+    if (off + ((uint64_t)take * bit_width + 7) / 8 > end) return IDX_ST_TRUNCATED;
+    r.n = take;
+    r.is_rle = 0;
+    r.value = 0;
+    r.payload = off;
+    r.next = off + (bytes < end - off ? bytes : end - off);
+  } else {
+    const uint64_t n = h >> 1;
+    const uint32_t vbytes = (bit_width + 7) / 8;
+    if (n == 0) return IDX_ST_BAD_RUN;
+    if (off + vbytes > end) return IDX_ST_TRUNCATED;
+    uint32_t v = 0;
+    for (uint32_t i = 0; i < vbytes; i++) v |= (uint32_t)base[off + i] << (8 * i);
+    r.n = n < (uint64_t)remaining ? (uint32_t)n : remaining;
+    r.is_rle = 1;
+    r.value = v;
+    r.payload = 0;
+    r.next = off + vbytes;
+  }
+  return 0;
+}
+// set bits among the first nbits bits at byte address p (arbitrary alignment)
+LK_HD uint32_t lk_popcount_bits(const uint8_t* p, uint32_t nbits) {
+  uint32_t c = 0, i = 0;
+  const uint32_t nbytes = nbits >> 3;
+  for (; i < nbytes; i++) {
+#if defined(__CUDA_ARCH__)
+    c += __popc((uint32_t)p[i]);
+#else
+    c += (uint32_t)__builtin_popcount(p[i]);
+#endif
+  }
+  if (nbits & 7) {
+    const uint32_t x = p[nbytes] & ((1u << (nbits & 7)) - 1);
+#if defined(__CUDA_ARCH__)
+    c += __popc(x);
+#else
+    c += (uint32_t)__builtin_popcount(x);
+#endif
+  }
+  return c;
+}
+
 // ---- record path finalize ----
 LK_HD uint32_t lk_rf_mix(uint64_t gid) {  // 32 well-mixed bits of a group id: the slot inside its bucket's region of the key table
   uint32_t h = (uint32_t)gid ^ (uint32_t)(gid >> 32) * 0x9E3779B1u;

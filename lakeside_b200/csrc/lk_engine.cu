@@ -277,12 +277,322 @@ void device_begin_upload(Query& q) {
     CUDA_CHECK(cudaMemcpyAsync(d.arena + u.arena_off, q.segs[u.seg].data + u.file_off, u.len, cudaMemcpyHostToDevice, d.st));
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// seek index on the device (Query::device_index): run tables of the hybrid streams + per-(tile, column) cursors
+// ------------------------------------------------------------------------------------------------------------
+// The host has walked the PAGE headers (lk_parquet.cpp, walk_runs = false); everything that used to cost ~0.6 host
+// core-seconds per 105 M rows -- every run header of every definition-level and dictionary-index stream, the non-null
+// prefix counts, the cursors of every tile -- is computed here, from the column chunks already in HBM:
+//   idx_def_count    one thread per page: walk the definition-level runs, count them and the non-null values
+//   idx_chunk_prefix one thread per chunk: first value index of every page
+//   idx_val_count    one thread per page: walk the dictionary-index runs (needs the page's value count)
+//   idx_layout       one block: lay the chunks' run lists out in the pool (definition runs, then value runs, per chunk)
+//   idx_fill         one thread per page: walk both streams again, write the Run entries (+ non-null count before each def run)
+//   idx_cursor       one thread per (tile, column): the ColCursor the host planner would have written (lk_plan.cpp)
+// A stream is inherently sequential (varint headers), so the parallelism is pages x columns: ~1000 threads for 100 segments;
+// the whole build is a few milliseconds on the GPU, overlapped with nothing yet (it needs the bytes in HBM).
+struct IdxTotals { uint32_t n_runs, status, pad[2]; };
+
+__global__ void idx_def_count_kernel(const uint8_t* __restrict__ arena, IdxPage* __restrict__ pages, uint32_t npages, IdxTotals* __restrict__ tot) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npages) return;
+  IdxPage pg = pages[i];
+  uint32_t runs = 0, nn = pg.num_rows, status = 0;
+  if (pg.def_end > pg.def_off) {
+    nn = 0;
+    uint64_t off = pg.def_off;
+    uint32_t done = 0;
+    while (done < pg.num_rows) {
+      HybridRun r;
+      status |= lk_hybrid_next(arena, off, pg.def_end, 1, pg.num_rows - done, r);
+      if (status) break;
+      nn += r.is_rle ? ((r.value & 1) ? r.n : 0u) : lk_popcount_bits(arena + r.payload, r.n);
+      runs++;
+      done += r.n;
+      off = r.next;
+    }
+  }
+  pages[i].def_runs = runs;
+  pages[i].nn = nn;
+  if (status) atomicOr(&tot->status, status);
+}
+
+__global__ void idx_chunk_prefix_kernel(IdxPage* __restrict__ pages, IdxChunk* __restrict__ chunks, uint32_t nchunks) {
+  const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= nchunks) return;
+  const IdxChunk ch = chunks[c];
+  uint32_t v = 0;
+  for (uint32_t k = 0; k < ch.npages; k++) {
+    pages[ch.page0 + k].first_vidx = v;
+    v += pages[ch.page0 + k].nn;
+  }
+  chunks[c].nn = v;
+}
+
+__global__ void idx_val_count_kernel(const uint8_t* __restrict__ arena, IdxPage* __restrict__ pages, const IdxChunk* __restrict__ chunks,
+                                     uint32_t npages, IdxTotals* __restrict__ tot) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npages) return;
+  const IdxPage pg = pages[i];
+  uint32_t runs = 0, status = 0;
+  if (pg.dict_coded) {
+    uint64_t off = pg.val_off;
+    uint32_t done = 0;
+    const uint32_t dict_n = chunks[pg.chunk].dict_n;
+    while (done < pg.nn) {
+      HybridRun r;
+      status |= lk_hybrid_next(arena, off, pg.val_end, pg.bit_width, pg.nn - done, r);
+      if (status) break;
+      if (r.is_rle && r.value >= dict_n) status |= IDX_ST_BAD_CODE;
+      runs++;
+      done += r.n;
+      off = r.next;
+    }
+  } else {
+    const IdxChunk ch = chunks[pg.chunk];
+    if (ch.string_typed && pg.nn > 0) status |= IDX_ST_PLAIN_STRING;
+    else if (pg.val_off + (uint64_t)pg.nn * ch.esz > pg.val_end) status |= IDX_ST_TRUNCATED;
+  }
+  pages[i].val_runs = runs;
+  if (status) atomicOr(&tot->status, status);
+}
+
+// one block: per chunk the number of def / value runs, then an exclusive scan over the chunks (a chunk's runs are contiguous:
+// its definition runs page by page, then its value runs page by page)
+__global__ void __launch_bounds__(1024) idx_layout_kernel(IdxPage* __restrict__ pages, IdxChunk* __restrict__ chunks, uint32_t nchunks, IdxTotals* __restrict__ tot) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t carry_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < nchunks; base += 1024) {
+    const uint32_t c = base + threadIdx.x;
+    uint32_t nd = 0, nv = 0;
+    IdxChunk ch;
+    if (c < nchunks) {
+      ch = chunks[c];
+      for (uint32_t k = 0; k < ch.npages; k++) { nd += pages[ch.page0 + k].def_runs; nv += pages[ch.page0 + k].val_runs; }
+    }
+    const uint32_t x = nd + nv;
+    uint32_t incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const uint32_t t = warp_tot[lane];
+      uint32_t ti = t;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, ti, d); if (lane >= d) ti += o; }
+      warp_tot[lane] = ti - t;
+    }
+    __syncthreads();
+    uint32_t run = carry_s + warp_tot[wid] + incl - x;
+    if (c < nchunks) {
+      chunks[c].def_run0 = run;
+      chunks[c].def_runs = nd;
+      for (uint32_t k = 0; k < ch.npages; k++) { pages[ch.page0 + k].def_run0 = run; run += pages[ch.page0 + k].def_runs; }
+      chunks[c].val_run0 = run;
+      chunks[c].val_runs = nv;
+      for (uint32_t k = 0; k < ch.npages; k++) { pages[ch.page0 + k].val_run0 = run; run += pages[ch.page0 + k].val_runs; }
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = run;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) tot->n_runs = carry_s;
+}
+
+__global__ void idx_fill_kernel(const uint8_t* __restrict__ arena, const IdxPage* __restrict__ pages, const IdxChunk* __restrict__ chunks, uint32_t npages,
+                                Run* __restrict__ runs, uint32_t* __restrict__ nn_before) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= npages) return;
+  const IdxPage pg = pages[i];
+  const uint64_t base = chunks[pg.chunk].base_off;
+  if (pg.def_end > pg.def_off) {
+    uint64_t off = pg.def_off;
+    uint32_t done = 0, nn = pg.first_vidx, k = pg.def_run0;
+    while (done < pg.num_rows) {
+      HybridRun r;
+      if (lk_hybrid_next(arena, off, pg.def_end, 1, pg.num_rows - done, r)) break;
+      Run run;
+      run.start = pg.first_row + done;
+      run.kind_value = r.is_rle ? (0x80000000u | (r.value & 1)) : (uint32_t)(r.payload - base);
+      runs[k] = run;
+      nn_before[k] = nn;
+      k++;
+      nn += r.is_rle ? ((r.value & 1) ? r.n : 0u) : lk_popcount_bits(arena + r.payload, r.n);
+      done += r.n;
+      off = r.next;
+    }
+  }
+  if (pg.dict_coded) {
+    uint64_t off = pg.val_off;
+    uint32_t done = 0, k = pg.val_run0;
+    while (done < pg.nn) {
+      HybridRun r;
+      if (lk_hybrid_next(arena, off, pg.val_end, pg.bit_width, pg.nn - done, r)) break;
+      Run run;
+      run.start = pg.first_vidx + done;
+      run.kind_value = r.is_rle ? (0x80000000u | (r.value & 0x7fffffffu)) : (uint32_t)(r.payload - base);
+      runs[k++] = run;
+      done += r.n;
+      off = r.next;
+    }
+  }
+}
+
+// non-null values of the chunk before row r (r may equal num_rows), and the definition run that holds r
+__device__ __forceinline__ uint32_t idx_vidx_at(const uint8_t* __restrict__ arena, const Run* __restrict__ dr, const uint32_t* __restrict__ nnb, uint32_t nd,
+                                                uint64_t base, uint32_t r, uint32_t& run_index) {
+  uint32_t lo = 0, hi = nd;
+  while (hi - lo > 1) {
+    const uint32_t mid = (lo + hi) >> 1;
+    if (dr[mid].start <= r) lo = mid; else hi = mid;
+  }
+  run_index = lo;
+  const Run run = dr[lo];
+  const uint32_t k = r - run.start;
+  if (run.kind_value >> 31) return nnb[lo] + ((run.kind_value & 1) ? k : 0u);
+  return nnb[lo] + lk_popcount_bits(arena + base + run.kind_value, k);
+}
+
+__global__ void idx_cursor_kernel(const uint8_t* __restrict__ arena, const TileDesc* __restrict__ tiles, uint32_t ntiles, uint32_t np,
+                                  const IdxPage* __restrict__ pages, IdxChunk* __restrict__ chunks, const Run* __restrict__ runs,
+                                  const uint32_t* __restrict__ nn_before, ColCursor* __restrict__ cursors) {
+  const uint64_t gi = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gi >= (uint64_t)ntiles * np) return;
+  const uint32_t t = (uint32_t)(gi / np), p = (uint32_t)(gi - (uint64_t)t * np);
+  const TileDesc td = tiles[t];
+  const uint32_t cidx = td.rg * np + p;
+  const IdxChunk ch = chunks[cidx];
+  ColCursor c;
+  memset(&c, 0, sizeof c);
+  if (!ch.present) {
+    c.flags = CUR_ALL_NULL;
+    cursors[gi] = c;
+    return;
+  }
+  const uint32_t r0 = td.row0, r1 = td.row0 + td.nrows;
+  uint32_t v0, v1, d0 = 0, d1 = 0;
+  const Run* dr = runs + ch.def_run0;
+  const uint32_t* nnb = nn_before + ch.def_run0;
+  if (ch.max_def == 0 || ch.def_runs == 0) {
+    v0 = ch.max_def == 0 ? r0 : 0u;
+    v1 = ch.max_def == 0 ? r1 : 0u;
+  } else {
+    v0 = idx_vidx_at(arena, dr, nnb, ch.def_runs, ch.base_off, r0, d0);
+    v1 = idx_vidx_at(arena, dr, nnb, ch.def_runs, ch.base_off, r1, d1);
+  }
+  c.vidx0 = v0;
+  c.nvals = v1 - v0;
+  if (c.nvals == r1 - r0) c.flags |= CUR_ALL_VALID;
+  else if (c.nvals == 0) c.flags |= CUR_ALL_NULL;
+  else {
+    if (dr[d1].start >= r1) d1--;  // the run holding row r1 - 1
+    c.drun_lo = ch.def_run0 + d0;
+    c.drun_n = (uint16_t)(d1 - d0 + 1);
+    chunks[cidx].mixed = 1;  // (benign race: every writer stores 1)
+  }
+  if (c.nvals > 0) {
+    uint32_t pi = 0;
+    while (pi + 1 < ch.npages && pages[ch.page0 + pi + 1].first_row <= r0) pi++;
+    const IdxPage pg = pages[ch.page0 + pi];
+    if (pg.dict_coded) {
+      c.flags |= CUR_DICT;
+      c.width = pg.bit_width;
+      const Run* vr = runs + ch.val_run0;
+      uint32_t lo = 0, hi = ch.val_runs;
+      while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (vr[mid].start <= v0) lo = mid; else hi = mid; }
+      uint32_t zlo = lo, zhi = ch.val_runs;
+      while (zhi - zlo > 1) { const uint32_t mid = (zlo + zhi) >> 1; if (vr[mid].start <= v1 - 1) zlo = mid; else zhi = mid; }
+      c.vrun_lo = ch.val_run0 + lo;
+      c.vrun_n = (uint16_t)(zlo - lo + 1);
+    } else {
+      c.plain_off = pg.val_off + (uint64_t)(v0 - pg.first_vidx) * ch.esz;
+    }
+  }
+  cursors[gi] = c;
+}
+
+// Builds runs / cursors / definition-chunk list on the device (after the column chunks are in HBM) and completes what the host
+// plan left open.  Two small read-backs: the run total (sizes the pool) and the per-chunk run ranges / mixed flags.
+static void device_build_index(Query& q) {
+  Query::Device& d = *q.dev;
+  const uint32_t npages = (uint32_t)q.idx_pages.size(), nchunks = (uint32_t)q.idx_chunks.size(), np = (uint32_t)q.pcols.size();
+  const uint32_t ntiles = (uint32_t)q.tiles.size();
+  IdxPage* dpages = nullptr;
+  IdxChunk* dchunks = nullptr;
+  IdxTotals* dtot = nullptr;
+  uint32_t* nn_before = nullptr;
+  CUDA_CHECK(cudaMallocAsync(&dpages, std::max<size_t>(1, npages) * sizeof(IdxPage), d.st));
+  CUDA_CHECK(cudaMallocAsync(&dchunks, std::max<size_t>(1, nchunks) * sizeof(IdxChunk), d.st));
+  CUDA_CHECK(cudaMallocAsync(&dtot, sizeof(IdxTotals), d.st));
+  CUDA_CHECK(cudaMemsetAsync(dtot, 0, sizeof(IdxTotals), d.st));
+  if (npages) CUDA_CHECK(cudaMemcpyAsync(dpages, q.idx_pages.data(), npages * sizeof(IdxPage), cudaMemcpyHostToDevice, d.st));
+  if (nchunks) CUDA_CHECK(cudaMemcpyAsync(dchunks, q.idx_chunks.data(), nchunks * sizeof(IdxChunk), cudaMemcpyHostToDevice, d.st));
+  IdxTotals tot{};
+  if (npages) {
+    const int pg_grid = (int)((npages + 31) / 32), ch_grid = (int)((nchunks + 63) / 64);
+    idx_def_count_kernel<<<pg_grid, 32, 0, d.st>>>(d.arena, dpages, npages, dtot);
+    idx_chunk_prefix_kernel<<<ch_grid, 64, 0, d.st>>>(dpages, dchunks, nchunks);
+    idx_val_count_kernel<<<pg_grid, 32, 0, d.st>>>(d.arena, dpages, dchunks, npages, dtot);
+    idx_layout_kernel<<<1, 1024, 0, d.st>>>(dpages, dchunks, nchunks, dtot);
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(&tot, dtot, sizeof tot, cudaMemcpyDeviceToHost, d.st));
+    CUDA_CHECK(cudaStreamSynchronize(d.st));
+    LK_CHECK(!(tot.status & IDX_ST_PLAIN_STRING), LK_ERR_UNSUPPORTED, "a string column has PLAIN (non-dictionary) pages");
+    LK_CHECK(!(tot.status & IDX_ST_BAD_CODE), LK_ERR_IO, "parquet: dictionary index out of range");
+    LK_CHECK(!(tot.status & IDX_ST_BAD_RUN), LK_ERR_IO, "parquet: malformed run header in a hybrid stream");
+    LK_CHECK(!(tot.status & IDX_ST_TRUNCATED), LK_ERR_IO, "parquet: hybrid stream / PLAIN page ends before all values are covered");
+  }
+  q.n_runs = tot.n_runs;
+  if (d.runs) { CUDA_CHECK(cudaFreeAsync(d.runs, d.st)); d.runs = nullptr; }
+  if (d.cursors) { CUDA_CHECK(cudaFreeAsync(d.cursors, d.st)); d.cursors = nullptr; }
+  CUDA_CHECK(cudaMallocAsync(&d.runs, std::max<size_t>(1, tot.n_runs) * sizeof(Run), d.st));
+  CUDA_CHECK(cudaMallocAsync(&nn_before, std::max<size_t>(1, tot.n_runs) * sizeof(uint32_t), d.st));
+  CUDA_CHECK(cudaMallocAsync(&d.cursors, std::max<size_t>(1, (size_t)ntiles * np) * sizeof(ColCursor), d.st));
+  if (npages) {
+    idx_fill_kernel<<<(int)((npages + 31) / 32), 32, 0, d.st>>>(d.arena, dpages, dchunks, npages, d.runs, nn_before);
+    if (ntiles) {
+      const uint64_t n = (uint64_t)ntiles * np;
+      idx_cursor_kernel<<<(int)((n + 127) / 128), 128, 0, d.st>>>(d.arena, d.tiles, ntiles, np, dpages, dchunks, d.runs, nn_before, d.cursors);
+    }
+    CUDA_CHECK(cudaGetLastError());
+    CUDA_CHECK(cudaMemcpyAsync(q.idx_chunks.data(), dchunks, nchunks * sizeof(IdxChunk), cudaMemcpyDeviceToHost, d.st));
+  }
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  // definition bitmaps for the chunks that have a tile mixing NULLs and values (same rule as the host planner)
+  std::vector<DefChunk> def_tmp(nchunks, DefChunk{});
+  uint32_t def_mask = 0;
+  for (uint32_t k = 0; k < nchunks; k++) {
+    const IdxChunk& ic = q.idx_chunks[k];
+    if (!ic.present || !ic.mixed) continue;
+    DefChunk& dc = def_tmp[k];
+    dc.base_off = ic.base_off;
+    dc.run_lo = ic.def_run0;
+    dc.run_n = ic.def_runs;
+    dc.num_rows = ic.num_rows;
+    def_mask |= 1u << (k % np);
+  }
+  layout_def_chunks(q, def_tmp);
+  q.params.def_mask = def_mask;
+  refresh_info_json(q);
+  CUDA_CHECK(cudaFreeAsync(dpages, d.st));
+  CUDA_CHECK(cudaFreeAsync(dchunks, d.st));
+  CUDA_CHECK(cudaFreeAsync(dtot, d.st));
+  CUDA_CHECK(cudaFreeAsync(nn_before, d.st));
+}
+
 void device_upload(Query& q) {
   device_begin_upload(q);
   Query::Device& d = *q.dev;
   upload_vec(d.tiles, q.tiles, d.st);
-  upload_vec(d.cursors, q.cursors, d.st);
-  upload_vec(d.runs, q.runs, d.st);
+  if (q.device_index) device_build_index(q);  // runs, cursors and the definition-chunk list come from the device
+  else {
+    upload_vec(d.cursors, q.cursors, d.st);
+    upload_vec(d.runs, q.runs, d.st);
+  }
   upload_vec(d.def_chunks, q.def_chunks, d.st);
   if (d.defbm) { CUDA_CHECK(cudaFreeAsync(d.defbm, d.st)); d.defbm = nullptr; }
   CUDA_CHECK(cudaMallocAsync(&d.defbm, std::max<size_t>(q.defbm_words * 4, 16), d.st));

@@ -377,7 +377,7 @@ void chunk_byte_range(const ColumnChunkMeta& cm, size_t file_len, const std::str
 }
 
 ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, const ColumnChunkMeta& cm, int64_t rg_rows,
-                       bool want_strings) {
+                       bool want_strings, bool walk_runs) {
   ChunkIndex ci;
   ci.present = true;
   ci.phys_type = cm.phys_type;
@@ -451,10 +451,12 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
           LK_CHECK(dl_end <= pend, LK_ERR_IO, "parquet: truncated definition levels");
           q = dl_end;
         }
+        pg.def_off = dl_off;
+        pg.def_end = dl_end;
         nn = 0;
         uint32_t base_row = row;
         uint32_t nn_base = vidx;
-        walk_hybrid(data, dl_off, dl_end, 1, pg.num_rows, [&](uint32_t s, uint32_t n, bool rle, uint32_t v, uint64_t off) {
+        if (walk_runs) walk_hybrid(data, dl_off, dl_end, 1, pg.num_rows, [&](uint32_t s, uint32_t n, bool rle, uint32_t v, uint64_t off) {
           Run run;
           run.start = base_row + s;
           run.kind_value = rle ? (0x80000000u | (v & 1)) : (uint32_t)(off - ci.file_start);
@@ -468,7 +470,7 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
         unsigned esz = (cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT) ? 4 : (cm.phys_type == PT_INT64 || cm.phys_type == PT_DOUBLE) ? 8 : 0;
         LK_CHECK(esz != 0, LK_ERR_UNSUPPORTED,
                  "column '" + leaf.name + "': PLAIN pages of this type are not supported (dictionary fallback of a string column?)");
-        LK_CHECK(q + (uint64_t)nn * esz <= pend, LK_ERR_IO, "parquet: truncated PLAIN page");
+        LK_CHECK(!walk_runs || q + (uint64_t)nn * esz <= pend, LK_ERR_IO, "parquet: truncated PLAIN page");
         pg.dict_coded = false;
         pg.values_off = q;
         pg.values_len = (uint32_t)(pend - q);
@@ -484,7 +486,7 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
         pg.values_off = q;
         pg.values_len = (uint32_t)(pend - q);
         uint32_t vbase = vidx;
-        if (nn > 0)
+        if (nn > 0 && walk_runs)
           walk_hybrid(data, q, pend, pg.bit_width, nn, [&](uint32_t s, uint32_t n, bool rle, uint32_t v, uint64_t off) {
             (void)n;
             Run run;
@@ -504,7 +506,9 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
   }
   LK_CHECK(row == ci.num_rows, LK_ERR_IO, "parquet: pages do not cover the row group");
   // the kernels address a chunk's bit-packed dictionary indices by a 32-bit BIT offset from the chunk's first byte
-  LK_CHECK(ci.val_runs.empty() || ci.file_len < (1ull << 29), LK_ERR_UNSUPPORTED,
+  bool any_dict_page = false;
+  for (auto& pg : ci.pages) any_dict_page |= pg.dict_coded;
+  LK_CHECK(!(any_dict_page || !ci.val_runs.empty()) || ci.file_len < (1ull << 29), LK_ERR_UNSUPPORTED,
            "dictionary-coded column chunk of '" + leaf.name + "' is larger than 512 MB");
   return ci;
 }

@@ -53,6 +53,7 @@ struct PageInfo {
   uint8_t bit_width = 0;
   uint64_t values_off = 0;  // file offset of the value bytes (after the bit-width byte for dictionary pages)
   uint32_t values_len = 0;
+  uint64_t def_off = 0, def_end = 0;  // file byte range of the definition-level stream (empty for REQUIRED columns)
 };
 
 // Index of one column chunk.  Bit-packed run offsets are relative to file_start (the chunk's first byte).
@@ -83,9 +84,11 @@ struct ChunkIndex {
 // Byte range [start, start + len) of a column chunk inside the file (dictionary page + data pages), from the footer alone.
 void chunk_byte_range(const ColumnChunkMeta& cm, size_t file_len, const std::string& name, uint64_t& start, uint64_t& len);
 
-// Walks every page header of the chunk and every run header of its hybrid streams.
+// Walks every page header of the chunk and -- walk_runs -- every run header of its hybrid streams.
 // want_strings: decode the BYTE_ARRAY dictionary into dict_strings.
+// walk_runs = false (the device builds the run index, lk_engine.cu): pages carry the byte ranges of their streams, nvals /
+// first_vidx are left at 0 and def_runs / val_runs stay empty.
 ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, const ColumnChunkMeta& cm, int64_t rg_rows,
-                       bool want_strings);
+                       bool want_strings, bool walk_runs = true);
 
 }  // namespace lk

@@ -112,6 +112,7 @@ static Truth eval_tree(const Clause& c, int& leaf_counter, const std::function<T
 }
 
 static void build_info_json(Query& q);
+void refresh_info_json(Query& q) { build_info_json(q); }
 
 namespace {
 struct PlanTrace {
@@ -308,7 +309,7 @@ void plan_query(Query& q) {
       if (li < 0) continue;  // union_by_name: the column is NULL for this file
       const PCol& pc = q.pcols[p];
       rp.chunks[p] = index_chunk(seg.data, seg.len, seg.meta.leaves[li], seg.meta.row_groups[rp.rg].columns[li],
-                                 seg.meta.row_groups[rp.rg].num_rows, pc.string_typed);
+                                 seg.meta.row_groups[rp.rg].num_rows, pc.string_typed, !q.device_index);
       if (pc.string_typed)
         for (auto& pg : rp.chunks[p].pages)
           LK_CHECK(pg.dict_coded || pg.nvals == 0, LK_ERR_UNSUPPORTED, "string column '" + pc.name + "' has PLAIN (non-dictionary) pages");
@@ -324,6 +325,7 @@ void plan_query(Query& q) {
   }
 
   trace.mark("index chunks");
+  uint32_t def_mask_out = 0;
   // ---- runs pool, tiles, cursors ----
   const uint32_t tile_rows = std::max(64u, std::min(opt.tile_rows, (uint32_t)LK_TILE_ROWS_MAX)) & ~31u;
   std::vector<size_t> run_base(q.rgs.size() + 1, 0), tile_base(q.rgs.size() + 1, 0);
@@ -344,10 +346,66 @@ void plan_query(Query& q) {
     tile_base[i + 1] = tile_base[i] + (b.size() - 1);
   }
   LK_CHECK(run_base.back() < 0xffffffffull && tile_base.back() * np < 0xffffffffull, LK_ERR_UNSUPPORTED, "glob too large for 32-bit index pools");
-  q.runs.resize_uninit(run_base.back());
   q.tiles.resize_uninit(tile_base.back());
-  q.cursors.resize_uninit(tile_base.back() * np);  // zeroed slice by slice by the workers below
   q.chunk_infos.assign(q.rgs.size() * np, ChunkInfo{});
+  if (q.device_index) {
+    // the device walks the run headers and computes the cursors (lk_engine.cu: idx_* kernels): hand it the pages and chunks
+    q.idx_pages.clear();
+    q.idx_chunks.assign(q.rgs.size() * np, IdxChunk{});
+    for (size_t i = 0; i < q.rgs.size(); i++) {
+      const RowGroupPlan& rp = q.rgs[i];
+      const std::vector<uint32_t>& b = bounds[i];
+      for (size_t t = 0; t + 1 < b.size(); t++) {
+        TileDesc& td = q.tiles[tile_base[i] + t];
+        td.row0 = b[t];
+        td.nrows = b[t + 1] - b[t];
+        td.rg = (uint32_t)i;
+        td.cursor0 = (uint32_t)((tile_base[i] + t) * np);
+      }
+      for (int p = 0; p < np; p++) {
+        const ChunkIndex& ci = rp.chunks[p];
+        ChunkInfo& info = q.chunk_infos[i * np + p];
+        info.phys_type = (uint32_t)std::max(0, q.pcols[p].phys_type);
+        info.seq_base = rp.seq_base;
+        IdxChunk& ic = q.idx_chunks[i * np + p];
+        ic.present = ci.present;
+        ic.page0 = (uint32_t)q.idx_pages.size();
+        if (!ci.present) continue;
+        auto rebase = [&](uint64_t foff) { return rp.arena_base[p] + (foff - ci.file_start); };
+        info.dict_off = ci.has_dict ? rebase(ci.dict_off) : 0;
+        info.dict_n = ci.dict_n;
+        info.base_off = rp.arena_base[p];
+        ic.base_off = rp.arena_base[p];
+        ic.max_def = (uint32_t)ci.max_def;
+        ic.esz = (ci.phys_type == PT_INT32 || ci.phys_type == PT_FLOAT) ? 4 : 8;
+        ic.num_rows = ci.num_rows;
+        ic.dict_n = ci.dict_n;
+        ic.string_typed = q.pcols[p].string_typed;
+        for (auto& pg : ci.pages) {
+          IdxPage ip;
+          memset(&ip, 0, sizeof ip);
+          ip.def_off = pg.def_end > pg.def_off ? rebase(pg.def_off) : 0;
+          ip.def_end = pg.def_end > pg.def_off ? rebase(pg.def_end) : 0;
+          ip.val_off = rebase(pg.values_off);
+          ip.val_end = ip.val_off + pg.values_len;
+          ip.first_row = pg.first_row;
+          ip.num_rows = pg.num_rows;
+          ip.chunk = (uint32_t)(i * np + p);
+          ip.dict_coded = pg.dict_coded;
+          ip.bit_width = pg.bit_width;
+          q.idx_pages.push_back(ip);
+        }
+        ic.npages = (uint32_t)q.idx_pages.size() - ic.page0;
+      }
+    }
+    LK_CHECK(q.idx_pages.size() < 0x7fffffffull, LK_ERR_UNSUPPORTED, "glob has too many pages");
+    q.def_chunks.clear();
+    q.defbm_words = 0;
+    q.def_blocks_total = 0;
+    def_mask_out = 0;
+  } else {
+  q.runs.resize_uninit(run_base.back());
+  q.cursors.resize_uninit(tile_base.back() * np);  // zeroed slice by slice by the workers below
   uint32_t def_mask = 0;
   std::vector<uint32_t> def_masks(q.rgs.size(), 0);
   std::vector<DefChunk> def_tmp(q.rgs.size() * np, DefChunk{});  // run_n > 0 <=> some tile of the chunk mixes NULLs and values
@@ -447,25 +505,10 @@ void plan_query(Query& q) {
     }
   });
   for (auto m : def_masks) def_mask |= m;
-  // definition bitmaps: one bit per row for every chunk that has a tile mixing NULLs and values; the device expands
-  // the chunk's hybrid RLE/bit-packed definition levels into it (def_expand_kernel) and the scan reads 16 bits per lane
-  q.def_chunks.clear();
-  q.defbm_words = 0;
-  q.def_blocks_total = 0;
-  for (size_t k = 0; k < def_tmp.size(); k++) {
-    DefChunk dc = def_tmp[k];
-    if (!dc.run_n) continue;
-    dc.word0 = (uint32_t)q.defbm_words;
-    dc.cum = (uint32_t)q.def_blocks_total;
-    q.chunk_infos[k].defbm_word0 = dc.word0;
-    q.defbm_words += (dc.num_rows + 31) / 32 + 2;  // + 2: the scan's funnel-shifted reads touch one word past the last
-    q.def_blocks_total += (dc.run_n + LK_DEF_BLOCK_RUNS - 1) / LK_DEF_BLOCK_RUNS;
-    q.def_chunks.push_back(dc);
+  layout_def_chunks(q, def_tmp);
+  def_mask_out = def_mask;
+  q.n_runs = q.runs.size();
   }
-  // lanes beyond a short last tile still read "their" 16 bits (and mask them away): up to 512 rows past the chunk's end
-  if (q.defbm_words) q.defbm_words += 32;
-  LK_CHECK(q.defbm_words < 0xffffffffull && q.def_blocks_total < 0x7fffffffull, LK_ERR_UNSUPPORTED, "glob too large for 32-bit definition bitmaps");
-
   trace.mark("tiles/cursors/runs");
   // ---- predicate: per-column classes over dictionary entries, then the pass bitmap over class combinations ----
   q.lut_cls.clear();
@@ -601,7 +644,7 @@ void plan_query(Query& q) {
   P.n_aggs = (int)q.aggs.size();
   for (size_t a = 0; a < q.aggs.size(); a++) { P.aggs[a].op = q.aggs[a].op; P.aggs[a].pcol = (uint8_t)q.agg_pcols[a]; }
   // chart-field filter `field$type IS NOT NULL`: expressed as one more conjunct on the value column being non-null
-  P.def_mask = def_mask;
+  P.def_mask = def_mask_out;
   P.ts_lo = q.ts_lo;
   P.ts_hi = q.ts_hi;
   P.step = q.step;
@@ -641,6 +684,27 @@ void plan_query(Query& q) {
   rebuild_group_tables(q);
   trace.mark("group tables");
   q.prepared = true;
+}
+
+void layout_def_chunks(Query& q, const std::vector<DefChunk>& def_tmp) {
+  // definition bitmaps: one bit per row for every chunk that has a tile mixing NULLs and values; the device expands
+  // the chunk's hybrid RLE/bit-packed definition levels into it (def_expand_kernel) and the scan reads 16 bits per lane
+  q.def_chunks.clear();
+  q.defbm_words = 0;
+  q.def_blocks_total = 0;
+  for (size_t k = 0; k < def_tmp.size(); k++) {
+    DefChunk dc = def_tmp[k];
+    if (!dc.run_n) continue;
+    dc.word0 = (uint32_t)q.defbm_words;
+    dc.cum = (uint32_t)q.def_blocks_total;
+    q.chunk_infos[k].defbm_word0 = dc.word0;
+    q.defbm_words += (dc.num_rows + 31) / 32 + 2;  // + 2: the scan's funnel-shifted reads touch one word past the last
+    q.def_blocks_total += (dc.run_n + LK_DEF_BLOCK_RUNS - 1) / LK_DEF_BLOCK_RUNS;
+    q.def_chunks.push_back(dc);
+  }
+  // lanes beyond a short last tile still read "their" 16 bits (and mask them away): up to 512 rows past the chunk's end
+  if (q.defbm_words) q.defbm_words += 32;
+  LK_CHECK(q.defbm_words < 0xffffffffull && q.def_blocks_total < 0x7fffffffull, LK_ERR_UNSUPPORTED, "glob too large for 32-bit definition bitmaps");
 }
 
 void rebuild_group_tables(Query& q) {
@@ -729,7 +793,7 @@ static void build_info_json(Query& q) {
   s += strf("\"n_groups\":%llu,\"n_buckets\":%u,\"n_cells\":%llu,\"hash_slots\":%llu,\"hash_stride\":%u,\"warp_agg\":%d,", (unsigned long long)q.n_groups,
             q.nbuckets, (unsigned long long)q.n_cells, (unsigned long long)q.hash_slots, q.hash_stride, q.params.warp_agg);
   s += strf("\"ts_lo\":%lld,\"ts_hi\":%lld,\"step\":%lld,\"base\":%lld,\"is_metrics\":%d,\"arena_bytes\":%llu,\"runs\":%zu,\"def_chunks\":%zu,\"def_bitmap_bytes\":%llu,", (long long)q.ts_lo,
-            (long long)q.ts_hi, (long long)q.step, (long long)q.base, (int)q.is_metrics, (unsigned long long)q.arena_bytes, q.runs.size(),
+            (long long)q.ts_hi, (long long)q.step, (long long)q.base, (int)q.is_metrics, (unsigned long long)q.arena_bytes, (size_t)q.n_runs,
             q.def_chunks.size(), (unsigned long long)q.defbm_words * 4);
   s += "\"columns\":[";
   for (size_t i = 0; i < q.pcols.size(); i++) {

@@ -143,6 +143,11 @@ struct Query {
   RawVec<ColCursor> cursors;
   RawVec<Run> runs;
   std::vector<ChunkInfo> chunk_infos;
+  // device-built seek index (device_index): page / chunk descriptors for the idx_* kernels instead of host-built runs / cursors
+  bool device_index = false;
+  std::vector<IdxPage> idx_pages;
+  std::vector<IdxChunk> idx_chunks;  // [row group][pcol]
+  uint64_t n_runs = 0;               // runs in the pool (device mode: known after the count pass)
   std::vector<DefChunk> def_chunks;  // chunks whose definition levels are expanded on the device before every scan
   uint64_t defbm_words = 0;          // size of the bitmap pool (32-bit words)
   uint64_t def_blocks_total = 0;     // CTAs of def_expand_kernel
@@ -185,6 +190,10 @@ struct HostResult {
 // planning (host only, no CUDA): lk_plan.cpp
 void plan_query(Query& q);           // parse + index + compile; fills the host pools and ScanParams (device pointers unset)
 void rebuild_group_tables(Query& q); // after key_dicts changed (dictionary import)
+// definition bitmaps: which chunks get one (run_n > 0 in def_tmp[row group * npcols + pcol]) and where; fills q.def_chunks,
+// chunk_infos[].defbm_word0, defbm_words
+void layout_def_chunks(Query& q, const std::vector<DefChunk>& def_tmp);
+void refresh_info_json(Query& q);     // after the device filled in what the host plan left open (run / definition-chunk counts)
 std::string export_dictionaries(const Query& q);
 void import_dictionaries(Query& q, const uint8_t* blob, size_t len);
 void parallel_for(int n, int threads, const std::function<void(int)>& fn);

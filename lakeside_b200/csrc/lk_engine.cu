@@ -174,6 +174,7 @@ struct Query::Device {
   unsigned long long* planes = nullptr;   // dense: (1 + n_aggs) planes of n_cells words
   HashArena* harena = nullptr;
   bool resident = false, executed = false, group_tables_stale = false;
+  size_t uploads_done = 0;  // entries of Query::uploads already on their way
   // compaction scratch + device result
   uint32_t* block_counts = nullptr;
   size_t block_counts_cap = 0;
@@ -270,11 +271,15 @@ void device_begin_upload(Query& q) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking));
     for (auto& e : d.ev) CUDA_CHECK(cudaEventCreate(&e));
   }
-  if (d.arena) return;
-  CUDA_CHECK(cudaEventRecord(d.ev[0], d.st));
-  CUDA_CHECK(cudaMallocAsync(&d.arena, q.arena_bytes, d.st));
-  for (auto& u : q.uploads)
-    CUDA_CHECK(cudaMemcpyAsync(d.arena + u.arena_off, q.segs[u.seg].data + u.file_off, u.len, cudaMemcpyHostToDevice, d.st));
+  if (!d.arena) {
+    CUDA_CHECK(cudaEventRecord(d.ev[0], d.st));
+    CUDA_CHECK(cudaMallocAsync(&d.arena, q.arena_bytes, d.st));
+  }
+  // (called again after the page walk: re-encoded PLAIN string pages join the list then)
+  for (; d.uploads_done < q.uploads.size(); d.uploads_done++) {
+    const Query::Upload& u = q.uploads[d.uploads_done];
+    CUDA_CHECK(cudaMemcpyAsync(d.arena + u.arena_off, u.src ? u.src : q.segs[u.seg].data + u.file_off, u.len, cudaMemcpyHostToDevice, d.st));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -1,5 +1,7 @@
 #include "lk_parquet.h"
 
+#include <unordered_map>
+
 #include <algorithm>
 #include <cstring>
 
@@ -129,6 +131,23 @@ ColumnChunkMeta read_column_meta(TReader& r) {
       case 7: m.total_compressed_size = r.zigzag(); break;
       case 9: m.data_page_offset = r.zigzag(); break;
       case 11: m.dictionary_page_offset = r.zigzag(); break;
+      case 13: {  // encoding_stats: list<PageEncodingStats {1: page_type, 2: encoding, 3: count}>
+        int n, et;
+        r.list_header(n, et);
+        m.plain_data_pages = 0;
+        for (int i = 0; i < n; i++) {
+          int f2, t2, l2 = 0, page_type = -1, enc = -1;
+          int64_t count = 0;
+          while (r.field(f2, t2, l2)) {
+            if (f2 == 1) page_type = (int)r.zigzag();
+            else if (f2 == 2) enc = (int)r.zigzag();
+            else if (f2 == 3) count = r.zigzag();
+            else r.skip(t2);
+          }
+          if ((page_type == 0 || page_type == 3) && enc == ENC_PLAIN) m.plain_data_pages += (int)std::min<int64_t>(count, 1 << 20);
+        }
+        break;
+      }
       default: r.skip(t);
     }
   }
@@ -366,6 +385,13 @@ uint32_t ChunkIndex::vidx_in_run(const uint8_t* file, int i, uint32_t r) const {
   return nn + popcount_bits(file + file_start + run.kind_value, k);
 }
 
+uint64_t synth_reserve(const ColumnChunkMeta& cm) {
+  if (cm.phys_type != PT_BYTE_ARRAY || cm.plain_data_pages == 0 || cm.num_values <= 0) return 0;
+  // one bit-packed run per page: at most 4 bytes per value + header and group padding per page (a page holds >= 1 value)
+  const uint64_t pages = cm.plain_data_pages > 0 ? (uint64_t)cm.plain_data_pages : (uint64_t)(cm.total_compressed_size >> 10) + 2;
+  return 4ull * (uint64_t)cm.num_values + 48ull * pages + 64;
+}
+
 void chunk_byte_range(const ColumnChunkMeta& cm, size_t file_len, const std::string& name, uint64_t& start_out, uint64_t& len_out) {
   int64_t start = cm.data_page_offset;
   if (cm.dictionary_page_offset > 0 && cm.dictionary_page_offset < start) start = cm.dictionary_page_offset;
@@ -392,6 +418,7 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
   const uint64_t cend = ci.file_start + ci.file_len;
   uint64_t p = ci.file_start;
   uint32_t row = 0, vidx = 0;
+  std::unordered_map<std::string, uint32_t> synth_lookup;  // string -> dictionary index, once a PLAIN string page shows up
   while (p < cend && row < ci.num_rows) {
     PageHeader h = read_page_header(data + p, data + cend);
     uint64_t payload = p + h.header_len;
@@ -466,10 +493,75 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
         });
       }
       pg.nvals = nn;
-      if (h.encoding == ENC_PLAIN) {
+      if (h.encoding == ENC_PLAIN && cm.phys_type == PT_BYTE_ARRAY) {
+        // length-prefixed strings (a string column whose dictionary outgrew its page): extend the chunk's dictionary and
+        // re-encode the page as ONE bit-packed run of indices (see ChunkIndex::synth)
+        LK_CHECK(want_strings, LK_ERR_UNSUPPORTED, "column '" + leaf.name + "': PLAIN string pages of a column that is not used as a string");
+        if (ci.synth.empty()) {
+          ci.synth_base = (ci.file_len + 7) & ~7ull;
+          for (uint32_t k = 0; k < (uint32_t)ci.dict_strings.size(); k++) synth_lookup.emplace(ci.dict_strings[k], k);
+          ci.has_dict = true;
+        }
+        std::vector<uint32_t> codes;
+        uint64_t v = q;
+        while (v < pend) {
+          LK_CHECK(v + 4 <= pend, LK_ERR_IO, "parquet: truncated PLAIN string page");
+          uint32_t n;
+          memcpy(&n, data + v, 4);
+          v += 4;
+          LK_CHECK(v + n <= pend, LK_ERR_IO, "parquet: truncated PLAIN string page");
+          std::string str((const char*)data + v, n);
+          v += n;
+          auto it = synth_lookup.find(str);
+          if (it == synth_lookup.end()) {
+            it = synth_lookup.emplace(str, (uint32_t)ci.dict_strings.size()).first;
+            ci.dict_strings.push_back(std::move(str));
+          }
+          codes.push_back(it->second);
+          if (walk_runs && codes.size() == nn) break;  // (a page may carry padding after its last value)
+        }
+        LK_CHECK(!walk_runs || codes.size() == nn, LK_ERR_IO, "parquet: PLAIN string page holds fewer values than its definition levels announce");
+        LK_CHECK(codes.size() <= pg.num_rows, LK_ERR_IO, "parquet: PLAIN string page holds more values than rows");
+        if (!walk_runs) nn = (uint32_t)codes.size();
+        pg.nvals = nn;
+        ci.dict_n = (uint32_t)ci.dict_strings.size();
+        uint32_t width = 1;
+        while (width < 31 && (ci.dict_n - 1) >> width) width++;
+        pg.dict_coded = true;
+        pg.synth = true;
+        pg.bit_width = (uint8_t)width;
+        // hybrid stream: varint((groups << 1) | 1), then groups * width bytes of LSB-first packed indices
+        const uint64_t groups = (codes.size() + 7) / 8;
+        const size_t at = ci.synth.size();
+        if (groups) {
+          uint64_t hdr = (groups << 1) | 1;
+          while (hdr >= 0x80) { ci.synth.push_back((uint8_t)(hdr | 0x80)); hdr >>= 7; }
+          ci.synth.push_back((uint8_t)hdr);
+          const size_t payload = ci.synth.size();
+          ci.synth.resize(payload + groups * width, 0);
+          uint64_t bit = 0;
+          for (uint32_t c : codes) {
+            for (uint32_t b = 0; b < width; b++, bit++)
+              if ((c >> b) & 1) ci.synth[payload + (bit >> 3)] |= (uint8_t)(1u << (bit & 7));
+          }
+        }
+        pg.values_off = at;  // offset inside ci.synth
+        pg.values_len = (uint32_t)(ci.synth.size() - at);
+        while (ci.synth.size() & 7) ci.synth.push_back(0);
+        if (walk_runs && nn > 0) {
+          uint32_t vbase = vidx;
+          walk_hybrid(ci.synth.data(), at, at + pg.values_len, pg.bit_width, nn, [&](uint32_t s2, uint32_t n2, bool rle, uint32_t v2, uint64_t off) {
+            (void)n2;
+            Run run;
+            run.start = vbase + s2;
+            run.kind_value = rle ? (0x80000000u | (v2 & 0x7fffffffu)) : (uint32_t)(ci.synth_base + off);
+            ci.val_runs.push_back(run);
+          });
+        }
+      } else if (h.encoding == ENC_PLAIN) {
         unsigned esz = (cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT) ? 4 : (cm.phys_type == PT_INT64 || cm.phys_type == PT_DOUBLE) ? 8 : 0;
         LK_CHECK(esz != 0, LK_ERR_UNSUPPORTED,
-                 "column '" + leaf.name + "': PLAIN pages of this type are not supported (dictionary fallback of a string column?)");
+                 "column '" + leaf.name + "': PLAIN pages of this type are not supported");
         LK_CHECK(!walk_runs || q + (uint64_t)nn * esz <= pend, LK_ERR_IO, "parquet: truncated PLAIN page");
         pg.dict_coded = false;
         pg.values_off = q;
@@ -508,7 +600,7 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
   // the kernels address a chunk's bit-packed dictionary indices by a 32-bit BIT offset from the chunk's first byte
   bool any_dict_page = false;
   for (auto& pg : ci.pages) any_dict_page |= pg.dict_coded;
-  LK_CHECK(!(any_dict_page || !ci.val_runs.empty()) || ci.file_len < (1ull << 29), LK_ERR_UNSUPPORTED,
+  LK_CHECK(!(any_dict_page || !ci.val_runs.empty()) || ci.file_len + ci.synth.size() + 8 < (1ull << 29), LK_ERR_UNSUPPORTED,
            "dictionary-coded column chunk of '" + leaf.name + "' is larger than 512 MB");
   return ci;
 }

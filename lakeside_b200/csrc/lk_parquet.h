@@ -22,6 +22,7 @@ struct ColumnChunkMeta {
   int64_t total_compressed_size = 0;
   int64_t data_page_offset = 0;
   int64_t dictionary_page_offset = -1;
+  int plain_data_pages = -1;  // data pages encoded PLAIN according to the footer's encoding_stats (-1: the writer left them out)
 };
 
 struct RowGroupMeta {
@@ -54,6 +55,7 @@ struct PageInfo {
   uint64_t values_off = 0;  // file offset of the value bytes (after the bit-width byte for dictionary pages)
   uint32_t values_len = 0;
   uint64_t def_off = 0, def_end = 0;  // file byte range of the definition-level stream (empty for REQUIRED columns)
+  bool synth = false;  // PLAIN string page re-encoded by the host: values_off / values_len address ChunkIndex::synth instead of the file
 };
 
 // Index of one column chunk.  Bit-packed run offsets are relative to file_start (the chunk's first byte).
@@ -72,6 +74,12 @@ struct ChunkIndex {
   uint64_t dict_off = 0;  // file offset of the PLAIN dictionary payload
   uint32_t dict_len = 0, dict_n = 0;
   std::vector<std::string> dict_strings;  // BYTE_ARRAY dictionaries, decoded on the host
+  // PLAIN (non-dictionary) BYTE_ARRAY data pages -- what a writer falls back to when a chunk's dictionary outgrows its page
+  // limit, i.e. high-cardinality tags -- are re-encoded here: their strings extend dict_strings and every such page becomes
+  // one bit-packed run of indices in `synth`, a hybrid stream like the file's own.  The bytes are placed right behind the
+  // chunk in the arena (offset synth_base from the chunk's first byte), so kernels and index builders see a dictionary page.
+  std::vector<uint8_t> synth;
+  uint64_t synth_base = 0;
   // chunk-level value index of row r (number of non-null values before r); r may equal num_rows
   uint32_t vidx_at(const uint8_t* file, uint32_t r) const;
   // same, when the def run `run_index` holding row r is already known (linear sweeps)
@@ -80,6 +88,9 @@ struct ChunkIndex {
   int val_run_at(uint32_t v) const;   // index of the value run containing value v
   int page_at(uint32_t r) const;
 };
+
+// Arena bytes to reserve behind a BYTE_ARRAY chunk for re-encoded PLAIN pages (0 when the footer says there are none).
+uint64_t synth_reserve(const ColumnChunkMeta& cm);
 
 // Byte range [start, start + len) of a column chunk inside the file (dictionary page + data pages), from the footer alone.
 void chunk_byte_range(const ColumnChunkMeta& cm, size_t file_len, const std::string& name, uint64_t& start, uint64_t& len);

@@ -294,6 +294,9 @@ void plan_query(Query& q) {
         rp.arena_base[p] = arena;
         q.uploads.push_back({rp.seg, start, len, arena});
         arena += len;
+        // room behind a string chunk for its PLAIN pages re-encoded as dictionary indices (none when the footer rules them out)
+        const uint64_t reserve = synth_reserve(cm);
+        if (reserve) arena = ((arena + 7) & ~7ull) + reserve;
       }
     }
     q.arena_bytes = ((arena + 255) & ~255ull) + 256;  // tail padding: lk_load_u64 may read the next aligned word
@@ -315,6 +318,17 @@ void plan_query(Query& q) {
           LK_CHECK(pg.dict_coded || pg.nvals == 0, LK_ERR_UNSUPPORTED, "string column '" + pc.name + "' has PLAIN (non-dictionary) pages");
     }
   });
+  for (auto& rp : q.rgs)
+    for (int p = 0; p < np; p++) {
+      const ChunkIndex& ci = rp.chunks[p];
+      if (!ci.present || ci.synth.empty()) continue;
+      const SegmentInput& seg = q.segs[rp.seg];
+      const ColumnChunkMeta& cm = seg.meta.row_groups[rp.rg].columns[seg.meta.leaf_index(q.pcols[p].name)];
+      LK_CHECK(ci.synth.size() <= synth_reserve(cm), LK_ERR_UNSUPPORTED, "column '" + q.pcols[p].name + "': PLAIN string pages need more room than the footer announced");
+      Query::Upload u{rp.seg, 0, ci.synth.size(), rp.arena_base[p] + ci.synth_base};
+      u.src = ci.synth.data();
+      q.uploads.push_back(u);
+    }
   q.total_rows = 0;
   q.touched_bytes = 0;
   for (auto& rp : q.rgs) {
@@ -386,7 +400,7 @@ void plan_query(Query& q) {
           memset(&ip, 0, sizeof ip);
           ip.def_off = pg.def_end > pg.def_off ? rebase(pg.def_off) : 0;
           ip.def_end = pg.def_end > pg.def_off ? rebase(pg.def_end) : 0;
-          ip.val_off = rebase(pg.values_off);
+          ip.val_off = pg.synth ? rp.arena_base[p] + ci.synth_base + pg.values_off : rebase(pg.values_off);
           ip.val_end = ip.val_off + pg.values_len;
           ip.first_row = pg.first_row;
           ip.num_rows = pg.num_rows;

@@ -154,7 +154,7 @@ struct Query {
   std::vector<uint8_t> lut_cls;
   std::vector<uint32_t> lut_gcode;
   std::vector<uint32_t> pass_bits;
-  struct Upload { int seg; uint64_t file_off, len, arena_off; };
+  struct Upload { int seg; uint64_t file_off, len, arena_off; const uint8_t* src = nullptr; };  // src: host bytes that are not in a segment (re-encoded pages)
   std::vector<Upload> uploads;
   uint64_t arena_bytes = 0;
   // called by plan_query as soon as the arena layout is known (footers only): the device layer starts the H2D copies

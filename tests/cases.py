@@ -173,6 +173,19 @@ def case_physical_layouts():
     p2 = [_write("types", 0, t2, "logs")]
     out.append(("layout/int64_value_wide_dict", p2, _req(_logs_be(F("pod", "regex", "^pod-1"), "sum", ["pod"]), 1, 600000), ["sum"]))
     out.append(("layout/field_float32_notnull", p2, _req(_logs_be(F(NAME, "eq", "a"), "max", [], fieldName="latency", fieldType="number"), 1, 600000), ["max"]))
+    # PLAIN (non-dictionary) string pages -- what a writer falls back to when a chunk's dictionary outgrows its page limit
+    # (high-cardinality tags such as pod names): (a) the whole column written without a dictionary, (b) a dictionary that
+    # overflows in the middle of the chunk (dictionary pages first, PLAIN pages after), as filter and as group-by column
+    hc = np.array([f"pod-{i:05d}-{'x' * (i % 7)}" for i in range(2500)], dtype=object)
+    t3 = pa.table({TS: np.sort(T0 + rng.integers(0, 3600000, n)).astype(np.int64), NAME: rng.choice(["a", "b"], n),
+                   "pod": pa.array(hc[rng.integers(0, 2500, n)], mask=rng.random(n) < 0.07),
+                   "level": pa.array(rng.choice(["info", "warn", "error"], n), mask=rng.random(n) < 0.1),
+                   VALUE: pa.array(rng.normal(0, 10, n))})
+    p3a = [_write("plain_str_all", 0, t3, "logs", use_dictionary=[NAME, "level"], data_page_size=4096)]
+    p3b = [_write("plain_str_fallback", 0, t3, "logs", dictionary_pagesize_limit=2048, data_page_size=4096, row_group_size=3000)]
+    for vid, pp in (("all_plain", p3a), ("dict_then_plain", p3b)):
+        out.append((f"layout/plain_strings_{vid}_group_by", pp, _req(_logs_be(F("level", "!=", "warn"), "sum", ["pod"]), 1, 600000), ["sum"]))
+        out.append((f"layout/plain_strings_{vid}_filter", pp, _req(_logs_be(F("pod", "regex", "^pod-0[0-3]"), "count", ["level"]), 1, 600000), ["count"]))
     out.append(("layout/field_datasize_int32", p2, _req(_logs_be(F(NAME, "eq", "b"), "sum", [], fieldName="bytes", fieldType="datasize"), 1, 600000), ["sum"]))
     return out
 

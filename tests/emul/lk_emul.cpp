@@ -50,7 +50,7 @@ static void run(Query& q, EmulResult& out) {
   out.info = q.info_json;
   std::vector<uint64_t> arena((q.arena_bytes + 7) / 8 + 2, 0);
   uint8_t* A = (uint8_t*)arena.data();
-  for (auto& u : q.uploads) memcpy(A + u.arena_off, q.segs[u.seg].data + u.file_off, u.len);
+  for (auto& u : q.uploads) memcpy(A + u.arena_off, u.src ? u.src : q.segs[u.seg].data + u.file_off, u.len);
   const ScanParams& P = q.params;
   const int np = (int)P.npcols;
   // definition bitmaps the way def_expand_kernel builds them: one run at a time, every chunk of q.def_chunks

@@ -71,7 +71,10 @@ int lk_eval(const char* pushdown_request_json, const char* const* parquet_paths,
  *    "path": "auto"|"dense"|"hash"|"records",                   aggregate layout (records: survivors are appended and
  *                                                               aggregated by a sort in finalize; auto picks it when
  *                                                               the group space is too large for dense planes)
- *    "exact_sums": false}                                       fixed-order (row order) bit-exact double sums */
+ *    "exact_sums": false,                                       fixed-order (segment order, then row order) double sums, bit-identical
+ *                                                               to a sequential evaluator; on every path, and sharded (record path + lk_comm)
+ *    "seq_offset": 0}                                           exact_sums, sharded: global row number of this shard's first row (shards hold
+ *                                                               contiguous blocks of the request's segments; = rows of the shards before it) */
 int lk_query_create(const char* pushdown_request_json, const char* options_json, lk_query** out);
 int lk_query_add_segment_file(lk_query* q, const char* path);
 /* The buffer is borrowed and must stay valid until lk_query_prepare returns. */

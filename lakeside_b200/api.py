@@ -167,9 +167,11 @@ class Query:
     """Staged evaluation of one glob: create -> add segments -> prepare (HBM resident) -> execute -> finalize."""
 
     def __init__(self, push_down_request_json: str, aggregates: Optional[Sequence[Tuple[str, str]]] = None,
-                 path: str = "auto", exact_sums: bool = False):
+                 path: str = "auto", exact_sums: bool = False, seq_offset: int = 0):
         lib = _lib.load()
         opts: Dict[str, Any] = {"path": path, "exact_sums": bool(exact_sums)}
+        if seq_offset:
+            opts["seq_offset"] = int(seq_offset)  # exact_sums, sharded: global sequence number of this shard's first row
         if aggregates:
             opts["aggregates"] = [{"aggregation": a, "rollup": r} for a, r in aggregates]
         self._h = ctypes.c_void_p()

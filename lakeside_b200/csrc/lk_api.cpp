@@ -99,6 +99,7 @@ int lk_query_create(const char* pushdown_request_json, const char* options_json,
         h->q.path_opt = p->str;
       }
       if (const Json* e = j.get("exact_sums")) h->q.exact_sums = e->as_bool();
+      if (const Json* e = j.get("seq_offset")) h->q.seq_offset = (uint64_t)e->as_i64();
       if (const Json* a = j.get("aggregates"); a && a->is_arr()) {
         const BaseExpr& e = h->q.req.expr;
         for (auto& x : a->arr) {

@@ -183,6 +183,8 @@ struct ScanParams {
   uint32_t rec_idx_bits;
   uint32_t rec_gid_bits;
   XchgParams x;         // path 3 (sharded record path): records are appended to the owner rank's pool instead
+  unsigned long long seq_offset;  // exact_sums, sharded: global sequence number of this shard's first row (shards hold contiguous
+                                  // blocks of the request's segment order)
   uint32_t* counters;   // [0] status flags, [1] phase min, [2] phase max, [3] #claimed slots, [4] tile ticket, [5] #records
   unsigned long long* survivors;  // [0] rows that passed the WHERE clause
 };

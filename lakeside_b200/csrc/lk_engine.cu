@@ -15,6 +15,7 @@
 namespace lk {
 
 static void device_exact_sums(Query& q, const ScanParams& base);
+static void rec_exact_finalize(Query& q);
 void device_resolve(Query& q);
 
 #define CUDA_CHECK(x)                                                                                        \
@@ -994,11 +995,13 @@ static void comm_fill_params(const Comm& c, XchgParams& X, uint32_t pool, size_t
 static void launch_scan(const Query& q, const ScanParams& P, bool emit) {
   cudaStream_t st = q.dev->st;
   const bool single = single_filter_ok(q);
-  if (emit) launch_scan_table<0, true>(P, single, st);  // record pass of exact_sums: cells are written out, no table
+  if (emit && P.path < 2) launch_scan_table<0, true>(P, single, st);  // record pass of exact_sums over a table: cells are written out
   else if (P.path == 0) launch_scan_table<0, false>(P, single, st);
   else if (P.path == 1) launch_scan_table<1, false>(P, single, st);
-  else if (P.path == 2) launch_scan_table<2, false>(P, single, st);
-  else launch_scan_table<3, false>(P, single, st);  // record path, sharded: appends go to the owner ranks' pools
+  else if (P.path == 2 && !emit) launch_scan_table<2, false>(P, single, st);
+  else if (P.path == 2) launch_scan_table<2, true>(P, single, st);   // exact_sums on the record path: rows carry their sequence number
+  else if (!emit) launch_scan_table<3, false>(P, single, st);        // record path, sharded: appends go to the owner ranks' pools
+  else launch_scan_table<3, true>(P, single, st);
 }
 
 void device_execute(Query& q) {
@@ -1035,11 +1038,13 @@ void device_execute(Query& q) {
     Comm& c = *q.comm;
     LK_CHECK(c.connected || c.world == 1, LK_ERR_INVALID, "lk_query_execute: the attached lk_comm is not connected");
     LK_CHECK(q.path == 2, LK_ERR_UNSUPPORTED, "an attached lk_comm exchanges the record path only (dense planes: lk_query_partial_dense + reduce)");
-    LK_CHECK((int)q.aggs.size() <= c.max_aggs, LK_ERR_INVALID, "the lk_comm was created for fewer aggregates than this query has");
+    LK_CHECK((int)q.aggs.size() + (q.exact_sums ? 1 : 0) <= c.max_aggs, LK_ERR_INVALID,
+             "the lk_comm was created for fewer aggregates than this query has (exact_sums needs one more word per record)");
     LK_CHECK(!d.rec_cell || d.rec_borrowed, LK_ERR_INVALID, "lk_query_set_comm after an unsharded execute");
     c.epoch++;
     const uint32_t pool = c.epoch & 1;
-    comm_fill_params(c, P.x, pool, q.aggs.size());
+    comm_fill_params(c, P.x, pool, q.aggs.size() + (q.exact_sums ? 1 : 0));
+    P.seq_offset = q.seq_offset;
     P.path = 3;
     d.rec_cell = c.keys(c.rank, pool);
     d.rec_vals = c.vals(c.rank, pool);
@@ -1065,7 +1070,7 @@ void device_execute(Query& q) {
         if (d.rec_vals) CUDA_CHECK(cudaFreeAsync(d.rec_vals, d.st));
         d.rec_cell = d.rec_vals = nullptr;
         CUDA_CHECK(cudaMallocAsync(&d.rec_cell, cap * 8, d.st));
-        CUDA_CHECK(cudaMallocAsync(&d.rec_vals, cap * 8 * q.aggs.size(), d.st));
+        CUDA_CHECK(cudaMallocAsync(&d.rec_vals, cap * 8 * (q.aggs.size() + (q.exact_sums ? 1 : 0)), d.st));
         d.rec_cap = cap;
       }
       P.rec_cell = d.rec_cell;
@@ -1073,9 +1078,9 @@ void device_execute(Query& q) {
       P.rec_cap = (uint32_t)std::min<size_t>(d.rec_cap, 0xffffffffu);
     }
     CUDA_CHECK(cudaEventRecord(d.ev[2], d.st));
-    launch_scan(q, P, false);
+    launch_scan(q, P, q.exact_sums && q.path == 2);
     CUDA_CHECK(cudaEventRecord(d.ev[3], d.st));
-    if (q.exact_sums) device_exact_sums(q, P);
+    if (q.exact_sums && q.path != 2) device_exact_sums(q, P);
   } else {
     CUDA_CHECK(cudaEventRecord(d.ev[2], d.st));
     CUDA_CHECK(cudaEventRecord(d.ev[3], d.st));
@@ -1764,6 +1769,12 @@ void device_finalize_device(Query& q) {
       CUDA_CHECK(cudaGetLastError());
       CUDA_CHECK(cudaEventRecord(d.ev[11], d.st));
     }
+    if (q.exact_sums) {
+      rec_exact_finalize(q);
+      d.finalized_device = true;
+      CUDA_CHECK(cudaEventRecord(d.ev[5], d.st));
+      return;
+    }
     if (d.fin_cap == 0) {
       // first finalize of this query: one read-back of the record count sizes the scratch and the result buffer
       CUDA_CHECK(cudaMemcpyAsync(d.h_counters, d.counters, sizeof d.h_counters, cudaMemcpyDeviceToHost, d.st));
@@ -2244,6 +2255,113 @@ static void device_exact_sums(Query& q, const ScanParams& base) {
   X.h_stride = base.h_stride;
   X.h_mask = base.h_mask;
   exact_fold_kernel<<<(int)((n + 255) / 256), 256, 0, d.st>>>(sorted_cell, order, n, X);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaFreeAsync(scratch, d.st));
+}
+
+// ---- exact_sums on the record path (single GPU and sharded): every record row starts with its global sequence number
+// (segment order, then row order; sharded: + the shard's offset).  The records of this rank -- its own list, or the regions
+// its sources filled -- are ordered by (key, sequence) with two stable radix sorts (CUB, this optional pass only), and one
+// thread per cell folds its records strictly in that order and writes the row: the sums are bit-identical to a sequential
+// evaluator's and do not depend on which rank scanned which segment (TimeGroupedSketchAggregator.scala:76-78 adds partials in
+// arrival order; this is the "fixed-order reduction option" of the north star).
+__global__ void exact_gather_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ rows, uint32_t n, int row_words,
+                                    const __grid_constant__ RecGeom G, unsigned long long* __restrict__ cell, unsigned long long* __restrict__ seq,
+                                    uint32_t* __restrict__ phys) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t pi = rec_phys(i, G);
+  cell[i] = keys[pi];
+  seq[i] = rows[(size_t)pi * row_words];
+  phys[i] = pi;
+}
+__global__ void exact_heads_kernel(const unsigned long long* __restrict__ sorted_cell, uint32_t n, uint32_t* __restrict__ block_counts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool head = i < n && (i == 0 || sorted_cell[i] != sorted_cell[i - 1]);
+  const int c = __syncthreads_count(head);
+  if (threadIdx.x == 0) block_counts[blockIdx.x] = (uint32_t)c;
+}
+__global__ void __launch_bounds__(256) exact_emit_kernel(const unsigned long long* __restrict__ sorted_cell, const uint32_t* __restrict__ order,
+                                                         const uint32_t* __restrict__ phys, uint32_t n, const unsigned long long* __restrict__ rows, int row_words,
+                                                         const uint32_t* __restrict__ block_offsets, const __grid_constant__ RecGeom G,
+                                                         const __grid_constant__ EmitParams E) {
+  __shared__ uint32_t warp_sums[8];
+  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned long long cell = i < n ? sorted_cell[i] : 0ull;
+  const bool head = i < n && (i == 0 || cell != sorted_cell[i - 1]);
+  const unsigned hm = __ballot_sync(0xffffffffu, head);
+  if (lane == 0) warp_sums[wid] = (uint32_t)__popc(hm);
+  __syncthreads();
+  if (!head) return;
+  uint32_t out = block_offsets[blockIdx.x] + (uint32_t)__popc(hm & ((1u << lane) - 1));
+  for (int w = 0; w < wid; w++) out += warp_sums[w];
+  unsigned long long acc[LK_MAX_AGGS];
+#pragma unroll
+  for (int a = 0; a < LK_MAX_AGGS; a++) acc[a] = 0;
+  for (uint32_t j = i; j < n && sorted_cell[j] == cell; j++) {  // strictly in (key, sequence) order
+    const unsigned long long* rec = rows + (size_t)phys[order[j]] * row_words + 1;
+    for (int a = 0; a < E.n_aggs; a++) {
+      const unsigned long long w = rec[a];
+      if (E.ops[a] == AGG_SUM) acc[a] = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)acc[a]) + __longlong_as_double((long long)w));
+      else if (E.ops[a] == AGG_COUNT) acc[a] += w;
+      else acc[a] = w > acc[a] ? w : acc[a];  // min (complemented key) and max (key): both stored as "max"
+    }
+  }
+  emit_row_bg(E, out, cell >> G.gid_bits, cell & ((1ull << G.gid_bits) - 1), [&](int a) { return acc[a]; });
+}
+
+static void rec_exact_finalize(Query& q) {
+  Query::Device& d = *q.dev;
+  CUDA_CHECK(cudaMemcpyAsync(d.h_counters, d.counters, sizeof d.h_counters, cudaMemcpyDeviceToHost, d.st));
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  check_scan_status(q, d.h_counters);
+  const uint32_t n = (uint32_t)std::min<size_t>(d.h_counters[5], d.rec_cap);
+  d.n_rows = 0;
+  d.dres_stride = 0;
+  if (n == 0) return;
+  RecGeom G;
+  memset(&G, 0, sizeof G);
+  G.idx_bits = q.params.rec_idx_bits;
+  G.gid_bits = q.params.rec_gid_bits;
+  G.nbuckets = q.nbuckets;
+  G.world = q.comm ? (uint32_t)q.comm->world : 1u;
+  G.region_cap = q.comm ? (uint32_t)q.comm->region_cap : 0u;
+  G.prefix = q.comm ? q.comm->ctrl(q.comm->rank)->prefix : nullptr;
+  const int row_words = (int)q.aggs.size() + 1;
+  size_t tmp_bytes = 0;
+  CUDA_CHECK(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, (const unsigned long long*)nullptr, (unsigned long long*)nullptr, (const uint32_t*)nullptr,
+                                             (uint32_t*)nullptr, (int)n, 0, 64, d.st));
+  // scratch: cell | seq | key_a | key_b (u64 each) | phys | idx_a | idx_b | block counts (u32 each) | cub temp
+  const uint32_t nblocks = (n + 255) / 256;
+  uint8_t* scratch = nullptr;
+  const size_t bytes = (size_t)n * 8 * 4 + (size_t)n * 4 * 3 + ((size_t)nblocks + 2) * 4 + tmp_bytes + 1024;
+  CUDA_CHECK(cudaMallocAsync(&scratch, bytes, d.st));
+  unsigned long long* cell = (unsigned long long*)scratch;
+  unsigned long long* seq = cell + n;
+  unsigned long long* key_a = seq + n;
+  unsigned long long* key_b = key_a + n;
+  uint32_t* phys = (uint32_t*)(key_b + n);
+  uint32_t* idx_a = phys + n;
+  uint32_t* idx_b = idx_a + n;
+  uint32_t* counts = idx_b + n;
+  void* tmp = (void*)(((uintptr_t)(counts + nblocks + 2) + 255) & ~(uintptr_t)255);
+  exact_gather_kernel<<<nblocks, 256, 0, d.st>>>(d.rec_cell, d.rec_vals, n, row_words, G, cell, seq, phys);
+  const unsigned long long* sorted_cell = nullptr;
+  const uint32_t* order = nullptr;
+  sort_order_by_two_keys(d.st, cell, seq, n, key_a, key_b, idx_a, idx_b, tmp, tmp_bytes, &sorted_cell, &order);
+  exact_heads_kernel<<<nblocks, 256, 0, d.st>>>(sorted_cell, n, counts);
+  exclusive_scan_kernel<<<1, 1024, 0, d.st>>>(counts, nblocks, counts + nblocks);
+  CUDA_CHECK(cudaGetLastError());
+  uint32_t n_rows = 0;
+  CUDA_CHECK(cudaMemcpyAsync(&n_rows, counts + nblocks, 4, cudaMemcpyDeviceToHost, d.st));
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  d.n_rows = n_rows;
+  d.dres_stride = n_rows;
+  ensure_dres(d, result_bytes(q, n_rows));
+  EmitParams E;
+  fill_emit_params(q, E, d.dres, n_rows);
+  exact_emit_kernel<<<nblocks, 256, 0, d.st>>>(sorted_cell, order, phys, n, d.rec_vals, row_words, counts, G, E);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaFreeAsync(scratch, d.st));
 }

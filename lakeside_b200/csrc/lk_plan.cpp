@@ -775,8 +775,8 @@ void rebuild_group_tables(Query& q) {
   q.path = dense ? 0 : 1;
   // Record path instead of the hash table whenever the group space is too large for dense planes: the survivors are
   // appended as records and aggregated by a sort in finalize (no table to probe, nothing to clear).  Measured on B200:
-  // C2 (1/16 of the rows survive) 2.16 -> 1.55 ms per step, C4 (47 % survive, 50 M records) 13.6 -> 7.9 ms.  Not with
-  // exact_sums (its fixed-order fold patches a table) and only while one record per row fits comfortably in HBM.
+  // C2 (1/16 of the rows survive) 2.16 -> 1.55 ms per step, C4 (47 % survive, 50 M records) 13.6 -> 7.9 ms.  Only while one
+  // record per row fits comfortably in HBM.
   // the record key packs (bucket, group id) into 64 bits
   uint32_t gid_bits = 1, bkt_bits = 1;
   while (gid_bits < 63 && (std::max<uint64_t>(q.n_groups, 1) - 1) >> gid_bits) gid_bits++;
@@ -785,7 +785,8 @@ void rebuild_group_tables(Query& q) {
   P.rec_gid_bits = gid_bits;
   const bool records_fit = (uint64_t)std::max<int64_t>(q.total_rows, 1) * 8 * (1 + q.aggs.size()) <= (16ull << 30) && q.total_rows < (1ll << 31) &&
                            gid_bits + bkt_bits <= 63;  // (the all-ones key marks a record folded into its owner)
-  if (!dense && !q.exact_sums && records_fit && (q.path_opt == "records" || q.path_opt == "auto")) q.path = 2;
+  // (exact_sums: every record also carries its sequence number, one more word per row)
+  if (!dense && records_fit && (!q.exact_sums || q.aggs.size() < (size_t)LK_MAX_AGGS) && (q.path_opt == "records" || q.path_opt == "auto")) q.path = 2;
   P.path = q.path;
   // few cells => many rows per cell => warp-level pre-reduction pays
   P.warp_agg = dense && q.n_groups <= 4096;

@@ -109,6 +109,7 @@ struct Query {
   std::vector<AggSpec> aggs;
   std::string path_opt = "auto";
   bool exact_sums = false;
+  uint64_t seq_offset = 0;  // exact_sums, sharded: global row sequence number of this shard's first row
   Comm* comm = nullptr;  // attached communicator: the record path exchanges its records through it during the scan
   std::vector<SegmentInput> segs;
 

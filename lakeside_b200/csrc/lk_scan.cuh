@@ -547,10 +547,10 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
               gid += (uint64_t)gcode * P.keys[k].stride;
             }
             // record path: the key keeps bucket and group id in separate bit fields (finalize bins on them without a division)
-            if constexpr (PATH >= 2 && !EMIT) cell = (bucket << P.rec_gid_bits) | gid;
+            if constexpr (PATH >= 2) cell = (bucket << P.rec_gid_bits) | gid;
             else cell = bucket * P.n_groups + gid;
             bucket32 = (uint32_t)bucket;
-            seq = s.ci[P.ts_pcol].seq_base + row0 + r;
+            seq = P.seq_offset + s.ci[P.ts_pcol].seq_base + row0 + r;
             if constexpr (PATH == 1 && !EMIT) {
               // first probe of the hash table: in flight while the values are gathered
               slot = lk_hash64(cell) & P.h_mask;
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
         }
       }
 
-      if constexpr (EMIT) {
+      if constexpr (EMIT && PATH < 2) {
         // fixed-order summation pass: the survivors are not aggregated here but written out as (cell, global row
         // sequence, value) records; they are sorted and folded strictly in row order afterwards (lk_exact.cu)
         const unsigned am = __ballot_sync(0xffffffffu, active);
@@ -701,7 +701,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
           if (active) {
             if (o < P.rec_cap) {
               P.rec_cell[o] = cell << P.rec_idx_bits;
-              unsigned long long* rec = P.rec_vals + (size_t)o * P.n_aggs;
+              // EMIT (exact_sums): the row starts with the record's global sequence number; finalize sorts by (key, sequence)
+              unsigned long long* rec = P.rec_vals + (size_t)o * (P.n_aggs + (EMIT ? 1 : 0));
+              if constexpr (EMIT) *rec++ = seq;
 #pragma unroll
               for (int a = 0; a < NA; a++)
                 if (a < P.n_aggs) rec[a] = !vvalid[a] ? 0ull : P.aggs[a].op == AGG_COUNT ? 1ull : vbits[a];
@@ -729,8 +731,9 @@ __global__ void __launch_bounds__(SCAN_BLOCK, SCAN_MIN_CTAS) scan_kernel(const _
               unsigned long long w[NA];
 #pragma unroll
               for (int a = 0; a < NA; a++) w[a] = (a >= P.n_aggs || !vvalid[a]) ? 0ull : P.aggs[a].op == AGG_COUNT ? 1ull : vbits[a];
-              unsigned long long* rec = X.vals[dest] + (size_t)o * P.n_aggs;
-              if (NA == 4 && P.n_aggs == 4) {
+              unsigned long long* rec = X.vals[dest] + (size_t)o * (P.n_aggs + (EMIT ? 1 : 0));
+              if constexpr (EMIT) *rec++ = seq;  // exact_sums: sequence number first (finalize sorts by (key, sequence))
+              if (!EMIT && NA == 4 && P.n_aggs == 4) {
                 asm volatile("st.global.v4.b64 [%0], {%1, %2, %3, %4};" ::"l"(rec), "l"(w[0]), "l"(w[1]), "l"(w[2]), "l"(w[3]) : "memory");
               } else {
 #pragma unroll

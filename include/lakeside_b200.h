@@ -199,6 +199,8 @@ int lk_merge_create(int k, const int64_t* const* ts, const int32_t* const* gid, 
                     const int64_t* lens, int reverse, lk_merge** out);
 int lk_merge_run(lk_merge* m);  /* asynchronous on the job's stream */
 int lk_merge_sync(lk_merge* m);
+/* ms: [0] H2D upload, [1] the merge kernels of the last run, [2] of which run detection + ordering of the runs,
+ * [3] which kernels ran: 1 = merge by runs (streams whose timestamps repeat: whole runs are ranked and copied), 2 = element-wise merge path. */
 int lk_merge_timings(lk_merge* m, double* ms /*[4]*/);
 int lk_merge_download(lk_merge* m, int64_t* out_ts, int32_t* out_gid, double* out_val, int32_t* out_src);
 /* TimeGroupedSketchAggregator map-sketch merge over the merged stream: combines equal (ts, gid) with

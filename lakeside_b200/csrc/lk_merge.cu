@@ -6,7 +6,9 @@
 // left head only when left < right: by timestamp, ties by stream index DESCENDING, then by position in the stream.
 // Every element therefore has a unique sort key (ts', K-1-src, pos) and the merge is a deterministic total order.
 //
-// One pass over the data: kernel 1 finds, for every output tile boundary (rank p * TILE), the exact per-stream split
+// Two sets of kernels.  Streams whose timestamps repeat (what the reference merges: step-aligned aggregates, hundreds of
+// elements per timestamp and stream) are merged by RUNS, see mrun_* below; everything else element-wise:
+// one pass over the data: kernel 1 finds, for every output tile boundary (rank p * TILE), the exact per-stream split
 // (multi-sequence selection by bisection over the key domain, a thread per stream); kernel 2 gives each CTA its K
 // sub-ranges (exactly TILE elements), loads their keys into shared memory, merges the K sorted runs pairwise
 // (log2 K levels of rank-by-binary-search, ping-pong buffers) and writes the tile out coalesced, gathering the
@@ -287,6 +289,336 @@ __global__ void __launch_bounds__(MG_BLOCK) merge_tile_kernel(const long long* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// merge by RUNS: the fast path for what the reference actually merges -- per-segment streams of step-aligned
+// aggregates, where one timestamp covers hundreds of consecutive elements of a stream (C5: 360 distinct timestamps,
+// 182 elements per run).  Inside a stream the elements of one timestamp are contiguous, and the tie rule (stream
+// index descending, then position) keeps them contiguous in the output: the merged stream is a permutation of whole
+// runs.  So instead of ranking 16.8 M elements the path ranks 92 k runs and then moves each run with one coalesced
+// copy -- one pass of 8 B read (run detection) + 12 B read + 24 B written per element:
+//   mrun_flags     a warp per 32 consecutive elements: head flag = first element of a stream or ts != predecessor's
+//                  (ballot -> one bit per element), heads counted per 2048-element block
+//   mrun_scan      single block: exclusive prefix of the block counts -> R runs
+//   mrun_fill      run r = (key, first element, stream); every key also enters a small hash set -> D distinct keys
+//   mrun_distinct  single block: bitonic sort of the D distinct keys in shared memory
+//   mrun_matrix    cell (d, K-1-stream) of a D x K matrix <- run index (a stream holds at most one run per key): the
+//                  matrix in row-major order IS the merged order of the runs
+//   mrun_cells_*   prefix over the cells of (run length, non-empty) -> output offset and rank of every run, compacted
+//   mrun_copy      a CTA per 2048 output elements: the runs that overlap it (two binary searches), then every element is
+//                  one coalesced gather of (gid, value) from its run's source position; ts and source come from the run
+// All counts stay on the device.  The path needs R <= total / 8 + K, D <= 8192 and D x K <= total / 4 + 64 Ki cells; the
+// first lk_merge_run of a job reads that verdict back once and otherwise takes the element-wise merge-path kernels.
+// ------------------------------------------------------------------------------------------------------------
+constexpr uint32_t MRUN_DMAX = 8192;            // distinct keys the run path sorts in one CTA's shared memory
+constexpr uint32_t MRUN_HSET = 4 * MRUN_DMAX;   // slots of the distinct-key hash set
+constexpr unsigned long long MRUN_EMPTY = ~0ull;
+constexpr uint32_t MRUN_CELLS_PER_CTA = 8192;   // 256 threads x 32 consecutive cells
+
+struct MrunCtl {
+  uint32_t n_runs;      // R
+  uint32_t n_hashed;    // distinct keys claimed in the hash set
+  uint32_t n_distinct;  // D (with the all-ones key, which the set cannot hold)
+  uint32_t has_max;     // the all-ones key occurs
+  uint32_t ok;          // the run path applies (set by mrun_scan, cleared by mrun_distinct)
+  uint32_t pad[3];
+};
+
+// exclusive prefix over the CTA (blockDim.x a multiple of 32, <= 1024); returns the CTA's total through *total
+__device__ __forceinline__ unsigned long long block_excl_scan(unsigned long long v, unsigned long long* warp_tot /*[32]*/, unsigned long long* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  unsigned long long incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+  __syncthreads();  // warp_tot may still be read from the previous call
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  unsigned long long woff = 0, tot = 0;
+  for (int w = 0; w < nw; w++) { const unsigned long long t = warp_tot[w]; if (w < wid) woff += t; tot += t; }
+  *total = tot;
+  return woff + incl - v;
+}
+
+__global__ void __launch_bounds__(MG_BLOCK) mrun_flags_kernel(const long long* __restrict__ ts, const uint32_t* __restrict__ offs, int K, uint64_t total,
+                                                              uint32_t* __restrict__ flags, uint32_t* __restrict__ block_counts) {
+  __shared__ uint32_t sflags[MG_TILE / 32];
+  const uint64_t lo = (uint64_t)blockIdx.x * MG_TILE, hi = min(total, lo + MG_TILE);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int IT = MG_TILE / MG_BLOCK;  // 32-element groups per warp
+  long long v[IT], first_prev[IT];
+#pragma unroll
+  for (int it = 0; it < IT; it++) {
+    const uint64_t i = lo + (uint64_t)(wid * IT + it) * 32 + lane;
+    v[it] = i < hi ? ts[i] : 0;
+    first_prev[it] = (lane == 0 && i > 0 && i < hi) ? ts[i - 1] : 0;
+  }
+#pragma unroll
+  for (int it = 0; it < IT; it++) {
+    const uint64_t i = lo + (uint64_t)(wid * IT + it) * 32 + lane;
+    long long prev = __shfl_up_sync(0xffffffffu, v[it], 1);
+    if (lane == 0) prev = first_prev[it];
+    const bool head = i < hi && (i == 0 || v[it] != prev);
+    const uint32_t w = __ballot_sync(0xffffffffu, head);
+    if (lane == 0) sflags[wid * IT + it] = w;
+  }
+  __syncthreads();
+  // streams that start inside this block: their first element is a head whatever its timestamp
+  {
+    int a = 0, b = K;  // first stream with offs[j] >= lo
+    while (a < b) { const int mid = (a + b) >> 1; if (offs[mid] < lo) a = mid + 1; else b = mid; }
+    for (int j = a + (int)threadIdx.x; j < K && offs[j] < hi; j += MG_BLOCK)
+      if (offs[j + 1] > offs[j]) { const uint32_t r = (uint32_t)(offs[j] - lo); atomicOr(&sflags[r >> 5], 1u << (r & 31)); }
+  }
+  __syncthreads();
+  if (threadIdx.x < MG_TILE / 32) flags[(size_t)blockIdx.x * (MG_TILE / 32) + threadIdx.x] = sflags[threadIdx.x];
+  if (threadIdx.x < 32) {
+    uint32_t c = __popc(sflags[threadIdx.x]) + __popc(sflags[threadIdx.x + 32]);
+#pragma unroll
+    for (int d = 16; d; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = c;
+  }
+}
+
+// in-place exclusive prefix of the block counts; R and the verdict "few enough runs" go to ctl
+__global__ void __launch_bounds__(1024) mrun_scan_kernel(uint32_t* __restrict__ counts, uint32_t n, uint32_t run_cap, MrunCtl* __restrict__ ctl) {
+  __shared__ unsigned long long warp_tot[32];
+  constexpr uint32_t PER = 8;
+  unsigned long long carry = 0;
+  for (uint32_t base = 0; base < n; base += 1024 * PER) {
+    const uint32_t i0 = base + threadIdx.x * PER;
+    uint32_t c[PER];
+    unsigned long long sum = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < PER; k++) { c[k] = i0 + k < n ? counts[i0 + k] : 0; sum += c[k]; }
+    unsigned long long tot;
+    unsigned long long ex = carry + block_excl_scan(sum, warp_tot, &tot);
+#pragma unroll
+    for (uint32_t k = 0; k < PER; k++) { if (i0 + k < n) counts[i0 + k] = (uint32_t)ex; ex += c[k]; }
+    carry += tot;
+  }
+  if (threadIdx.x == 0) {
+    ctl->n_runs = (uint32_t)carry;
+    ctl->ok = carry <= run_cap ? 1u : 0u;
+  }
+}
+
+__device__ __forceinline__ uint32_t mrun_hash(unsigned long long k) {
+  k ^= k >> 33; k *= 0xff51afd7ed558ccdull; k ^= k >> 33;
+  return (uint32_t)k;
+}
+
+__global__ void __launch_bounds__(64) mrun_fill_kernel(const long long* __restrict__ ts, const uint32_t* __restrict__ offs, int K, uint64_t total,
+                                                       const uint32_t* __restrict__ flags, const uint32_t* __restrict__ block_prefix, int reverse,
+                                                       MrunCtl* __restrict__ ctl, unsigned long long* __restrict__ run_key, uint32_t* __restrict__ run_start,
+                                                       uint32_t* __restrict__ run_stream, unsigned long long* __restrict__ hset,
+                                                       unsigned long long* __restrict__ dlist) {
+  if (!ctl->ok) return;
+  __shared__ unsigned long long warp_tot[32];
+  if (blockIdx.x == 0 && threadIdx.x == 0) run_start[ctl->n_runs] = (uint32_t)total;
+  uint32_t w = flags[(size_t)blockIdx.x * 64 + threadIdx.x];
+  unsigned long long tot;
+  uint32_t pos = block_prefix[blockIdx.x] + (uint32_t)block_excl_scan(__popc(w), warp_tot, &tot);
+  while (w) {
+    const int bit = __ffs(w) - 1;
+    w &= w - 1;
+    const uint32_t i = blockIdx.x * MG_TILE + threadIdx.x * 32 + bit;
+    const unsigned long long key = ts_key(ts[i], reverse);
+    int a = 0, b = K;  // last stream with offs[j] <= i (empty streams in front of it share the offset and lose)
+    while (b - a > 1) { const int mid = (a + b) >> 1; if (offs[mid] <= i) a = mid; else b = mid; }
+    run_key[pos] = key;
+    run_start[pos] = i;
+    run_stream[pos] = (uint32_t)a;
+    pos++;
+    if (key == MRUN_EMPTY) { ctl->has_max = 1; continue; }
+    if (*(volatile uint32_t*)&ctl->n_hashed > MRUN_DMAX) continue;  // too many distinct keys: the verdict is already "no"
+    uint32_t h = mrun_hash(key) & (MRUN_HSET - 1);
+    for (uint32_t probes = 0; probes < MRUN_HSET; probes++, h = (h + 1) & (MRUN_HSET - 1)) {
+      unsigned long long cur = *(volatile unsigned long long*)&hset[h];
+      if (cur == MRUN_EMPTY) cur = atomicCAS(&hset[h], MRUN_EMPTY, key);
+      if (cur == MRUN_EMPTY) {
+        const uint32_t idx = atomicAdd(&ctl->n_hashed, 1u);
+        if (idx < MRUN_DMAX) dlist[idx] = key;
+        break;
+      }
+      if (cur == key) break;
+    }
+  }
+}
+
+// sorts the distinct keys (bitonic, shared memory) and closes the verdict
+__global__ void __launch_bounds__(1024) mrun_distinct_kernel(MrunCtl* __restrict__ ctl, const unsigned long long* __restrict__ dlist,
+                                                             unsigned long long* __restrict__ dsorted, int K, uint64_t cell_cap) {
+  extern __shared__ unsigned long long skeys[];
+  if (!ctl->ok) return;
+  const uint32_t nh = ctl->n_hashed;
+  const uint32_t D = nh + (ctl->has_max ? 1u : 0u);
+  if (nh > MRUN_DMAX || D > MRUN_DMAX || (uint64_t)D * (uint64_t)K > cell_cap) {
+    __syncthreads();
+    if (threadIdx.x == 0) ctl->ok = 0;
+    return;
+  }
+  uint32_t P = 1;
+  while (P < D) P <<= 1;
+  for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) skeys[i] = i < nh ? dlist[i] : MRUN_EMPTY;  // the all-ones key sorts last, like the padding
+  __syncthreads();
+  for (uint32_t k = 2; k <= P; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
+        const uint32_t l = i ^ j;
+        if (l > i) {
+          const unsigned long long a = skeys[i], b = skeys[l];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { skeys[i] = b; skeys[l] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) dsorted[i] = skeys[i];
+  if (threadIdx.x == 0) ctl->n_distinct = D;
+}
+
+__global__ void __launch_bounds__(256) mrun_zero_kernel(const MrunCtl* __restrict__ ctl, int K, uint32_t* __restrict__ mat) {
+  if (!ctl->ok) return;
+  const uint64_t n = (uint64_t)ctl->n_distinct * K;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) mat[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) mrun_matrix_kernel(const MrunCtl* __restrict__ ctl, const unsigned long long* __restrict__ run_key,
+                                                          const uint32_t* __restrict__ run_stream, const unsigned long long* __restrict__ dsorted, int K,
+                                                          uint32_t* __restrict__ mat) {
+  if (!ctl->ok) return;
+  const uint32_t R = ctl->n_runs, D = ctl->n_distinct;
+  for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
+    const unsigned long long key = run_key[r];
+    uint32_t a = 0, b = D;
+    while (a < b) { const uint32_t mid = (a + b) >> 1; if (dsorted[mid] < key) a = mid + 1; else b = mid; }
+    mat[(uint64_t)a * K + (uint32_t)(K - 1) - run_stream[r]] = r + 1;
+  }
+}
+
+// prefix over the cells of (elements << 32 | 1) per non-empty cell: phase 1 = per-CTA sums, phase 2 = one block over the
+// sums, phase 3 = the CTA's cells again with its carry; every run then knows its output offset and its rank
+__device__ __forceinline__ unsigned long long mrun_cell_weight(uint32_t cell, const uint32_t* __restrict__ run_start) {
+  if (!cell) return 0;
+  return ((unsigned long long)(run_start[cell] - run_start[cell - 1]) << 32) | 1ull;
+}
+
+__global__ void __launch_bounds__(256) mrun_cells_sum_kernel(const MrunCtl* __restrict__ ctl, int K, const uint32_t* __restrict__ mat,
+                                                             const uint32_t* __restrict__ run_start, unsigned long long* __restrict__ partials) {
+  __shared__ unsigned long long warp_tot[32];
+  if (!ctl->ok) return;
+  const uint64_t n = (uint64_t)ctl->n_distinct * K;
+  const uint64_t base = (uint64_t)blockIdx.x * MRUN_CELLS_PER_CTA;
+  unsigned long long s = 0;
+  if (base < n)
+    for (uint32_t k = threadIdx.x; k < MRUN_CELLS_PER_CTA && base + k < n; k += 256) s += mrun_cell_weight(mat[base + k], run_start);
+  unsigned long long tot;
+  block_excl_scan(s, warp_tot, &tot);
+  if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) mrun_cells_scan_kernel(unsigned long long* __restrict__ partials, uint32_t n) {
+  __shared__ unsigned long long warp_tot[32];
+  unsigned long long carry = 0;
+  for (uint32_t base = 0; base < n; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const unsigned long long v = i < n ? partials[i] : 0;
+    unsigned long long tot;
+    const unsigned long long ex = carry + block_excl_scan(v, warp_tot, &tot);
+    if (i < n) partials[i] = ex;
+    carry += tot;
+  }
+}
+
+__global__ void __launch_bounds__(256) mrun_cells_emit_kernel(const MrunCtl* __restrict__ ctl, int K, uint64_t total, const uint32_t* __restrict__ mat,
+                                                              const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ run_stream,
+                                                              const unsigned long long* __restrict__ run_key, const unsigned long long* __restrict__ partials,
+                                                              uint32_t* __restrict__ m_dst, uint32_t* __restrict__ m_src, uint32_t* __restrict__ m_stream,
+                                                              unsigned long long* __restrict__ m_key) {
+  __shared__ unsigned long long warp_tot[32];
+  if (!ctl->ok) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) m_dst[ctl->n_runs] = (uint32_t)total;
+  const uint64_t n = (uint64_t)ctl->n_distinct * K;
+  const uint64_t base = (uint64_t)blockIdx.x * MRUN_CELLS_PER_CTA + (uint64_t)threadIdx.x * 32;
+  uint32_t cells[32];
+  unsigned long long s = 0;
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    cells[k] = base + k < n ? mat[base + k] : 0;
+    s += mrun_cell_weight(cells[k], run_start);
+  }
+  unsigned long long tot;
+  unsigned long long ex = partials[blockIdx.x] + block_excl_scan(s, warp_tot, &tot);
+#pragma unroll
+  for (int k = 0; k < 32; k++) {
+    const uint32_t c = cells[k];
+    if (!c) continue;
+    const uint32_t rank = (uint32_t)ex;
+    m_dst[rank] = (uint32_t)(ex >> 32);
+    m_src[rank] = run_start[c - 1];
+    m_stream[rank] = run_stream[c - 1];
+    m_key[rank] = run_key[c - 1];
+    ex += mrun_cell_weight(c, run_start);
+  }
+}
+
+__global__ void __launch_bounds__(MG_BLOCK) mrun_copy_kernel(const MrunCtl* __restrict__ ctl, const int* __restrict__ gid, const double* __restrict__ val,
+                                                             uint64_t total, int reverse, const uint32_t* __restrict__ m_dst, const uint32_t* __restrict__ m_src,
+                                                             const uint32_t* __restrict__ m_stream, const unsigned long long* __restrict__ m_key,
+                                                             long long* __restrict__ out_ts, int* __restrict__ out_gid, double* __restrict__ out_val,
+                                                             int* __restrict__ out_src) {
+  __shared__ uint32_t s_dst[MG_TILE + 1];
+  __shared__ uint32_t s_src[MG_TILE];
+  __shared__ uint32_t s_stream[MG_TILE];
+  __shared__ unsigned long long s_key[MG_TILE];
+  __shared__ uint32_t s_e[2];
+  if (!ctl->ok) return;
+  const uint32_t R = ctl->n_runs;
+  const uint64_t lo64 = (uint64_t)blockIdx.x * MG_TILE;
+  const uint32_t lo = (uint32_t)lo64, hi = (uint32_t)min(total, lo64 + MG_TILE);
+  if (threadIdx.x == 0 || threadIdx.x == 32) {
+    const uint32_t x = threadIdx.x == 0 ? lo : hi - 1;  // last run whose first output slot is <= x
+    uint32_t a = 0, b = R;                              // m_dst[0] = 0 <= x
+    while (b - a > 1) { const uint32_t mid = (a + b) >> 1; if (m_dst[mid] <= x) a = mid; else b = mid; }
+    s_e[threadIdx.x ? 1 : 0] = a;
+  }
+  __syncthreads();
+  const uint32_t e0 = s_e[0], ne = s_e[1] - e0 + 1;  // <= MG_TILE: every run holds at least one element
+  for (uint32_t k = threadIdx.x; k < ne; k += MG_BLOCK) {
+    s_dst[k] = m_dst[e0 + k];
+    s_src[k] = m_src[e0 + k];
+    s_stream[k] = m_stream[e0 + k];
+    s_key[k] = m_key[e0 + k];
+  }
+  __syncthreads();
+  constexpr int PER = MG_TILE / MG_BLOCK;
+  uint32_t src[PER], e[PER];
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    const uint32_t o = lo + k * MG_BLOCK + threadIdx.x;
+    uint32_t a = 0, b = ne;
+    while (b - a > 1) { const uint32_t mid = (a + b) >> 1; if (s_dst[mid] <= o) a = mid; else b = mid; }
+    e[k] = a;
+    src[k] = s_src[a] + (o - s_dst[a]);
+  }
+  int g[PER];
+  double v[PER];
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    const bool in = lo + k * MG_BLOCK + threadIdx.x < hi;
+    g[k] = (in && out_gid) ? gid[src[k]] : 0;
+    v[k] = (in && out_val) ? val[src[k]] : 0.0;
+  }
+#pragma unroll
+  for (int k = 0; k < PER; k++) {
+    const uint32_t o = lo + k * MG_BLOCK + threadIdx.x;
+    if (o >= hi) continue;
+    out_ts[o] = key_ts(s_key[e[k]], reverse);
+    if (out_gid) out_gid[o] = g[k];
+    if (out_val) out_val[o] = v[k];
+    if (out_src) out_src[o] = (int)s_stream[e[k]];
+  }
+}
+
 // ---- map-sketch re-aggregation of the merged stream (TimeGroupedSketchAggregator.scala:63-93) ----
 // Elements with equal timestamp are contiguous after the merge; equal (ts, gid) pairs are combined with
 // op 0: + (sum / count), 2: min, 3: max.  Output: one element per (ts, gid), sorted by ts then gid.
@@ -361,6 +693,26 @@ struct lk_merge {
   uint32_t ntiles = 0;
   bool ran = false;
   double ms[4] = {0, 0, 0, 0};
+  // merge by runs (see mrun_* above): scratch + the verdict of the job's first run
+  int mode = 0;  // 0 not decided yet, 1 runs, 2 element-wise merge path
+  uint32_t run_cap = 0, cell_parts = 0;
+  uint64_t cell_cap = 0;
+  lk::MrunCtl* r_ctl = nullptr;
+  uint32_t* r_flags = nullptr;
+  uint32_t* r_blocks = nullptr;
+  unsigned long long* r_hset = nullptr;
+  unsigned long long* r_dlist = nullptr;
+  unsigned long long* r_dsorted = nullptr;
+  unsigned long long* r_key = nullptr;
+  uint32_t* r_start = nullptr;
+  uint32_t* r_stream = nullptr;
+  uint32_t* r_mat = nullptr;
+  unsigned long long* r_parts = nullptr;
+  uint32_t* m_dst = nullptr;
+  uint32_t* m_src = nullptr;
+  uint32_t* m_stream = nullptr;
+  unsigned long long* m_key = nullptr;
+  cudaEvent_t ev_mid = nullptr;
 };
 
 namespace lk {
@@ -414,6 +766,27 @@ lk_merge* merge_create(int k, const int64_t* const* ts, const int32_t* const* gi
     CUDA_CHECK(cudaMallocAsync(&m->d_coarse, (ncoarse + 1) * std::max(k, 1) * 4, m->st));
     CUDA_CHECK(cudaMallocAsync(&m->d_ckey, (ncoarse + 1) * 8, m->st));
     CUDA_CHECK(cudaMemcpyAsync(m->d_offs, offs.data(), (k + 1) * 4, cudaMemcpyHostToDevice, m->st));
+    // merge by runs: scratch sized for the shapes the path accepts (see the limits above)
+    m->run_cap = (uint32_t)std::min<uint64_t>(total / 8 + (uint64_t)k + 1, 0xfffffff0ull);
+    m->cell_cap = total / 4 + 65536;
+    m->cell_parts = (uint32_t)((m->cell_cap + MRUN_CELLS_PER_CTA - 1) / MRUN_CELLS_PER_CTA);
+    if (const char* e = getenv("LK_MERGE_MODE")) m->mode = !strcmp(e, "elems") ? 2 : 0;  // tests: force the element-wise kernels
+    CUDA_CHECK(cudaEventCreate(&m->ev_mid));
+    CUDA_CHECK(cudaMallocAsync(&m->r_ctl, sizeof(MrunCtl), m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->r_flags, ((size_t)m->ntiles + 1) * (MG_TILE / 32) * 4, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->r_blocks, ((size_t)m->ntiles + 1) * 4, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->r_hset, (size_t)MRUN_HSET * 8, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->r_dlist, (size_t)MRUN_DMAX * 8, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->r_dsorted, (size_t)MRUN_DMAX * 8, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->r_key, ((size_t)m->run_cap + 1) * 8, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->r_start, ((size_t)m->run_cap + 1) * 4, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->r_stream, ((size_t)m->run_cap + 1) * 4, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->r_mat, (size_t)m->cell_cap * 4, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->r_parts, ((size_t)m->cell_parts + 1) * 8, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->m_dst, ((size_t)m->run_cap + 1) * 4, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->m_src, ((size_t)m->run_cap + 1) * 4, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->m_stream, ((size_t)m->run_cap + 1) * 4, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->m_key, ((size_t)m->run_cap + 1) * 8, m->st));
     for (int j = 0; j < k; j++) {
       if (!lens[j]) continue;
       CUDA_CHECK(cudaMemcpyAsync(m->d_ts + offs[j], ts[j], lens[j] * 8, cudaMemcpyHostToDevice, m->st));
@@ -432,6 +805,7 @@ lk_merge* merge_create(int k, const int64_t* const* ts, const int32_t* const* gi
     LK_CHECK(smem <= 200 * 1024, LK_ERR_UNSUPPORTED, "merge: too many streams for one shared-memory tile");
     (void)attr_set;
     CUDA_CHECK(cudaFuncSetAttribute(merge_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_CHECK(cudaFuncSetAttribute(mrun_distinct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(MRUN_DMAX * 8)));
   } catch (...) {
     merge_destroy(m);
     throw;
@@ -439,19 +813,54 @@ lk_merge* merge_create(int k, const int64_t* const* ts, const int32_t* const* gi
   return m;
 }
 
+static void merge_run_elems(lk_merge* m) {
+  size_t smem = 2 * MG_TILE_PADDED * sizeof(MergeElem) + 3 * (size_t)(m->K + 1) * 4 + 16;
+  const uint32_t ncoarse = (m->ntiles + MG_COARSE - 1) / MG_COARSE;  // coarse boundaries 0..ncoarse (the last one is the sentinel)
+  merge_split_kernel<<<ncoarse + 1, MG_BLOCK, 0, m->st>>>(m->d_ts, m->d_offs, m->K, m->total, m->kmin, m->kmax, m->reverse ? 1 : 0, m->d_coarse,
+                                                          (uint64_t)MG_COARSE * MG_TILE, nullptr, nullptr, 1, m->d_ckey);
+  merge_split_kernel<<<m->ntiles + 1, MG_BLOCK, 0, m->st>>>(m->d_ts, m->d_offs, m->K, m->total, m->kmin, m->kmax, m->reverse ? 1 : 0, m->d_splits,
+                                                            (uint64_t)MG_TILE, m->d_coarse, m->d_ckey, MG_COARSE, nullptr);
+  merge_tile_kernel<<<m->ntiles, MG_BLOCK, smem, m->st>>>(m->d_ts, m->d_gid, m->d_val, m->d_offs, m->K, m->total, m->reverse ? 1 : 0, m->d_splits,
+                                                          m->o_ts, m->o_gid, m->o_val, m->o_src);
+  CUDA_CHECK(cudaGetLastError());
+}
+
 void merge_run(lk_merge* m) {
   CUDA_CHECK(cudaSetDevice(global_options().device));
   CUDA_CHECK(cudaEventRecord(m->ev[2], m->st));
-  if (m->total > 0) {
-    size_t smem = 2 * MG_TILE_PADDED * sizeof(MergeElem) + 3 * (size_t)(m->K + 1) * 4 + 16;
-    const uint32_t ncoarse = (m->ntiles + MG_COARSE - 1) / MG_COARSE;  // coarse boundaries 0..ncoarse (the last one is the sentinel)
-    merge_split_kernel<<<ncoarse + 1, MG_BLOCK, 0, m->st>>>(m->d_ts, m->d_offs, m->K, m->total, m->kmin, m->kmax, m->reverse ? 1 : 0, m->d_coarse,
-                                                            (uint64_t)MG_COARSE * MG_TILE, nullptr, nullptr, 1, m->d_ckey);
-    merge_split_kernel<<<m->ntiles + 1, MG_BLOCK, 0, m->st>>>(m->d_ts, m->d_offs, m->K, m->total, m->kmin, m->kmax, m->reverse ? 1 : 0, m->d_splits,
-                                                              (uint64_t)MG_TILE, m->d_coarse, m->d_ckey, MG_COARSE, nullptr);
-    merge_tile_kernel<<<m->ntiles, MG_BLOCK, smem, m->st>>>(m->d_ts, m->d_gid, m->d_val, m->d_offs, m->K, m->total, m->reverse ? 1 : 0, m->d_splits,
-                                                            m->o_ts, m->o_gid, m->o_val, m->o_src);
+  const int rev = m->reverse ? 1 : 0;
+  if (m->total > 0 && m->mode != 2) {
+    // run detection and the verdict (R, D, cells) -- see mrun_* above
+    CUDA_CHECK(cudaMemsetAsync(m->r_ctl, 0, sizeof(MrunCtl), m->st));
+    CUDA_CHECK(cudaMemsetAsync(m->r_hset, 0xff, (size_t)MRUN_HSET * 8, m->st));
+    mrun_flags_kernel<<<m->ntiles, MG_BLOCK, 0, m->st>>>(m->d_ts, m->d_offs, m->K, m->total, m->r_flags, m->r_blocks);
+    mrun_scan_kernel<<<1, 1024, 0, m->st>>>(m->r_blocks, m->ntiles, m->run_cap, m->r_ctl);
+    mrun_fill_kernel<<<m->ntiles, 64, 0, m->st>>>(m->d_ts, m->d_offs, m->K, m->total, m->r_flags, m->r_blocks, rev, m->r_ctl, m->r_key, m->r_start,
+                                                  m->r_stream, m->r_hset, m->r_dlist);
+    mrun_distinct_kernel<<<1, 1024, MRUN_DMAX * 8, m->st>>>(m->r_ctl, m->r_dlist, m->r_dsorted, m->K, m->cell_cap);
     CUDA_CHECK(cudaGetLastError());
+    if (m->mode == 0) {  // first run of this job: one read-back decides which kernels follow (the inputs never change)
+      MrunCtl h;
+      CUDA_CHECK(cudaMemcpyAsync(&h, m->r_ctl, sizeof h, cudaMemcpyDeviceToHost, m->st));
+      CUDA_CHECK(cudaStreamSynchronize(m->st));
+      m->mode = h.ok ? 1 : 2;
+    }
+  }
+  if (m->total > 0 && m->mode == 1) {
+    const int wide = num_sms() * 4;
+    mrun_zero_kernel<<<wide, 256, 0, m->st>>>(m->r_ctl, m->K, m->r_mat);
+    mrun_matrix_kernel<<<wide, 256, 0, m->st>>>(m->r_ctl, m->r_key, m->r_stream, m->r_dsorted, m->K, m->r_mat);
+    mrun_cells_sum_kernel<<<m->cell_parts, 256, 0, m->st>>>(m->r_ctl, m->K, m->r_mat, m->r_start, m->r_parts);
+    mrun_cells_scan_kernel<<<1, 1024, 0, m->st>>>(m->r_parts, m->cell_parts);
+    mrun_cells_emit_kernel<<<m->cell_parts, 256, 0, m->st>>>(m->r_ctl, m->K, m->total, m->r_mat, m->r_start, m->r_stream, m->r_key, m->r_parts, m->m_dst,
+                                                             m->m_src, m->m_stream, m->m_key);
+    CUDA_CHECK(cudaEventRecord(m->ev_mid, m->st));
+    mrun_copy_kernel<<<m->ntiles, MG_BLOCK, 0, m->st>>>(m->r_ctl, m->d_gid, m->d_val, m->total, rev, m->m_dst, m->m_src, m->m_stream, m->m_key, m->o_ts,
+                                                        m->o_gid, m->o_val, m->o_src);
+    CUDA_CHECK(cudaGetLastError());
+  } else if (m->total > 0) {
+    CUDA_CHECK(cudaEventRecord(m->ev_mid, m->st));
+    merge_run_elems(m);
   }
   CUDA_CHECK(cudaEventRecord(m->ev[3], m->st));
   m->ran = true;
@@ -463,6 +872,9 @@ void merge_timings(lk_merge* m, double* ms) {
   merge_sync(m);
   float f = 0;
   if (m->ran && cudaEventElapsedTime(&f, m->ev[2], m->ev[3]) == cudaSuccess) m->ms[1] = f;
+  // [2]: run detection + ordering of the runs (or, element-wise path, the wait for the verdict); [3]: 1 = merged by runs, 2 = element-wise
+  if (m->ran && m->total > 0 && cudaEventElapsedTime(&f, m->ev[2], m->ev_mid) == cudaSuccess) m->ms[2] = f;
+  m->ms[3] = m->mode;
   cudaGetLastError();
   for (int i = 0; i < 4; i++) ms[i] = m->ms[i];
 }
@@ -533,12 +945,15 @@ void merge_destroy(lk_merge* m) {
   if (!m) return;
   if (m->st) {
     cudaStreamSynchronize(m->st);
-    void* ptrs[] = {m->d_ts, m->d_gid, m->d_val, m->d_offs, m->d_splits, m->d_coarse, m->d_ckey, m->o_ts, m->o_gid, m->o_val, m->o_src};
+    void* ptrs[] = {m->d_ts, m->d_gid, m->d_val, m->d_offs, m->d_splits, m->d_coarse, m->d_ckey, m->o_ts, m->o_gid, m->o_val, m->o_src,
+                    m->r_ctl, m->r_flags, m->r_blocks, m->r_hset, m->r_dlist, m->r_dsorted, m->r_key, m->r_start, m->r_stream, m->r_mat, m->r_parts,
+                    m->m_dst, m->m_src, m->m_stream, m->m_key};
     for (void* p : ptrs) if (p) cudaFreeAsync(p, m->st);
     cudaStreamSynchronize(m->st);
     cudaStreamDestroy(m->st);
   }
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
+  if (m->ev_mid) cudaEventDestroy(m->ev_mid);
   delete m;
 }
 

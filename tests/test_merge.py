@@ -49,6 +49,85 @@ def test_gpu_merge_matches_oracle(k, m, distinct):
     assert np.array_equal(src, wsrc) and np.array_equal(pos, wpos)
 
 
+def _merge_full(ts, gid, val, reverse=False, twice=False):
+    """create / run / timings / download through the C ABI; returns (ts, gid, val, src, mode) -- mode 1 = merged by runs."""
+    import ctypes
+
+    from lakeside_b200 import _lib, api
+
+    api.init()
+    lib = _lib.load()
+    k = len(ts)
+    n = sum(len(t) for t in ts)
+    P = ctypes.c_void_p
+    h = ctypes.c_void_p()
+    _lib.check(lib.lk_merge_create(k, (P * k)(*[t.ctypes.data for t in ts]), (P * k)(*[g.ctypes.data for g in gid]),
+                                   (P * k)(*[v.ctypes.data for v in val]), (ctypes.c_int64 * k)(*[len(t) for t in ts]), 1 if reverse else 0,
+                                   ctypes.byref(h)))
+    try:
+        for _ in range(2 if twice else 1):  # the second run takes the remembered verdict (no read-back)
+            _lib.check(lib.lk_merge_run(h))
+        ms = (ctypes.c_double * 4)()
+        _lib.check(lib.lk_merge_timings(h, ms))
+        o_ts, o_gid, o_val, o_src = np.empty(n, np.int64), np.empty(n, np.int32), np.empty(n, np.float64), np.empty(n, np.int32)
+        _lib.check(lib.lk_merge_download(h, o_ts.ctypes.data, o_gid.ctypes.data, o_val.ctypes.data, o_src.ctypes.data))
+    finally:
+        lib.lk_merge_destroy(h)
+    return o_ts, o_gid, o_val, o_src, int(ms[3])
+
+
+def _expected(ts, gid, val, reverse=False):
+    allsrc = np.concatenate([np.full(len(s), j) for j, s in enumerate(ts)])
+    allpos = np.concatenate([np.arange(len(s)) for s in ts])
+    allts = np.concatenate(ts)
+    order = np.lexsort((allpos, -allsrc, -allts if reverse else allts))
+    return allts[order], np.concatenate(gid)[order], np.concatenate(val)[order], allsrc[order]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,m,distinct,want_mode", [(256, 4096, 100, 1), (3, 60000, 7, 1), (256, 4096, 360, 2), (40, 3000, 5000, 2), (2, 100000, 1, 1)])
+def test_gpu_merge_by_runs_and_elementwise_agree_with_oracle(k, m, distinct, want_mode, monkeypatch):
+    # the run path (timestamps repeat: whole runs are ranked and copied) and the element-wise merge path produce the same stream
+    rng = np.random.default_rng(k + m + distinct)
+    ts = _streams(k, m, rng, distinct=distinct)
+    ts[k // 2] = np.zeros(0, np.int64)  # an empty stream in the middle
+    gid = [rng.integers(0, 1000, len(t)).astype(np.int32) for t in ts]
+    val = [rng.standard_normal(len(t)) for t in ts]
+    want = _expected(ts, gid, val)
+    got = _merge_full(ts, gid, val, twice=True)
+    assert got[4] == (want_mode if sum(len(t) for t in ts) else got[4])
+    for g, w in zip(got[:4], want):
+        assert np.array_equal(g, w)
+    monkeypatch.setenv("LK_MERGE_MODE", "elems")
+    forced = _merge_full(ts, gid, val)
+    assert forced[4] == 2
+    for g, w in zip(forced[:4], want):
+        assert np.array_equal(g, w)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("reverse", [False, True])
+def test_gpu_merge_by_runs_extreme_timestamps(reverse):
+    # INT64_MIN / INT64_MAX timestamps: the all-ones key cannot live in the distinct-key set and is handled beside it
+    rng = np.random.default_rng(5)
+    pool = np.array([-2**63, -2**63 + 1, -1, 0, 1, 2**63 - 2, 2**63 - 1], np.int64)
+    ts = []
+    for j in range(12):
+        t = np.sort(pool[rng.integers(0, len(pool), 4000)])
+        ts.append(t[::-1].copy() if reverse else t)
+    gid = [rng.integers(0, 9, len(t)).astype(np.int32) for t in ts]
+    val = [rng.standard_normal(len(t)) for t in ts]
+    allsrc = np.concatenate([np.full(len(s), j) for j, s in enumerate(ts)])
+    allpos = np.concatenate([np.arange(len(s)) for s in ts])
+    allts = np.concatenate(ts)
+    rank = np.searchsorted(pool, allts)  # order-preserving small keys: negating INT64_MIN would overflow
+    order = np.lexsort((allpos, -allsrc, -rank if reverse else rank))
+    got = _merge_full(ts, gid, val, reverse=reverse)
+    assert got[4] == 1
+    assert np.array_equal(got[0], allts[order]) and np.array_equal(got[3], allsrc[order])
+    assert np.array_equal(got[1], np.concatenate(gid)[order]) and np.array_equal(got[2], np.concatenate(val)[order])
+
+
 @pytest.mark.gpu
 def test_gpu_merge_payload_reverse_and_empty():
     import ctypes

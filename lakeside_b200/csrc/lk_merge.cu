@@ -312,7 +312,8 @@ __global__ void __launch_bounds__(MG_BLOCK) merge_tile_kernel(const long long* _
 constexpr uint32_t MRUN_DMAX = 8192;            // distinct keys the run path sorts in one CTA's shared memory
 constexpr uint32_t MRUN_HSET = 4 * MRUN_DMAX;   // slots of the distinct-key hash set
 constexpr unsigned long long MRUN_EMPTY = ~0ull;
-constexpr uint32_t MRUN_CELLS_PER_CTA = 8192;   // 256 threads x 32 consecutive cells
+constexpr uint32_t MRUN_CELLS_PER_CTA = 1024;   // 256 threads x 4 consecutive cells
+constexpr int MRUN_CPT = MRUN_CELLS_PER_CTA / 256;
 
 struct MrunCtl {
   uint32_t n_runs;      // R
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(64) mrun_fill_kernel(const long long* __restri
 }
 
 // sorts the distinct keys (bitonic, shared memory) and closes the verdict
-__global__ void __launch_bounds__(1024) mrun_distinct_kernel(MrunCtl* __restrict__ ctl, const unsigned long long* __restrict__ dlist,
+__global__ void __launch_bounds__(256) mrun_distinct_kernel(MrunCtl* __restrict__ ctl, const unsigned long long* __restrict__ dlist,
                                                              unsigned long long* __restrict__ dsorted, int K, uint64_t cell_cap) {
   extern __shared__ unsigned long long skeys[];
   if (!ctl->ok) return;
@@ -460,6 +461,16 @@ __global__ void __launch_bounds__(1024) mrun_distinct_kernel(MrunCtl* __restrict
   while (P < D) P <<= 1;
   for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) skeys[i] = i < nh ? dlist[i] : MRUN_EMPTY;  // the all-ones key sorts last, like the padding
   __syncthreads();
+  if (D <= 1024) {  // few keys (the usual case: one per step of the query range): every key counts the smaller ones, no stage barriers
+    for (uint32_t i = threadIdx.x; i < D; i += blockDim.x) {
+      const unsigned long long k = skeys[i];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < D; j++) rank += skeys[j] < k;  // keys are distinct (the padding equals the all-ones key but sits behind it)
+      dsorted[i < nh ? rank : D - 1] = k;
+    }
+    if (threadIdx.x == 0) ctl->n_distinct = D;
+    return;
+  }
   for (uint32_t k = 2; k <= P; k <<= 1)
     for (uint32_t j = k >> 1; j > 0; j >>= 1) {
       for (uint32_t i = threadIdx.x; i < P; i += blockDim.x) {
@@ -476,48 +487,45 @@ __global__ void __launch_bounds__(1024) mrun_distinct_kernel(MrunCtl* __restrict
   if (threadIdx.x == 0) ctl->n_distinct = D;
 }
 
-__global__ void __launch_bounds__(256) mrun_zero_kernel(const MrunCtl* __restrict__ ctl, int K, uint32_t* __restrict__ mat) {
-  if (!ctl->ok) return;
-  const uint64_t n = (uint64_t)ctl->n_distinct * K;
-  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) mat[i] = 0;
-}
-
 __global__ void __launch_bounds__(256) mrun_matrix_kernel(const MrunCtl* __restrict__ ctl, const unsigned long long* __restrict__ run_key,
-                                                          const uint32_t* __restrict__ run_stream, const unsigned long long* __restrict__ dsorted, int K,
-                                                          uint32_t* __restrict__ mat) {
+                                                          const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ run_stream,
+                                                          const unsigned long long* __restrict__ dsorted, int K, unsigned long long* __restrict__ mat) {
   if (!ctl->ok) return;
   const uint32_t R = ctl->n_runs, D = ctl->n_distinct;
   for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < R; r += gridDim.x * blockDim.x) {
     const unsigned long long key = run_key[r];
     uint32_t a = 0, b = D;
     while (a < b) { const uint32_t mid = (a + b) >> 1; if (dsorted[mid] < key) a = mid + 1; else b = mid; }
-    mat[(uint64_t)a * K + (uint32_t)(K - 1) - run_stream[r]] = r + 1;
+    // cell = run length << 32 | run index + 1: the prefix kernels never go back to the run arrays for an empty cell
+    mat[(uint64_t)a * K + (uint32_t)(K - 1) - run_stream[r]] = ((unsigned long long)(run_start[r + 1] - run_start[r]) << 32) | (r + 1);
   }
 }
 
 // prefix over the cells of (elements << 32 | 1) per non-empty cell: phase 1 = per-CTA sums, phase 2 = one block over the
 // sums, phase 3 = the CTA's cells again with its carry; every run then knows its output offset and its rank
-__device__ __forceinline__ unsigned long long mrun_cell_weight(uint32_t cell, const uint32_t* __restrict__ run_start) {
-  if (!cell) return 0;
-  return ((unsigned long long)(run_start[cell] - run_start[cell - 1]) << 32) | 1ull;
+__device__ __forceinline__ unsigned long long mrun_cell_weight(unsigned long long cell) {
+  return (cell & 0xffffffff00000000ull) | (cell ? 1ull : 0ull);
 }
 
-__global__ void __launch_bounds__(256) mrun_cells_sum_kernel(const MrunCtl* __restrict__ ctl, int K, const uint32_t* __restrict__ mat,
-                                                             const uint32_t* __restrict__ run_start, unsigned long long* __restrict__ partials) {
+__global__ void __launch_bounds__(256) mrun_cells_sum_kernel(const MrunCtl* __restrict__ ctl, int K, const unsigned long long* __restrict__ mat,
+                                                             unsigned long long* __restrict__ partials) {
   __shared__ unsigned long long warp_tot[32];
   if (!ctl->ok) return;
   const uint64_t n = (uint64_t)ctl->n_distinct * K;
   const uint64_t base = (uint64_t)blockIdx.x * MRUN_CELLS_PER_CTA;
+  if (base >= n) return;
   unsigned long long s = 0;
-  if (base < n)
-    for (uint32_t k = threadIdx.x; k < MRUN_CELLS_PER_CTA && base + k < n; k += 256) s += mrun_cell_weight(mat[base + k], run_start);
+#pragma unroll
+  for (int k = 0; k < MRUN_CPT; k++) { const uint64_t i = base + k * 256 + threadIdx.x; if (i < n) s += mrun_cell_weight(mat[i]); }
   unsigned long long tot;
   block_excl_scan(s, warp_tot, &tot);
   if (threadIdx.x == 0) partials[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(1024) mrun_cells_scan_kernel(unsigned long long* __restrict__ partials, uint32_t n) {
+__global__ void __launch_bounds__(1024) mrun_cells_scan_kernel(const MrunCtl* __restrict__ ctl, int K, unsigned long long* __restrict__ partials) {
   __shared__ unsigned long long warp_tot[32];
+  if (!ctl->ok) return;
+  const uint32_t n = (uint32_t)(((uint64_t)ctl->n_distinct * K + MRUN_CELLS_PER_CTA - 1) / MRUN_CELLS_PER_CTA);  // CTAs that hold cells
   unsigned long long carry = 0;
   for (uint32_t base = 0; base < n; base += 1024) {
     const uint32_t i = base + threadIdx.x;
@@ -529,7 +537,7 @@ __global__ void __launch_bounds__(1024) mrun_cells_scan_kernel(unsigned long lon
   }
 }
 
-__global__ void __launch_bounds__(256) mrun_cells_emit_kernel(const MrunCtl* __restrict__ ctl, int K, uint64_t total, const uint32_t* __restrict__ mat,
+__global__ void __launch_bounds__(256) mrun_cells_emit_kernel(const MrunCtl* __restrict__ ctl, int K, uint64_t total, unsigned long long* __restrict__ mat,
                                                               const uint32_t* __restrict__ run_start, const uint32_t* __restrict__ run_stream,
                                                               const unsigned long long* __restrict__ run_key, const unsigned long long* __restrict__ partials,
                                                               uint32_t* __restrict__ m_dst, uint32_t* __restrict__ m_src, uint32_t* __restrict__ m_stream,
@@ -538,26 +546,28 @@ __global__ void __launch_bounds__(256) mrun_cells_emit_kernel(const MrunCtl* __r
   if (!ctl->ok) return;
   if (blockIdx.x == 0 && threadIdx.x == 0) m_dst[ctl->n_runs] = (uint32_t)total;
   const uint64_t n = (uint64_t)ctl->n_distinct * K;
-  const uint64_t base = (uint64_t)blockIdx.x * MRUN_CELLS_PER_CTA + (uint64_t)threadIdx.x * 32;
-  uint32_t cells[32];
+  const uint64_t base = (uint64_t)blockIdx.x * MRUN_CELLS_PER_CTA + (uint64_t)threadIdx.x * MRUN_CPT;
+  if ((uint64_t)blockIdx.x * MRUN_CELLS_PER_CTA >= n) return;
+  unsigned long long cells[MRUN_CPT];
   unsigned long long s = 0;
 #pragma unroll
-  for (int k = 0; k < 32; k++) {
+  for (int k = 0; k < MRUN_CPT; k++) {
     cells[k] = base + k < n ? mat[base + k] : 0;
-    s += mrun_cell_weight(cells[k], run_start);
+    if (cells[k]) mat[base + k] = 0;  // the matrix goes back to all-empty for the job's next run
+    s += mrun_cell_weight(cells[k]);
   }
   unsigned long long tot;
   unsigned long long ex = partials[blockIdx.x] + block_excl_scan(s, warp_tot, &tot);
 #pragma unroll
-  for (int k = 0; k < 32; k++) {
-    const uint32_t c = cells[k];
+  for (int k = 0; k < MRUN_CPT; k++) {
+    const unsigned long long c = cells[k];
     if (!c) continue;
-    const uint32_t rank = (uint32_t)ex;
+    const uint32_t r = (uint32_t)c - 1, rank = (uint32_t)ex;
     m_dst[rank] = (uint32_t)(ex >> 32);
-    m_src[rank] = run_start[c - 1];
-    m_stream[rank] = run_stream[c - 1];
-    m_key[rank] = run_key[c - 1];
-    ex += mrun_cell_weight(c, run_start);
+    m_src[rank] = run_start[r];
+    m_stream[rank] = run_stream[r];
+    m_key[rank] = run_key[r];
+    ex += mrun_cell_weight(c);
   }
 }
 
@@ -575,11 +585,19 @@ __global__ void __launch_bounds__(MG_BLOCK) mrun_copy_kernel(const MrunCtl* __re
   const uint32_t R = ctl->n_runs;
   const uint64_t lo64 = (uint64_t)blockIdx.x * MG_TILE;
   const uint32_t lo = (uint32_t)lo64, hi = (uint32_t)min(total, lo64 + MG_TILE);
-  if (threadIdx.x == 0 || threadIdx.x == 32) {
-    const uint32_t x = threadIdx.x == 0 ? lo : hi - 1;  // last run whose first output slot is <= x
-    uint32_t a = 0, b = R;                              // m_dst[0] = 0 <= x
-    while (b - a > 1) { const uint32_t mid = (a + b) >> 1; if (m_dst[mid] <= x) a = mid; else b = mid; }
-    s_e[threadIdx.x ? 1 : 0] = a;
+  if (threadIdx.x < 64) {  // warps 0 and 1: 32-ary search for the last run whose first output slot is <= x (m_dst[0] = 0 <= x)
+    const uint32_t x = threadIdx.x < 32 ? lo : hi - 1, lane = threadIdx.x & 31;
+    uint32_t a = 0, b = R;  // answer in [a, b)
+    while (b - a > 1) {
+      const uint32_t step = (b - a + 31) / 32;              // lane probes a + lane * step
+      const uint32_t p = a + lane * step;
+      const bool le = p < b && m_dst[p] <= x;               // monotone: true for lanes 0..c-1
+      const uint32_t c = __popc(__ballot_sync(0xffffffffu, le));  // >= 1 (lane 0 probes a)
+      const uint32_t na = a + (c - 1) * step;
+      b = min(b, na + step);
+      a = na;
+    }
+    if (lane == 0) s_e[threadIdx.x >> 5] = a;
   }
   __syncthreads();
   const uint32_t e0 = s_e[0], ne = s_e[1] - e0 + 1;  // <= MG_TILE: every run holds at least one element
@@ -695,7 +713,7 @@ struct lk_merge {
   double ms[4] = {0, 0, 0, 0};
   // merge by runs (see mrun_* above): scratch + the verdict of the job's first run
   int mode = 0;  // 0 not decided yet, 1 runs, 2 element-wise merge path
-  uint32_t run_cap = 0, cell_parts = 0;
+  uint32_t run_cap = 0, cell_parts = 0, known_distinct = 0;
   uint64_t cell_cap = 0;
   lk::MrunCtl* r_ctl = nullptr;
   uint32_t* r_flags = nullptr;
@@ -706,7 +724,7 @@ struct lk_merge {
   unsigned long long* r_key = nullptr;
   uint32_t* r_start = nullptr;
   uint32_t* r_stream = nullptr;
-  uint32_t* r_mat = nullptr;
+  unsigned long long* r_mat = nullptr;
   unsigned long long* r_parts = nullptr;
   uint32_t* m_dst = nullptr;
   uint32_t* m_src = nullptr;
@@ -781,7 +799,8 @@ lk_merge* merge_create(int k, const int64_t* const* ts, const int32_t* const* gi
     CUDA_CHECK(cudaMallocAsync(&m->r_key, ((size_t)m->run_cap + 1) * 8, m->st));
     CUDA_CHECK(cudaMallocAsync(&m->r_start, ((size_t)m->run_cap + 1) * 4, m->st));
     CUDA_CHECK(cudaMallocAsync(&m->r_stream, ((size_t)m->run_cap + 1) * 4, m->st));
-    CUDA_CHECK(cudaMallocAsync(&m->r_mat, (size_t)m->cell_cap * 4, m->st));
+    CUDA_CHECK(cudaMallocAsync(&m->r_mat, (size_t)m->cell_cap * 8, m->st));
+    CUDA_CHECK(cudaMemsetAsync(m->r_mat, 0, (size_t)m->cell_cap * 8, m->st));  // all cells empty; mrun_cells_emit restores that after every run
     CUDA_CHECK(cudaMallocAsync(&m->r_parts, ((size_t)m->cell_parts + 1) * 8, m->st));
     CUDA_CHECK(cudaMallocAsync(&m->m_dst, ((size_t)m->run_cap + 1) * 4, m->st));
     CUDA_CHECK(cudaMallocAsync(&m->m_src, ((size_t)m->run_cap + 1) * 4, m->st));
@@ -837,21 +856,23 @@ void merge_run(lk_merge* m) {
     mrun_scan_kernel<<<1, 1024, 0, m->st>>>(m->r_blocks, m->ntiles, m->run_cap, m->r_ctl);
     mrun_fill_kernel<<<m->ntiles, 64, 0, m->st>>>(m->d_ts, m->d_offs, m->K, m->total, m->r_flags, m->r_blocks, rev, m->r_ctl, m->r_key, m->r_start,
                                                   m->r_stream, m->r_hset, m->r_dlist);
-    mrun_distinct_kernel<<<1, 1024, MRUN_DMAX * 8, m->st>>>(m->r_ctl, m->r_dlist, m->r_dsorted, m->K, m->cell_cap);
+    // shared memory for the keys it sorts: all MRUN_DMAX until the first run has told how many there are
+    const size_t dsmem = (m->mode == 0 || m->known_distinct > 1024) ? (size_t)MRUN_DMAX * 8 : 1024 * 8;
+    mrun_distinct_kernel<<<1, 256, dsmem, m->st>>>(m->r_ctl, m->r_dlist, m->r_dsorted, m->K, m->cell_cap);
     CUDA_CHECK(cudaGetLastError());
     if (m->mode == 0) {  // first run of this job: one read-back decides which kernels follow (the inputs never change)
       MrunCtl h;
       CUDA_CHECK(cudaMemcpyAsync(&h, m->r_ctl, sizeof h, cudaMemcpyDeviceToHost, m->st));
       CUDA_CHECK(cudaStreamSynchronize(m->st));
       m->mode = h.ok ? 1 : 2;
+      m->known_distinct = h.n_distinct;
     }
   }
   if (m->total > 0 && m->mode == 1) {
     const int wide = num_sms() * 4;
-    mrun_zero_kernel<<<wide, 256, 0, m->st>>>(m->r_ctl, m->K, m->r_mat);
-    mrun_matrix_kernel<<<wide, 256, 0, m->st>>>(m->r_ctl, m->r_key, m->r_stream, m->r_dsorted, m->K, m->r_mat);
-    mrun_cells_sum_kernel<<<m->cell_parts, 256, 0, m->st>>>(m->r_ctl, m->K, m->r_mat, m->r_start, m->r_parts);
-    mrun_cells_scan_kernel<<<1, 1024, 0, m->st>>>(m->r_parts, m->cell_parts);
+    mrun_matrix_kernel<<<wide, 256, 0, m->st>>>(m->r_ctl, m->r_key, m->r_start, m->r_stream, m->r_dsorted, m->K, m->r_mat);
+    mrun_cells_sum_kernel<<<m->cell_parts, 256, 0, m->st>>>(m->r_ctl, m->K, m->r_mat, m->r_parts);
+    mrun_cells_scan_kernel<<<1, 1024, 0, m->st>>>(m->r_ctl, m->K, m->r_parts);
     mrun_cells_emit_kernel<<<m->cell_parts, 256, 0, m->st>>>(m->r_ctl, m->K, m->total, m->r_mat, m->r_start, m->r_stream, m->r_key, m->r_parts, m->m_dst,
                                                              m->m_src, m->m_stream, m->m_key);
     CUDA_CHECK(cudaEventRecord(m->ev_mid, m->st));

@@ -524,6 +524,13 @@ def main():
             q.add_segment_buffer(ptr, n)
         return q
 
+    def new_query_files():
+        # segment FILES: their column chunks go through the library's HBM-resident segment cache (keyed by path, size, mtime, inode)
+        q = api.Query(rq, aggregates=aggs, path=table_path)
+        for p in paths:
+            q.add_segment_file(p)
+        return q
+
     def _as_tensor(ptr, n, typestr, dtype):
         class _A:
             pass
@@ -692,9 +699,9 @@ def main():
     e2e_steps = max(2, min(args.steps, 5))
     e2e_trace = []
 
-    def e2e_step():
+    def e2e_step(files=False):
         t = [time.perf_counter()]
-        qq = new_query()
+        qq = new_query_files() if files else new_query()
         t.append(time.perf_counter())
         qq.plan()  # the column chunks start moving here; they overlap the index build and the dictionary agreement
         agree_on_dictionaries(qq)
@@ -734,6 +741,39 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_dt = float(t.item())
     e2e_value = total_rows / e2e_dt
+    # warm arm: the same call sequence over the segment FILES once the library's segment cache holds their column chunks
+    # (the first evaluation fills it): no file read, no segment byte over PCIe; planning, the device-side index build, the
+    # kernels and the D2H of the result rows remain
+    e2e_warm = None
+    cache_cap = api.cache_stats()["capacity_bytes"]
+    if os.environ.get("LK_BENCH_WARM", "1") != "0" and cache_cap > 2 * touched:
+        gc.collect()
+        for _ in range(2):
+            e2e_step(files=True)  # cold fill, then one warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        st0 = api.cache_stats()
+        gc.disable()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step(files=True)
+        torch.cuda.synchronize()
+        warm_dt = (time.perf_counter() - t0) / e2e_steps
+        gc.enable()
+        st1 = api.cache_stats()
+        if world > 1:
+            t = torch.tensor([warm_dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            warm_dt = float(t.item())
+        e2e_warm = {"value": total_rows / warm_dt, "unit": UNIT, "ms_per_step": warm_dt * 1e3, "steps": e2e_steps,
+                    "h2d_segment_bytes_per_step": 0, "d2h_bytes_per_step": int(d2h_b),
+                    "cache": {"column_hits_per_step": (st1["column_hits"] - st0["column_hits"]) // e2e_steps,
+                              "column_misses_per_step": (st1["column_misses"] - st0["column_misses"]) // e2e_steps,
+                              "resident_bytes": st1["resident_bytes"], "capacity_bytes": st1["capacity_bytes"]},
+                    "what": "lk_query_create + add_segment_file + prepare + execute + finalize (D2H) with every touched column chunk found in the "
+                            "library's HBM-resident segment cache (WorkerApi.scala:53-64 analogue); reported beside e2e, which stays the cold figure"}
+        api.cache_clear()
     if os.environ.get("LK_BENCH_TRACE") and rank == 0:
         print("e2e trace (ms) [create, plan+prepare, execute+exchange+finalize, close]:", e2e_trace[-e2e_steps:], file=sys.stderr)
 
@@ -779,7 +819,9 @@ def main():
             "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d_b), "d2h_bytes_per_step": int(d2h_b),
                     "ms_per_step": e2e_dt * 1e3, "steps": e2e_steps,
-                    "what": "lk_query_create + add_segment_buffer(pinned host bytes) + prepare (host index + H2D) + execute + finalize (D2H)"},
+                    "what": "cold: lk_query_create + add_segment_buffer(pinned host bytes) + prepare (host index + H2D) + execute + finalize (D2H); "
+                            "caller buffers are never cached"},
+            "e2e_warm": e2e_warm,
             # this library's own kernels per step -- records: def_expand, scan, rec_bhist, rec_regions, rec_group, rec_rowscan, rec_emit
             # (+ comm_publish, comm_wait when sharded); hash: scan, hist, exclusive_scan, scatter, emit (+ sparse_hist, sparse_scatter,
             # sparse_merge); dense: scan, count, exclusive_scan, emit.  No library (CUB / NCCL) kernel on the record path.

@@ -42,7 +42,7 @@ typedef struct lk_comm lk_comm;     /* sharded evaluation: this rank's receive p
 
 /* ---- library ------------------------------------------------------------------------------------------ */
 /* options_json (may be NULL): {"device": 0, "max_hash_slots": 134217728, "dense_max_cells": 33554432,
- *                              "tile_rows": 512, "host_threads": 8, "tune_host_malloc": 1}
+ *                              "tile_rows": 512, "host_threads": 8, "tune_host_malloc": 1, "segment_cache_bytes": -1}
  * tune_host_malloc (default 1, glibc only): raises the process's M_TRIM_THRESHOLD / M_MMAP_THRESHOLD so that the
  * ~0.3 GB of transient host index memory a query builds is recycled inside the process instead of being unmapped at
  * the end of every query and faulted in again by the next (8 ms per 100-segment query); pass 0 to leave the host's
@@ -52,6 +52,19 @@ void lk_shutdown(void);
 const char* lk_last_error(void);
 const char* lk_version(void);
 int lk_device_count(void); /* 0 when no CUDA device is visible; never fails */
+
+/* ---- HBM-resident segment cache ------------------------------------------------------------------------------
+ * Column chunks of segment FILES (lk_eval, lk_query_add_segment_file) stay in device memory after the query that uploaded
+ * them, keyed by the file's identity (path, size, mtime, inode) and column, together with the footer / page / dictionary
+ * index the host built: a later query over the same segments reads no file and moves no segment byte over PCIe.  The
+ * analogue of the worker's cache of downloaded segment files (query-worker WorkerApi.scala:53-64), one level further down.
+ * Owned by the library, thread-safe, least-recently-used segments evicted first; queries pin what they use.  Capacity:
+ * lk_init option "segment_cache_bytes" (default: a third of the device's memory; 0 = off) or lk_cache_configure.
+ * Segments handed over as caller buffers (lk_query_add_segment_buffer) have no identity and are never cached.
+ * stats: [0] capacity bytes, [1] resident bytes, [2] segments, [3] column hits, [4] column misses, [5] evicted segments. */
+int lk_cache_stats(int64_t* stats /*[6]*/);
+int lk_cache_configure(int64_t capacity_bytes);
+void lk_cache_clear(void);
 
 /* Pinned host memory for segment bytes handed to lk_query_add_segment_buffer (fast H2D). */
 void* lk_host_alloc(size_t bytes);

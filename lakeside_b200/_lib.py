@@ -37,6 +37,9 @@ _SIGNATURES = {
     "lk_last_error": (c_char_p, []),
     "lk_version": (c_char_p, []),
     "lk_device_count": (c_int, []),
+    "lk_cache_stats": (c_int, [POINTER(ctypes.c_int64)]),
+    "lk_cache_configure": (c_int, [ctypes.c_int64]),
+    "lk_cache_clear": (None, []),
     "lk_host_alloc": (c_void_p, [c_size_t]),
     "lk_host_free": (None, [c_void_p]),
     "lk_eval": (c_int, [c_char_p, POINTER(c_char_p), c_int, POINTER(c_void_p)]),

@@ -28,6 +28,21 @@ def device_count() -> int:
     return int(_lib.load().lk_device_count())
 
 
+def cache_stats() -> Dict[str, int]:
+    """HBM-resident segment cache (lk_cache_stats): column chunks of segment files kept in device memory across queries."""
+    out = (ctypes.c_int64 * 6)()
+    _lib.check(_lib.load().lk_cache_stats(out))
+    return dict(zip(["capacity_bytes", "resident_bytes", "segments", "column_hits", "column_misses", "evicted_segments"], [int(x) for x in out]))
+
+
+def cache_configure(capacity_bytes: int) -> None:
+    _lib.check(_lib.load().lk_cache_configure(int(capacity_bytes)))
+
+
+def cache_clear() -> None:
+    _lib.load().lk_cache_clear()
+
+
 @dataclass
 class DataPoint:
     timestamp: int

@@ -11,6 +11,7 @@
 #include <malloc.h>
 #endif
 
+#include "lk_cache.h"
 #include "lk_engine.h"
 #include "lk_merge.h"
 
@@ -56,6 +57,7 @@ int lk_init(const char* options_json) {
       if (const Json* v = j.get("device")) o.device = (int)v->as_i64();
       if (const Json* v = j.get("max_hash_slots")) o.max_hash_slots = (uint64_t)v->as_i64();
       if (const Json* v = j.get("dense_max_cells")) o.dense_max_cells = (uint64_t)v->as_i64();
+      if (const Json* v = j.get("segment_cache_bytes")) o.segment_cache_bytes = v->as_i64();
       if (const Json* v = j.get("tile_rows")) o.tile_rows = (uint32_t)v->as_i64();
       if (const Json* v = j.get("host_threads")) o.host_threads = (int)v->as_i64();
       if (const Json* v = j.get("tune_host_malloc")) o.tune_host_malloc = v->as_i64() != 0;
@@ -85,6 +87,22 @@ void* lk_host_alloc(size_t bytes) {
   return p;
 }
 void lk_host_free(void* p) { pinned_free(p); }
+
+int lk_cache_stats(int64_t* out) {
+  if (!out) return LK_ERR_INVALID;
+  SegmentCacheStats st = segment_cache().stats();
+  out[0] = st.capacity_bytes; out[1] = st.resident_bytes; out[2] = st.segments;
+  out[3] = st.column_hits; out[4] = st.column_misses; out[5] = st.evicted_segments;
+  return LK_OK;
+}
+int lk_cache_configure(int64_t capacity_bytes) {
+  return guard([&] {
+    LK_CHECK(capacity_bytes >= 0, LK_ERR_INVALID, "capacity_bytes must be >= 0");
+    global_options().segment_cache_bytes = capacity_bytes;
+    segment_cache().set_capacity((size_t)capacity_bytes);
+  });
+}
+void lk_cache_clear(void) { segment_cache().clear(); }
 
 int lk_query_create(const char* pushdown_request_json, const char* options_json, lk_query** out) {
   return guard([&] {
@@ -146,29 +164,23 @@ int lk_query_add_segment_file(lk_query* q, const char* path) {
   return guard([&] {
     LK_CHECK(q && path, LK_ERR_INVALID, "null argument");
     LK_CHECK(!q->q.prepared, LK_ERR_INVALID, "query already prepared");
-    int fd = open(path, O_RDONLY);
-    LK_CHECK(fd >= 0, LK_ERR_IO, std::string("IO Error: cannot open ") + path);
     struct stat st;
-    if (fstat(fd, &st) != 0) { close(fd); fail(LK_ERR_IO, std::string("IO Error: cannot stat ") + path); }
-    size_t len = (size_t)st.st_size;
-    void* buf = nullptr;
-    try {
-      device_init();
-      buf = pinned_alloc(len + 16);
-    } catch (...) { close(fd); throw; }
-    size_t got = 0;
-    while (got < len) {
-      ssize_t r = read(fd, (char*)buf + got, len - got);
-      if (r <= 0) break;
-      got += (size_t)r;
-    }
-    close(fd);
-    if (got != len) { pinned_free(buf); fail(LK_ERR_IO, std::string("IO Error: short read on ") + path); }
+    LK_CHECK(stat(path, &st) == 0 && S_ISREG(st.st_mode), LK_ERR_IO, std::string("IO Error: cannot open ") + path);
+    device_init();
     SegmentInput s;
-    s.data = (const uint8_t*)buf;
-    s.len = len;
+    s.len = (size_t)st.st_size;
     s.name = path;
-    s.owned_pinned = buf;
+    s.has_identity = true;
+    s.id_mtime_ns = (uint64_t)st.st_mtim.tv_sec * 1000000000ull + (uint64_t)st.st_mtim.tv_nsec;
+    s.id_ino = (uint64_t)st.st_ino;
+    // a segment the cache knows (same path, size, mtime, inode) brings its footer along and is only read if a column misses
+    SegmentIdentity id;
+    id.path = s.name; id.size = s.len; id.mtime_ns = s.id_mtime_ns; id.ino = s.id_ino;
+    s.cached = segment_cache().lookup(id);
+    if (s.cached) {
+      s.meta = s.cached->meta;
+      s.meta_from_cache = true;
+    } else segment_load(s);
     q->q.segs.push_back(std::move(s));
   });
 }
@@ -182,7 +194,7 @@ int lk_query_plan(lk_query* q) {
     // lk_query_prepare; without one (host-logic tests, dictionary agreement on a CPU box) planning is host-only.
     Query* qp = &q->q;
     if (device_count() > 0) {
-      q->q.on_layout = [qp] { device_begin_upload(*qp); };
+      q->q.on_layout = [qp] { device_layout(*qp); };
       q->q.device_index = !getenv("LK_HOST_INDEX");  // run headers and cursors are built on the device during prepare
     }
     plan_query(q->q);
@@ -199,7 +211,7 @@ int lk_query_prepare(lk_query* q) {
       double t0 = now_ms();
       device_init();  // fail before any host work when there is no GPU
       Query* qp = &q->q;
-      q->q.on_layout = [qp] { device_begin_upload(*qp); };  // column chunks start moving while the host walks the page headers
+      q->q.on_layout = [qp] { device_layout(*qp); };  // column chunks start moving while the host walks the page headers
       q->q.device_index = !getenv("LK_HOST_INDEX");          // run headers and cursors are built on the device (LK_HOST_INDEX: on the host)
       plan_query(q->q);
       q->q.on_layout = nullptr;

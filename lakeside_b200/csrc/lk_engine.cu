@@ -1,12 +1,15 @@
 // Device layer of liblakeside_b200: HBM residency of a prepared query, kernel launches, result compaction.
 #include <cuda_runtime.h>
+#include <fcntl.h>
 #include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
 #include <cstring>
+#include <map>
 #include <mutex>
 
+#include "lk_cache.h"
 #include "lk_engine.h"
 #include "lk_scan.cuh"
 
@@ -30,6 +33,7 @@ void device_resolve(Query& q);
 static std::mutex g_mu;
 static bool g_inited = false;
 static int g_num_sms = 148;
+static cudaStream_t g_cache_stream = nullptr;
 
 int device_count() {
   int n = 0;
@@ -58,7 +62,21 @@ void device_init() {
   CUDA_CHECK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
   PoolAlloc::alloc = pinned_alloc;   // index pools of later queries live in pinned memory
   PoolAlloc::release = pinned_free;
+  // HBM-resident segment cache (lk_cache.h): a third of the device's memory unless lk_init said otherwise
+  int64_t cache_bytes = global_options().segment_cache_bytes;
+  if (cache_bytes < 0) cache_bytes = (int64_t)(prop.totalGlobalMem / 3);
+  segment_cache().set_capacity((size_t)cache_bytes);
+  CUDA_CHECK(cudaStreamCreateWithFlags(&g_cache_stream, cudaStreamNonBlocking));
   g_inited = true;
+}
+
+// device blocks of cached columns are released here: nothing uses a block any more when its last reference goes away
+// (queries drop theirs after synchronising their stream)
+void cache_free_device(void* p) {
+  if (!p) return;
+  if (g_cache_stream) cudaFreeAsync(p, g_cache_stream);
+  else cudaFree(p);
+  cudaGetLastError();
 }
 
 int num_sms() { return g_num_sms; }
@@ -148,6 +166,7 @@ static void arena_release(HashArena* a) {
 }
 
 void device_shutdown() {
+  segment_cache().clear();
   std::lock_guard<std::mutex> lk(g_mu);
   for (auto& a : g_arenas) { cudaFree(a.entries); cudaFree(a.occ); cudaFree(a.occ_bkt); }
   g_arenas.clear();
@@ -224,6 +243,8 @@ Query::~Query() {
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
     if (d.st) { cudaStreamSynchronize(d.st); cudaStreamDestroy(d.st); }
   }
+  cache_fresh.clear();  // the stream is idle: cached columns this query pinned may go (freed when no one else holds them)
+  cache_refs.clear();
   for (auto& s : segs) if (s.owned_pinned) pinned_free(s.owned_pinned);
   if (getenv("LK_PLAN_TRACE"))
     fprintf(stderr, "[lk destroy] device part %23.2f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_destroy0).count());
@@ -260,11 +281,38 @@ static void upload_group_tables(Query& q) {
   d.group_tables_stale = false;
 }
 
-// Starts the H2D copies of the touched column chunks (asynchronous; called from plan_query's on_layout hook so that
-// the copies run while the host still walks page and run headers).
-bool device_is_resident(const Query& q) { return q.dev && q.dev->resident; }
+// Reads a segment file into pinned memory owned by the query (the whole file: a cache miss on one column usually comes with
+// misses on the others, and H2D copies want pinned source bytes).
+void segment_load(SegmentInput& s) {
+  if (s.data) return;
+  int fd = open(s.name.c_str(), O_RDONLY);
+  LK_CHECK(fd >= 0, LK_ERR_IO, "IO Error: cannot open " + s.name);
+  void* buf = nullptr;
+  try {
+    buf = pinned_alloc(s.len + 16);
+  } catch (...) { close(fd); throw; }
+  size_t got = 0;
+  while (got < s.len) {
+    ssize_t r = read(fd, (char*)buf + got, s.len - got);
+    if (r <= 0) break;
+    got += (size_t)r;
+  }
+  close(fd);
+  if (got != s.len) { pinned_free(buf); fail(LK_ERR_IO, "IO Error: short read on " + s.name); }
+  s.data = (const uint8_t*)buf;
+  s.owned_pinned = buf;
+}
 
-void device_begin_upload(Query& q) {
+static SegmentIdentity segment_identity(const SegmentInput& s) {
+  SegmentIdentity id;
+  id.path = s.name;
+  id.size = s.len;
+  id.mtime_ns = s.id_mtime_ns;
+  id.ino = s.id_ino;
+  return id;
+}
+
+static void ensure_stream(Query& q) {
   device_init();
   if (!q.dev) q.dev = std::make_unique<Query::Device>();
   Query::Device& d = *q.dev;
@@ -272,6 +320,111 @@ void device_begin_upload(Query& q) {
     CUDA_CHECK(cudaStreamCreateWithFlags(&d.st, cudaStreamNonBlocking));
     for (auto& e : d.ev) CUDA_CHECK(cudaEventCreate(&e));
   }
+}
+
+// plan_query's on_layout hook: decides where every touched column chunk lives in device memory and starts the copies.
+// Chunks of identified segment files go through the segment cache -- one device block per (file, column), found there
+// (nothing to read, parse or copy) or allocated now and published once the query is resident; everything else (caller
+// buffers) is laid out in the query's private arena.  Kernels address all of it as `arena + offset`: a cached chunk's
+// offset is its address minus the private arena's, in 64-bit wrap-around arithmetic, so nothing downstream knows the
+// difference.
+void device_layout(Query& q) {
+  ensure_stream(q);
+  Query::Device& d = *q.dev;
+  SegmentCache& cache = segment_cache();
+  const int np = (int)q.pcols.size();
+  std::vector<uint8_t> placed(q.slots.size(), 0);
+  std::vector<uint64_t> abs_addr(q.slots.size(), 0);
+  std::vector<uint8_t> fresh(q.slots.size(), 0);
+  q.cache_fresh.clear();
+  bool any_file = false;
+  for (auto& sg : q.segs) any_file = any_file || sg.has_identity;
+  const bool use_cache = any_file && q.device_index && cache.capacity() > 0;
+  if (use_cache) {
+    std::map<std::pair<int, int>, std::vector<size_t>> groups;  // (segment, touched column) -> its chunk slots, one per row group
+    for (size_t k = 0; k < q.slots.size(); k++)
+      if (q.segs[q.slots[k].seg].has_identity) groups[{q.slots[k].seg, q.slots[k].pcol}].push_back(k);
+    for (auto& g : groups) {
+      SegmentInput& seg = q.segs[g.first.first];
+      const int leaf = q.slots[g.second[0]].leaf;
+      std::shared_ptr<CachedColumn> col = seg.cached ? cache.column(seg.cached, leaf) : nullptr;
+      if (col)
+        for (size_t k : g.second)
+          if (col->chunk_off[q.rgs[q.slots[k].rgi].rg] == ~0ull) { col = nullptr; break; }
+      const bool hit = col != nullptr;
+      if (!hit) {
+        segment_load(seg);
+        col = std::make_shared<CachedColumn>();
+        col->chunk_off.assign(seg.meta.row_groups.size(), ~0ull);
+        col->index.resize(seg.meta.row_groups.size());
+        uint64_t off = 0;
+        for (size_t k : g.second) {
+          const ChunkSlot& sl = q.slots[k];
+          off = (off + 255) & ~255ull;
+          col->chunk_off[q.rgs[sl.rgi].rg] = off;
+          off += sl.len;
+          if (sl.reserve) off = ((off + 7) & ~7ull) + sl.reserve;
+        }
+        col->bytes = ((off + 255) & ~255ull) + 256;  // tail padding, as for the private arena
+        cudaError_t e = cudaMallocAsync(&col->dev, col->bytes, d.st);
+        if (e != cudaSuccess) { cudaGetLastError(); col->dev = nullptr; fail(LK_ERR_NOMEM, strf("segment cache block of %zu bytes: %s", col->bytes, cudaGetErrorString(e))); }
+        q.cache_fresh.push_back({g.first.first, g.first.second, leaf, col});
+      }
+      for (size_t k : g.second) {
+        const ChunkSlot& sl = q.slots[k];
+        RowGroupPlan& rp = q.rgs[sl.rgi];
+        abs_addr[k] = (uint64_t)(uintptr_t)col->dev + col->chunk_off[rp.rg];
+        placed[k] = 1;
+        fresh[k] = hit ? 0 : 1;
+        if (hit) {
+          rp.chunks[sl.pcol] = col->index[rp.rg];
+          rp.from_cache[sl.pcol] = 1;
+        }
+      }
+      q.cache_refs.push_back(col);
+    }
+  }
+  for (auto& sg : q.segs) if (!sg.data && !use_cache) segment_load(sg);
+  layout_private_arena(q, placed);
+  if (!d.arena) {
+    CUDA_CHECK(cudaEventRecord(d.ev[0], d.st));
+    CUDA_CHECK(cudaMallocAsync(&d.arena, q.arena_bytes, d.st));
+  }
+  const uint64_t origin = (uint64_t)(uintptr_t)d.arena;
+  for (size_t k = 0; k < q.slots.size(); k++) {
+    if (!placed[k]) continue;
+    const ChunkSlot& sl = q.slots[k];
+    q.rgs[sl.rgi].arena_base[sl.pcol] = abs_addr[k] - origin;
+    if (fresh[k]) q.uploads.push_back({sl.seg, sl.file_off, sl.len, abs_addr[k] - origin});
+  }
+  (void)np;
+  device_begin_upload(q);
+}
+
+// the query is resident: the columns it brought in become visible to later queries
+static void cache_publish(Query& q) {
+  if (q.cache_fresh.empty()) return;
+  SegmentCache& cache = segment_cache();
+  for (auto& f : q.cache_fresh) {
+    const SegmentInput& seg = q.segs[f.seg];
+    for (auto& rp : q.rgs) {
+      if (rp.seg != f.seg) continue;
+      ChunkIndex ci = rp.chunks[f.pcol];
+      std::vector<uint8_t>().swap(ci.synth);  // already in the block, behind the chunk
+      f.col->index[rp.rg] = std::move(ci);
+    }
+    cache.publish(segment_identity(seg), seg.meta, f.leaf, f.col);
+  }
+  q.cache_fresh.clear();
+}
+
+// Starts the H2D copies of the touched column chunks (asynchronous; called from plan_query's on_layout hook so that
+// the copies run while the host still walks page and run headers).
+bool device_is_resident(const Query& q) { return q.dev && q.dev->resident; }
+
+void device_begin_upload(Query& q) {
+  ensure_stream(q);
+  Query::Device& d = *q.dev;
   if (!d.arena) {
     CUDA_CHECK(cudaEventRecord(d.ev[0], d.st));
     CUDA_CHECK(cudaMallocAsync(&d.arena, q.arena_bytes, d.st));
@@ -611,6 +764,7 @@ void device_upload(Query& q) {
   // the borrowed host buffers may be released by the caller once prepare returns
   CUDA_CHECK(cudaStreamSynchronize(d.st));
   d.resident = true;
+  cache_publish(q);
   float ms = 0;
   CUDA_CHECK(cudaEventElapsedTime(&ms, d.ev[0], d.ev[1]));
   q.t_ms[0] = ms;

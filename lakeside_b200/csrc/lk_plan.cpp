@@ -127,6 +127,20 @@ struct PlanTrace {
 };
 }  // namespace
 
+void layout_private_arena(Query& q, const std::vector<uint8_t>& placed) {
+  uint64_t arena = 0;
+  for (size_t k = 0; k < q.slots.size(); k++) {
+    if (k < placed.size() && placed[k]) continue;
+    const ChunkSlot& sl = q.slots[k];
+    arena = (arena + 255) & ~255ull;
+    q.rgs[sl.rgi].arena_base[sl.pcol] = arena;
+    q.uploads.push_back({sl.seg, sl.file_off, sl.len, arena});
+    arena += sl.len;
+    if (sl.reserve) arena = ((arena + 7) & ~7ull) + sl.reserve;
+  }
+  q.arena_bytes = ((arena + 255) & ~255ull) + 256;  // tail padding: lk_load_u64 may read the next aligned word
+}
+
 void plan_query(Query& q) {
   PlanTrace trace;
   const BaseExpr& e = q.req.expr;
@@ -152,7 +166,9 @@ void plan_query(Query& q) {
   const bool value_not_null = !q.is_metrics && e.chart.has_field_name && e.chart.field_name != VALUE;  // BaseExpr.scala:407-426
 
   // ---- footers: DESCRIBE SELECT * FROM read_parquet([...], union_by_name=True) (Commons.scala:213-221) ----
-  parallel_for((int)q.segs.size(), opt.host_threads, [&](int i) { q.segs[i].meta = parse_footer(q.segs[i].data, q.segs[i].len); });
+  parallel_for((int)q.segs.size(), opt.host_threads, [&](int i) {
+    if (!q.segs[i].meta_from_cache) q.segs[i].meta = parse_footer(q.segs[i].data, q.segs[i].len);  // else: the segment cache remembered it
+  });
   auto exists = [&](const std::string& name) {
     for (auto& s : q.segs)
       if (s.meta.leaf_index(name) >= 0) return true;
@@ -279,37 +295,37 @@ void plan_query(Query& q) {
   // ---- arena layout + upload list: needs the footers only, so the H2D copies of the column chunks can start NOW
   //      (q.on_layout) and overlap the page/run indexing below ----
   q.uploads.clear();
-  {
-    uint64_t arena = 0;
-    for (auto& rp : q.rgs) {
-      const SegmentInput& seg = q.segs[rp.seg];
-      rp.arena_base.assign(np, 0);
-      for (int p = 0; p < np; p++) {
-        int li = seg.meta.leaf_index(q.pcols[p].name);
-        if (li < 0) continue;
-        const ColumnChunkMeta& cm = seg.meta.row_groups[rp.rg].columns[li];
-        uint64_t start, len;
-        chunk_byte_range(cm, seg.len, q.pcols[p].name, start, len);
-        arena = (arena + 255) & ~255ull;
-        rp.arena_base[p] = arena;
-        q.uploads.push_back({rp.seg, start, len, arena});
-        arena += len;
-        // room behind a string chunk for its PLAIN pages re-encoded as dictionary indices (none when the footer rules them out)
-        const uint64_t reserve = synth_reserve(cm);
-        if (reserve) arena = ((arena + 7) & ~7ull) + reserve;
-      }
-    }
-    q.arena_bytes = ((arena + 255) & ~255ull) + 256;  // tail padding: lk_load_u64 may read the next aligned word
-  }
-  trace.mark("arena layout");
-  if (q.on_layout) q.on_layout();
-  parallel_for((int)q.rgs.size(), opt.host_threads, [&](int i) {
+  q.slots.clear();
+  for (size_t i = 0; i < q.rgs.size(); i++) {
     RowGroupPlan& rp = q.rgs[i];
     const SegmentInput& seg = q.segs[rp.seg];
+    rp.arena_base.assign(np, 0);
+    rp.from_cache.assign(np, 0);
+    rp.chunks.clear();
     rp.chunks.resize(np);
     for (int p = 0; p < np; p++) {
       int li = seg.meta.leaf_index(q.pcols[p].name);
+      if (li < 0) continue;
+      const ColumnChunkMeta& cm = seg.meta.row_groups[rp.rg].columns[li];
+      ChunkSlot sl;
+      sl.rgi = (int)i; sl.pcol = p; sl.seg = rp.seg; sl.leaf = li;
+      chunk_byte_range(cm, seg.len, q.pcols[p].name, sl.file_off, sl.len);
+      // room behind a string chunk for its PLAIN pages re-encoded as dictionary indices (none when the footer rules them out)
+      sl.reserve = synth_reserve(cm);
+      q.slots.push_back(sl);
+    }
+  }
+  trace.mark("arena layout");
+  // the device layer places the chunks (segment cache, private arena) and starts the copies; without one: all private
+  if (q.on_layout) q.on_layout();
+  else layout_private_arena(q, std::vector<uint8_t>());
+  parallel_for((int)q.rgs.size(), opt.host_threads, [&](int i) {
+    RowGroupPlan& rp = q.rgs[i];
+    const SegmentInput& seg = q.segs[rp.seg];
+    for (int p = 0; p < np; p++) {
+      int li = seg.meta.leaf_index(q.pcols[p].name);
       if (li < 0) continue;  // union_by_name: the column is NULL for this file
+      if (rp.from_cache[p]) continue;  // index (and bytes) came with the cached column
       const PCol& pc = q.pcols[p];
       rp.chunks[p] = index_chunk(seg.data, seg.len, seg.meta.leaves[li], seg.meta.row_groups[rp.rg].columns[li],
                                  seg.meta.row_groups[rp.rg].num_rows, pc.string_typed, !q.device_index);
@@ -321,7 +337,7 @@ void plan_query(Query& q) {
   for (auto& rp : q.rgs)
     for (int p = 0; p < np; p++) {
       const ChunkIndex& ci = rp.chunks[p];
-      if (!ci.present || ci.synth.empty()) continue;
+      if (!ci.present || ci.synth.empty() || rp.from_cache[p]) continue;
       const SegmentInput& seg = q.segs[rp.seg];
       const ColumnChunkMeta& cm = seg.meta.row_groups[rp.rg].columns[seg.meta.leaf_index(q.pcols[p].name)];
       LK_CHECK(ci.synth.size() <= synth_reserve(cm), LK_ERR_UNSUPPORTED, "column '" + q.pcols[p].name + "': PLAIN string pages need more room than the footer announced");

@@ -49,6 +49,7 @@ struct RawVec {
 
 struct Options {
   int device = 0;
+  int64_t segment_cache_bytes = -1;  // HBM-resident segment cache: -1 = a third of the device's memory, 0 = off
   uint64_t max_hash_slots = 1ull << 27;
   uint64_t dense_max_cells = 1ull << 25;
   uint32_t tile_rows = LK_TILE_ROWS_MAX;
@@ -64,12 +65,26 @@ struct AggSpec {
   double divisor = 1.0;
 };
 
+struct CachedSegment;  // lk_cache.h
+struct CachedColumn;
+
 struct SegmentInput {
-  const uint8_t* data = nullptr;
+  const uint8_t* data = nullptr;  // null for a file whose footer came from the segment cache, until a cache miss needs its bytes
   size_t len = 0;
   std::string name;
   void* owned_pinned = nullptr;  // file read into pinned memory owned by the query
   FileMeta meta;
+  // files only: identity for the HBM-resident segment cache (path + size + mtime + inode) and the entry found at add time
+  bool has_identity = false;
+  uint64_t id_mtime_ns = 0, id_ino = 0;
+  std::shared_ptr<CachedSegment> cached;
+  bool meta_from_cache = false;
+};
+
+// one touched column chunk: where its bytes are in the file and how much room it needs in device memory
+struct ChunkSlot {
+  int rgi = -1, pcol = -1, seg = -1, leaf = -1;  // row-group slot (Query::rgs), touched column, segment, leaf index in the file
+  uint64_t file_off = 0, len = 0, reserve = 0;
 };
 
 // one physical column touched by the query
@@ -98,6 +113,7 @@ struct RowGroupPlan {
   uint32_t num_rows = 0;
   std::vector<ChunkIndex> chunks;  // per pcol
   std::vector<uint64_t> arena_base;  // per pcol: arena offset of the chunk's first byte
+  std::vector<uint8_t> from_cache;   // per pcol: bytes and index of the chunk came from the segment cache (nothing to parse or upload)
   uint64_t seq_base = 0;
 };
 
@@ -158,6 +174,11 @@ struct Query {
   struct Upload { int seg; uint64_t file_off, len, arena_off; const uint8_t* src = nullptr; };  // src: host bytes that are not in a segment (re-encoded pages)
   std::vector<Upload> uploads;
   uint64_t arena_bytes = 0;
+  std::vector<ChunkSlot> slots;  // every touched column chunk, in (row group, column) order
+  // segment cache: columns this query uses (pinned for its lifetime) and the ones it uploaded itself, published once resident
+  std::vector<std::shared_ptr<CachedColumn>> cache_refs;
+  struct FreshColumn { int seg, pcol, leaf; std::shared_ptr<CachedColumn> col; };
+  std::vector<FreshColumn> cache_fresh;
   // called by plan_query as soon as the arena layout is known (footers only): the device layer starts the H2D copies
   // of the column chunks there so that they overlap the host-side page/run indexing
   std::function<void()> on_layout;
@@ -189,6 +210,9 @@ struct HostResult {
 };
 
 // planning (host only, no CUDA): lk_plan.cpp
+// places the chunk slots that are not marked in `placed` one after the other in the query's private arena (arena_base,
+// uploads, arena_bytes); the default layout when no device layer takes part (on_layout unset)
+void layout_private_arena(Query& q, const std::vector<uint8_t>& placed);
 void plan_query(Query& q);           // parse + index + compile; fills the host pools and ScanParams (device pointers unset)
 void rebuild_group_tables(Query& q); // after key_dicts changed (dictionary import)
 // definition bitmaps: which chunks get one (run_n > 0 in def_tmp[row group * npcols + pcol]) and where; fills q.def_chunks,

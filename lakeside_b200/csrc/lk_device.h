@@ -385,7 +385,20 @@ struct IdxChunk {
   uint32_t def_run0, def_runs, val_run0, val_runs;
   uint32_t nn, mixed;         // non-null values; some tile of the chunk mixes NULLs and values (needs a definition bitmap)
 };
-enum : uint32_t { IDX_ST_TRUNCATED = 1, IDX_ST_BAD_RUN = 2, IDX_ST_BAD_CODE = 4, IDX_ST_PLAIN_STRING = 8 };
+enum : uint32_t { IDX_ST_TRUNCATED = 1, IDX_ST_BAD_RUN = 2, IDX_ST_BAD_CODE = 4, IDX_ST_PLAIN_STRING = 8, IDX_ST_BAD_SNAPPY = 16 };
+
+// One compressed page (SNAPPY) of a touched column chunk.  The device inflates [src_off, src_off + src_len) into
+// [dst_off, dst_off + dst_len) -- room reserved behind the chunk in the same device block -- and then reads from the inflated
+// bytes what the host reads from an uncompressed page's first bytes: the length prefix of a V1 page's definition levels and
+// the bit width of a dictionary-coded page, completing the page's IdxPage.
+enum : uint32_t { ZP_DECODE = 1 /* not inflated yet (a cached block already is) */, ZP_V1_DEF = 2 /* V1 page of an OPTIONAL column: 4-byte length + definition levels first */,
+                  ZP_DICT_CODED = 4 /* values start with the bit-width byte */, ZP_VALUES_ONLY = 8 /* V2: the inflated bytes are the values section only */ };
+struct ZPage {
+  uint64_t src_off, dst_off;  // arena offsets
+  uint32_t src_len, dst_len;
+  uint32_t page;              // index into IdxPage[] (0xffffffff: a numeric dictionary page, nothing to complete)
+  uint32_t flags;
+};
 
 struct HybridRun {
   uint32_t n;        // elements the run contributes (clipped to what the page still needs)

@@ -452,6 +452,122 @@ void device_begin_upload(Query& q) {
 // the whole build is a few milliseconds on the GPU, overlapped with nothing yet (it needs the bytes in HBM).
 struct IdxTotals { uint32_t n_runs, status, pad[2]; };
 
+// ---- SNAPPY pages (format breadth): inflated on the device, a warp per page ----
+// The element stream of a page is sequential (a tag says how many literal bytes follow or which earlier output bytes to
+// repeat), so the parallelism is pages x columns -- thousands for a glob -- plus the 32 lanes that move each element's
+// bytes together.  All lanes parse the tags redundantly (uniform loads), so no lane ever waits for a broadcast.
+__global__ void __launch_bounds__(128) snappy_decode_kernel(uint8_t* arena, const ZPage* __restrict__ zp, uint32_t n, IdxTotals* __restrict__ tot) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  const ZPage z = zp[w];
+  if (!(z.flags & ZP_DECODE)) return;
+  const uint8_t* __restrict__ src = arena + z.src_off;
+  uint8_t* dst = arena + z.dst_off;
+  const uint32_t slen = z.src_len, dlen = z.dst_len;
+  uint32_t ip = 0, op = 0;
+  bool bad = false;
+  {  // preamble: the uncompressed length
+    uint64_t ulen = 0;
+    int sh = 0;
+    while (true) {
+      if (ip >= slen || sh > 35) { bad = true; break; }
+      const uint8_t c = src[ip++];
+      ulen |= (uint64_t)(c & 0x7f) << sh;
+      if (!(c & 0x80)) break;
+      sh += 7;
+    }
+    if (ulen != dlen) bad = true;
+  }
+  while (!bad && ip < slen) {
+    const uint32_t tag = src[ip++];
+    uint32_t len, off = 0;
+    if ((tag & 3) == 0) {
+      len = (tag >> 2) + 1;
+      if (len > 60) {
+        const uint32_t nb = len - 60;
+        if (ip + nb > slen) { bad = true; break; }
+        len = 0;
+        for (uint32_t i = 0; i < nb; i++) len |= (uint32_t)src[ip + i] << (8 * i);
+        len += 1;
+        ip += nb;
+      }
+      if (len > slen - ip || len > dlen - op) { bad = true; break; }
+      const uint8_t* s = src + ip;
+      uint8_t* d = dst + op;
+      // long literals (incompressible PLAIN values): 4-byte words once source and destination are aligned alike
+      uint32_t i0 = 0;
+      if (len >= 256 && (((uintptr_t)s ^ (uintptr_t)d) & 3) == 0) {
+        const uint32_t head = (4 - ((uintptr_t)d & 3)) & 3;
+        if (lane < head) d[lane] = s[lane];
+        const uint32_t words = (len - head) >> 2;
+        const uint32_t* s4 = reinterpret_cast<const uint32_t*>(s + head);
+        uint32_t* d4 = reinterpret_cast<uint32_t*>(d + head);
+        for (uint32_t i = lane; i < words; i += 32) d4[i] = s4[i];
+        i0 = head + (words << 2);
+      }
+      for (uint32_t i = i0 + lane; i < len; i += 32) d[i] = s[i];
+      ip += len;
+      op += len;
+    } else {
+      if ((tag & 3) == 1) {
+        if (ip + 1 > slen) { bad = true; break; }
+        len = 4 + ((tag >> 2) & 7);
+        off = ((tag >> 5) << 8) | src[ip];
+        ip += 1;
+      } else if ((tag & 3) == 2) {
+        if (ip + 2 > slen) { bad = true; break; }
+        len = (tag >> 2) + 1;
+        off = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8);
+        ip += 2;
+      } else {
+        if (ip + 4 > slen) { bad = true; break; }
+        len = (tag >> 2) + 1;
+        off = (uint32_t)src[ip] | ((uint32_t)src[ip + 1] << 8) | ((uint32_t)src[ip + 2] << 16) | ((uint32_t)src[ip + 3] << 24);
+        ip += 4;
+      }
+      if (off == 0 || off > op || len > dlen - op) { bad = true; break; }
+      // earlier output, possibly overlapping what is being written (a pattern of period `off`): every lane reads only
+      // bytes in front of `op`, which the __syncwarp below has made visible
+      const uint8_t* from = dst + (op - off);
+      if (off >= len) { for (uint32_t i = lane; i < len; i += 32) dst[op + i] = from[i]; }
+      else { for (uint32_t i = lane; i < len; i += 32) dst[op + i] = from[i % off]; }
+      op += len;
+    }
+    __syncwarp();
+  }
+  if (!bad && op != dlen) bad = true;
+  if (bad && lane == 0) atomicOr(&tot->status, (uint32_t)IDX_ST_BAD_SNAPPY);
+}
+
+// completes the IdxPage of every SNAPPY page from its inflated bytes: what the host reads from an uncompressed page's
+// first bytes (lk_parquet.cpp: index_chunk) -- the length prefix of a V1 page's definition levels, the bit-width byte
+__global__ void zpage_parse_kernel(const uint8_t* __restrict__ arena, const ZPage* __restrict__ zp, uint32_t n, IdxPage* __restrict__ pages, IdxTotals* __restrict__ tot) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const ZPage z = zp[i];
+  if (z.page == 0xffffffffu) return;
+  IdxPage& pg = pages[z.page];
+  uint64_t q = z.dst_off;
+  const uint64_t end = z.dst_off + z.dst_len;
+  uint32_t status = 0;
+  if (z.flags & ZP_V1_DEF) {
+    if (q + 4 > end) status |= IDX_ST_TRUNCATED;
+    else {
+      const uint32_t dl = (uint32_t)arena[q] | ((uint32_t)arena[q + 1] << 8) | ((uint32_t)arena[q + 2] << 16) | ((uint32_t)arena[q + 3] << 24);
+      if (q + 4 + (uint64_t)dl > end) status |= IDX_ST_TRUNCATED;
+      else { pg.def_off = q + 4; pg.def_end = q + 4 + dl; q = pg.def_end; }
+    }
+  }
+  if ((z.flags & ZP_DICT_CODED) && q < end) {
+    pg.bit_width = arena[q];
+    if (pg.bit_width > 31) status |= IDX_ST_BAD_RUN;
+    q += 1;
+  }
+  pg.val_off = q;
+  pg.val_end = end;
+  if (status) atomicOr(&tot->status, status);
+}
+
 __global__ void idx_def_count_kernel(const uint8_t* __restrict__ arena, IdxPage* __restrict__ pages, uint32_t npages, IdxTotals* __restrict__ tot) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= npages) return;
@@ -691,6 +807,15 @@ static void device_build_index(Query& q) {
   if (npages) CUDA_CHECK(cudaMemcpyAsync(dpages, q.idx_pages.data(), npages * sizeof(IdxPage), cudaMemcpyHostToDevice, d.st));
   if (nchunks) CUDA_CHECK(cudaMemcpyAsync(dchunks, q.idx_chunks.data(), nchunks * sizeof(IdxChunk), cudaMemcpyHostToDevice, d.st));
   IdxTotals tot{};
+  ZPage* dz = nullptr;
+  if (npages && !q.zpages.empty()) {  // SNAPPY pages first: inflate (what no cached block holds yet), then complete their IdxPage
+    const uint32_t nz = (uint32_t)q.zpages.size();
+    CUDA_CHECK(cudaMallocAsync(&dz, nz * sizeof(ZPage), d.st));
+    CUDA_CHECK(cudaMemcpyAsync(dz, q.zpages.data(), nz * sizeof(ZPage), cudaMemcpyHostToDevice, d.st));
+    snappy_decode_kernel<<<(int)((nz + 3) / 4), 128, 0, d.st>>>(d.arena, dz, nz, dtot);
+    zpage_parse_kernel<<<(int)((nz + 127) / 128), 128, 0, d.st>>>(d.arena, dz, nz, dpages, dtot);
+    CUDA_CHECK(cudaGetLastError());
+  }
   if (npages) {
     const int pg_grid = (int)((npages + 31) / 32), ch_grid = (int)((nchunks + 63) / 64);
     idx_def_count_kernel<<<pg_grid, 32, 0, d.st>>>(d.arena, dpages, npages, dtot);
@@ -700,6 +825,7 @@ static void device_build_index(Query& q) {
     CUDA_CHECK(cudaGetLastError());
     CUDA_CHECK(cudaMemcpyAsync(&tot, dtot, sizeof tot, cudaMemcpyDeviceToHost, d.st));
     CUDA_CHECK(cudaStreamSynchronize(d.st));
+    LK_CHECK(!(tot.status & IDX_ST_BAD_SNAPPY), LK_ERR_IO, "parquet: malformed SNAPPY page");
     LK_CHECK(!(tot.status & IDX_ST_PLAIN_STRING), LK_ERR_UNSUPPORTED, "a string column has PLAIN (non-dictionary) pages");
     LK_CHECK(!(tot.status & IDX_ST_BAD_CODE), LK_ERR_IO, "parquet: dictionary index out of range");
     LK_CHECK(!(tot.status & IDX_ST_BAD_RUN), LK_ERR_IO, "parquet: malformed run header in a hybrid stream");
@@ -737,6 +863,7 @@ static void device_build_index(Query& q) {
   layout_def_chunks(q, def_tmp);
   q.params.def_mask = def_mask;
   refresh_info_json(q);
+  if (dz) CUDA_CHECK(cudaFreeAsync(dz, d.st));
   CUDA_CHECK(cudaFreeAsync(dpages, d.st));
   CUDA_CHECK(cudaFreeAsync(dchunks, d.st));
   CUDA_CHECK(cudaFreeAsync(dtot, d.st));

@@ -128,6 +128,7 @@ ColumnChunkMeta read_column_meta(TReader& r) {
       case 1: m.phys_type = (int)r.zigzag(); break;
       case 4: m.codec = (int)r.zigzag(); break;
       case 5: m.num_values = r.zigzag(); break;
+      case 6: m.total_uncompressed_size = r.zigzag(); break;
       case 7: m.total_compressed_size = r.zigzag(); break;
       case 9: m.data_page_offset = r.zigzag(); break;
       case 11: m.dictionary_page_offset = r.zigzag(); break;
@@ -248,6 +249,7 @@ struct PageHeader {
   int def_encoding = ENC_RLE;
   // v2
   int32_t num_nulls = 0, num_rows = 0, def_len = 0, rep_len = 0;
+  bool v2_compressed = true;  // DataPageHeaderV2.is_compressed (values section only; levels are never compressed)
   size_t header_len = 0;
 };
 
@@ -280,6 +282,7 @@ PageHeader read_page_header(const uint8_t* p, const uint8_t* end) {
             case 4: h.encoding = (int)r.zigzag(); break;
             case 5: h.def_len = (int32_t)r.zigzag(); break;
             case 6: h.rep_len = (int32_t)r.zigzag(); break;
+            case 7: h.v2_compressed = t2 == T_TRUE; break;
             default: r.skip(t2);
           }
         }
@@ -385,7 +388,63 @@ uint32_t ChunkIndex::vidx_in_run(const uint8_t* file, int i, uint32_t r) const {
   return nn + popcount_bits(file + file_start + run.kind_value, k);
 }
 
+bool snappy_uncompress(const uint8_t* src, size_t n, std::vector<uint8_t>& out) {
+  size_t ip = 0;
+  uint64_t ulen = 0;
+  for (int sh = 0;; sh += 7) {
+    if (ip >= n || sh > 35) return false;
+    const uint8_t c = src[ip++];
+    ulen |= (uint64_t)(c & 0x7f) << sh;
+    if (!(c & 0x80)) break;
+  }
+  if (ulen > (1ull << 31)) return false;
+  out.assign((size_t)ulen, 0);
+  size_t op = 0;
+  while (ip < n) {
+    const uint8_t tag = src[ip++];
+    size_t len, off = 0;
+    if ((tag & 3) == 0) {
+      len = (size_t)(tag >> 2) + 1;
+      if (len > 60) {
+        const size_t nb = len - 60;
+        if (ip + nb > n) return false;
+        len = 0;
+        for (size_t i = 0; i < nb; i++) len |= (size_t)src[ip + i] << (8 * i);
+        len += 1;
+        ip += nb;
+      }
+      if (ip + len > n || op + len > ulen) return false;
+      memcpy(out.data() + op, src + ip, len);
+      ip += len;
+      op += len;
+      continue;
+    }
+    if ((tag & 3) == 1) {
+      if (ip + 1 > n) return false;
+      len = 4 + ((tag >> 2) & 7);
+      off = ((size_t)(tag >> 5) << 8) | src[ip];
+      ip += 1;
+    } else if ((tag & 3) == 2) {
+      if (ip + 2 > n) return false;
+      len = (size_t)(tag >> 2) + 1;
+      off = (size_t)src[ip] | ((size_t)src[ip + 1] << 8);
+      ip += 2;
+    } else {
+      if (ip + 4 > n) return false;
+      len = (size_t)(tag >> 2) + 1;
+      off = (size_t)src[ip] | ((size_t)src[ip + 1] << 8) | ((size_t)src[ip + 2] << 16) | ((size_t)src[ip + 3] << 24);
+      ip += 4;
+    }
+    if (off == 0 || off > op || op + len > ulen) return false;
+    for (size_t i = 0; i < len; i++) out[op + i] = out[op - off + i];  // byte by byte: the ranges may overlap (run-length patterns)
+    op += len;
+  }
+  return op == ulen;
+}
+
 uint64_t synth_reserve(const ColumnChunkMeta& cm) {
+  // compressed chunk: room for its inflated pages (the footer's total_uncompressed_size also counts the page headers)
+  if (cm.codec == CODEC_SNAPPY) return (uint64_t)std::max<int64_t>(cm.total_uncompressed_size, 0) + 64;
   if (cm.phys_type != PT_BYTE_ARRAY || cm.plain_data_pages == 0 || cm.num_values <= 0) return 0;
   // one bit-packed run per page: at most 4 bytes per value + header and group padding per page (a page holds >= 1 value)
   const uint64_t pages = cm.plain_data_pages > 0 ? (uint64_t)cm.plain_data_pages : (uint64_t)(cm.total_compressed_size >> 10) + 2;
@@ -409,8 +468,10 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
   ci.phys_type = cm.phys_type;
   ci.max_def = leaf.max_def;
   ci.total_compressed_size = cm.total_compressed_size;
-  LK_CHECK(cm.codec == 0, LK_ERR_UNSUPPORTED,
-           "column '" + leaf.name + "': compressed pages (codec " + std::to_string(cm.codec) + ") are not supported yet; write segments with compression=NONE");
+  LK_CHECK(cm.codec == CODEC_NONE || cm.codec == CODEC_SNAPPY, LK_ERR_UNSUPPORTED,
+           "column '" + leaf.name + "': compression codec " + std::to_string(cm.codec) + " is not supported (UNCOMPRESSED and SNAPPY are)");
+  const bool snappy = cm.codec == CODEC_SNAPPY;
+  LK_CHECK(!snappy || !walk_runs, LK_ERR_UNSUPPORTED, "column '" + leaf.name + "': SNAPPY pages are inflated on the device and need the device-built index");
   LK_CHECK(rg_rows >= 0 && rg_rows < (int64_t)0xfffffff0u, LK_ERR_UNSUPPORTED, "row group too large");
   ci.num_rows = (uint32_t)rg_rows;
   LK_CHECK(cm.num_values == rg_rows, LK_ERR_UNSUPPORTED, "column '" + leaf.name + "': repeated values are not supported");
@@ -423,8 +484,92 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
     PageHeader h = read_page_header(data + p, data + cend);
     uint64_t payload = p + h.header_len;
     LK_CHECK(h.compressed >= 0 && payload + (uint64_t)h.compressed <= cend, LK_ERR_IO, "parquet: page out of chunk bounds");
-    LK_CHECK(h.compressed == h.uncompressed, LK_ERR_UNSUPPORTED, "parquet: compressed page in an UNCOMPRESSED chunk");
+    LK_CHECK(snappy || h.compressed == h.uncompressed, LK_ERR_UNSUPPORTED, "parquet: compressed page in an UNCOMPRESSED chunk");
     uint64_t pend = payload + (uint64_t)h.compressed;
+    if (snappy && !((h.type == 3 && !h.v2_compressed))) {
+      // ---- SNAPPY page: recorded for the device (see ChunkIndex::zpages); only a string dictionary is inflated here ----
+      LK_CHECK(h.uncompressed >= 0, LK_ERR_IO, "parquet: negative page size");
+      if (ci.zpages.empty() && ci.z_base == 0) ci.z_base = (ci.file_len + 7) & ~7ull;
+      auto reserve_z = [&](uint32_t n) {
+        const uint64_t virt = ci.file_start + ci.z_base + ci.z_len;
+        ci.z_len += n;
+        LK_CHECK(ci.z_len + 64 <= synth_reserve(cm), LK_ERR_IO, "parquet: pages inflate to more than the footer's total_uncompressed_size");
+        return virt;
+      };
+      if (h.type == 2) {
+        LK_CHECK(h.encoding == ENC_PLAIN || h.encoding == ENC_PLAIN_DICTIONARY, LK_ERR_UNSUPPORTED, "parquet: dictionary page encoding");
+        LK_CHECK(!ci.has_dict, LK_ERR_IO, "parquet: two dictionary pages in one chunk");
+        ci.has_dict = true;
+        ci.dict_n = (uint32_t)h.num_values;
+        ci.dict_len = (uint32_t)h.uncompressed;
+        if (cm.phys_type == PT_BYTE_ARRAY) {
+          if (want_strings) {
+            std::vector<uint8_t> buf;
+            LK_CHECK(snappy_uncompress(data + payload, (size_t)h.compressed, buf) && buf.size() == (size_t)h.uncompressed, LK_ERR_IO,
+                     "parquet: malformed SNAPPY dictionary page");
+            ci.dict_strings.reserve(ci.dict_n);
+            size_t q = 0;
+            for (uint32_t i = 0; i < ci.dict_n; i++) {
+              LK_CHECK(q + 4 <= buf.size(), LK_ERR_IO, "parquet: truncated dictionary page");
+              uint32_t n;
+              memcpy(&n, buf.data() + q, 4);
+              q += 4;
+              LK_CHECK(q + n <= buf.size(), LK_ERR_IO, "parquet: truncated dictionary page");
+              ci.dict_strings.emplace_back((const char*)buf.data() + q, n);
+              q += n;
+            }
+          }
+        } else {
+          unsigned esz = (cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT) ? 4 : 8;
+          LK_CHECK(cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT || cm.phys_type == PT_INT64 || cm.phys_type == PT_DOUBLE,
+                   LK_ERR_UNSUPPORTED, "column '" + leaf.name + "': unsupported physical type");
+          LK_CHECK((uint64_t)ci.dict_n * esz <= ci.dict_len, LK_ERR_IO, "parquet: truncated numeric dictionary");
+          ci.dict_off = reserve_z((uint32_t)h.uncompressed);
+          ci.zpages.push_back({payload, (uint32_t)h.compressed, ci.dict_off, (uint32_t)h.uncompressed, -1, ZP_DECODE});
+        }
+      } else if (h.type == 0 || h.type == 3) {
+        LK_CHECK(h.num_values >= 0 && (uint64_t)row + (uint64_t)h.num_values <= ci.num_rows, LK_ERR_IO, "parquet: page rows exceed row group");
+        PageInfo pg;
+        pg.first_row = row;
+        pg.num_rows = (uint32_t)h.num_values;
+        pg.first_vidx = vidx;
+        pg.deferred = true;
+        uint32_t flags = ZP_DECODE;
+        uint64_t src = payload;
+        uint32_t src_len = (uint32_t)h.compressed, dst_len = (uint32_t)h.uncompressed;
+        if (h.type == 3) {  // V2: repetition / definition levels sit uncompressed in front of the compressed values
+          LK_CHECK(h.rep_len == 0, LK_ERR_UNSUPPORTED, "parquet: repetition levels");
+          LK_CHECK(h.def_len >= 0 && h.def_len <= h.compressed && h.def_len <= h.uncompressed, LK_ERR_IO, "parquet: truncated definition levels");
+          if (leaf.max_def > 0) { pg.def_off = payload; pg.def_end = payload + (uint64_t)h.def_len; }
+          src += (uint64_t)h.def_len;
+          src_len -= (uint32_t)h.def_len;
+          dst_len -= (uint32_t)h.def_len;
+          flags |= ZP_VALUES_ONLY;
+        } else if (leaf.max_def > 0) {
+          LK_CHECK(h.def_encoding == ENC_RLE, LK_ERR_UNSUPPORTED, "parquet: BIT_PACKED definition levels");
+          flags |= ZP_V1_DEF;
+        }
+        if (h.encoding == ENC_RLE_DICTIONARY || h.encoding == ENC_PLAIN_DICTIONARY) {
+          LK_CHECK(ci.has_dict, LK_ERR_IO, "parquet: dictionary-encoded page without a dictionary page");
+          pg.dict_coded = true;
+          flags |= ZP_DICT_CODED;
+        } else if (h.encoding == ENC_PLAIN) {
+          LK_CHECK(cm.phys_type != PT_BYTE_ARRAY, LK_ERR_UNSUPPORTED,
+                   "column '" + leaf.name + "': PLAIN (non-dictionary) string pages inside a compressed chunk are not supported");
+          LK_CHECK(cm.phys_type == PT_INT32 || cm.phys_type == PT_FLOAT || cm.phys_type == PT_INT64 || cm.phys_type == PT_DOUBLE, LK_ERR_UNSUPPORTED,
+                   "column '" + leaf.name + "': PLAIN pages of this type are not supported");
+        } else {
+          fail(LK_ERR_UNSUPPORTED, "column '" + leaf.name + "': page encoding " + std::to_string(h.encoding) + " is not supported");
+        }
+        pg.values_off = reserve_z(dst_len);  // start of the inflated bytes; the device moves it past levels / bit width
+        pg.values_len = dst_len;
+        ci.zpages.push_back({src, src_len, pg.values_off, dst_len, (int)ci.pages.size(), flags});
+        ci.pages.push_back(pg);
+        row += pg.num_rows;
+      }
+      p = pend;
+      continue;
+    }
     if (h.type == 2) {  // dictionary page
       LK_CHECK(h.encoding == ENC_PLAIN || h.encoding == ENC_PLAIN_DICTIONARY, LK_ERR_UNSUPPORTED, "parquet: dictionary page encoding");
       LK_CHECK(!ci.has_dict, LK_ERR_IO, "parquet: two dictionary pages in one chunk");
@@ -600,7 +745,7 @@ ChunkIndex index_chunk(const uint8_t* data, size_t len, const LeafColumn& leaf, 
   // the kernels address a chunk's bit-packed dictionary indices by a 32-bit BIT offset from the chunk's first byte
   bool any_dict_page = false;
   for (auto& pg : ci.pages) any_dict_page |= pg.dict_coded;
-  LK_CHECK(!(any_dict_page || !ci.val_runs.empty()) || ci.file_len + ci.synth.size() + 8 < (1ull << 29), LK_ERR_UNSUPPORTED,
+  LK_CHECK(!(any_dict_page || !ci.val_runs.empty()) || ci.file_len + ci.synth.size() + ci.z_len + 16 < (1ull << 29), LK_ERR_UNSUPPORTED,
            "dictionary-coded column chunk of '" + leaf.name + "' is larger than 512 MB");
   return ci;
 }

@@ -13,6 +13,7 @@
 namespace lk {
 
 enum PhysType : int { PT_BOOLEAN = 0, PT_INT32 = 1, PT_INT64 = 2, PT_INT96 = 3, PT_FLOAT = 4, PT_DOUBLE = 5, PT_BYTE_ARRAY = 6, PT_FLBA = 7 };
+enum Codec : int { CODEC_NONE = 0, CODEC_SNAPPY = 1 };
 enum Encoding : int { ENC_PLAIN = 0, ENC_PLAIN_DICTIONARY = 2, ENC_RLE = 3, ENC_BIT_PACKED = 4, ENC_RLE_DICTIONARY = 8 };
 
 struct ColumnChunkMeta {
@@ -20,6 +21,7 @@ struct ColumnChunkMeta {
   int codec = 0;
   int64_t num_values = 0;
   int64_t total_compressed_size = 0;
+  int64_t total_uncompressed_size = 0;
   int64_t data_page_offset = 0;
   int64_t dictionary_page_offset = -1;
   int plain_data_pages = -1;  // data pages encoded PLAIN according to the footer's encoding_stats (-1: the writer left them out)
@@ -55,6 +57,7 @@ struct PageInfo {
   uint64_t values_off = 0;  // file offset of the value bytes (after the bit-width byte for dictionary pages)
   uint32_t values_len = 0;
   uint64_t def_off = 0, def_end = 0;  // file byte range of the definition-level stream (empty for REQUIRED columns)
+  bool deferred = false;  // compressed page: def_off / def_end (V1) and bit_width are read by the device from the inflated bytes
   bool synth = false;  // PLAIN string page re-encoded by the host: values_off / values_len address ChunkIndex::synth instead of the file
 };
 
@@ -80,6 +83,13 @@ struct ChunkIndex {
   // chunk in the arena (offset synth_base from the chunk's first byte), so kernels and index builders see a dictionary page.
   std::vector<uint8_t> synth;
   uint64_t synth_base = 0;
+  // SNAPPY chunks: every compressed page is inflated ON THE DEVICE into room reserved behind the chunk (at z_base from the
+  // chunk's first byte, pages back to back); page offsets that point into inflated bytes are "virtual file offsets"
+  // file_start + z_base + position, so that the rebasing of file offsets to arena offsets works for them unchanged.  The
+  // host inflates only BYTE_ARRAY dictionary pages (it needs the strings; they never reach the device).
+  struct ZPageInfo { uint64_t src_off; uint32_t src_len; uint64_t dst_virt; uint32_t dst_len; int page; uint32_t flags; };
+  std::vector<ZPageInfo> zpages;
+  uint64_t z_base = 0, z_len = 0;
   // chunk-level value index of row r (number of non-null values before r); r may equal num_rows
   uint32_t vidx_at(const uint8_t* file, uint32_t r) const;
   // same, when the def run `run_index` holding row r is already known (linear sweeps)
@@ -89,8 +99,12 @@ struct ChunkIndex {
   int page_at(uint32_t r) const;
 };
 
-// Arena bytes to reserve behind a BYTE_ARRAY chunk for re-encoded PLAIN pages (0 when the footer says there are none).
+// Arena bytes to reserve behind a BYTE_ARRAY chunk for re-encoded PLAIN pages (0 when the footer says there are none), or
+// behind a compressed chunk for its inflated pages (the footer's total_uncompressed_size).
 uint64_t synth_reserve(const ColumnChunkMeta& cm);
+// SNAPPY block format (length preamble + literal / copy elements); returns false on malformed input.  Host side: dictionary
+// pages of string columns only -- data pages are inflated by snappy_decode_kernel (lk_engine.cu).
+bool snappy_uncompress(const uint8_t* src, size_t n, std::vector<uint8_t>& out);
 
 // Byte range [start, start + len) of a column chunk inside the file (dictionary page + data pages), from the footer alone.
 void chunk_byte_range(const ColumnChunkMeta& cm, size_t file_len, const std::string& name, uint64_t& start, uint64_t& len);

@@ -360,20 +360,31 @@ void plan_query(Query& q) {
   const uint32_t tile_rows = std::max(64u, std::min(opt.tile_rows, (uint32_t)LK_TILE_ROWS_MAX)) & ~31u;
   std::vector<size_t> run_base(q.rgs.size() + 1, 0), tile_base(q.rgs.size() + 1, 0);
   std::vector<std::vector<uint32_t>> bounds(q.rgs.size());
-  for (size_t i = 0; i < q.rgs.size(); i++) {
+  std::vector<size_t> nruns_of(q.rgs.size(), 0);
+  parallel_for((int)q.rgs.size(), opt.host_threads, [&](int i) {
     const RowGroupPlan& rp = q.rgs[i];
     size_t nr = 0;
     std::vector<uint32_t>& b = bounds[i];
-    for (uint32_t r = 0; r < rp.num_rows; r += tile_rows) b.push_back(r);
+    // tile boundaries: every tile_rows rows and every page boundary of every touched column (both lists ascending: merged)
+    std::vector<uint32_t> pg_rows;
     for (auto& c : rp.chunks) {
       nr += c.def_runs.size() + c.val_runs.size();
-      for (auto& pg : c.pages) b.push_back(pg.first_row);
+      for (auto& pg : c.pages) pg_rows.push_back(pg.first_row);
     }
-    b.push_back(rp.num_rows);
-    std::sort(b.begin(), b.end());
-    b.erase(std::unique(b.begin(), b.end()), b.end());
-    run_base[i + 1] = run_base[i] + nr;
-    tile_base[i + 1] = tile_base[i] + (b.size() - 1);
+    pg_rows.push_back(rp.num_rows);
+    std::sort(pg_rows.begin(), pg_rows.end());
+    b.reserve(rp.num_rows / tile_rows + pg_rows.size() + 2);
+    size_t k = 0;
+    for (uint32_t r = 0; r < rp.num_rows; r += tile_rows) {
+      while (k < pg_rows.size() && pg_rows[k] < r) { if (b.empty() || b.back() != pg_rows[k]) b.push_back(pg_rows[k]); k++; }
+      if (b.empty() || b.back() != r) b.push_back(r);
+    }
+    for (; k < pg_rows.size(); k++) if (b.empty() || b.back() != pg_rows[k]) b.push_back(pg_rows[k]);
+    nruns_of[i] = nr;
+  });
+  for (size_t i = 0; i < q.rgs.size(); i++) {
+    run_base[i + 1] = run_base[i] + nruns_of[i];
+    tile_base[i + 1] = tile_base[i] + (bounds[i].size() - 1);
   }
   LK_CHECK(run_base.back() < 0xffffffffull && tile_base.back() * np < 0xffffffffull, LK_ERR_UNSUPPORTED, "glob too large for 32-bit index pools");
   q.tiles.resize_uninit(tile_base.back());
@@ -381,9 +392,9 @@ void plan_query(Query& q) {
   if (q.device_index) {
     // the device walks the run headers and computes the cursors (lk_engine.cu: idx_* kernels): hand it the pages and chunks
     q.idx_pages.clear();
+    q.zpages.clear();
     q.idx_chunks.assign(q.rgs.size() * np, IdxChunk{});
-    for (size_t i = 0; i < q.rgs.size(); i++) {
-      const RowGroupPlan& rp = q.rgs[i];
+    parallel_for((int)q.rgs.size(), opt.host_threads, [&](int i) {
       const std::vector<uint32_t>& b = bounds[i];
       for (size_t t = 0; t + 1 < b.size(); t++) {
         TileDesc& td = q.tiles[tile_base[i] + t];
@@ -392,6 +403,9 @@ void plan_query(Query& q) {
         td.rg = (uint32_t)i;
         td.cursor0 = (uint32_t)((tile_base[i] + t) * np);
       }
+    });
+    for (size_t i = 0; i < q.rgs.size(); i++) {
+      const RowGroupPlan& rp = q.rgs[i];
       for (int p = 0; p < np; p++) {
         const ChunkIndex& ci = rp.chunks[p];
         ChunkInfo& info = q.chunk_infos[i * np + p];
@@ -411,6 +425,17 @@ void plan_query(Query& q) {
         ic.num_rows = ci.num_rows;
         ic.dict_n = ci.dict_n;
         ic.string_typed = q.pcols[p].string_typed;
+        const uint32_t chunk_page0 = (uint32_t)q.idx_pages.size();
+        for (auto& zp : ci.zpages) {
+          ZPage z;
+          z.src_off = rebase(zp.src_off);
+          z.dst_off = rebase(zp.dst_virt);
+          z.src_len = zp.src_len;
+          z.dst_len = zp.dst_len;
+          z.page = zp.page < 0 ? 0xffffffffu : chunk_page0 + (uint32_t)zp.page;
+          z.flags = rp.from_cache[p] ? (zp.flags & ~(uint32_t)ZP_DECODE) : zp.flags;  // a cached block holds the inflated bytes already
+          q.zpages.push_back(z);
+        }
         for (auto& pg : ci.pages) {
           IdxPage ip;
           memset(&ip, 0, sizeof ip);

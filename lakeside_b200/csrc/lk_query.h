@@ -164,6 +164,7 @@ struct Query {
   bool device_index = false;
   std::vector<IdxPage> idx_pages;
   std::vector<IdxChunk> idx_chunks;  // [row group][pcol]
+  std::vector<ZPage> zpages;         // SNAPPY pages: inflated (unless their block came from the segment cache) and parsed by the device before the index build
   uint64_t n_runs = 0;               // runs in the pool (device mode: known after the count pass)
   std::vector<DefChunk> def_chunks;  // chunks whose definition levels are expanded on the device before every scan
   uint64_t defbm_words = 0;          // size of the bitmap pool (32-bit words)

@@ -51,6 +51,7 @@ class SynthSpec:
     prefixes: Tuple[str, str, str, str] = ("svc", "ns", "pod", "az")
     extra_nan_inf: bool = False  # sprinkle NaN / +-inf / -0.0 into value columns (edge-case tests)
     drop_columns: Tuple[str, ...] = ()  # schema drift between segments (union_by_name tests)
+    compression: str = "NONE"  # the benchmark's writer is pinned to NONE; "SNAPPY" for the format-breadth tests
 
 
 def tag_values(prefix: str, k: int) -> List[str]:
@@ -134,7 +135,7 @@ def write_segment(path: str, spec: SynthSpec, index: int) -> str:
     pq.write_table(
         tbl,
         path,
-        compression="NONE",
+        compression=spec.compression,
         use_dictionary=True,
         data_page_version="1.0",
         data_page_size=1 << 20,

@@ -190,6 +190,35 @@ def case_physical_layouts():
     return out
 
 
+def case_compressed():
+    """SNAPPY pages (inflated on the device; the CPU emulator of the tests has no inflater, so these are GPU-only cases):
+    V1 and V2 data pages, many small pages and row groups, numeric dictionary pages, metrics segments with NULL tags."""
+    base = _small_logs(20000, 21, null_value=True)
+    be = _logs_be({"q1": F("resource.service.name", "regex", "svc-[ab]"), "q2": F("level", "!=", "warn"), "op": "and"}, "sum", ["level"])
+    rq = _req(be, 1, 60000)
+    variants = {
+        "snappy": {"compression": "SNAPPY"},
+        "snappy_v2": {"compression": "SNAPPY", "data_page_version": "2.0"},
+        "snappy_small_pages_row_groups": {"compression": "SNAPPY", "row_group_size": 4500, "data_page_size": 300, "write_batch_size": 32},
+        "snappy_no_dictionary": {"compression": "SNAPPY", "use_dictionary": ["resource.service.name", "level", NAME]},
+        "snappy_mixed_codecs": {"compression": {TS: "SNAPPY", NAME: "NONE", "resource.service.name": "SNAPPY", "level": "NONE", VALUE: "SNAPPY"}},
+    }
+    out = []
+    for vid, kw in variants.items():
+        out.append((f"layout/{vid}", [_write("layout_" + vid, 0, base, "logs", **kw)], rq, ["sum"]))
+    n = 5000
+    rng = np.random.default_rng(3)
+    wide = np.array([f"pod-{i:04d}" for i in range(3000)], dtype=object)
+    t2 = pa.table({TS: np.sort(T0 + rng.integers(0, 3600000, n)).astype(np.int64), NAME: rng.choice(["a", "b"], n),
+                   "pod": pa.array(wide[rng.integers(0, 3000, n)], mask=rng.random(n) < 0.05),
+                   VALUE: pa.array(rng.integers(-1000, 1000, n).astype(np.int64)),
+                   "latency$number": pa.array(rng.random(n).astype(np.float32), mask=rng.random(n) < 0.3)})
+    p2 = [_write("types_snappy", 0, t2, "logs", compression="SNAPPY")]
+    out.append(("layout/snappy_int64_value_wide_dict", p2, _req(_logs_be(F("pod", "regex", "^pod-1"), "sum", ["pod"]), 1, 600000), ["sum"]))
+    out.append(("layout/snappy_field_float32_notnull", p2, _req(_logs_be(F(NAME, "eq", "a"), "max", [], fieldName="latency", fieldType="number"), 1, 600000), ["max"]))
+    return out
+
+
 def case_empty():
     e = _small_logs(0, 1)
     nz = _small_logs(500, 2)
@@ -198,6 +227,10 @@ def case_empty():
     return [("empty/zero_rows_only", [pe], _req(_logs_be(F(NAME, "eq", "alpha"), "sum", []), 1, 60000), ["sum"]),
             ("empty/zero_rows_plus_data", [pe, pn], _req(_logs_be(F(NAME, "eq", "alpha"), "sum", []), 2, 60000), ["sum"]),
             ("empty/nothing_passes", [pn], _req(_logs_be(F(NAME, "eq", "no-such-name"), "sum", ["level"]), 1, 60000), ["sum"])]
+
+
+def gpu_only_cases():
+    return case_compressed()
 
 
 def all_cases():
@@ -211,7 +244,7 @@ def all_cases():
 def error_cases():
     p = [_write("ops", 0, _small_logs(), "logs")]
     svc = "resource.service.name"
-    snappy = [_write("snappy", 0, _small_logs(), "logs", compression="SNAPPY")]
+    snappy = [_write("zstd", 0, _small_logs(), "logs", compression="ZSTD")]
     tagq = json.loads(_req(_logs_be(F(svc, "eq", "svc-a")), 1, 60000))
     tagq["isTagQuery"] = True
     noch = json.loads(_req(_logs_be(F(svc, "eq", "svc-a")), 1, 60000))

@@ -5,7 +5,7 @@ import cases
 import helpers as H
 
 pytestmark = pytest.mark.gpu
-CASES = cases.all_cases()
+CASES = cases.all_cases() + cases.gpu_only_cases()
 ERRORS = cases.error_cases()
 
 

@@ -131,7 +131,7 @@ def test_layout_cases_warm():
     # every file-layout case (PLAIN string pages re-encoded behind their chunk, several row groups, DataPage V2, NULL runs ...)
     # evaluated twice: the second time from cached chunks and cached page / dictionary indexes
     n = 0
-    for name, paths, rq, ops in C.all_cases():
+    for name, paths, rq, ops in C.all_cases() + C.gpu_only_cases():
         if not name.startswith("layout/"):
             continue
         want = H.oracle_single(rq, paths)

@@ -52,6 +52,20 @@ def test_c2_four_aggregates(path):
     assert got["survivors"] >= len(want["rows"])
 
 
+def test_c2_snappy_segments():
+    # SNAPPY-compressed metric segments (1 MiB pages: long literals for the PLAIN doubles, dense copy elements for the tag
+    # indices, a compressed numeric dictionary for the timestamps), inflated on the device; same rows, same answers
+    spec = synth.SynthSpec(dataset="metrics", rows=200000, compression="SNAPPY")
+    _, paths = H.dataset("c2_m200k_snappy", spec, 2)
+    rq = H.request_json(synth.c2_base_expr(), [0, 1], 10000)
+    want = H.oracle_multi(rq, paths, synth.C2_AGGREGATES)
+    for tag in ("cold", "warm"):  # warm: inflated pages come from the segment cache
+        got = H.gpu_eval_multi(rq, paths, synth.C2_AGGREGATES)
+        H.assert_same(got, want, ["sum", "sum", "min", "max"], "c2/snappy/" + tag)
+    plain = H.dataset("c2_m200k", synth.SynthSpec(dataset="metrics", rows=200000), 2)[1]
+    assert H.oracle_multi(H.request_json(synth.c2_base_expr(), [0, 1], 10000), plain, synth.C2_AGGREGATES)["rows"] == want["rows"]
+
+
 @pytest.mark.parametrize("path", ["dense", "hash", "records"])
 def test_small_group_space_dense_and_hash(path):
     spec = synth.SynthSpec(dataset="metrics", rows=150000, n_names=4, cards=(16, 4, 4, 2))

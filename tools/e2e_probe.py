@@ -17,6 +17,7 @@ ap.add_argument("--segments", type=int, default=100)
 ap.add_argument("--rows", type=int, default=1 << 20)
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--data", default="/tmp/lk_probe")
+ap.add_argument("--files", action="store_true", help="segment files through the HBM-resident segment cache instead of caller buffers")
 ap.add_argument("--torch", action="store_true", help="initialise torch.cuda first, as bench.py does")
 a = ap.parse_args()
 
@@ -40,8 +41,12 @@ out = []
 for _ in range(a.steps):
     t = [time.perf_counter()]
     q = api.Query(rq, aggregates=synth.C2_AGGREGATES)
-    for ptr, n in bufs:
-        q.add_segment_buffer(ptr, n)
+    if a.files:
+        for p in paths:
+            q.add_segment_file(p)
+    else:
+        for ptr, n in bufs:
+            q.add_segment_buffer(ptr, n)
     t.append(time.perf_counter())
     q.prepare(); t.append(time.perf_counter())
     q.execute(); q.sync(); t.append(time.perf_counter())

@@ -183,7 +183,11 @@ const double* lk_result_value(const lk_result* r, int a);       /* SQL NULL read
 const uint8_t* lk_result_value_null(const lk_result* r, int a); /* 1 where the aggregate is SQL NULL */
 const int32_t* lk_result_tag_codes(const lk_result* r, int t);  /* -1 = SQL NULL */
 int lk_result_tag_dict(const lk_result* r, int t, int32_t* n, const char* const** strings);
-/* Row-at-a-time accessors for a java.sql.ResultSet shim (1-based column index like JDBC). */
+/* Row-at-a-time accessors for a java.sql.ResultSet shim (1-based column index like JDBC).
+ * Tag queries (PushDownRequest.isTagQuery with a tagDataType; BaseExpr.scala:127-143: SELECT "tag" as "tag", COUNT(*) AS count
+ * ... GROUP BY "tag") have the two JDBC columns (tag, "count") instead: get_string(row, 1) = the tag value (NULL for the NULL
+ * group), get_string(row, 2) / get_long(row, 2) = the row count (the string is valid until the calling thread's next
+ * lk_result_get_string); in the column view the tag is tag column 0 and the count is value column 0. */
 int64_t lk_result_get_long(const lk_result* r, int64_t row, int col);
 double lk_result_get_double(const lk_result* r, int64_t row, int col);
 const char* lk_result_get_string(const lk_result* r, int64_t row, int col); /* NULL for SQL NULL */

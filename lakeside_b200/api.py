@@ -124,6 +124,12 @@ class GlobResult:
         assert got == need
         return buf.raw[:need]
 
+    def tag_counts(self) -> Dict[Optional[str], int]:
+        """Tag query result (BaseExpr.scala:127-143: SELECT "tag", COUNT(*) ... GROUP BY "tag"): {tag value (None = NULL group): rows}."""
+        assert self.columns[1:] == ["count"], "not a tag-query result"
+        d = self.tag_dicts[0]
+        return {(None if c < 0 else d[c]): int(v) for c, v in zip(self.tag_codes[0].tolist(), self.values[0].tolist())}
+
     def to_data_points(self, query_tags: Optional[Dict[str, Any]] = None, value_index: int = 0) -> List[DataPoint]:
         """``Commons.toDataPoint`` aggregate branch (Commons.scala:424-461): null / "" / "null" tags are dropped and
         an empty tag map falls back to the segment's queryTags."""

@@ -389,18 +389,27 @@ int lk_result_tag_dict(const lk_result* r, int t, int32_t* n, const char* const*
 }
 int64_t lk_result_get_long(const lk_result* r, int64_t row, int col) {
   if (!r || row < 0 || row >= r->r->n) return 0;
+  if (r->r->tag_query) return col == 2 ? (int64_t)r->r->values[0][row] : 0;
   if (col == 1) return r->r->ts[row];
   if (col >= 2 && col < 2 + r->r->n_values) return (int64_t)r->r->values[col - 2][row];
   return 0;
 }
 double lk_result_get_double(const lk_result* r, int64_t row, int col) {
   if (!r || row < 0 || row >= r->r->n) return 0.0;
+  if (r->r->tag_query) return col == 2 ? r->r->values[0][row] : 0.0;
   if (col == 1) return (double)r->r->ts[row];
   if (col >= 2 && col < 2 + r->r->n_values) return r->r->values[col - 2][row];
   return 0.0;
 }
 const char* lk_result_get_string(const lk_result* r, int64_t row, int col) {
   if (!r || row < 0 || row >= r->r->n) return nullptr;
+  if (r->r->tag_query) {  // (tag, count): Commons.toDataPoint reads BOTH through getString (Commons.scala:407-416)
+    if (col == 1) { int32_t c = r->r->codes[0][row]; return c < 0 ? nullptr : r->r->dict_ptrs[0][c]; }
+    if (col != 2) return nullptr;
+    static thread_local char buf[32];  // valid until the calling thread's next lk_result_get_string
+    snprintf(buf, sizeof buf, "%lld", (long long)r->r->values[0][row]);
+    return buf;
+  }
   int t = col - 2 - r->r->n_values;
   if (t < 0 || t >= r->r->n_tags) return nullptr;
   int32_t c = r->r->codes[t][row];

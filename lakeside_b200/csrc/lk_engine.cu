@@ -2172,11 +2172,17 @@ HostResult* device_fetch(Query& q) {
   r->n = n;
   r->n_values = (int)q.aggs.size();
   r->n_tags = (int)q.key_pcols.size();
-  r->col_names.push_back(q.ts_col_name);
-  for (size_t a = 0; a < q.aggs.size(); a++)
-    r->col_names.push_back(q.is_metrics ? (q.aggs.size() == 1 ? std::string("value") : "value_" + std::to_string(a))
-                                         : q.aggs[a].aggregation + "(\"" + q.aggs[a].value_column + "\")");
-  for (auto& k : q.key_names) r->col_names.push_back(k);
+  r->tag_query = q.tag_query;
+  if (q.tag_query) {  // SELECT "tag" as "tag", COUNT(*) AS count
+    r->col_names.push_back(q.key_names[0]);
+    r->col_names.push_back("count");
+  } else {
+    r->col_names.push_back(q.ts_col_name);
+    for (size_t a = 0; a < q.aggs.size(); a++)
+      r->col_names.push_back(q.is_metrics ? (q.aggs.size() == 1 ? std::string("value") : "value_" + std::to_string(a))
+                                           : q.aggs[a].aggregation + "(\"" + q.aggs[a].value_column + "\")");
+    for (auto& k : q.key_names) r->col_names.push_back(k);
+  }
   r->dicts = q.key_dicts;
   r->dict_ptrs.resize(r->dicts.size());
   for (size_t k = 0; k < r->dicts.size(); k++)

@@ -127,7 +127,13 @@ PushDownRequest parse_push_down_request(const std::string& json) {
   }
   if (const Json* j = root.get("reverseSort")) r.reverse_sort = j->as_bool();
   if (const Json* j = root.get("isTagQuery")) r.is_tag_query = j->as_bool();
-  if (const Json* j = root.get("tagDataType"); j && !j->is_null()) r.has_tag_data_type = true;
+  if (const Json* j = root.get("tagDataType"); j && !j->is_null()) {
+    LK_CHECK(j->is_obj(), LK_ERR_INVALID, "tagDataType must be an object");
+    r.has_tag_data_type = true;
+    if (const Json* n = j->get("tagName"); n && n->text()) r.tag_name = n->str;
+    if (const Json* t = j->get("dataType"); t && t->text()) r.tag_type = t->str;
+    LK_CHECK(!r.tag_name.empty(), LK_ERR_INVALID, "tagDataType needs a tagName");
+  }
   return r;
 }
 

@@ -53,6 +53,7 @@ struct PushDownRequest {
   BaseExpr expr;
   std::vector<SegmentRequest> segments;
   bool reverse_sort = false, is_tag_query = false, has_tag_data_type = false;
+  std::string tag_name, tag_type;  // tagDataType {tagName, dataType} (model/query/common/TagDataType.scala:19)
 };
 
 PushDownRequest parse_push_down_request(const std::string& json);

@@ -146,13 +146,19 @@ void plan_query(Query& q) {
   const BaseExpr& e = q.req.expr;
   const Options& opt = global_options();
   // ---- shape checks: everything that is not the aggregate push-down is outside the GPU path ----
-  LK_CHECK(!q.req.is_tag_query, LK_ERR_UNSUPPORTED, "tag queries (isTagQuery) are outside the GPU path");
-  LK_CHECK(e.has_chart, LK_ERR_UNSUPPORTED, "exemplar queries (no chart options) are outside the GPU path");
+  // Tag query with a tagDataType (BaseExpr.scala:127-143, the branch for a tag that is a column of the files):
+  //   SELECT "tag" as "tag", COUNT(*) AS count FROM T WHERE <filter> AND ts >= S AND ts < E GROUP BY "tag"
+  // = this engine with the tag as the only key column, one time bucket and COUNT over the timestamp column (a row that
+  // passes `ts >= S` has a timestamp, so that count IS the row count).  Without a tagDataType the reference selects whole
+  // rows (SELECT *): not an aggregate, outside the GPU path.
+  q.tag_query = q.req.is_tag_query;
+  LK_CHECK(!q.tag_query || q.req.has_tag_data_type, LK_ERR_UNSUPPORTED, "tag queries without a tagDataType (SELECT *) are outside the GPU path");
+  LK_CHECK(q.tag_query || e.has_chart, LK_ERR_UNSUPPORTED, "exemplar queries (no chart options) are outside the GPU path");
   LK_CHECK(!e.has_extract && !e.has_compute, LK_ERR_UNSUPPORTED, "extract / compute sub-queries are outside the GPU path");
   LK_CHECK(!q.req.segments.empty(), LK_ERR_INVALID, "PushDownRequest has no segmentRequests");
   LK_CHECK(q.segs.size() == q.req.segments.size(), LK_ERR_INVALID,
            strf("%zu segment(s) added but the request lists %zu segmentRequests", q.segs.size(), q.req.segments.size()));
-  q.is_metrics = e.dataset == "metrics";
+  q.is_metrics = e.dataset == "metrics" && !q.tag_query;  // (a tag query has no timestamp grid to check: one bucket)
   q.ts_col_name = q.is_metrics ? TIMESTAMP : "step_ts";
   // Commons.scala:225-232: startTs = min, endTs = max over the glob, step of the HEAD segment
   q.ts_lo = q.req.segments[0].start_ts;
@@ -161,6 +167,17 @@ void plan_query(Query& q) {
   q.step = q.req.segments[0].step_ms;
   LK_CHECK(q.step > 0, LK_ERR_INVALID, "stepInMillis must be positive");
   LK_CHECK(q.ts_lo >= 0, LK_ERR_UNSUPPORTED, "negative startTs");
+  if (q.tag_query) {
+    LK_CHECK(q.aggs.empty(), LK_ERR_INVALID, "a tag query takes no aggregates option");
+    LK_CHECK(q.req.tag_type.empty() || q.req.tag_type == "string", LK_ERR_UNSUPPORTED, "tag queries on non-string tags");
+    AggSpec a;
+    a.op = AGG_COUNT;
+    a.aggregation = "count";
+    a.value_column = TIMESTAMP;
+    q.aggs.push_back(a);
+    // one bucket over [startTs, endTs): bucket = (ts - base) / step with base = startTs, step = the whole range
+    q.step = std::max<int64_t>(1, q.ts_hi - q.ts_lo);
+  }
   if (q.aggs.empty()) q.aggs.push_back(resolve_agg(e, e.chart.aggregation, e.chart.has_rollup, e.chart.rollup, true));
   LK_CHECK(q.aggs.size() <= (size_t)LK_MAX_AGGS, LK_ERR_UNSUPPORTED, "too many aggregates in one pass");
   const bool value_not_null = !q.is_metrics && e.chart.has_field_name && e.chart.field_name != VALUE;  // BaseExpr.scala:407-426
@@ -187,7 +204,7 @@ void plan_query(Query& q) {
   q.ts_pcol = pcol_index(q, TIMESTAMP);
   q.pcols[q.ts_pcol].is_ts = true;
   LK_CHECK(exists(TIMESTAMP), LK_ERR_QUERY, std::string("Binder Error: column ") + TIMESTAMP + " not found");
-  LK_CHECK(exists(NAME), LK_ERR_QUERY, std::string("Binder Error: column ") + NAME + " not found");
+  LK_CHECK(q.tag_query || exists(NAME), LK_ERR_QUERY, std::string("Binder Error: column ") + NAME + " not found");
 
   // filter leaves
   q.leaves.clear();
@@ -219,7 +236,14 @@ void plan_query(Query& q) {
   // key columns: name, then the group-bys that exist (BaseExpr.scala:338-346), in chart order
   q.key_pcols.clear();
   q.key_names.clear();
-  {
+  if (q.tag_query) {  // GROUP BY "tag" alone
+    LK_CHECK(exists(q.req.tag_name), LK_ERR_QUERY, "Binder Error: column " + q.req.tag_name + " not found");
+    int p = pcol_index(q, q.req.tag_name);
+    q.pcols[p].is_key = true;
+    q.pcols[p].key_slot = 0;
+    q.key_pcols.push_back(p);
+    q.key_names.push_back(q.req.tag_name);
+  } else {
     int p = pcol_index(q, NAME);
     q.pcols[p].is_key = true;
     q.pcols[p].key_slot = 0;
@@ -705,7 +729,7 @@ void plan_query(Query& q) {
   P.step = q.step;
   P.is_metrics = q.is_metrics;
   if (q.ts_hi <= q.ts_lo) { q.nbuckets = 0; q.base = q.ts_lo; }
-  else if (q.is_metrics) {
+  else if (q.is_metrics || q.tag_query) {
     q.base = q.ts_lo;
     uint64_t nb = ((uint64_t)(q.ts_hi - q.ts_lo) + q.step - 1) / q.step;
     LK_CHECK(nb < (1ull << 31), LK_ERR_UNSUPPORTED, "too many time buckets");

@@ -132,6 +132,7 @@ struct Query {
   // ---- plan ----
   bool prepared = false;
   bool is_metrics = false;
+  bool tag_query = false;  // isTagQuery with a tagDataType: SELECT "tag", COUNT(*) ... GROUP BY "tag" (BaseExpr.scala:127-143)
   int64_t ts_lo = 0, ts_hi = 0, step = 0, base = 0;
   uint32_t nbuckets = 0;
   std::string ts_col_name;
@@ -197,6 +198,7 @@ struct Query {
 };
 
 struct HostResult {
+  bool tag_query = false;  // JDBC columns are (tag, "count") instead of (timestamp, value.., name, group-bys..)
   int64_t n = 0;
   int n_values = 0, n_tags = 0;
   std::vector<std::string> col_names;

@@ -839,6 +839,121 @@ def evaluate_glob_rowwise(req: PushDownRequest, paths: Sequence[str]) -> GlobRes
     return _finish(plan, acc)
 
 
+def _select_rows(t, base_filter, start_ts: int, end_ts: int, non_existent) -> Tuple[Optional[np.ndarray], Optional[np.ndarray]]:
+    """Timestamp range + WHERE clause of one file (3-valued logic; BaseExpr.scala:159-161, 433-513): returns (ts, keep mask),
+    or (None, None) for a file without a timestamp column."""
+    import pyarrow as pa
+
+    n = t.num_rows
+    if TIMESTAMP not in t.column_names:
+        return None, None
+    ts_col = t.column(TIMESTAMP).combine_chunks()
+    ts = ts_col.fill_null(0).to_numpy(zero_copy_only=False).astype(np.int64)
+    sel = (ts >= start_ts) & (ts < end_ts)
+    if ts_col.null_count:
+        sel &= ~ts_col.is_null().to_numpy(zero_copy_only=False)
+
+    def leaf_vec(f: Filter) -> np.ndarray:
+        if f.k in non_existent and not f.extracted and not f.computed:
+            return np.full(n, F, np.uint8)
+        if f.k not in t.column_names:  # union_by_name NULL column
+            return np.full(n, F if f.op in (HAS, EXISTS) else N, np.uint8)
+        col = t.column(f.k).combine_chunks()
+        if pa.types.is_string(col.type) or pa.types.is_large_string(col.type):
+            if _is_numeric_op(f):
+                raise OracleUnsupported(f"numeric operator {f.op} on string column {f.k}")
+            de = col.dictionary_encode()
+            dvals = de.dictionary.to_pylist()
+            lut = np.array([leaf_truth_string(f, s) for s in dvals] + [leaf_truth_string(f, None)], np.uint8)
+            idx = de.indices.fill_null(len(dvals)).to_numpy(zero_copy_only=False).astype(np.int64)
+            return lut[idx]
+        if not (f.op in (HAS, EXISTS) or _is_numeric_op(f)):
+            raise OracleUnsupported(f"string operator {f.op} on numeric column {f.k}")
+        isnull = col.is_null().to_numpy(zero_copy_only=False)
+        x = col.fill_null(0).to_numpy(zero_copy_only=False).astype(np.float64)
+        out = np.empty(n, np.uint8)
+        if f.op in (HAS, EXISTS):
+            out[:] = T
+            out[isnull] = F
+            return out
+        c = _normalized_value(f)
+        xn = np.isnan(x)
+        cn = c != c
+        with np.errstate(invalid="ignore"):
+            if f.op == GT:
+                r = (x > c) | (xn & (not cn))
+            elif f.op == GE:
+                r = (x >= c) | xn
+            elif f.op == LT:
+                r = (x < c) | ((~xn) & cn)
+            else:
+                r = (x <= c) | cn
+            if f.op in (GT, LT):
+                r = r & ~(xn & cn)
+        out[:] = np.where(r, T, F)
+        out[isnull] = N
+        return out
+
+    def tree(q) -> np.ndarray:
+        if isinstance(q, Filter):
+            return leaf_vec(q)
+        if isinstance(q, BinaryClause):
+            a, b = tree(q.q1), tree(q.q2)
+            if q.op == "and":
+                return np.where((a == F) | (b == F), F, np.where((a == N) | (b == N), N, T)).astype(np.uint8)
+            return np.where((a == T) | (b == T), T, np.where((a == N) | (b == N), N, F)).astype(np.uint8)
+        if isinstance(q, NotClause):
+            a = tree(q.not_)
+            return np.where(a == N, N, np.where(a == T, F, T)).astype(np.uint8)
+        raise TypeError(q)
+
+    sel &= tree(base_filter) == T
+    return ts, sel
+
+
+def evaluate_tag_query(req: PushDownRequest, paths: Sequence[str]) -> Dict[Optional[str], int]:
+    """Tag query with a tagDataType (BaseExpr.scala:127-143, the non-synthetic branch):
+    ``SELECT "tag" as "tag", COUNT(*) AS count FROM T WHERE <filter> AND ts >= S AND ts < E GROUP BY "tag"`` over the glob
+    (Commons.scala:200-254: start = min, end = max over the segment requests).  Returns {tag value (None = the NULL group):
+    count}; the reference reads both columns through ``getString`` (Commons.scala:407-416)."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    import pyarrow.parquet as pq
+
+    if not req.isTagQuery or not req.tagDataType:
+        raise OracleUnsupported("tag query without a tagDataType (SELECT *)")
+    b = req.baseExpr
+    if b.extractor is not None or b.compute is not None:
+        raise OracleUnsupported("extract/compute sub-queries")
+    tag = req.tagDataType["tagName"]
+    columns = set()
+    for p_ in paths:
+        columns |= set(pq.read_schema(p_).names)
+    if tag not in columns:
+        raise OracleQueryError(f"Binder Error: column {tag} not found")
+    referenced = _referenced_columns(b.filter)
+    non_existent = {c for c in referenced if c not in columns}  # only the filter's fields: a tag query has no group-bys to drop
+    srs = req.segmentRequests
+    start_ts, end_ts = min(s.startTs for s in srs), max(s.endTs for s in srs)
+    want = sorted({TIMESTAMP, tag, *(c for c in referenced if c in columns)})
+    out: Dict[Optional[str], int] = {}
+    for t in _read_tables(paths, want):
+        ts, sel = _select_rows(t, b.filter, start_ts, end_ts, non_existent)
+        if ts is None:
+            raise OracleQueryError(f"Binder Error: column {TIMESTAMP} not found")
+        idx = np.nonzero(sel)[0]
+        if tag in t.column_names:
+            col = t.column(tag).combine_chunks()
+            if not (pa.types.is_string(col.type) or pa.types.is_large_string(col.type)):
+                raise OracleUnsupported(f"tag query on non-string column {tag}")
+            vals = col.take(pa.array(idx)).to_pylist()
+        else:
+            vals = [None] * len(idx)  # union_by_name: NULL for this file
+        for v in vals:
+            out[v] = out.get(v, 0) + 1
+    return out
+
+
 def evaluate_glob(req: PushDownRequest, paths: Sequence[str], aggs: Optional[Sequence[Tuple[str, str]]] = None):
     """Vectorised evaluation (Arrow C++ Parquet decode + NumPy), same semantics as ``evaluate_glob_rowwise``.
 
@@ -894,69 +1009,9 @@ def evaluate_glob(req: PushDownRequest, paths: Sequence[str], aggs: Optional[Seq
     ts_all, keycode_all, val_all = [], [[] for _ in key_cols], [[] for _ in agg_list]
     for t in per_file:
         n = t.num_rows
-        if TIMESTAMP not in t.column_names:
+        ts, sel = _select_rows(t, req.baseExpr.filter, plan.start_ts, plan.end_ts, plan.non_existent)
+        if ts is None:
             continue
-        ts_col = t.column(TIMESTAMP).combine_chunks()
-        ts = ts_col.fill_null(0).to_numpy(zero_copy_only=False).astype(np.int64)
-        sel = (ts >= plan.start_ts) & (ts < plan.end_ts)
-        if ts_col.null_count:
-            sel &= ~ts_col.is_null().to_numpy(zero_copy_only=False)
-
-        def leaf_vec(f: Filter) -> np.ndarray:
-            if f.k in plan.non_existent and not f.extracted and not f.computed:
-                return np.full(n, F, np.uint8)
-            if f.k not in t.column_names:  # union_by_name NULL column
-                return np.full(n, F if f.op in (HAS, EXISTS) else N, np.uint8)
-            col = t.column(f.k).combine_chunks()
-            if pa.types.is_string(col.type) or pa.types.is_large_string(col.type):
-                if _is_numeric_op(f):
-                    raise OracleUnsupported(f"numeric operator {f.op} on string column {f.k}")
-                de = col.dictionary_encode()
-                dvals = de.dictionary.to_pylist()
-                lut = np.array([leaf_truth_string(f, s) for s in dvals] + [leaf_truth_string(f, None)], np.uint8)
-                idx = de.indices.fill_null(len(dvals)).to_numpy(zero_copy_only=False).astype(np.int64)
-                return lut[idx]
-            if not (f.op in (HAS, EXISTS) or _is_numeric_op(f)):
-                raise OracleUnsupported(f"string operator {f.op} on numeric column {f.k}")
-            isnull = col.is_null().to_numpy(zero_copy_only=False)
-            x = col.fill_null(0).to_numpy(zero_copy_only=False).astype(np.float64)
-            out = np.empty(n, np.uint8)
-            if f.op in (HAS, EXISTS):
-                out[:] = T
-                out[isnull] = F
-                return out
-            c = _normalized_value(f)
-            xn = np.isnan(x)
-            cn = c != c
-            with np.errstate(invalid="ignore"):
-                if f.op == GT:
-                    r = (x > c) | (xn & (not cn))
-                elif f.op == GE:
-                    r = (x >= c) | xn
-                elif f.op == LT:
-                    r = (x < c) | ((~xn) & cn)
-                else:
-                    r = (x <= c) | cn
-                if f.op in (GT, LT):
-                    r = r & ~(xn & cn)
-            out[:] = np.where(r, T, F)
-            out[isnull] = N
-            return out
-
-        def tree(q) -> np.ndarray:
-            if isinstance(q, Filter):
-                return leaf_vec(q)
-            if isinstance(q, BinaryClause):
-                a, b = tree(q.q1), tree(q.q2)
-                if q.op == "and":
-                    return np.where((a == F) | (b == F), F, np.where((a == N) | (b == N), N, T)).astype(np.uint8)
-                return np.where((a == T) | (b == T), T, np.where((a == N) | (b == N), N, F)).astype(np.uint8)
-            if isinstance(q, NotClause):
-                a = tree(q.not_)
-                return np.where(a == N, N, np.where(a == T, F, T)).astype(np.uint8)
-            raise TypeError(q)
-
-        sel &= tree(req.baseExpr.filter) == T
         vals = []
         for _, vc in agg_list:
             if vc in t.column_names:

@@ -158,6 +158,23 @@ int64_t lk_query_survivors(lk_query* q);
  * division of step first -- else identity.  Computed on the device from the result columns still in HBM; rows are in
  * the order of lk_result_*.  Returns the number of rows written, -1 on error. */
 int64_t lk_query_eval(lk_query* q, const char* aggregation, const char* chart_type, const char* metric_type, double* out, int64_t cap);
+/* Formula.eval (core/.../utils/ast/Formula.scala:32-69; evaluated per SketchGroup by QueryEngineV2.scala:310-389) over the
+ * reduced rows of two finalized queries, on the device: e1 <op> e2 per (timestamp, group key).
+ *   spec_json: {"op": "add" | "sub" | "mul" | "div",
+ *               "e1": {"aggregation": "sum", "chartType": "line", "metricType": "gauge", "groupBys": [..]} | {"constant": 2.0},
+ *               "e2": the same}
+ * A BaseExpr side is the query handed in for it (e1 / e2; NULL for a constant side); its per-row value is that of
+ * lk_query_eval, its group key the side's sorted group-by values joined by ":" (ASTUtils.scala:87-89; NULL, "" and "null"
+ * read as ""; groupBys defaults to the request's chart group-bys), and a later row of the same (timestamp, key) replaces an
+ * earlier one, as in the reference's map.  Equal keys are combined; `add` takes a missing side as 0, the other operators
+ * give no result; a zero divisor gives no result.  A constant side takes the keys of the other side (ASTUtils.scala:50-64).
+ * Output, in timestamp order: timestamp, value, and where the result's tags come from -- side (1 = e1's row, 2 = e2's row:
+ * e1 is the constant or the side `add` filled in; 0 = no tags: a constant e1 without group-bys) and the row index in that
+ * side's lk_result (for side 0: the e2 row the value was computed from).
+ * *n_out = the number of rows (they must fit cap).  LK_ERR_UNSUPPORTED: sides with different numbers of group-bys,
+ * group-by values containing ':' with two or more group-bys (the joined keys would be ambiguous), two constants. */
+int lk_formula_eval(lk_query* e1, lk_query* e2, const char* spec_json, int64_t cap, int64_t* out_ts, double* out_value,
+                    int32_t* out_side, int64_t* out_row, int64_t* n_out);
 /* Timings of the last execute/finalize in milliseconds (CUDA events on the query's stream):
  * [0] H2D upload, [1] scan kernel, [2] finalize kernels, [3] D2H, [4] host planning, [5] definition-level expansion
  * (def_expand_kernel + the clear of its bitmaps, at the start of every execute), [6] sharded record path: the device-side wait

@@ -58,6 +58,7 @@ _SIGNATURES = {
     "lk_query_finalize_device": (c_int, [c_void_p]),
     "lk_query_finalize": (c_int, [c_void_p, POINTER(c_void_p)]),
     "lk_query_survivors": (c_int64, [c_void_p]),
+    "lk_formula_eval": (c_int, [c_void_p, c_void_p, c_char_p, c_int64, POINTER(c_int64), POINTER(c_double), POINTER(c_int32), POINTER(c_int64), POINTER(c_int64)]),
     "lk_query_eval": (c_int64, [c_void_p, c_char_p, c_char_p, c_char_p, POINTER(c_double), c_int64]),
     "lk_query_timings": (c_int, [c_void_p, POINTER(c_double)]),
     "lk_query_touched_bytes": (c_int64, [c_void_p]),

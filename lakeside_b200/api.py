@@ -243,10 +243,14 @@ class Query:
     def finalize_device(self):
         _lib.check(_lib.load().lk_query_finalize_device(self._h))
 
+    result_rows = 0  # rows of the last finalize()
+
     def finalize(self) -> GlobResult:
         r = ctypes.c_void_p()
         _lib.check(_lib.load().lk_query_finalize(self._h, ctypes.byref(r)))
-        return GlobResult(r.value)
+        res = GlobResult(r.value)
+        self.result_rows = res.num_rows
+        return res
 
     def export_dictionaries(self) -> bytes:
         p, n = ctypes.c_void_p(), ctypes.c_size_t()
@@ -332,6 +336,35 @@ class Query:
             self.close()
         except Exception:
             pass
+
+
+def formula_eval(op: str, e1, e2, cap: Optional[int] = None):
+    """``Formula.eval`` (Formula.scala:32-69) on the device over the reduced rows of two finalized queries.
+    ``e1`` / ``e2``: ``(Query, spec dict)`` for a BaseExpr side (spec: aggregation, chartType, metricType, groupBys) or a
+    number for a ConstantExpr.  Returns (timestamps, values, side, row): ``side[i]`` says whose tags result i carries (1 = the
+    e1 query's result row ``row[i]``, 2 = the e2 query's)."""
+    def side(x):
+        if isinstance(x, (int, float)):
+            return None, {"constant": float(x)}
+        return x[0], dict(x[1])
+
+    q1, s1 = side(e1)
+    q2, s2 = side(e2)
+    spec = json.dumps({"op": op, "e1": s1, "e2": s2}).encode()
+    if cap is None:
+        cap = 1
+        for q in (q1, q2):
+            if q is not None:
+                cap += q.result_rows
+    ts, val = np.empty(cap, np.int64), np.empty(cap, np.float64)
+    sd, row = np.empty(cap, np.int32), np.empty(cap, np.int64)
+    n_out = ctypes.c_int64()
+    _lib.check(_lib.load().lk_formula_eval(q1._h if q1 else None, q2._h if q2 else None, spec, cap,
+                                           ts.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)), val.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                           sd.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), row.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)),
+                                           ctypes.byref(n_out)))
+    n = int(n_out.value)
+    return ts[:n], val[:n], sd[:n], row[:n]
 
 
 def eval_glob(push_down_request_json: str, parquet_paths: Sequence[str]) -> GlobResult:

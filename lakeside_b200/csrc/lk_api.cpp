@@ -308,6 +308,14 @@ int64_t lk_query_eval(lk_query* q, const char* aggregation, const char* chart_ty
   return n;
 }
 
+int lk_formula_eval(lk_query* e1, lk_query* e2, const char* spec_json, int64_t cap, int64_t* out_ts, double* out_value, int32_t* out_side,
+                    int64_t* out_row, int64_t* n_out) {
+  return guard([&] {
+    LK_CHECK(spec_json && n_out && (cap == 0 || (out_ts && out_value && out_side && out_row)), LK_ERR_INVALID, "lk_formula_eval: bad arguments");
+    *n_out = device_formula(e1 ? &e1->q : nullptr, e2 ? &e2->q : nullptr, spec_json, cap, out_ts, out_value, out_side, out_row);
+  });
+}
+
 int lk_comm_create(int rank, int world, int64_t pool_records, int max_aggs, lk_comm** out) {
   return guard([&] {
     LK_CHECK(out, LK_ERR_INVALID, "null argument");

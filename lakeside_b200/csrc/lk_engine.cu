@@ -2163,6 +2163,340 @@ int64_t device_eval(Query& q, const std::string& aggregation, const std::string&
   return n;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Formula.eval (core/.../utils/ast/Formula.scala:32-69) over the reduced rows of two finalized queries, still in HBM
+// ------------------------------------------------------------------------------------------------------------
+// Per SketchGroup (= timestamp) the reference evaluates both sides into maps groupKey -> EvalResult -- BaseExpr.eval keys a
+// side by ITS sorted group-by values joined with ":" (tags dropped by toDataPoint -- NULL, "", "null" -- read as "";
+// ASTUtils.scala:87-89), a later row of the same key replaces an earlier one -- and combines equal keys: add / sub / mul /
+// div, `add` fills a missing side with 0, a zero divisor gives no result.  Here: every row gets the integer key
+// (timestamp - base) * G + mixed radix of its group-by values in dictionaries COMMON to both sides; both sides meet in one
+// hash table {key, last row of side 1, last row of side 2} (atomicMax: "the later row wins"); the winners are compacted in
+// row order (= timestamp order) into (timestamp, value, side whose tags the result carries, row in that side's result).
+struct FormulaSlot { unsigned long long key; uint32_t row1, row2; };
+struct FormulaKeyParams {
+  int n_pos;                           // group-by positions (sorted group-by names)
+  const int32_t* code[LK_MAX_KEYS];    // result column of the side's key column at this position (null: the group-by does not exist -> "")
+  const uint32_t* remap[LK_MAX_KEYS];  // side's dictionary code -> common id (one more entry at the end: SQL NULL)
+  uint32_t null_slot[LK_MAX_KEYS];     // index of that last entry
+  uint64_t stride[LK_MAX_KEYS];
+  uint64_t groups;                     // product of the common dictionary sizes
+  int64_t base;
+};
+
+__device__ __forceinline__ unsigned long long formula_key(const FormulaKeyParams& K, const int64_t* __restrict__ ts, int64_t i) {
+  unsigned long long g = 0;
+  for (int j = 0; j < K.n_pos; j++) {
+    uint32_t id = 0;
+    if (K.code[j]) { const int32_t c = K.code[j][i]; id = K.remap[j][c < 0 ? K.null_slot[j] : (uint32_t)c]; }
+    g += (unsigned long long)id * K.stride[j];
+  }
+  return (unsigned long long)(ts[i] - K.base) * K.groups + g;
+}
+
+__device__ __forceinline__ uint32_t formula_find(FormulaSlot* __restrict__ tab, uint32_t mask, unsigned long long key, bool insert) {
+  unsigned long long h = key * 0x9E3779B97F4A7C15ull;
+  uint32_t s = (uint32_t)(h >> 32) & mask;
+  const unsigned long long want = key + 1;  // 0 = empty
+  while (true) {
+    unsigned long long cur = *(volatile unsigned long long*)&tab[s].key;
+    if (cur == 0 && insert) cur = atomicCAS(&tab[s].key, 0ull, want), cur = cur == 0 ? want : cur;
+    if (cur == want) return s;
+    if (cur == 0) return 0xffffffffu;
+    s = (s + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(256) formula_insert_kernel(const __grid_constant__ FormulaKeyParams K, const int64_t* __restrict__ ts, int64_t n, int side,
+                                                             FormulaSlot* __restrict__ tab, uint32_t mask) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t s = formula_find(tab, mask, formula_key(K, ts, i), true);
+  atomicMax(side == 1 ? &tab[s].row1 : &tab[s].row2, (uint32_t)i + 1);
+}
+
+// pass 0 counts the results of every 256-row block, pass 1 (after the prefix over the blocks) writes them in row order
+struct FormulaEmit {
+  int op;            // 0 add 1 sub 2 mul 3 div
+  int side;          // rows of which side this launch walks (1 or 2)
+  int other_const;   // the other side is a constant
+  double cval;
+  const double* v1;  // per-row values of side 1 / side 2 (null for a constant side)
+  const double* v2;
+  int const_is_e1;   // constant side is e1 (the walked side is then e2)
+  int64_t* out_ts; double* out_val; int32_t* out_side; int64_t* out_row;
+};
+
+__device__ __forceinline__ bool formula_row(const FormulaKeyParams& K, const FormulaEmit& F, const int64_t* __restrict__ ts, int64_t i,
+                                            const FormulaSlot* __restrict__ tab, uint32_t mask, double& value) {
+  const uint32_t s = formula_find(const_cast<FormulaSlot*>(tab), mask, formula_key(K, ts, i), false);
+  const FormulaSlot sl = tab[s];
+  if (F.side == 1) {
+    if (sl.row1 != (uint32_t)i + 1) return false;  // a later row of the same key replaced this one
+    double a = F.v1[i], b;
+    if (F.other_const) b = F.cval;
+    else if (sl.row2) b = F.v2[sl.row2 - 1];
+    else if (F.op == 0) b = 0.0;  // add: the missing side counts as 0 (Formula.scala:45-47)
+    else return false;
+    if (F.const_is_e1) { const double t = a; a = b; b = t; }
+    if (F.op == 3 && b == 0.0) return false;  // divide by zero = missing data (Formula.scala:60-64)
+    value = F.op == 0 ? a + b : F.op == 1 ? a - b : F.op == 2 ? a * b : a / b;
+    return true;
+  }
+  // side 2: only what `add` contributes when side 1 has no row for the key
+  if (sl.row2 != (uint32_t)i + 1 || sl.row1 != 0 || F.op != 0) return false;
+  value = 0.0 + F.v2[i];
+  return true;
+}
+
+__global__ void __launch_bounds__(256) formula_emit_kernel(const __grid_constant__ FormulaKeyParams K, const __grid_constant__ FormulaEmit F,
+                                                           const int64_t* __restrict__ ts, int64_t n, const FormulaSlot* __restrict__ tab, uint32_t mask,
+                                                           uint32_t* __restrict__ block_counts, int pass, uint32_t out_base) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  double value = 0;
+  const bool keep = i < n && formula_row(K, F, ts, i, tab, mask, value);
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  __shared__ uint32_t wcnt[8];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane == 0) wcnt[wid] = __popc(bal);
+  __syncthreads();
+  uint32_t before = 0, total = 0;
+  for (int w = 0; w < 8; w++) { if (w < wid) before += wcnt[w]; total += wcnt[w]; }
+  if (pass == 0) { if (threadIdx.x == 0) block_counts[blockIdx.x] = total; return; }
+  if (!keep) return;
+  const uint32_t o = out_base + block_counts[blockIdx.x] + before + __popc(bal & ((1u << lane) - 1));
+  F.out_ts[o] = ts[i];
+  F.out_val[o] = value;
+  // whose tags: e1's -- for a constant e1 those of the sketch input it was keyed by (= this e2 row), or none at all without
+  // group-bys (ASTUtils.scala:51-55: tags = Map())
+  F.out_side[o] = F.const_is_e1 ? (K.n_pos ? 2 : 0) : F.side;
+  F.out_row[o] = i;
+}
+
+namespace {
+struct FormulaSideSpec {
+  bool constant = false;
+  double cval = 0;
+  std::string aggregation = "sum", chart_type = "line", metric_type = "gauge";
+  std::vector<std::string> group_bys;
+  bool has_group_bys = false;
+};
+FormulaSideSpec parse_formula_side(const Json* j, const char* which) {
+  FormulaSideSpec s;
+  LK_CHECK(j && j->is_obj(), LK_ERR_INVALID, std::string("formula spec needs an object '") + which + "'");
+  if (const Json* c = j->get("constant")) {
+    s.constant = true;
+    s.cval = c->kind == Json::Num ? c->num : c->kind == Json::Str ? atof(c->str.c_str()) : 0.0;
+    if (c->kind == Json::Num && c->is_int) s.cval = (double)c->i64;
+    return s;
+  }
+  if (const Json* a = j->get("aggregation"); a && a->text()) s.aggregation = a->str;
+  if (const Json* a = j->get("chartType"); a && a->text()) s.chart_type = a->str;
+  if (const Json* a = j->get("metricType"); a && a->text()) s.metric_type = a->str;
+  if (const Json* g = j->get("groupBys"); g && g->is_arr()) {
+    s.has_group_bys = true;
+    for (auto& x : g->arr) if (x.text()) s.group_bys.push_back(x.str);
+  }
+  return s;
+}
+std::string canon_tag(const std::string& v) { return (v.empty() || v == "null") ? std::string() : v; }  // Commons.scala:433: dropped tags read as ""
+}  // namespace
+
+// the per-row value of a BaseExpr side: getFromSketch + getTransformerFunc, as device_eval
+static double* formula_side_values(Query& q, const FormulaSideSpec& sp, cudaStream_t st) {
+  Query::Device& d = *q.dev;
+  const int64_t n = d.n_rows;
+  EmitParams E;
+  fill_emit_params(q, E, d.dres, (int64_t)d.dres_stride);
+  auto column = [&](const char* name) -> const double* {
+    if (q.is_metrics)
+      for (size_t a = 0; a < q.aggs.size(); a++)
+        if (q.aggs[a].value_column == std::string("rollup_") + name) return E.val[a];
+    for (size_t a = 0; a < q.aggs.size(); a++)
+      if (q.aggs[a].aggregation == name) return E.val[a];
+    return nullptr;
+  };
+  const bool avg = sp.aggregation == "avg";
+  const double* a = avg ? column("sum") : column(sp.aggregation.c_str());
+  const double* b = avg ? column("count") : nullptr;
+  int transform = 0;
+  if (q.is_metrics) {
+    if (sp.chart_type == "count" && sp.metric_type == "rate") transform = 1;
+    else if (sp.chart_type == "rate" && sp.metric_type == "count") transform = 2;
+  } else if (sp.chart_type == "rate") transform = 2;
+  double* out = nullptr;
+  CUDA_CHECK(cudaMallocAsync(&out, std::max<size_t>((size_t)n * 8, 16), st));
+  if (n) eval_transform_kernel<<<(int)((n + 255) / 256), 256, 0, st>>>(a, b, n, avg ? 1 : 0, transform, (double)(q.step / 1000), out);
+  return out;
+}
+
+int64_t device_formula(Query* q1, Query* q2, const std::string& spec_json, int64_t cap, int64_t* out_ts, double* out_val, int32_t* out_side, int64_t* out_row) {
+  Json spec = parse_json(spec_json);
+  LK_CHECK(spec.is_obj(), LK_ERR_INVALID, "formula spec must be a JSON object");
+  const Json* opj = spec.get("op");
+  LK_CHECK(opj && opj->text(), LK_ERR_INVALID, "formula spec needs op");
+  const int op = opj->str == "add" ? 0 : opj->str == "sub" ? 1 : opj->str == "mul" ? 2 : opj->str == "div" ? 3 : -1;
+  LK_CHECK(op >= 0, LK_ERR_INVALID, "formula op must be add | sub | mul | div");
+  FormulaSideSpec sp[2] = {parse_formula_side(spec.get("e1"), "e1"), parse_formula_side(spec.get("e2"), "e2")};
+  Query* qs[2] = {q1, q2};
+  LK_CHECK(!(sp[0].constant && sp[1].constant), LK_ERR_UNSUPPORTED, "formula of two constants has no rows to evaluate on");
+  for (int s = 0; s < 2; s++) {
+    if (sp[s].constant) continue;
+    LK_CHECK(qs[s] && qs[s]->dev && qs[s]->dev->finalized_device, LK_ERR_INVALID, "lk_formula_eval needs finalized queries for its BaseExpr sides");
+    LK_CHECK(!qs[s]->tag_query, LK_ERR_INVALID, "lk_formula_eval over a tag query");
+    device_resolve(*qs[s]);
+    if (!sp[s].has_group_bys) sp[s].group_bys = qs[s]->req.expr.chart.group_bys;
+    std::sort(sp[s].group_bys.begin(), sp[s].group_bys.end());
+    sp[s].group_bys.erase(std::unique(sp[s].group_bys.begin(), sp[s].group_bys.end()), sp[s].group_bys.end());
+  }
+  const int walk = sp[0].constant ? 1 : 0;           // the side whose rows drive the output (e1 unless it is the constant)
+  const int other = 1 - walk;
+  const bool other_const = sp[other].constant;
+  Query& qa = *qs[walk];
+  CUDA_CHECK(cudaSetDevice(global_options().device));
+  cudaStream_t st = qa.dev->st;
+  if (!other_const) {
+    LK_CHECK(sp[0].group_bys.size() == sp[1].group_bys.size(), LK_ERR_UNSUPPORTED,
+             "formula sides with different numbers of group-bys (their group keys can only meet by accident)");
+    LK_CHECK(qs[other]->base - qa.base < (1ll << 40) && qa.base - qs[other]->base < (1ll << 40), LK_ERR_UNSUPPORTED, "formula sides over distant time ranges");
+    CUDA_CHECK(cudaStreamSynchronize(qs[other]->dev->st));  // its result columns are read on the other query's stream
+  }
+  const int m = (int)sp[walk].group_bys.size();
+  LK_CHECK(m <= LK_MAX_KEYS, LK_ERR_UNSUPPORTED, "too many group-bys in a formula");
+  // ---- common dictionaries per group-by position ----
+  auto key_col = [](const Query& q, const std::string& name) -> int {
+    for (size_t k = 1; k < q.key_names.size(); k++) if (q.key_names[k] == name) return (int)k;  // (slot 0 is "name")
+    return -1;
+  };
+  std::vector<std::vector<std::string>> common(m);
+  for (int j = 0; j < m; j++) {
+    std::vector<std::string>& c = common[j];
+    c.push_back(std::string());
+    for (int s = 0; s < 2; s++) {
+      if (sp[s].constant) continue;
+      const int k = key_col(*qs[s], sp[s].group_bys[j]);
+      if (k >= 0) for (auto& v : qs[s]->key_dicts[k]) c.push_back(canon_tag(v));
+    }
+    std::sort(c.begin(), c.end());
+    c.erase(std::unique(c.begin(), c.end()), c.end());
+    if (m >= 2) for (auto& v : c) LK_CHECK(v.find(':') == std::string::npos, LK_ERR_UNSUPPORTED, "group-by values containing ':' make the reference's joined group keys ambiguous");
+  }
+  FormulaKeyParams K[2];
+  std::vector<uint32_t*> dev_tmp;
+  unsigned __int128 groups = 1;
+  std::vector<uint64_t> strides(m);
+  for (int j = m - 1; j >= 0; j--) { strides[j] = (uint64_t)groups; groups *= common[j].size(); LK_CHECK(groups < ((unsigned __int128)1 << 40), LK_ERR_UNSUPPORTED, "formula group space too large"); }
+  int64_t base = qa.base;
+  if (!other_const) base = std::min(base, qs[other]->base);
+  EmitParams E[2];
+  for (int s = 0; s < 2; s++) {
+    if (sp[s].constant) continue;
+    Query& q = *qs[s];
+    fill_emit_params(q, E[s], q.dev->dres, (int64_t)q.dev->dres_stride);
+    LK_CHECK((unsigned __int128)((uint64_t)(q.ts_hi - base) + (uint64_t)q.step + 1) * groups < ((unsigned __int128)1 << 62), LK_ERR_UNSUPPORTED, "formula key space too large");
+    FormulaKeyParams& P = K[s];
+    memset(&P, 0, sizeof P);
+    P.n_pos = m;
+    P.groups = (uint64_t)groups;
+    P.base = base;
+    for (int j = 0; j < m; j++) {
+      P.stride[j] = strides[j];
+      const int k = key_col(q, sp[s].group_bys[j]);
+      if (k < 0) continue;  // the group-by does not exist in this side's files: "" for every row
+      const auto& dict = q.key_dicts[k];
+      std::vector<uint32_t> remap(dict.size() + 1, 0);
+      for (size_t c = 0; c <= dict.size(); c++) {
+        const std::string v = c < dict.size() ? canon_tag(dict[c]) : std::string();
+        remap[c] = (uint32_t)(std::lower_bound(common[j].begin(), common[j].end(), v) - common[j].begin());
+      }
+      uint32_t* dr = nullptr;
+      CUDA_CHECK(cudaMallocAsync(&dr, remap.size() * 4, st));
+      CUDA_CHECK(cudaMemcpyAsync(dr, remap.data(), remap.size() * 4, cudaMemcpyHostToDevice, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));  // `remap` is a local
+      dev_tmp.push_back(dr);
+      P.code[j] = E[s].code[k];
+      P.remap[j] = dr;
+      P.null_slot[j] = (uint32_t)dict.size();
+    }
+  }
+  // ---- values, table, insert ----
+  const int64_t n_walk = qa.dev->n_rows, n_other = other_const ? 0 : qs[other]->dev->n_rows;
+  LK_CHECK(n_walk < 0x7fffffff && n_other < 0x7fffffff, LK_ERR_UNSUPPORTED, "formula over more than 2^31 rows");
+  double* v[2] = {nullptr, nullptr};
+  for (int s = 0; s < 2; s++) if (!sp[s].constant) v[s] = formula_side_values(*qs[s], sp[s], st);
+  uint64_t slots = 1024;
+  while (slots < 2 * (uint64_t)(n_walk + n_other)) slots <<= 1;
+  FormulaSlot* tab = nullptr;
+  CUDA_CHECK(cudaMallocAsync(&tab, slots * sizeof(FormulaSlot), st));
+  CUDA_CHECK(cudaMemsetAsync(tab, 0, slots * sizeof(FormulaSlot), st));
+  const uint32_t mask = (uint32_t)(slots - 1);
+  // the walked side is "side 1" of the table, the other one "side 2"
+  if (n_walk) formula_insert_kernel<<<(int)((n_walk + 255) / 256), 256, 0, st>>>(K[walk], E[walk].ts, n_walk, 1, tab, mask);
+  if (n_other) formula_insert_kernel<<<(int)((n_other + 255) / 256), 256, 0, st>>>(K[other], E[other].ts, n_other, 2, tab, mask);
+  // ---- ordered compaction: rows of the walked side, then (add) the rows only the other side has ----
+  const size_t cap_rows = (size_t)(n_walk + n_other) + 1;
+  int64_t* d_ts = nullptr; double* d_val = nullptr; int32_t* d_side = nullptr; int64_t* d_row = nullptr;
+  uint32_t* d_bc = nullptr;
+  uint32_t* d_tot = nullptr;
+  CUDA_CHECK(cudaMallocAsync(&d_ts, cap_rows * 8, st));
+  CUDA_CHECK(cudaMallocAsync(&d_val, cap_rows * 8, st));
+  CUDA_CHECK(cudaMallocAsync(&d_side, cap_rows * 4, st));
+  CUDA_CHECK(cudaMallocAsync(&d_row, cap_rows * 8, st));
+  const uint32_t nb1 = (uint32_t)((n_walk + 255) / 256), nb2 = (uint32_t)((n_other + 255) / 256);
+  CUDA_CHECK(cudaMallocAsync(&d_bc, ((size_t)nb1 + nb2 + 2) * 4, st));
+  CUDA_CHECK(cudaMallocAsync(&d_tot, 8, st));
+  FormulaEmit F;
+  memset(&F, 0, sizeof F);
+  F.op = op; F.cval = sp[other].constant ? sp[other].cval : 0.0; F.other_const = other_const ? 1 : 0; F.const_is_e1 = walk == 1 ? 1 : 0;
+  F.v1 = v[walk]; F.v2 = v[other];
+  F.out_ts = d_ts; F.out_val = d_val; F.out_side = d_side; F.out_row = d_row;
+  uint32_t counts[2] = {0, 0};
+  if (nb1) {
+    F.side = 1;
+    formula_emit_kernel<<<nb1, 256, 0, st>>>(K[walk], F, E[walk].ts, n_walk, tab, mask, d_bc, 0, 0);
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(d_bc, nb1, d_tot);
+    formula_emit_kernel<<<nb1, 256, 0, st>>>(K[walk], F, E[walk].ts, n_walk, tab, mask, d_bc, 1, 0);
+    CUDA_CHECK(cudaMemcpyAsync(&counts[0], d_tot, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  if (nb2 && op == 0) {
+    F.side = 2;
+    // rows only e2 has: their tags are e2's.  (walk == other is impossible here: a constant side has no rows.)
+    F.v2 = v[other];
+    formula_emit_kernel<<<nb2, 256, 0, st>>>(K[other], F, E[other].ts, n_other, tab, mask, d_bc + nb1 + 1, 0, 0);
+    exclusive_scan_kernel<<<1, 1024, 0, st>>>(d_bc + nb1 + 1, nb2, d_tot + 1);
+    formula_emit_kernel<<<nb2, 256, 0, st>>>(K[other], F, E[other].ts, n_other, tab, mask, d_bc + nb1 + 1, 1, counts[0]);
+    CUDA_CHECK(cudaMemcpyAsync(&counts[1], d_tot + 1, 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  CUDA_CHECK(cudaGetLastError());
+  const int64_t n_out = (int64_t)counts[0] + counts[1];
+  LK_CHECK(cap >= n_out, LK_ERR_INVALID, strf("lk_formula_eval: %lld rows do not fit the output buffers (%lld)", (long long)n_out, (long long)cap));
+  // both lists are in timestamp order; the result interleaves them by timestamp (e1's rows first on ties)
+  std::vector<int64_t> h_ts((size_t)n_out), h_row((size_t)n_out);
+  std::vector<double> h_val((size_t)n_out);
+  std::vector<int32_t> h_side((size_t)n_out);
+  if (n_out) {
+    CUDA_CHECK(cudaMemcpyAsync(h_ts.data(), d_ts, (size_t)n_out * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h_val.data(), d_val, (size_t)n_out * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h_side.data(), d_side, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaMemcpyAsync(h_row.data(), d_row, (size_t)n_out * 8, cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  size_t a = 0, b = counts[0], o = 0;
+  const size_t a_end = counts[0], b_end = (size_t)n_out;
+  while (a < a_end || b < b_end) {
+    const bool take_a = b >= b_end || (a < a_end && h_ts[a] <= h_ts[b]);
+    const size_t i = take_a ? a++ : b++;
+    out_ts[o] = h_ts[i]; out_val[o] = h_val[i]; out_side[o] = h_side[i]; out_row[o] = h_row[i];
+    o++;
+  }
+  for (void* p : {(void*)tab, (void*)d_ts, (void*)d_val, (void*)d_side, (void*)d_row, (void*)d_bc, (void*)d_tot, (void*)v[0], (void*)v[1]}) if (p) cudaFreeAsync(p, st);
+  for (auto* p : dev_tmp) cudaFreeAsync(p, st);
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  return n_out;
+}
+
 HostResult* device_fetch(Query& q) {
   Query::Device& d = *q.dev;
   LK_CHECK(d.finalized_device, LK_ERR_INVALID, "fetch before finalize");

@@ -35,6 +35,8 @@ void comm_connect(Comm* c, const void* blobs, size_t len_each);
 void comm_destroy(Comm* c);
 int comm_world(const Comm* c);
 
+// Formula.eval (Formula.scala:32-69) over the reduced rows of two finalized queries (either may be null for a constant side)
+int64_t device_formula(Query* q1, Query* q2, const std::string& spec_json, int64_t cap, int64_t* out_ts, double* out_val, int32_t* out_side, int64_t* out_row);
 int64_t device_eval(Query& q, const std::string& aggregation, const std::string& chart_type, const std::string& metric_type, double* out, int64_t cap);  // BaseExpr.eval on the reduced rows
 
 }  // namespace lk

@@ -1417,6 +1417,49 @@ def base_expr_eval(b: BaseExpr, sketches: List[SketchInput], step_ms: int, aggre
     return out
 
 
+def constant_expr_eval(value: float, group_by_keys, ts: int, sketches: List[SketchInput]):
+    """ASTUtils.eval, ConstantExpr branch (ASTUtils.scala:50-64): one "default" result without group-bys, else one result per
+    sketch input of the group, keyed by the formula's final grouping (a later input of the same key replaces an earlier one)."""
+    keys = set(group_by_keys)
+    if not keys:
+        return {"default": (ts, float(value), {})}
+    return {to_group_by_key(keys, s.tags): (ts, float(value), s.tags) for s in sketches}
+
+
+def formula_eval(op: str, e1_map: Dict[str, tuple], e2_map: Dict[str, tuple]) -> Dict[str, tuple]:
+    """Formula.eval (Formula.scala:32-69) for one SketchGroup: both sides already evaluated into {groupKey: (ts, value, tags)}.
+    Equal keys are combined; `add` takes a missing side as 0 (with the other side's timestamp and tags), the other operators
+    give no result; a zero divisor gives no result.  The result carries e1's timestamp and tags."""
+    out = {}
+    for k in list(e1_map.keys()) + [k for k in e2_map if k not in e1_map]:
+        r1, r2 = e1_map.get(k), e2_map.get(k)
+        if r1 is None and r2 is None:
+            continue
+        if r2 is None:
+            if op != "add":
+                continue
+            r2 = (r1[0], 0.0, r1[2])
+        elif r1 is None:
+            if op != "add":
+                continue
+            r1 = (r2[0], 0.0, r2[2])
+        a, b = float(r1[1]), float(r2[1])
+        if op == "add":
+            v = a + b
+        elif op == "sub":
+            v = a - b
+        elif op == "mul":
+            v = a * b
+        elif op == "div":
+            if not (b != 0):  # e2Result.value != 0: NaN passes, +-0.0 does not
+                continue
+            v = a / b
+        else:
+            raise ValueError(op)
+        out[k] = (r1[0], v, r1[2])
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # a3: evaluatePushDownRequest -- globs of 10 (local) / 5 (S3), merged by timestamp (Commons.scala:343-397)
 # ----------------------------------------------------------------------------------------------

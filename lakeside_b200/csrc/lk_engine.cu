@@ -19,6 +19,7 @@ namespace lk {
 
 static void device_exact_sums(Query& q, const ScanParams& base);
 static void rec_exact_finalize(Query& q);
+static void rec_clear_scratch(Query& q, cudaStream_t st);
 void device_resolve(Query& q);
 
 #define CUDA_CHECK(x)                                                                                        \
@@ -211,6 +212,10 @@ struct Query::Device {
   uint32_t* rf_tables = nullptr;
   struct RecFin* fin = nullptr;
   uint32_t* fin_host = nullptr;  // pinned: [0..7] RecFin, [8..15] the scan's counters, copied back at the end of finalize
+  // the finalize scratch is cleared on a side stream WHILE the scan runs (execute forks, finalize joins)
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_clear = nullptr;
+  bool pre_cleared = false;
   size_t fin_cap = 0;            // records the finalize scratch and the result buffer hold
   bool fin_pending = false;      // finalize kernels enqueued, row count / status not yet read back
   size_t dres_stride = 0;        // rows per result column in dres
@@ -227,6 +232,7 @@ Query::~Query() {
   const auto t_destroy0 = std::chrono::steady_clock::now();
   if (dev) {
     Device& d = *dev;
+    if (d.st2) cudaStreamSynchronize(d.st2);
     if (d.st) cudaStreamSynchronize(d.st);
     auto fr = [&](void* p) { if (p) cudaFreeAsync(p, d.st); };
     fr(d.arena); fr(d.tiles); fr(d.cursors); fr(d.runs); fr(d.chunks); fr(d.def_chunks); fr(d.defbm); fr(d.lut_cls); fr(d.lut_gcode); fr(d.pass_bits);
@@ -241,6 +247,9 @@ Query::~Query() {
       arena_release(d.harena);
     }
     for (auto& e : d.ev) if (e) cudaEventDestroy(e);
+    if (d.st2) { cudaStreamSynchronize(d.st2); cudaStreamDestroy(d.st2); }
+    if (d.ev_fork) cudaEventDestroy(d.ev_fork);
+    if (d.ev_clear) cudaEventDestroy(d.ev_clear);
     if (d.st) { cudaStreamSynchronize(d.st); cudaStreamDestroy(d.st); }
   }
   cache_fresh.clear();  // the stream is idle: cached columns this query pinned may go (freed when no one else holds them)
@@ -1307,6 +1316,21 @@ void device_execute(Query& q) {
   CUDA_CHECK(cudaEventRecord(d.ev[8], d.st));
   launch_def_expand(q, P);  // part of every execute: the definition levels are decoded on the device, inside the timed step
   CUDA_CHECK(cudaEventRecord(d.ev[9], d.st));
+  static const bool no_preclear = getenv("LK_NO_PRECLEAR") != nullptr;  // tuning aid: clear the finalize scratch inline instead
+  if (q.path == 2 && !q.exact_sums && !no_preclear && d.fin_cap > 0 && d.rf_sorted && d.rf_tables && d.fin) {
+    // record path, scratch already sized by an earlier finalize: its clears (56 MB of key table for C2) do not wait for
+    // the scan -- fork here, join at the start of the finalize
+    if (!d.st2) {
+      CUDA_CHECK(cudaStreamCreateWithFlags(&d.st2, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
+      CUDA_CHECK(cudaEventCreateWithFlags(&d.ev_clear, cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaEventRecord(d.ev_fork, d.st));  // the previous finalize (reader of the scratch) is in front of this point
+    CUDA_CHECK(cudaStreamWaitEvent(d.st2, d.ev_fork, 0));
+    rec_clear_scratch(q, d.st2);
+    CUDA_CHECK(cudaEventRecord(d.ev_clear, d.st2));
+    d.pre_cleared = true;
+  }
   static const uint32_t init_counters[8] = {0, 0xffffffffu, 0, 0, 0, 0, 0, 0};
   CUDA_CHECK(cudaMemcpyAsync(d.counters, init_counters, sizeof init_counters, cudaMemcpyHostToDevice, d.st));
   CUDA_CHECK(cudaMemsetAsync(d.survivors, 0, sizeof(unsigned long long), d.st));
@@ -1780,21 +1804,47 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long*
   const unsigned long long gid_mask = (1ull << G.gid_bits) - 1;
   const uint32_t fp_shift = G.fp_shift, idx_field = fp_shift < 32 ? (1u << fp_shift) - 1 : 0xffffffffu;  // fp_shift == 32: no fingerprint bits
   uint32_t my_status = 0;
-  for (uint32_t i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n32; i += gridDim.x * RF_BLOCK) {
-    const uint32_t pi = i < nrec ? rec_phys(i, G) : 0u;
-    const unsigned long long key = i < nrec ? keys[pi] : RF_CONSUMED;
+  // Two records ahead of the one being inserted the key is requested, one record ahead its table slot is pulled into L2
+  // (prefetch.global.L2): the CAS of a record then meets a resident sector instead of paying the DRAM round trip of a random
+  // 32-byte access itself (ncu: 76 % of this kernel's stall samples sat behind that one CAS).
+  const uint32_t stride = gridDim.x * RF_BLOCK;
+  const uint32_t i0 = blockIdx.x * RF_BLOCK + threadIdx.x;
+  auto load_key = [&](uint32_t i, uint32_t& pi) -> unsigned long long {
+    pi = i < nrec ? rec_phys(i, G) : 0u;
+    return i < nrec ? keys[pi] : RF_CONSUMED;
+  };
+  auto slot_of = [&](unsigned long long key, uint32_t& bucket, uint32_t& width, uint32_t*& region, uint32_t& h) -> uint32_t {
+    const unsigned long long cellx = key >> G.idx_bits;
+    bucket = (uint32_t)(cellx >> G.gid_bits);
+    const uint32_t s0 = __ldg(rec_start + bucket), s1 = __ldg(rec_start + bucket + 1);
+    width = 2u * (s1 - s0);  // >= 2: this record is one of the bucket's
+    region = table + 2ull * s0;
+    h = lk_rf_mix(cellx & gid_mask);
+    return __umulhi(h, width);
+  };
+  uint32_t pi_a = 0, pi_b = 0, pi_c = 0;
+  unsigned long long key_a = load_key(i0, pi_a);                                  // record being inserted
+  unsigned long long key_b = i0 + stride < n32 ? load_key(i0 + stride, pi_b) : RF_CONSUMED;  // next
+  for (uint32_t i = i0; i < n32; i += stride) {
+    unsigned long long key_c = RF_CONSUMED;                                       // the one after
+    if (i + 2 * stride < n32) key_c = load_key(i + 2 * stride, pi_c);
+    if (key_b != RF_CONSUMED) {
+      uint32_t b2, w2, h2;
+      uint32_t* r2;
+      const uint32_t sl = slot_of(key_b, b2, w2, r2, h2);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + sl));
+    }
+    const uint32_t pi = pi_a;
+    const unsigned long long key = key_a;
     const bool valid = key != RF_CONSUMED;
     bool owner = false;
     uint32_t bucket = 0;
     if (valid) {
       const unsigned long long cellx = key >> G.idx_bits;
-      bucket = (uint32_t)(cellx >> G.gid_bits);
-      const uint32_t s0 = __ldg(rec_start + bucket), s1 = __ldg(rec_start + bucket + 1);
-      const uint32_t width = 2u * (s1 - s0);  // >= 2: this record is one of the bucket's
-      uint32_t* const region = table + 2ull * s0;
-      const uint32_t h = lk_rf_mix(cellx & gid_mask);
+      uint32_t width, h;
+      uint32_t* region;
+      uint32_t slot = slot_of(key, bucket, width, region, h), probe = 0;
       const uint32_t entry = (fp_shift < 32 ? (h * 0x2545F491u) >> fp_shift << fp_shift : 0u) | (pi + 1);
-      uint32_t slot = __umulhi(h, width), probe = 0;
       for (; probe < width; probe++) {
         const uint32_t prev = atomicCAS(region + slot, 0u, entry);
         if (prev == 0u) { owner = true; break; }
@@ -1819,6 +1869,8 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long*
       if (probe == width) my_status |= RF_ST_TABLE;  // cannot happen: the region has two slots per record of its bucket
     }
     warp_bucket_bump<false>(bkt_rows, G.cstride, bucket, owner, nullptr);
+    key_a = key_b; pi_a = pi_b;
+    key_b = key_c; pi_b = pi_c;
   }
   if (my_status) atomicOr(&fin->status, my_status);
 }
@@ -1839,22 +1891,38 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_emit_kernel(const unsigned long 
   const uint32_t nrec = fin->nrec;
   const uint32_t n32 = (nrec + 31u) & ~31u;
   const unsigned long long gid_mask = (1ull << G.gid_bits) - 1;
-  for (uint32_t i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n32; i += gridDim.x * RF_BLOCK) {
-    unsigned long long key = RF_CONSUMED;
-    const uint32_t pi = i < nrec ? rec_phys(i, G) : 0u;
-    if (i < nrec) key = keys[pi];
+  // the next record's key and accumulator row (address known without the key) are requested before this record's cursor
+  // round trip and row stores: two records in flight per thread
+  const uint32_t stride = gridDim.x * RF_BLOCK;
+  const bool four = E.n_aggs == 4;  // one 32-byte sector per record
+  auto load_rec = [&](uint32_t i, uint32_t& pi, ulonglong2& lo, ulonglong2& hi) -> unsigned long long {
+    pi = i < nrec ? rec_phys(i, G) : 0u;
+    if (i >= nrec) return RF_CONSUMED;
+    if (four) {
+      const ulonglong2* rec = reinterpret_cast<const ulonglong2*>(vals + (size_t)pi * 4);
+      lo = rec[0];
+      hi = rec[1];
+    }
+    return keys[pi];
+  };
+  uint32_t pi_n = 0;
+  ulonglong2 lo_n = make_ulonglong2(0, 0), hi_n = make_ulonglong2(0, 0);
+  unsigned long long key_n = load_rec(blockIdx.x * RF_BLOCK + threadIdx.x, pi_n, lo_n, hi_n);
+  for (uint32_t i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n32; i += stride) {
+    const unsigned long long key = key_n;
+    const uint32_t pi = pi_n;
+    const ulonglong2 lo = lo_n, hi = hi_n;
+    if (i + stride < n32) key_n = load_rec(i + stride, pi_n, lo_n, hi_n);
     const bool owner = key != RF_CONSUMED;
     const unsigned long long cellx = key >> G.idx_bits;
     const uint32_t bucket = owner ? (uint32_t)(cellx >> G.gid_bits) : 0u;
-    // the accumulator row is requested before the cursor's round trip
     unsigned long long w[LK_MAX_AGGS];
     if (owner) {
-      const unsigned long long* rec = vals + (size_t)pi * E.n_aggs;
-      if (E.n_aggs == 4) {  // one 32-byte sector
-        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(rec), b2 = *(reinterpret_cast<const ulonglong2*>(rec) + 1);
-        w[0] = a.x; w[1] = a.y; w[2] = b2.x; w[3] = b2.y;
+      if (four) {
+        w[0] = lo.x; w[1] = lo.y; w[2] = hi.x; w[3] = hi.y;
         w[4] = w[5] = w[6] = 0;
       } else {
+        const unsigned long long* rec = vals + (size_t)pi * E.n_aggs;
 #pragma unroll
         for (int a = 0; a < LK_MAX_AGGS; a++) w[a] = a < E.n_aggs ? rec[a] : 0ull;
       }
@@ -1946,8 +2014,19 @@ static void check_scan_status(Query& q, const uint32_t* h) {
 // kernels verify that it still fits) and enqueues the kernels; nothing here waits for the device once sized ----
 static size_t rec_counter_stride(const Query& q) { return q.nbuckets <= 8192 ? 32 : 1; }
 
+// the three clears a record finalize starts from: per-bucket counters, the key table, the bookkeeping block
+static void rec_clear_scratch(Query& q, cudaStream_t st) {
+  Query::Device& d = *q.dev;
+  const size_t nb = (size_t)q.nbuckets + 1, cs = rec_counter_stride(q);
+  CUDA_CHECK(cudaMemsetAsync(d.rf_tables, 0, nb * cs * 4, st));
+  CUDA_CHECK(cudaMemsetAsync(d.rf_sorted, 0, 2 * d.fin_cap * 4, st));
+  CUDA_CHECK(cudaMemsetAsync(d.fin, 0, sizeof(RecFin), st));
+}
+
 static void rec_finalize_size(Query& q, uint32_t nrec) {
   Query::Device& d = *q.dev;
+  if (d.st2) CUDA_CHECK(cudaStreamSynchronize(d.st2));  // a clear of the old scratch may still be running there
+  d.pre_cleared = false;
   const size_t cap = std::min<size_t>(std::max<size_t>(d.rec_cap, 1), (size_t)nrec + nrec / 8 + 4096);
   if (d.rf_sorted) CUDA_CHECK(cudaFreeAsync(d.rf_sorted, d.st));
   if (d.rf_tables) CUDA_CHECK(cudaFreeAsync(d.rf_tables, d.st));
@@ -1984,9 +2063,10 @@ static void rec_finalize_launch(Query& q) {
   uint32_t* row_cursor = bkt_rows + nb * cs;
   uint32_t* rec_start = row_cursor + nb * cs;
   uint32_t* row_start = rec_start + nb;
-  CUDA_CHECK(cudaMemsetAsync(bkt_recs, 0, nb * cs * 4, d.st));
-  CUDA_CHECK(cudaMemsetAsync(d.rf_sorted, 0, 2 * d.fin_cap * 4, d.st));
-  CUDA_CHECK(cudaMemsetAsync(d.fin, 0, sizeof(RecFin), d.st));
+  if (d.pre_cleared) {  // cleared on the side stream while the scan ran (device_execute)
+    CUDA_CHECK(cudaStreamWaitEvent(d.st, d.ev_clear, 0));
+    d.pre_cleared = false;
+  } else rec_clear_scratch(q, d.st);
   EmitParams E;
   fill_emit_params(q, E, d.dres, (int64_t)d.fin_cap);
   E.phase_ptr = d.counters + 1;  // the scan's timestamp phase (metrics), read on the device: nothing waits for the host

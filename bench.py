@@ -558,6 +558,11 @@ def main():
                 merges and finalises its own partition."""
         if world == 1 or path == "records":
             return
+        # the timestamp phase every rank saw (MIN / MAX over the ranks): the finalizing ranks stamp reduced / foreign cells with it
+        pmin, pmax = qq.phase()
+        pt = torch.tensor([-pmin, pmax], dtype=torch.int64, device="cuda")
+        dist.all_reduce(pt, op=dist.ReduceOp.MAX)
+        qq.set_phase(int(-pt[0].item()), int(pt[1].item()))
         if path == "dense":
             n_cells, planes = qq.partial_dense()
             qq.sync()

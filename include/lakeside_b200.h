@@ -114,6 +114,15 @@ int lk_query_sync(lk_query* q);
  *   plane 1 + a        : aggregate a; sum -> float64, count -> uint64, min/max -> order-preserving uint64 keys
  * Layout: cell = bucket * n_groups + group.  op[a]: 0 sum(f64 add) 1 count(u64 add) 2 min(u64 min) 3 max(u64 max). */
 int lk_query_partial_dense(lk_query* q, int64_t* n_cells, int* n_planes, void** plane_ptrs /*[8]*/, int* plane_ops /*[8]*/);
+/* Sharded dense / hash paths, metrics: GROUP BY "_cardinalhq.timestamp" buckets the raw timestamps, which sit at one offset
+ * ("phase") from startTs modulo the step.  A rank learns the phase from its own surviving rows; the rank that finalizes
+ * reduced or foreign cells must use the phase ALL ranks saw -- it may have kept no row itself, and ranks that saw different
+ * phases must fail instead of merging distinct timestamps.  After execute: lk_query_phase gives this rank's [min, max]
+ * (min = 0xffffffff: no surviving row); the host reduces MIN / MAX over the ranks next to the data exchange and hands the
+ * global pair to every finalizing rank with lk_query_set_phase before lk_query_finalize*.  (The record path exchanges the
+ * phase by itself through its lk_comm.) */
+int lk_query_phase(lk_query* q, uint32_t* phase_min, uint32_t* phase_max);
+int lk_query_set_phase(lk_query* q, uint32_t phase_min, uint32_t phase_max);
 /* Hash path, sharded evaluation: the (group x bucket) cells are hash-partitioned over `nparts` owners (ranks).
  * partial_sparse moves every occupied entry {uint64 key = cell + 1; uint64 acc[..]} (stride_bytes each) out of the
  * table into one device buffer ordered by partition (counts[p] entries for partition p) and leaves the table empty;

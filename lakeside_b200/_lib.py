@@ -58,6 +58,8 @@ _SIGNATURES = {
     "lk_query_finalize_device": (c_int, [c_void_p]),
     "lk_query_finalize": (c_int, [c_void_p, POINTER(c_void_p)]),
     "lk_query_survivors": (c_int64, [c_void_p]),
+    "lk_query_phase": (c_int, [c_void_p, POINTER(ctypes.c_uint32), POINTER(ctypes.c_uint32)]),
+    "lk_query_set_phase": (c_int, [c_void_p, ctypes.c_uint32, ctypes.c_uint32]),
     "lk_formula_eval": (c_int, [c_void_p, c_void_p, c_char_p, c_int64, POINTER(c_int64), POINTER(c_double), POINTER(c_int32), POINTER(c_int64), POINTER(c_int64)]),
     "lk_query_eval": (c_int64, [c_void_p, c_char_p, c_char_p, c_char_p, POINTER(c_double), c_int64]),
     "lk_query_timings": (c_int, [c_void_p, POINTER(c_double)]),

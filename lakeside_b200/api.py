@@ -237,6 +237,16 @@ class Query:
     def execute(self):
         _lib.check(_lib.load().lk_query_execute(self._h))
 
+    def phase(self) -> Tuple[int, int]:
+        """(min, max) timestamp phase of this rank's last scan (lk_query_phase); min = 0xffffffff: no surviving row."""
+        a, b = ctypes.c_uint32(), ctypes.c_uint32()
+        _lib.check(_lib.load().lk_query_phase(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
+
+    def set_phase(self, phase_min: int, phase_max: int):
+        """The phase range reduced over all ranks (MIN, MAX), before finalizing reduced / foreign cells (lk_query_set_phase)."""
+        _lib.check(_lib.load().lk_query_set_phase(self._h, int(phase_min), int(phase_max)))
+
     def sync(self):
         _lib.check(_lib.load().lk_query_sync(self._h))
 

@@ -248,6 +248,13 @@ int lk_query_sync(lk_query* q) {
   return guard([&] { LK_CHECK(q, LK_ERR_INVALID, "null argument"); device_sync(q->q); });
 }
 
+int lk_query_phase(lk_query* q, uint32_t* phase_min, uint32_t* phase_max) {
+  return guard([&] { LK_CHECK(q && phase_min && phase_max, LK_ERR_INVALID, "null argument"); device_phase(q->q, phase_min, phase_max); });
+}
+int lk_query_set_phase(lk_query* q, uint32_t phase_min, uint32_t phase_max) {
+  return guard([&] { LK_CHECK(q, LK_ERR_INVALID, "null argument"); device_set_phase(q->q, phase_min, phase_max); });
+}
+
 int lk_query_partial_dense(lk_query* q, int64_t* n_cells, int* n_planes, void** plane_ptrs, int* plane_ops) {
   return guard([&] {
     LK_CHECK(q && n_cells && n_planes && plane_ptrs && plane_ops, LK_ERR_INVALID, "null argument");

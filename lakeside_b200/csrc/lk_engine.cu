@@ -223,6 +223,10 @@ struct Query::Device {
   size_t sparse_cap = 0;
   int64_t n_rows = 0;
   uint32_t phase = 0;
+  // sharded dense / hash paths: the phase range over ALL ranks, handed in by the host (lk_query_set_phase) between the
+  // exchange and the finalize; valid for the current execute only
+  bool phase_global = false;
+  uint32_t phase_gmin = 0xffffffffu, phase_gmax = 0;
   uint32_t h_counters[8] = {};
   bool finalized_device = false;
 };
@@ -1335,6 +1339,7 @@ void device_execute(Query& q) {
   CUDA_CHECK(cudaMemcpyAsync(d.counters, init_counters, sizeof init_counters, cudaMemcpyHostToDevice, d.st));
   CUDA_CHECK(cudaMemsetAsync(d.survivors, 0, sizeof(unsigned long long), d.st));
   d.finalized_device = false;
+  d.phase_global = false;
   d.fin_pending = false;  // a finalize nobody waited for is superseded by this execute
   d.executed = true;
   const bool sharded = q.comm != nullptr;
@@ -1403,6 +1408,24 @@ void device_sync(Query& q) {
 }
 
 void* device_stream(Query& q) { return q.dev ? (void*)q.dev->st : nullptr; }
+
+// timestamp phase range of this rank's last scan (metrics: (ts - startTs) mod step over its surviving rows; min = 0xffffffff
+// when it kept none) and the global range the host reduced over the ranks
+void device_phase(Query& q, uint32_t* pmin, uint32_t* pmax) {
+  LK_CHECK(q.dev && q.dev->executed, LK_ERR_INVALID, "lk_query_phase before lk_query_execute");
+  Query::Device& d = *q.dev;
+  uint32_t h[3] = {0, 0xffffffffu, 0};
+  CUDA_CHECK(cudaMemcpyAsync(h, d.counters, sizeof h, cudaMemcpyDeviceToHost, d.st));
+  CUDA_CHECK(cudaStreamSynchronize(d.st));
+  *pmin = q.is_metrics ? h[1] : 0xffffffffu;
+  *pmax = q.is_metrics ? h[2] : 0u;
+}
+void device_set_phase(Query& q, uint32_t pmin, uint32_t pmax) {
+  LK_CHECK(q.dev && q.dev->executed && !q.dev->finalized_device, LK_ERR_INVALID, "lk_query_set_phase belongs between lk_query_execute and the finalize");
+  q.dev->phase_global = true;
+  q.dev->phase_gmin = pmin;
+  q.dev->phase_gmax = pmax;
+}
 
 void device_partial_dense(Query& q, int64_t* n_cells, int* n_planes, void** ptrs, int* ops) {
   LK_CHECK(q.dev && q.dev->executed, LK_ERR_INVALID, "lk_query_partial_dense before lk_query_execute");
@@ -1998,6 +2021,9 @@ static void check_scan_status(Query& q, const uint32_t* h) {
                                    : strf("aggregate hash table of %llu slots overflowed; raise max_hash_slots in lk_init", (unsigned long long)q.hash_slots));
   }
   LK_CHECK(!(h[0] & ST_BAD_CODE), LK_ERR_IO, "corrupt segment: dictionary index out of range");
+  uint32_t ph[3] = {0, h[1], h[2]};
+  if (d.phase_global) { ph[1] = d.phase_gmin; ph[2] = d.phase_gmax; }  // what all ranks saw, not just this one
+  h = ph;
   if (q.is_metrics && h[1] != 0xffffffffu) {
     // GROUP BY "_cardinalhq.timestamp": metric segments are pre-rolled to the step grid (QueryEngineV2.scala:746-752);
     // every timestamp must sit at one offset from startTs modulo step, otherwise buckets would merge distinct rows.

@@ -20,6 +20,8 @@ void device_mark_group_tables_stale(Query& q);
 void device_execute(Query& q);             // clear table + fused scan kernel (async)
 void device_sync(Query& q);
 void* device_stream(Query& q);
+void device_phase(Query& q, uint32_t* pmin, uint32_t* pmax);
+void device_set_phase(Query& q, uint32_t pmin, uint32_t pmax);
 void device_partial_dense(Query& q, int64_t* n_cells, int* n_planes, void** ptrs, int* ops);
 void device_partial_sparse(Query& q, int nparts, void** entries_out, int64_t* counts, int* stride_out);
 void device_merge_sparse(Query& q, const void* dev_entries, int64_t n);

@@ -80,6 +80,74 @@ def test_dense_partials_reduce_like_nccl():
         q.close()
 
 
+def test_dense_reduce_phase_from_the_other_rank():
+    """sharded dense path with an unaligned startTs.  Rank 0 -- the rank that finalizes the reduced planes -- keeps
+    no row itself (its segment has no svc-03), so the phase must come from rank 1 (lk_query_phase -> host MIN / MAX ->
+    lk_query_set_phase); without it the rows would be stamped with phase 0.  Ranks that saw different phases are an error."""
+    import torch
+    from lakeside_b200 import api
+
+    api.init()
+    be = synth.c2_base_expr()
+    sa = synth.SynthSpec(dataset="metrics", rows=40000, n_names=3, cards=(1, 4, 6, 2))   # one service value: no svc-03
+    sb = synth.SynthSpec(dataset="metrics", rows=40000, n_names=3, cards=(16, 4, 6, 2))
+    pa = H.dataset("dphase_a", sa, 1)[1]
+    pb = H.dataset("dphase_b", sb, 1, first_index=100)[1]
+    paths = pa + pb
+    start = synth.T0 - 3000
+    full = synth.push_down_request(be, [0, 100], 10000, start_ts=start, end_ts=synth.T0 + synth.HOUR_MS)
+    qs = []
+    for rank in range(2):
+        q = api.Query(json.dumps(dict(full, segmentRequests=[full["segmentRequests"][rank]])), aggregates=synth.C2_AGGREGATES, path="dense")
+        q.add_segment_file(paths[rank])
+        q.plan()
+        qs.append(q)
+    blob = api.union_dictionaries([q.export_dictionaries() for q in qs])
+    for q in qs:
+        q.import_dictionaries(blob)
+        q.prepare()
+        q.execute()
+    phases = [q.phase() for q in qs]
+    assert phases[0][0] == 0xFFFFFFFF and phases[1] == (3000, 3000)
+    assert qs[0].survivors == 0
+    parts = [q.partial_dense() for q in qs]
+    n_cells = parts[0][0]
+
+    def tensor(ptr, f64):
+        class A:
+            pass
+        a = A()
+        a.__cuda_array_interface__ = {"shape": (n_cells,), "typestr": "<f8" if f64 else "<i8", "data": (ptr, False), "version": 3}
+        return torch.as_tensor(a, device="cuda")
+
+    for (p0, op), (p1, _) in zip(parts[0][1], parts[1][1]):
+        if op == 0:
+            tensor(p0, True).add_(tensor(p1, True))
+        elif op == 1:
+            tensor(p0, False).add_(tensor(p1, False))
+        else:
+            a, b = tensor(p0, False), tensor(p1, False)
+            a.bitwise_xor_(torch.iinfo(torch.int64).min)
+            b.bitwise_xor_(torch.iinfo(torch.int64).min)
+            torch.maximum(a, b, out=a)
+            a.bitwise_xor_(torch.iinfo(torch.int64).min)
+    torch.cuda.synchronize()
+    qs[0].set_phase(min(p[0] for p in phases), max(p[1] for p in phases))
+    res = qs[0].finalize()
+    got = H.canon_from_gpu(res)
+    res.close()
+    want = H.oracle_multi(json.dumps(full), paths, synth.C2_AGGREGATES)
+    assert len(want["rows"]) > 100
+    H.assert_same(got, want, ["sum", "sum", "min", "max"], "sharded/dense/phase")
+    assert all((ts - start) % 10000 == 3000 for ts in got["ts_order"])
+    # ranks that disagree on the phase: distinct raw timestamps would fold into one row
+    qs[1].set_phase(1000, 3000)
+    with pytest.raises(api.LakesideUnsupported):
+        qs[1].finalize()
+    for q in qs:
+        q.close()
+
+
 def test_hash_partials_partitioned_exchange():
     be = synth.c2_base_expr()
     sa = synth.SynthSpec(dataset="metrics", rows=80000, cards=(16, 20, 32, 16))

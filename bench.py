@@ -683,6 +683,10 @@ def main():
         res = q.finalize()
         got = result_summary(res, survivors)
         res.close()
+        if world > 1 and info["path"] == "dense" and rank != 0:
+            # the planes were reduced to rank 0: only ITS rows are the result; the other ranks still hold (and emit) their own
+            # partial planes, which must not be counted a second time
+            got.update(rows=0, s=0.0, c=0.0, wc=0.0, ws=0.0, mn=float("inf"), mx=float("-inf"), sorted=True)
         want = arrow_summary(wl, paths)
         if world > 1:
             def allred(d, keys_sum, keys_min, keys_max):

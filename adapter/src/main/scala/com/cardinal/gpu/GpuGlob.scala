@@ -29,7 +29,10 @@ object GpuGlob {
   def tryEvaluate(queryId: String, request: PushDownRequest, localParquet: Boolean, pathOf: SegmentRequest => String): Outcome = {
     // the GPU path covers the aggregate push-down over local, sealed segments; the library itself answers LK_ERR_UNSUPPORTED for
     // percentile / ces rollups, extract / compute sub-queries, compressed pages ... (SURVEY §8b "Error convention")
-    if (!LakesideB200.enabled || !localParquet || request.isTagQuery || request.baseExpr.chartOpts.isEmpty) return UseDuckDb
+    // aggregate push-downs and tag queries with a tagDataType (two JDBC columns: tag, count); exemplar queries and `SELECT *`
+    // tag queries select whole rows and stay with DuckDB
+    val tagCount = request.isTagQuery && request.tagDataType.isDefined
+    if (!LakesideB200.enabled || !localParquet || (request.isTagQuery && !tagCount) || (!tagCount && request.baseExpr.chartOpts.isEmpty)) return UseDuckDb
     val lib = LakesideB200.lib
     val paths = request.segmentRequests.map(pathOf).toArray
     val out = new PointerByReference()

@@ -22,6 +22,11 @@ trait LakesideB200 extends Library {
   def lk_version(): String
   def lk_device_count(): Int
 
+  // ---- HBM-resident segment cache (device-side continuation of the worker's segment file cache, WorkerApi.scala:53-64) ----
+  def lk_cache_stats(stats: Array[Long]): Int   // [capacity, resident bytes, segments, column hits, column misses, evicted segments]
+  def lk_cache_configure(capacityBytes: Long): Int
+  def lk_cache_clear(): Unit
+
   // ---- one-shot glob evaluation: Commons.toGlobResultSet ----
   def lk_eval(pushDownRequestJson: String, parquetPaths: Array[String], nPaths: Int, out: PointerByReference): Int
 
@@ -33,6 +38,9 @@ trait LakesideB200 extends Library {
   def lk_query_finalize(q: Pointer, out: PointerByReference): Int
   def lk_query_eval(q: Pointer, aggregation: String, chartType: String, metricType: String, out: Array[Double], cap: Long): Long
   def lk_query_destroy(q: Pointer): Unit
+  // Formula.eval (Formula.scala:32-69) over the reduced rows of two finalized queries; a constant side passes null
+  def lk_formula_eval(e1: Pointer, e2: Pointer, specJson: String, cap: Long, outTs: Array[Long], outValue: Array[Double], outSide: Array[Int],
+                      outRow: Array[Long], nOut: LongByReference): Int
 
   // ---- result: what Commons.toDataPoint reads from the JDBC ResultSet (Commons.scala:399-462) ----
   def lk_result_num_rows(r: Pointer): Long

@@ -210,6 +210,9 @@ struct Query::Device {
   // checked on the device)
   unsigned long long* rf_sorted = nullptr;
   uint32_t* rf_tables = nullptr;
+  // records partitioned by bucket before grouping (rec_scatter_kernel): second copy of the record arrays, fin_cap records
+  unsigned long long* rec2_cell = nullptr;
+  unsigned long long* rec2_vals = nullptr;
   struct RecFin* fin = nullptr;
   uint32_t* fin_host = nullptr;  // pinned: [0..7] RecFin, [8..15] the scan's counters, copied back at the end of finalize
   // the finalize scratch is cleared on a side stream WHILE the scan runs (execute forks, finalize joins)
@@ -242,7 +245,7 @@ Query::~Query() {
     fr(d.arena); fr(d.tiles); fr(d.cursors); fr(d.runs); fr(d.chunks); fr(d.def_chunks); fr(d.defbm); fr(d.lut_cls); fr(d.lut_gcode); fr(d.pass_bits);
     fr(d.counters); fr(d.survivors); fr(d.planes); fr(d.block_counts); fr(d.dres); fr(d.sparse_out);
     if (!d.rec_borrowed) { fr(d.rec_cell); fr(d.rec_vals); }
-    fr(d.rf_sorted); fr(d.rf_tables); fr(d.fin);
+    fr(d.rf_sorted); fr(d.rf_tables); fr(d.fin); fr(d.rec2_cell); fr(d.rec2_vals);
     if (d.fin_host) pinned_free(d.fin_host);
     if (d.harena) {
       // an arena that was written but never emitted is dirty: clear it before handing it back
@@ -1719,8 +1722,12 @@ struct RecGeom {
 // position of record i of the list in the record arrays
 __device__ __forceinline__ uint32_t rec_phys(uint32_t i, const RecGeom& G) {
   if (G.world <= 1) return i;
+  // source region of record i: count the region starts at or below i -- independent loads (one cache line, all hits) instead
+  // of a walk whose every step waits for the previous one (three kernels do this once per record)
   uint32_t s = 0;
-  while (s + 1 < G.world && i >= __ldg(G.prefix + s + 1)) s++;
+#pragma unroll
+  for (int k = 1; k < LK_MAX_RANKS; k++)
+    if (k < (int)G.world) s += i >= __ldg(G.prefix + k) ? 1u : 0u;
   return s * G.region_cap + (i - __ldg(G.prefix + s));
 }
 
@@ -1898,6 +1905,58 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long*
   if (my_status) atomicOr(&fin->status, my_status);
 }
 
+// Partition of the record list by bucket (counting sort: rec_bhist counted, rec_regions laid the buckets out) into a second
+// copy of the record arrays.  The list arrives in the order the scans appended -- 32 survivors of one tile at a time on one
+// GPU, a few records per tile and destination when sharded -- from tiles anywhere in the time range, so a warp's 32 records
+// belong to several buckets (~2.5 on one GPU, ~8 at 8 ranks): after this pass they belong to ONE, which is what the grouping
+// and the emit want (one counter bump per warp, table probes inside one ~140 KB region, rows stored in whole lines).  One
+// 8-byte key + one 32-byte accumulator row moved per record instead of 13 scattered column stores later.
+__global__ void __launch_bounds__(RF_BLOCK) rec_scatter_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ vals,
+                                                               const uint32_t* __restrict__ rec_start, uint32_t* __restrict__ cursor,
+                                                               const RecFin* __restrict__ fin, const __grid_constant__ RecGeom G, int n_aggs,
+                                                               unsigned long long* __restrict__ keys2, unsigned long long* __restrict__ vals2) {
+  if (fin->status & RF_ST_CAP) return;
+  const uint32_t nrec = fin->nrec;
+  const uint32_t n32 = (nrec + 31u) & ~31u;
+  const uint32_t sh = G.idx_bits + G.gid_bits;
+  const uint32_t stride = gridDim.x * RF_BLOCK;
+  const bool four = n_aggs == 4;
+  auto load_rec = [&](uint32_t i, uint32_t& pi, ulonglong2& lo, ulonglong2& hi) -> unsigned long long {
+    pi = i < nrec ? rec_phys(i, G) : 0u;
+    if (i >= nrec) return RF_CONSUMED;
+    if (four) {
+      const ulonglong2* rec = reinterpret_cast<const ulonglong2*>(vals + (size_t)pi * 4);
+      lo = rec[0];
+      hi = rec[1];
+    }
+    return keys[pi];
+  };
+  uint32_t pi_n = 0;
+  ulonglong2 lo_n = make_ulonglong2(0, 0), hi_n = make_ulonglong2(0, 0);
+  unsigned long long key_n = load_rec(blockIdx.x * RF_BLOCK + threadIdx.x, pi_n, lo_n, hi_n);
+  for (uint32_t i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n32; i += stride) {
+    const unsigned long long key = key_n;
+    const uint32_t pi = pi_n;
+    const ulonglong2 lo = lo_n, hi = hi_n;
+    if (i + stride < n32) key_n = load_rec(i + stride, pi_n, lo_n, hi_n);
+    const bool valid = i < nrec;
+    const uint32_t bucket = valid ? (uint32_t)(key >> sh) : 0u;
+    uint32_t base = 0;
+    const uint32_t rank = warp_bucket_bump<true>(cursor, G.cstride, bucket, valid, &base);
+    if (valid) {
+      const uint32_t out = __ldg(rec_start + bucket) + base + rank;  // < nrec <= fin_cap
+      keys2[out] = key;
+      if (four) {
+        ulonglong2* dst = reinterpret_cast<ulonglong2*>(vals2 + (size_t)out * 4);
+        dst[0] = lo;
+        dst[1] = hi;
+      } else {
+        for (int a = 0; a < n_aggs; a++) vals2[(size_t)out * n_aggs + a] = vals[(size_t)pi * n_aggs + a];
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(BS_BLOCK) rec_rowscan_kernel(const uint32_t* __restrict__ bkt_rows, uint32_t nbuckets, uint32_t cstride,
                                                                uint32_t* __restrict__ row_start, uint32_t* __restrict__ row_cursor, RecFin* __restrict__ fin) {
   if (fin->status & RF_ST_CAP) return;
@@ -2039,12 +2098,21 @@ static void check_scan_status(Query& q, const uint32_t* h) {
 // ---- record path: sizes the scratch (from the record count of the first finalize; later finalizes re-use it and the
 // kernels verify that it still fits) and enqueues the kernels; nothing here waits for the device once sized ----
 static size_t rec_counter_stride(const Query& q) { return q.nbuckets <= 8192 ? 32 : 1; }
+// Partition the records by bucket before grouping them?  Measured on B200, C2: one GPU 0.395 ms without / 0.48 ms with (the
+// extra pass costs more than the locality buys while a warp's 32 records already share ~2.5 buckets); 4 ranks 0.574 / 0.525;
+// the list of a rank is then a mix of short appends from all sources and the gap widens with the rank count.  So: from three
+// ranks on.  LK_REC_SCATTER=0|1 overrides (tests run both ways).
+static bool rec_scatter_on(const Query& q) {
+  if (const char* e = getenv("LK_REC_SCATTER")) return atoi(e) != 0;
+  return q.comm != nullptr && q.comm->world >= 3;
+}
 
 // the three clears a record finalize starts from: per-bucket counters, the key table, the bookkeeping block
 static void rec_clear_scratch(Query& q, cudaStream_t st) {
   Query::Device& d = *q.dev;
   const size_t nb = (size_t)q.nbuckets + 1, cs = rec_counter_stride(q);
   CUDA_CHECK(cudaMemsetAsync(d.rf_tables, 0, nb * cs * 4, st));
+  CUDA_CHECK(cudaMemsetAsync(d.rf_tables + 3 * nb * cs + 2 * nb, 0, nb * cs * 4, st));  // scatter cursors
   CUDA_CHECK(cudaMemsetAsync(d.rf_sorted, 0, 2 * d.fin_cap * 4, st));
   CUDA_CHECK(cudaMemsetAsync(d.fin, 0, sizeof(RecFin), st));
 }
@@ -2061,7 +2129,14 @@ static void rec_finalize_size(Query& q, uint32_t nrec) {
   CUDA_CHECK(cudaMallocAsync(&d.rf_sorted, 2 * cap * 4 + 64, d.st));  // the key table: two 32-bit slots per record
   // u32 words: bkt_recs[nb * cs] | bkt_rows[nb * cs] | row_cursor[nb * cs] | rec_start[nb] | row_start[nb]
   const size_t nb = (size_t)q.nbuckets + 1, cs = rec_counter_stride(q);
-  CUDA_CHECK(cudaMallocAsync(&d.rf_tables, (3 * nb * cs + 2 * nb) * 4 + 64, d.st));
+  CUDA_CHECK(cudaMallocAsync(&d.rf_tables, (4 * nb * cs + 2 * nb) * 4 + 64, d.st));  // (+ the scatter cursors, last)
+  if (d.rec2_cell) CUDA_CHECK(cudaFreeAsync(d.rec2_cell, d.st));
+  if (d.rec2_vals) CUDA_CHECK(cudaFreeAsync(d.rec2_vals, d.st));
+  d.rec2_cell = d.rec2_vals = nullptr;
+  if (rec_scatter_on(q)) {
+    CUDA_CHECK(cudaMallocAsync(&d.rec2_cell, cap * 8 + 64, d.st));
+    CUDA_CHECK(cudaMallocAsync(&d.rec2_vals, cap * 8 * q.aggs.size() + 64, d.st));
+  }
   if (!d.fin) CUDA_CHECK(cudaMallocAsync(&d.fin, sizeof(RecFin), d.st));
   if (!d.fin_host) d.fin_host = static_cast<uint32_t*>(pinned_alloc(64));
   d.fin_cap = cap;
@@ -2080,7 +2155,8 @@ static void rec_finalize_launch(Query& q) {
   G.region_cap = q.comm ? (uint32_t)q.comm->region_cap : 0u;
   G.prefix = q.comm ? q.comm->ctrl(q.comm->rank)->prefix : nullptr;
   G.fp_shift = 1;
-  const uint64_t max_index = G.world > 1 ? (uint64_t)d.rec_cap : (uint64_t)d.fin_cap;
+  const bool scatter = rec_scatter_on(q) && d.rec2_cell != nullptr;
+  const uint64_t max_index = (G.world > 1 && !scatter) ? (uint64_t)d.rec_cap : (uint64_t)d.fin_cap;
   while (G.fp_shift < 32 && (max_index + 1) >> G.fp_shift) G.fp_shift++;  // bits of (largest record position + 1)
   const size_t nb = (size_t)q.nbuckets + 1, cs = rec_counter_stride(q);
   G.cstride = (uint32_t)cs;
@@ -2100,9 +2176,20 @@ static void rec_finalize_launch(Query& q) {
   const int grid = (int)std::max<size_t>(1, std::min<size_t>((d.fin_cap + RF_BLOCK * 16 - 1) / (RF_BLOCK * 16), (size_t)num_sms() * 8));
   rec_bhist_kernel<<<grid, RF_BLOCK, 0, d.st>>>(d.rec_cell, d.counters, G, bkt_recs);
   rec_regions_kernel<<<1, BS_BLOCK, 0, d.st>>>(d.counters, G, bkt_recs, rec_start, bkt_rows, d.fin);
-  rec_group_kernel<<<grid, RF_BLOCK, 0, d.st>>>(d.rec_cell, d.rec_vals, rec_start, reinterpret_cast<uint32_t*>(d.rf_sorted), bkt_rows, d.fin, G, E);
+  unsigned long long* gk = d.rec_cell;
+  unsigned long long* gv = d.rec_vals;
+  RecGeom G2 = G;
+  if (scatter) {
+    uint32_t* scat_cursor = rec_start + 2 * nb;
+    rec_scatter_kernel<<<grid, RF_BLOCK, 0, d.st>>>(d.rec_cell, d.rec_vals, rec_start, scat_cursor, d.fin, G, (int)q.aggs.size(), d.rec2_cell, d.rec2_vals);
+    gk = d.rec2_cell;
+    gv = d.rec2_vals;
+    G2.world = 1;  // one plain list from here on
+    G2.rec_cap = G.fin_cap;
+  }
+  rec_group_kernel<<<grid, RF_BLOCK, 0, d.st>>>(gk, gv, rec_start, reinterpret_cast<uint32_t*>(d.rf_sorted), bkt_rows, d.fin, G2, E);
   rec_rowscan_kernel<<<1, BS_BLOCK, 0, d.st>>>(bkt_rows, q.nbuckets, G.cstride, row_start, row_cursor, d.fin);
-  rec_emit_kernel<<<grid, RF_BLOCK, 0, d.st>>>(d.rec_cell, d.rec_vals, row_start, row_cursor, d.fin, G, E);
+  rec_emit_kernel<<<grid, RF_BLOCK, 0, d.st>>>(gk, gv, row_start, row_cursor, d.fin, G2, E);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaMemcpyAsync(d.fin_host, d.fin, sizeof(RecFin), cudaMemcpyDeviceToHost, d.st));
   CUDA_CHECK(cudaMemcpyAsync(d.fin_host + 8, d.counters, 8 * sizeof(uint32_t), cudaMemcpyDeviceToHost, d.st));

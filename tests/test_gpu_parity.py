@@ -52,6 +52,21 @@ def test_c2_four_aggregates(path):
     assert got["survivors"] >= len(want["rows"])
 
 
+def test_c2_records_partitioned_by_bucket_first(monkeypatch):
+    # the record finalize with its bucket partition pass (what sharded queries of three ranks and more take by default)
+    monkeypatch.setenv("LK_REC_SCATTER", "1")
+    spec = synth.SynthSpec(dataset="metrics", rows=200000)
+    _, paths = H.dataset("c2_m200k", spec, 3)
+    rq = H.request_json(synth.c2_base_expr(), [0, 1, 2], 10000)
+    want = H.oracle_multi(rq, paths, synth.C2_AGGREGATES)
+    for _ in range(2):  # the second run re-uses the scratch (cleared on the side stream)
+        got = H.gpu_eval_multi(rq, paths, synth.C2_AGGREGATES, path="records")
+        H.assert_same(got, want, ["sum", "sum", "min", "max"], "c2/records+scatter")
+    # three aggregates: the generic (not 32-byte) record row
+    got = H.gpu_eval_multi(rq, paths, synth.C2_AGGREGATES[:3], path="records")
+    H.assert_same(got, H.oracle_multi(rq, paths, synth.C2_AGGREGATES[:3]), ["sum", "sum", "min"], "c2/records+scatter/3 aggs")
+
+
 def test_c2_snappy_segments():
     # SNAPPY-compressed metric segments (1 MiB pages: long literals for the PLAIN doubles, dense copy elements for the tag
     # indices, a compressed numeric dictionary for the timestamps), inflated on the device; same rows, same answers

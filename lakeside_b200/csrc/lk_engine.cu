@@ -1824,6 +1824,11 @@ __global__ void __launch_bounds__(BS_BLOCK) rec_regions_kernel(const uint32_t* _
 // One record per thread and iteration, small code, full occupancy: the batched variants of this pass (8 records per lane in
 // flight, 120 registers, 5-14 k SASS instructions) measured 330-400 us per 6.2 M records on B200, stalled on instruction fetch
 // and on the longest probe chain of every 8 x 32 batch.
+// SORTED: the list is partitioned by bucket (rec_scatter_kernel ran).  Every warp then walks one contiguous stretch of the list
+// -- one or two buckets -- and counts its owners in registers, adding them once at the end: with the records of a bucket side
+// by side, one counter bump per warp and 32 records would put hundreds of atomics on ONE address back to back (measured:
+// 208 us for this kernel against 153 us on the unsorted list; atomics on one line serialise at ~7 ns each).
+template <bool SORTED>
 __global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals,
                                                              const uint32_t* __restrict__ rec_start, uint32_t* __restrict__ table,
                                                              uint32_t* __restrict__ bkt_rows, RecFin* __restrict__ fin, const __grid_constant__ RecGeom G,
@@ -1837,8 +1842,15 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long*
   // Two records ahead of the one being inserted the key is requested, one record ahead its table slot is pulled into L2
   // (prefetch.global.L2): the CAS of a record then meets a resident sector instead of paying the DRAM round trip of a random
   // 32-byte access itself (ncu: 76 % of this kernel's stall samples sat behind that one CAS).
-  const uint32_t stride = gridDim.x * RF_BLOCK;
-  const uint32_t i0 = blockIdx.x * RF_BLOCK + threadIdx.x;
+  uint32_t stride = gridDim.x * RF_BLOCK, i0 = blockIdx.x * RF_BLOCK + threadIdx.x, i_end = n32;
+  if (SORTED) {
+    const uint32_t warps = gridDim.x * (RF_BLOCK / 32), gw = (blockIdx.x * RF_BLOCK + threadIdx.x) >> 5;
+    const uint32_t per = ((n32 >> 5) + warps - 1) / warps;  // 32-record groups per warp
+    stride = 32;
+    i0 = min(gw * per * 32u, n32) + (threadIdx.x & 31);
+    i_end = min((gw + 1) * per * 32u, n32);
+  }
+  uint32_t cur_b = 0xffffffffu, cur_n = 0;  // SORTED: owners of bucket cur_b seen by this lane, not yet added to its counter
   auto load_key = [&](uint32_t i, uint32_t& pi) -> unsigned long long {
     pi = i < nrec ? rec_phys(i, G) : 0u;
     return i < nrec ? keys[pi] : RF_CONSUMED;
@@ -1853,11 +1865,11 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long*
     return __umulhi(h, width);
   };
   uint32_t pi_a = 0, pi_b = 0, pi_c = 0;
-  unsigned long long key_a = load_key(i0, pi_a);                                  // record being inserted
-  unsigned long long key_b = i0 + stride < n32 ? load_key(i0 + stride, pi_b) : RF_CONSUMED;  // next
-  for (uint32_t i = i0; i < n32; i += stride) {
+  unsigned long long key_a = i0 < i_end ? load_key(i0, pi_a) : RF_CONSUMED;       // record being inserted
+  unsigned long long key_b = i0 + stride < i_end ? load_key(i0 + stride, pi_b) : RF_CONSUMED;  // next
+  for (uint32_t i = i0; i < i_end; i += stride) {
     unsigned long long key_c = RF_CONSUMED;                                       // the one after
-    if (i + 2 * stride < n32) key_c = load_key(i + 2 * stride, pi_c);
+    if (i + 2 * stride < i_end) key_c = load_key(i + 2 * stride, pi_c);
     if (key_b != RF_CONSUMED) {
       uint32_t b2, w2, h2;
       uint32_t* r2;
@@ -1898,9 +1910,96 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long*
       }
       if (probe == width) my_status |= RF_ST_TABLE;  // cannot happen: the region has two slots per record of its bucket
     }
-    warp_bucket_bump<false>(bkt_rows, G.cstride, bucket, owner, nullptr);
+    if (SORTED) {
+      if (owner) {
+        if (bucket != cur_b) {  // (rare: a bucket boundary inside this warp's stretch)
+          if (cur_n) atomicAdd(&bkt_rows[(size_t)cur_b * G.cstride], cur_n);
+          cur_b = bucket;
+          cur_n = 0;
+        }
+        cur_n++;
+      }
+    } else warp_bucket_bump<false>(bkt_rows, G.cstride, bucket, owner, nullptr);
     key_a = key_b; pi_a = pi_b;
     key_b = key_c; pi_b = pi_c;
+  }
+  if (SORTED) {  // one add per warp and bucket for the whole stretch
+    const unsigned peers = __match_any_sync(0xffffffffu, cur_n ? cur_b : 0xffffffffu);
+    const uint32_t sum = __reduce_add_sync(peers, cur_n);
+    if (cur_n && (int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&bkt_rows[(size_t)cur_b * G.cstride], sum);
+  }
+  if (my_status) atomicOr(&fin->status, my_status);
+}
+
+// Grouping of a bucket-partitioned list: ONE CTA PER BUCKET with the bucket's key table in SHARED memory (two 32-bit slots per
+// record: 17 k records of a C2 bucket = 138 KB), so that no insert leaves the SM -- on the partitioned list the global table is
+// the wrong tool: the ~300 k inserts in flight all land in the regions of a few neighbouring buckets, a dozen atomics per
+// 128-byte line, and atomics on one line serialise (measured: 208 us against 153 us on the unpartitioned list).  Entry =
+// 16-bit fingerprint << 16 | (index in the bucket + 1).  The owners are counted per CTA and stored, not added.  A bucket too
+// large for shared memory (more than 3/4 of RG_SLOTS records) is grouped in its region of the global table by the same CTA.
+constexpr uint32_t RG_SLOTS = 53248;  // 208 KB
+constexpr int RG_BLOCK = 1024;
+__global__ void __launch_bounds__(RG_BLOCK) rec_group_bucket_kernel(unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals,
+                                                                    const uint32_t* __restrict__ rec_start, uint32_t* __restrict__ table,
+                                                                    uint32_t* __restrict__ bkt_rows, RecFin* __restrict__ fin,
+                                                                    const __grid_constant__ RecGeom G, const __grid_constant__ EmitParams E) {
+  extern __shared__ uint32_t stab[];
+  __shared__ uint32_t s_owners[RG_BLOCK / 32];
+  if (fin->status & RF_ST_CAP) return;
+  const uint32_t b = blockIdx.x;
+  if (b >= G.nbuckets) return;
+  const uint32_t s0 = rec_start[b], s1 = rec_start[b + 1], n = s1 - s0;
+  if (n == 0) return;  // (its counter was zeroed by rec_regions)
+  const bool in_smem = n <= RG_SLOTS / 4 * 3 && n < 0xffffu;
+  const uint32_t width = in_smem ? min(2u * n, RG_SLOTS) : 2u * n;
+  uint32_t* const tab = in_smem ? stab : table + 2ull * s0;  // (the global region is already zero)
+  if (in_smem) {
+    for (uint32_t k = threadIdx.x; k < width; k += RG_BLOCK) stab[k] = 0;
+    __syncthreads();
+  }
+  const unsigned long long gid_mask = (1ull << G.gid_bits) - 1;
+  const uint32_t idx_field = in_smem ? 0xffffu : (G.fp_shift < 32 ? (1u << G.fp_shift) - 1 : 0xffffffffu);
+  const uint32_t fp_shift = in_smem ? 16u : G.fp_shift;
+  uint32_t owners = 0, my_status = 0;
+  unsigned long long key_n = threadIdx.x < n ? keys[s0 + threadIdx.x] : 0ull;
+  for (uint32_t k = threadIdx.x; k < n; k += RG_BLOCK) {
+    const unsigned long long key = key_n;
+    if (k + RG_BLOCK < n) key_n = keys[s0 + k + RG_BLOCK];  // the next record's key is on its way while this one is inserted
+    const uint32_t pi = s0 + k;
+    const unsigned long long cellx = key >> G.idx_bits;
+    const uint32_t h = lk_rf_mix(cellx & gid_mask);
+    const uint32_t entry = (fp_shift < 32 ? (h * 0x2545F491u) >> fp_shift << fp_shift : 0u) | ((in_smem ? k : pi) + 1);
+    uint32_t slot = __umulhi(h, width), probe = 0;
+    for (; probe < width; probe++) {
+      const uint32_t prev = atomicCAS(tab + slot, 0u, entry);
+      if (prev == 0u) { owners++; break; }
+      if (((prev ^ entry) & ~idx_field) == 0u) {  // same fingerprint: look at the owner's key
+        const uint32_t oi = (in_smem ? s0 : 0u) + (prev & idx_field) - 1;
+        if ((keys[oi] >> G.idx_bits) == cellx) {
+          const unsigned long long* mine = vals + (size_t)pi * E.n_aggs;
+          unsigned long long* own = vals + (size_t)oi * E.n_aggs;
+          for (int a = 0; a < E.n_aggs; a++) {
+            const unsigned long long x = mine[a];
+            if (E.ops[a] == AGG_SUM) atomicAdd(reinterpret_cast<double*>(own + a), __longlong_as_double((long long)x));
+            else if (E.ops[a] == AGG_COUNT) atomicAdd(own + a, x);
+            else if (x) atomicMax(own + a, x);
+          }
+          keys[pi] = RF_CONSUMED;
+          break;
+        }
+      }
+      slot = slot + 1 == width ? 0u : slot + 1;
+    }
+    if (probe == width) my_status |= RF_ST_TABLE;
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) owners += __shfl_xor_sync(0xffffffffu, owners, d);
+  if ((threadIdx.x & 31) == 0) s_owners[threadIdx.x >> 5] = owners;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t t = 0;
+    for (int w = 0; w < RG_BLOCK / 32; w++) t += s_owners[w];
+    bkt_rows[(size_t)b * G.cstride] = t;
   }
   if (my_status) atomicOr(&fin->status, my_status);
 }
@@ -2187,7 +2286,11 @@ static void rec_finalize_launch(Query& q) {
     G2.world = 1;  // one plain list from here on
     G2.rec_cap = G.fin_cap;
   }
-  rec_group_kernel<<<grid, RF_BLOCK, 0, d.st>>>(gk, gv, rec_start, reinterpret_cast<uint32_t*>(d.rf_sorted), bkt_rows, d.fin, G2, E);
+  if (scatter) {
+    static bool attr = false;
+    if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(rec_group_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RG_SLOTS * 4))); attr = true; }
+    rec_group_bucket_kernel<<<std::max<uint32_t>(q.nbuckets, 1), RG_BLOCK, RG_SLOTS * 4, d.st>>>(gk, gv, rec_start, reinterpret_cast<uint32_t*>(d.rf_sorted), bkt_rows, d.fin, G2, E);
+  } else rec_group_kernel<false><<<grid, RF_BLOCK, 0, d.st>>>(gk, gv, rec_start, reinterpret_cast<uint32_t*>(d.rf_sorted), bkt_rows, d.fin, G2, E);
   rec_rowscan_kernel<<<1, BS_BLOCK, 0, d.st>>>(bkt_rows, q.nbuckets, G.cstride, row_start, row_cursor, d.fin);
   rec_emit_kernel<<<grid, RF_BLOCK, 0, d.st>>>(gk, gv, row_start, row_cursor, d.fin, G2, E);
   CUDA_CHECK(cudaGetLastError());

@@ -213,6 +213,8 @@ struct Query::Device {
   // records partitioned by bucket before grouping (rec_scatter_kernel): second copy of the record arrays, fin_cap records
   unsigned long long* rec2_cell = nullptr;
   unsigned long long* rec2_vals = nullptr;
+  bool rec_scatter = false;   // decided when the scratch is sized (rec_finalize_size)
+  uint32_t rec_slices = 1;    // partitions per time bucket on the partitioned path
   struct RecFin* fin = nullptr;
   uint32_t* fin_host = nullptr;  // pinned: [0..7] RecFin, [8..15] the scan's counters, copied back at the end of finalize
   // the finalize scratch is cleared on a side stream WHILE the scan runs (execute forks, finalize joins)
@@ -1702,13 +1704,18 @@ __global__ void __launch_bounds__(HS_BLOCK) hash_emit_kernel(const uint32_t* __r
 //                the order inside a bucket is unspecified there too), positions from one warp-aggregated cursor per bucket
 // No library call and no host round trip: every size the kernels need is computed on the device.
 constexpr int RF_BLOCK = 256;
+#ifndef REC_EMIT_CTAS
+#define REC_EMIT_CTAS 5
+#endif
 struct RecFin {  // device-resident bookkeeping of one finalize
   uint32_t nrec, nrows, status, pad;
 };
 enum : uint32_t { RF_ST_CAP = 1, RF_ST_TABLE = 2 };
 constexpr unsigned long long RF_CONSUMED = ~0ull;  // key of a record folded into its owner (real keys use at most 63 bits)
 struct RecGeom {
-  uint32_t idx_bits, gid_bits, nbuckets;
+  uint32_t idx_bits, gid_bits, nbuckets;  // nbuckets: partitions of the list = time buckets x slices
+  uint32_t slices;   // partitions per time bucket (by a hash of the group id): > 1 only on the partitioned (scatter) path, so that a
+                     // partition's key table fits shared memory however many records a time bucket holds (C4: 139 k)
   uint32_t rec_cap;  // capacity of the record arrays
   uint32_t fin_cap;  // records the key table (2 slots each) and the result columns hold
   uint32_t world, region_cap;  // sharded: the list is the concatenation of one region per source rank (world <= 1: one plain list)
@@ -1718,6 +1725,15 @@ struct RecGeom {
                      // gets its own 128-byte line (atomics on one line serialise at ~7 ns each on B200: 360 counters packed
                      // into 12 lines kept ONE L2 slice 97 % busy and cost 120 us per pass over 6.2 M records)
 };
+
+// partition of a record: its time bucket, or (bucket, hash slice of its group id)
+__device__ __forceinline__ uint32_t rec_part(unsigned long long key, const RecGeom& G) {
+  const unsigned long long cellx = key >> G.idx_bits;
+  const uint32_t bucket = (uint32_t)(cellx >> G.gid_bits);
+  if (G.slices <= 1) return bucket;
+  const uint32_t h = lk_rf_mix(cellx & ((1ull << G.gid_bits) - 1)) * 0x85EBCA6Bu + 0x6A09E667u;  // (other bits than the table slot uses)
+  return bucket * G.slices + __umulhi(h ^ (h >> 15), G.slices);
+}
 
 // position of record i of the list in the record arrays
 __device__ __forceinline__ uint32_t rec_phys(uint32_t i, const RecGeom& G) {
@@ -1753,12 +1769,11 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_bhist_kernel(const unsigned long
                                                              const __grid_constant__ RecGeom G, uint32_t* __restrict__ bkt_recs) {
   const uint32_t nrec = min(counters[5], G.rec_cap);
   if (nrec > G.fin_cap) return;  // rec_regions_kernel raises RF_ST_CAP; the host grows the scratch and finalizes again
-  const uint32_t sh = G.idx_bits + G.gid_bits;
   const uint32_t n32 = (nrec + 31u) & ~31u;  // whole warps
   for (uint32_t i = blockIdx.x * RF_BLOCK + threadIdx.x; i < n32; i += gridDim.x * RF_BLOCK) {
     const unsigned long long key = i < nrec ? keys[rec_phys(i, G)] : RF_CONSUMED;
     const bool valid = key != RF_CONSUMED;
-    warp_bucket_bump<false>(bkt_recs, G.cstride, valid ? (uint32_t)(key >> sh) : 0u, valid, nullptr);
+    warp_bucket_bump<false>(bkt_recs, G.cstride, valid ? rec_part(key, G) : 0u, valid, nullptr);
   }
 }
 
@@ -1829,7 +1844,7 @@ __global__ void __launch_bounds__(BS_BLOCK) rec_regions_kernel(const uint32_t* _
 // by side, one counter bump per warp and 32 records would put hundreds of atomics on ONE address back to back (measured:
 // 208 us for this kernel against 153 us on the unsorted list; atomics on one line serialise at ~7 ns each).
 template <bool SORTED>
-__global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals,
+__global__ void __launch_bounds__(RF_BLOCK, 8) rec_group_kernel(unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals,
                                                              const uint32_t* __restrict__ rec_start, uint32_t* __restrict__ table,
                                                              uint32_t* __restrict__ bkt_rows, RecFin* __restrict__ fin, const __grid_constant__ RecGeom G,
                                                              const __grid_constant__ EmitParams E) {
@@ -1857,7 +1872,7 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_group_kernel(unsigned long long*
   };
   auto slot_of = [&](unsigned long long key, uint32_t& bucket, uint32_t& width, uint32_t*& region, uint32_t& h) -> uint32_t {
     const unsigned long long cellx = key >> G.idx_bits;
-    bucket = (uint32_t)(cellx >> G.gid_bits);
+    bucket = (uint32_t)(cellx >> G.gid_bits);  // (this kernel only sees lists partitioned by time bucket alone: slices == 1)
     const uint32_t s0 = __ldg(rec_start + bucket), s1 = __ldg(rec_start + bucket + 1);
     width = 2u * (s1 - s0);  // >= 2: this record is one of the bucket's
     region = table + 2ull * s0;
@@ -2017,7 +2032,6 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_scatter_kernel(const unsigned lo
   if (fin->status & RF_ST_CAP) return;
   const uint32_t nrec = fin->nrec;
   const uint32_t n32 = (nrec + 31u) & ~31u;
-  const uint32_t sh = G.idx_bits + G.gid_bits;
   const uint32_t stride = gridDim.x * RF_BLOCK;
   const bool four = n_aggs == 4;
   auto load_rec = [&](uint32_t i, uint32_t& pi, ulonglong2& lo, ulonglong2& hi) -> unsigned long long {
@@ -2039,7 +2053,7 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_scatter_kernel(const unsigned lo
     const ulonglong2 lo = lo_n, hi = hi_n;
     if (i + stride < n32) key_n = load_rec(i + stride, pi_n, lo_n, hi_n);
     const bool valid = i < nrec;
-    const uint32_t bucket = valid ? (uint32_t)(key >> sh) : 0u;
+    const uint32_t bucket = valid ? rec_part(key, G) : 0u;
     uint32_t base = 0;
     const uint32_t rank = warp_bucket_bump<true>(cursor, G.cstride, bucket, valid, &base);
     if (valid) {
@@ -2064,7 +2078,7 @@ __global__ void __launch_bounds__(BS_BLOCK) rec_rowscan_kernel(const uint32_t* _
 }
 
 // rows: every owner copies its record out at (first row of its bucket) + (cursor of the bucket, bumped once per warp and bucket)
-__global__ void __launch_bounds__(RF_BLOCK) rec_emit_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ vals,
+__global__ void __launch_bounds__(RF_BLOCK, REC_EMIT_CTAS) rec_emit_kernel(const unsigned long long* __restrict__ keys, const unsigned long long* __restrict__ vals,
                                                             const uint32_t* __restrict__ row_start, uint32_t* __restrict__ row_cursor,
                                                             const RecFin* __restrict__ fin, const __grid_constant__ RecGeom G,
                                                             const __grid_constant__ EmitParams E) {
@@ -2096,7 +2110,7 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_emit_kernel(const unsigned long 
     if (i + stride < n32) key_n = load_rec(i + stride, pi_n, lo_n, hi_n);
     const bool owner = key != RF_CONSUMED;
     const unsigned long long cellx = key >> G.idx_bits;
-    const uint32_t bucket = owner ? (uint32_t)(cellx >> G.gid_bits) : 0u;
+    const uint32_t bucket = owner ? rec_part(key, G) : 0u;  // the partition: cursor and first row are per partition
     unsigned long long w[LK_MAX_AGGS];
     if (owner) {
       if (four) {
@@ -2112,7 +2126,7 @@ __global__ void __launch_bounds__(RF_BLOCK) rec_emit_kernel(const unsigned long 
     const uint32_t rank = warp_bucket_bump<true>(row_cursor, G.cstride, bucket, owner, &base);
     if (owner) {
       const uint32_t out = __ldg(row_start + bucket) + base + rank;
-      if (out < G.fin_cap) emit_row_bg(E, out, bucket, cellx & gid_mask, [&](int a) { return w[a]; });
+      if (out < G.fin_cap) emit_row_bg(E, out, (uint32_t)(cellx >> G.gid_bits), cellx & gid_mask, [&](int a) { return w[a]; });
     }
   }
 }
@@ -2196,20 +2210,24 @@ static void check_scan_status(Query& q, const uint32_t* h) {
 
 // ---- record path: sizes the scratch (from the record count of the first finalize; later finalizes re-use it and the
 // kernels verify that it still fits) and enqueues the kernels; nothing here waits for the device once sized ----
-static size_t rec_counter_stride(const Query& q) { return q.nbuckets <= 8192 ? 32 : 1; }
+static size_t rec_parts(const Query& q) { return (size_t)q.nbuckets * (q.dev ? q.dev->rec_slices : 1u); }
+static size_t rec_counter_stride(const Query& q) { return rec_parts(q) <= 8192 ? 32 : 1; }
 // Partition the records by bucket before grouping them?  Measured on B200, C2: one GPU 0.395 ms without / 0.48 ms with (the
 // extra pass costs more than the locality buys while a warp's 32 records already share ~2.5 buckets); 4 ranks 0.574 / 0.525;
 // the list of a rank is then a mix of short appends from all sources and the gap widens with the rank count.  So: from three
 // ranks on.  LK_REC_SCATTER=0|1 overrides (tests run both ways).
-static bool rec_scatter_on(const Query& q) {
+// ... and on any number of ranks when the list is long (>= 16 M records: a key table of 128 MB and more lives in DRAM, every
+// insert of the unpartitioned grouping is a DRAM round trip: C4, 49.9 M records, 4.25 ms) -- then with several partitions per time
+// bucket, so that each still fits the shared-memory table of rec_group_bucket_kernel.
+static bool rec_scatter_on(const Query& q, uint32_t nrec) {
   if (const char* e = getenv("LK_REC_SCATTER")) return atoi(e) != 0;
-  return q.comm != nullptr && q.comm->world >= 3;
+  return (q.comm != nullptr && q.comm->world >= 3) || nrec >= (16u << 20);
 }
 
 // the three clears a record finalize starts from: per-bucket counters, the key table, the bookkeeping block
 static void rec_clear_scratch(Query& q, cudaStream_t st) {
   Query::Device& d = *q.dev;
-  const size_t nb = (size_t)q.nbuckets + 1, cs = rec_counter_stride(q);
+  const size_t nb = rec_parts(q) + 1, cs = rec_counter_stride(q);
   CUDA_CHECK(cudaMemsetAsync(d.rf_tables, 0, nb * cs * 4, st));
   CUDA_CHECK(cudaMemsetAsync(d.rf_tables + 3 * nb * cs + 2 * nb, 0, nb * cs * 4, st));  // scatter cursors
   CUDA_CHECK(cudaMemsetAsync(d.rf_sorted, 0, 2 * d.fin_cap * 4, st));
@@ -2220,6 +2238,16 @@ static void rec_finalize_size(Query& q, uint32_t nrec) {
   Query::Device& d = *q.dev;
   if (d.st2) CUDA_CHECK(cudaStreamSynchronize(d.st2));  // a clear of the old scratch may still be running there
   d.pre_cleared = false;
+  d.rec_scatter = rec_scatter_on(q, nrec);
+  d.rec_slices = 1;
+  if (d.rec_scatter && q.nbuckets > 0) {
+    // aim at ~24 k records per partition (RG_SLOTS holds 3/4 x 53 k), at most 64 Ki partitions
+    const uint64_t per_bucket = ((uint64_t)nrec + q.nbuckets - 1) / q.nbuckets;
+    uint64_t sl = (per_bucket + 24575) / 24576;
+    if (const char* e = getenv("LK_REC_SLICES")) sl = (uint64_t)std::max(1, atoi(e));  // tests
+    sl = std::min<uint64_t>(std::max<uint64_t>(sl, 1), std::max<uint64_t>(1, 65536 / q.nbuckets));
+    d.rec_slices = (uint32_t)sl;
+  }
   const size_t cap = std::min<size_t>(std::max<size_t>(d.rec_cap, 1), (size_t)nrec + nrec / 8 + 4096);
   if (d.rf_sorted) CUDA_CHECK(cudaFreeAsync(d.rf_sorted, d.st));
   if (d.rf_tables) CUDA_CHECK(cudaFreeAsync(d.rf_tables, d.st));
@@ -2227,12 +2255,12 @@ static void rec_finalize_size(Query& q, uint32_t nrec) {
   d.rf_tables = nullptr;
   CUDA_CHECK(cudaMallocAsync(&d.rf_sorted, 2 * cap * 4 + 64, d.st));  // the key table: two 32-bit slots per record
   // u32 words: bkt_recs[nb * cs] | bkt_rows[nb * cs] | row_cursor[nb * cs] | rec_start[nb] | row_start[nb]
-  const size_t nb = (size_t)q.nbuckets + 1, cs = rec_counter_stride(q);
+  const size_t nb = rec_parts(q) + 1, cs = rec_counter_stride(q);
   CUDA_CHECK(cudaMallocAsync(&d.rf_tables, (4 * nb * cs + 2 * nb) * 4 + 64, d.st));  // (+ the scatter cursors, last)
   if (d.rec2_cell) CUDA_CHECK(cudaFreeAsync(d.rec2_cell, d.st));
   if (d.rec2_vals) CUDA_CHECK(cudaFreeAsync(d.rec2_vals, d.st));
   d.rec2_cell = d.rec2_vals = nullptr;
-  if (rec_scatter_on(q)) {
+  if (d.rec_scatter) {
     CUDA_CHECK(cudaMallocAsync(&d.rec2_cell, cap * 8 + 64, d.st));
     CUDA_CHECK(cudaMallocAsync(&d.rec2_vals, cap * 8 * q.aggs.size() + 64, d.st));
   }
@@ -2247,17 +2275,18 @@ static void rec_finalize_launch(Query& q) {
   RecGeom G;
   G.idx_bits = q.params.rec_idx_bits;
   G.gid_bits = q.params.rec_gid_bits;
-  G.nbuckets = q.nbuckets;
+  G.nbuckets = (uint32_t)rec_parts(q);
+  G.slices = d.rec_slices;
   G.rec_cap = (uint32_t)std::min<size_t>(d.rec_cap, 0xffffffffu);
   G.fin_cap = (uint32_t)std::min<size_t>(d.fin_cap, 0xffffffffu);
   G.world = q.comm ? (uint32_t)q.comm->world : 1u;
   G.region_cap = q.comm ? (uint32_t)q.comm->region_cap : 0u;
   G.prefix = q.comm ? q.comm->ctrl(q.comm->rank)->prefix : nullptr;
   G.fp_shift = 1;
-  const bool scatter = rec_scatter_on(q) && d.rec2_cell != nullptr;
+  const bool scatter = d.rec_scatter && d.rec2_cell != nullptr;
   const uint64_t max_index = (G.world > 1 && !scatter) ? (uint64_t)d.rec_cap : (uint64_t)d.fin_cap;
   while (G.fp_shift < 32 && (max_index + 1) >> G.fp_shift) G.fp_shift++;  // bits of (largest record position + 1)
-  const size_t nb = (size_t)q.nbuckets + 1, cs = rec_counter_stride(q);
+  const size_t nb = rec_parts(q) + 1, cs = rec_counter_stride(q);
   G.cstride = (uint32_t)cs;
   uint32_t* bkt_recs = d.rf_tables;
   uint32_t* bkt_rows = bkt_recs + nb * cs;
@@ -2289,9 +2318,9 @@ static void rec_finalize_launch(Query& q) {
   if (scatter) {
     static bool attr = false;
     if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(rec_group_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RG_SLOTS * 4))); attr = true; }
-    rec_group_bucket_kernel<<<std::max<uint32_t>(q.nbuckets, 1), RG_BLOCK, RG_SLOTS * 4, d.st>>>(gk, gv, rec_start, reinterpret_cast<uint32_t*>(d.rf_sorted), bkt_rows, d.fin, G2, E);
+    rec_group_bucket_kernel<<<std::max<uint32_t>(G.nbuckets, 1), RG_BLOCK, RG_SLOTS * 4, d.st>>>(gk, gv, rec_start, reinterpret_cast<uint32_t*>(d.rf_sorted), bkt_rows, d.fin, G2, E);
   } else rec_group_kernel<false><<<grid, RF_BLOCK, 0, d.st>>>(gk, gv, rec_start, reinterpret_cast<uint32_t*>(d.rf_sorted), bkt_rows, d.fin, G2, E);
-  rec_rowscan_kernel<<<1, BS_BLOCK, 0, d.st>>>(bkt_rows, q.nbuckets, G.cstride, row_start, row_cursor, d.fin);
+  rec_rowscan_kernel<<<1, BS_BLOCK, 0, d.st>>>(bkt_rows, G.nbuckets, G.cstride, row_start, row_cursor, d.fin);
   rec_emit_kernel<<<grid, RF_BLOCK, 0, d.st>>>(gk, gv, row_start, row_cursor, d.fin, G2, E);
   CUDA_CHECK(cudaGetLastError());
   CUDA_CHECK(cudaMemcpyAsync(d.fin_host, d.fin, sizeof(RecFin), cudaMemcpyDeviceToHost, d.st));

@@ -52,9 +52,12 @@ def test_c2_four_aggregates(path):
     assert got["survivors"] >= len(want["rows"])
 
 
-def test_c2_records_partitioned_by_bucket_first(monkeypatch):
-    # the record finalize with its bucket partition pass (what sharded queries of three ranks and more take by default)
+@pytest.mark.parametrize("slices", [1, 3])
+def test_c2_records_partitioned_by_bucket_first(monkeypatch, slices):
+    # the record finalize with its partition pass (what sharded queries of three ranks and more, and long record lists, take by
+    # default); slices > 1: several partitions per time bucket (by a hash of the group id), as for C4's 139 k records per bucket
     monkeypatch.setenv("LK_REC_SCATTER", "1")
+    monkeypatch.setenv("LK_REC_SLICES", str(slices))
     spec = synth.SynthSpec(dataset="metrics", rows=200000)
     _, paths = H.dataset("c2_m200k", spec, 3)
     rq = H.request_json(synth.c2_base_expr(), [0, 1, 2], 10000)

@@ -215,6 +215,7 @@ struct Query::Device {
   unsigned long long* rec2_vals = nullptr;
   bool rec_scatter = false;   // decided when the scratch is sized (rec_finalize_size)
   uint32_t rec_slices = 1;    // partitions per time bucket on the partitioned path
+  uint32_t rec_smem_slots = 0;  // shared-memory key table of rec_group_bucket_kernel: slots per CTA
   struct RecFin* fin = nullptr;
   uint32_t* fin_host = nullptr;  // pinned: [0..7] RecFin, [8..15] the scan's counters, copied back at the end of finalize
   // the finalize scratch is cleared on a side stream WHILE the scan runs (execute forks, finalize joins)
@@ -1957,7 +1958,8 @@ constexpr int RG_BLOCK = 1024;
 __global__ void __launch_bounds__(RG_BLOCK) rec_group_bucket_kernel(unsigned long long* __restrict__ keys, unsigned long long* __restrict__ vals,
                                                                     const uint32_t* __restrict__ rec_start, uint32_t* __restrict__ table,
                                                                     uint32_t* __restrict__ bkt_rows, RecFin* __restrict__ fin,
-                                                                    const __grid_constant__ RecGeom G, const __grid_constant__ EmitParams E) {
+                                                                    const __grid_constant__ RecGeom G, const __grid_constant__ EmitParams E,
+                                                                    uint32_t smem_slots) {
   extern __shared__ uint32_t stab[];
   __shared__ uint32_t s_owners[RG_BLOCK / 32];
   if (fin->status & RF_ST_CAP) return;
@@ -1965,8 +1967,8 @@ __global__ void __launch_bounds__(RG_BLOCK) rec_group_bucket_kernel(unsigned lon
   if (b >= G.nbuckets) return;
   const uint32_t s0 = rec_start[b], s1 = rec_start[b + 1], n = s1 - s0;
   if (n == 0) return;  // (its counter was zeroed by rec_regions)
-  const bool in_smem = n <= RG_SLOTS / 4 * 3 && n < 0xffffu;
-  const uint32_t width = in_smem ? min(2u * n, RG_SLOTS) : 2u * n;
+  const bool in_smem = n <= smem_slots / 4 * 3 && n < 0xffffu;
+  const uint32_t width = in_smem ? min(2u * n, smem_slots) : 2u * n;
   uint32_t* const tab = in_smem ? stab : table + 2ull * s0;  // (the global region is already zero)
   if (in_smem) {
     for (uint32_t k = threadIdx.x; k < width; k += RG_BLOCK) stab[k] = 0;
@@ -2241,12 +2243,20 @@ static void rec_finalize_size(Query& q, uint32_t nrec) {
   d.rec_scatter = rec_scatter_on(q, nrec);
   d.rec_slices = 1;
   if (d.rec_scatter && q.nbuckets > 0) {
-    // aim at ~24 k records per partition (RG_SLOTS holds 3/4 x 53 k), at most 64 Ki partitions
+    // records per partition to aim at (its key table: two slots per record, 1.5 x headroom for uneven partitions; at most 8192
+    // partitions, so that every counter keeps its own 128-byte line).  Measured on B200: C2 (6.2 M records, 17 k per time
+    // bucket) 0.405 ms with one partition per bucket, 0.385-0.39 with two (8.6 k each: two CTAs per SM), 0.426 with six;
+    // C4 (49.9 M records, 139 k per bucket) 2.98 ms with 6 partitions per bucket, 3.20 with 9, 3.37 with 17 -- the partition
+    // pass pays for every extra partition with less coalesced stores.
+    const uint64_t target = getenv("LK_REC_PART_TARGET") ? (uint64_t)std::max(256, atoi(getenv("LK_REC_PART_TARGET")))
+                                                          : (nrec >= (16u << 20) ? 24576 : 12288);
     const uint64_t per_bucket = ((uint64_t)nrec + q.nbuckets - 1) / q.nbuckets;
-    uint64_t sl = (per_bucket + 24575) / 24576;
+    uint64_t sl = (per_bucket + target - 1) / target;
     if (const char* e = getenv("LK_REC_SLICES")) sl = (uint64_t)std::max(1, atoi(e));  // tests
-    sl = std::min<uint64_t>(std::max<uint64_t>(sl, 1), std::max<uint64_t>(1, 65536 / q.nbuckets));
+    sl = std::min<uint64_t>(std::max<uint64_t>(sl, 1), std::max<uint64_t>(1, 8192 / q.nbuckets));
     d.rec_slices = (uint32_t)sl;
+    const uint64_t per_part = (per_bucket + sl - 1) / sl;
+    d.rec_smem_slots = (uint32_t)std::min<uint64_t>(RG_SLOTS, std::max<uint64_t>(4096, (3 * per_part + 1023) & ~1023ull));
   }
   const size_t cap = std::min<size_t>(std::max<size_t>(d.rec_cap, 1), (size_t)nrec + nrec / 8 + 4096);
   if (d.rf_sorted) CUDA_CHECK(cudaFreeAsync(d.rf_sorted, d.st));
@@ -2318,7 +2328,9 @@ static void rec_finalize_launch(Query& q) {
   if (scatter) {
     static bool attr = false;
     if (!attr) { CUDA_CHECK(cudaFuncSetAttribute(rec_group_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RG_SLOTS * 4))); attr = true; }
-    rec_group_bucket_kernel<<<std::max<uint32_t>(G.nbuckets, 1), RG_BLOCK, RG_SLOTS * 4, d.st>>>(gk, gv, rec_start, reinterpret_cast<uint32_t*>(d.rf_sorted), bkt_rows, d.fin, G2, E);
+    const uint32_t slots = d.rec_smem_slots ? d.rec_smem_slots : RG_SLOTS;
+    rec_group_bucket_kernel<<<std::max<uint32_t>(G.nbuckets, 1), RG_BLOCK, (size_t)slots * 4, d.st>>>(gk, gv, rec_start, reinterpret_cast<uint32_t*>(d.rf_sorted), bkt_rows, d.fin, G2,
+                                                                                                    E, slots);
   } else rec_group_kernel<false><<<grid, RF_BLOCK, 0, d.st>>>(gk, gv, rec_start, reinterpret_cast<uint32_t*>(d.rf_sorted), bkt_rows, d.fin, G2, E);
   rec_rowscan_kernel<<<1, BS_BLOCK, 0, d.st>>>(bkt_rows, G.nbuckets, G.cstride, row_start, row_cursor, d.fin);
   rec_emit_kernel<<<grid, RF_BLOCK, 0, d.st>>>(gk, gv, row_start, row_cursor, d.fin, G2, E);

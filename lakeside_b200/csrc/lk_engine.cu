@@ -2216,14 +2216,15 @@ static size_t rec_parts(const Query& q) { return (size_t)q.nbuckets * (q.dev ? q
 static size_t rec_counter_stride(const Query& q) { return rec_parts(q) <= 8192 ? 32 : 1; }
 // Partition the records by bucket before grouping them?  Measured on B200, C2: one GPU 0.395 ms without / 0.48 ms with (the
 // extra pass costs more than the locality buys while a warp's 32 records already share ~2.5 buckets); 4 ranks 0.574 / 0.525;
-// the list of a rank is then a mix of short appends from all sources and the gap widens with the rank count.  So: from three
-// ranks on.  LK_REC_SCATTER=0|1 overrides (tests run both ways).
+// the list of a rank is then a mix of short appends from all sources and the gap widens with the rank count (2 ranks, after the
+// partitioned path got its shared-memory grouping: 0.49 / 0.45).  So: whenever the query is sharded.  LK_REC_SCATTER=0|1
+// overrides (tests run both ways).
 // ... and on any number of ranks when the list is long (>= 16 M records: a key table of 128 MB and more lives in DRAM, every
 // insert of the unpartitioned grouping is a DRAM round trip: C4, 49.9 M records, 4.25 ms) -- then with several partitions per time
 // bucket, so that each still fits the shared-memory table of rec_group_bucket_kernel.
 static bool rec_scatter_on(const Query& q, uint32_t nrec) {
   if (const char* e = getenv("LK_REC_SCATTER")) return atoi(e) != 0;
-  return (q.comm != nullptr && q.comm->world >= 3) || nrec >= (16u << 20);
+  return (q.comm != nullptr && q.comm->world >= 2) || nrec >= (16u << 20);
 }
 
 // the three clears a record finalize starts from: per-bucket counters, the key table, the bookkeeping block

@@ -54,7 +54,7 @@ def test_c2_four_aggregates(path):
 
 @pytest.mark.parametrize("slices", [1, 3])
 def test_c2_records_partitioned_by_bucket_first(monkeypatch, slices):
-    # the record finalize with its partition pass (what sharded queries of three ranks and more, and long record lists, take by
+    # the record finalize with its partition pass (what sharded queries and long record lists take by
     # default); slices > 1: several partitions per time bucket (by a hash of the group id), as for C4's 139 k records per bucket
     monkeypatch.setenv("LK_REC_SCATTER", "1")
     monkeypatch.setenv("LK_REC_SLICES", str(slices))

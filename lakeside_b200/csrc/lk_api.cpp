@@ -180,7 +180,7 @@ int lk_query_add_segment_file(lk_query* q, const char* path) {
     if (s.cached) {
       s.meta = s.cached->meta;
       s.meta_from_cache = true;
-    } else segment_load(s);
+    } else segment_open(s);
     q->q.segs.push_back(std::move(s));
   });
 }

@@ -322,6 +322,64 @@ void segment_load(SegmentInput& s) {
   s.owned_pinned = buf;
 }
 
+// A segment file that the cache does not know: only its footer is read now (from the file's tail); the column chunks the query
+// touches follow in device_layout, once the plan knows which they are -- a wide segment (hundreds of tag columns) is never read
+// whole for the ten columns a chart needs.
+void segment_open(SegmentInput& s) {
+  int fd = open(s.name.c_str(), O_RDONLY);
+  LK_CHECK(fd >= 0, LK_ERR_IO, "IO Error: cannot open " + s.name);
+  std::vector<uint8_t> tail;
+  size_t want = std::min<size_t>(s.len, 64 << 10);
+  try {
+    for (int attempt = 0;; attempt++) {
+      tail.resize(want);
+      size_t got = 0;
+      while (got < want) {
+        ssize_t r = pread(fd, tail.data() + got, want - got, (off_t)(s.len - want + got));
+        if (r <= 0) break;
+        got += (size_t)r;
+      }
+      LK_CHECK(got == want, LK_ERR_IO, "IO Error: short read on " + s.name);
+      size_t need = 0;
+      if (parse_footer_tail(tail.data(), tail.size(), s.len, &s.meta, &need)) break;
+      LK_CHECK(attempt == 0 && need <= s.len, LK_ERR_IO, "parquet: bad footer length");
+      want = need;
+    }
+    char magic[4] = {0, 0, 0, 0};
+    LK_CHECK(pread(fd, magic, 4, 0) == 4 && memcmp(magic, "PAR1", 4) == 0, LK_ERR_IO, "not a Parquet file (bad magic)");
+  } catch (...) { close(fd); throw; }
+  close(fd);
+  s.sparse = true;
+}
+
+// reads the byte ranges of `slots` (all of one sparse segment) into one pinned block, back to back, and points the slots at them
+static void segment_read_chunks(SegmentInput& s, std::vector<ChunkSlot*>& slots) {
+  if (slots.empty()) return;
+  size_t total = 0;
+  for (auto* sl : slots) total += ((size_t)sl->len + 15) & ~(size_t)15;
+  int fd = open(s.name.c_str(), O_RDONLY);
+  LK_CHECK(fd >= 0, LK_ERR_IO, "IO Error: cannot open " + s.name);
+  uint8_t* buf = nullptr;
+  try {
+    buf = static_cast<uint8_t*>(pinned_alloc(total + 16));
+    size_t at = 0;
+    for (auto* sl : slots) {
+      size_t got = 0;
+      while (got < sl->len) {
+        ssize_t r = pread(fd, buf + at + got, sl->len - got, (off_t)(sl->file_off + got));
+        if (r <= 0) break;
+        got += (size_t)r;
+      }
+      LK_CHECK(got == sl->len, LK_ERR_IO, "IO Error: short read on " + s.name);
+      sl->host = buf + at;
+      at += ((size_t)sl->len + 15) & ~(size_t)15;
+    }
+  } catch (...) { close(fd); if (buf) pinned_free(buf); throw; }
+  close(fd);
+  s.owned_pinned = buf;  // (a sparse segment owns nothing else)
+  s.sparse_bytes = total;
+}
+
 static SegmentIdentity segment_identity(const SegmentInput& s) {
   SegmentIdentity id;
   id.path = s.name;
@@ -372,7 +430,6 @@ void device_layout(Query& q) {
           if (col->chunk_off[q.rgs[q.slots[k].rgi].rg] == ~0ull) { col = nullptr; break; }
       const bool hit = col != nullptr;
       if (!hit) {
-        segment_load(seg);
         col = std::make_shared<CachedColumn>();
         col->chunk_off.assign(seg.meta.row_groups.size(), ~0ull);
         col->index.resize(seg.meta.row_groups.size());
@@ -403,7 +460,22 @@ void device_layout(Query& q) {
       q.cache_refs.push_back(col);
     }
   }
-  for (auto& sg : q.segs) if (!sg.data && !use_cache) segment_load(sg);
+  // host-built index (LK_HOST_INDEX): the planner reads run payloads anywhere in a chunk through the whole-file pointer
+  if (!q.device_index)
+    for (auto& sg : q.segs)
+      if (!sg.data) { segment_load(sg); sg.sparse = false; }
+  for (auto& sl : q.slots)
+    if (!sl.host && q.segs[sl.seg].data) sl.host = q.segs[sl.seg].data + sl.file_off;
+  // sparse files: the chunks that are not resident are read now, all segments in parallel
+  {
+    std::vector<std::vector<ChunkSlot*>> todo(q.segs.size());
+    for (size_t k = 0; k < q.slots.size(); k++) {
+      ChunkSlot& sl = q.slots[k];
+      const bool resident = placed[k] && !fresh[k];
+      if (!sl.host && !resident) todo[sl.seg].push_back(&sl);
+    }
+    parallel_for((int)q.segs.size(), global_options().host_threads, [&](int i) { segment_read_chunks(q.segs[i], todo[i]); });
+  }
   layout_private_arena(q, placed);
   if (!d.arena) {
     CUDA_CHECK(cudaEventRecord(d.ev[0], d.st));
@@ -415,6 +487,17 @@ void device_layout(Query& q) {
     const ChunkSlot& sl = q.slots[k];
     q.rgs[sl.rgi].arena_base[sl.pcol] = abs_addr[k] - origin;
     if (fresh[k]) q.uploads.push_back({sl.seg, sl.file_off, sl.len, abs_addr[k] - origin});
+  }
+  // the copies read from where the chunks are in host memory (whole file or sparse block)
+  {
+    std::map<std::pair<int, uint64_t>, const uint8_t*> host_of;
+    for (auto& sl : q.slots) if (sl.host) host_of[{sl.seg, sl.file_off}] = sl.host;
+    for (auto& u : q.uploads)
+      if (!u.src) {
+        auto it = host_of.find({u.seg, u.file_off});
+        LK_CHECK(it != host_of.end(), LK_ERR_IO, "segment '" + q.segs[u.seg].name + "': column chunk bytes were not read");
+        u.src = it->second;
+      }
   }
   (void)np;
   device_begin_upload(q);
@@ -449,10 +532,36 @@ void device_begin_upload(Query& q) {
     CUDA_CHECK(cudaMallocAsync(&d.arena, q.arena_bytes, d.st));
   }
   // (called again after the page walk: re-encoded PLAIN string pages join the list then)
-  for (; d.uploads_done < q.uploads.size(); d.uploads_done++) {
-    const Query::Upload& u = q.uploads[d.uploads_done];
-    CUDA_CHECK(cudaMemcpyAsync(d.arena + u.arena_off, u.src ? u.src : q.segs[u.seg].data + u.file_off, u.len, cudaMemcpyHostToDevice, d.st));
+  // LK_UPLOAD_STREAMS=n (tuning aid, default 1): the copies go round robin over n side streams that the query's stream then
+  // waits for.  Measured on B200 / PCIe 5 x16 (C2, 1000 copies, 3.02 GB from pinned memory): see DESIGN.md §4.
+  static const int n_up = std::min(4, std::max(1, getenv("LK_UPLOAD_STREAMS") ? atoi(getenv("LK_UPLOAD_STREAMS")) : 1));
+  if (n_up <= 1 || d.uploads_done >= q.uploads.size()) {
+    for (; d.uploads_done < q.uploads.size(); d.uploads_done++) {
+      const Query::Upload& u = q.uploads[d.uploads_done];
+      CUDA_CHECK(cudaMemcpyAsync(d.arena + u.arena_off, u.src ? u.src : q.segs[u.seg].data + u.file_off, u.len, cudaMemcpyHostToDevice, d.st));
+    }
+    return;
   }
+  cudaStream_t up[4] = {};
+  cudaEvent_t fork = nullptr, join[4] = {};
+  CUDA_CHECK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventRecord(fork, d.st));  // the destination blocks are allocated in front of this point
+  for (int k = 0; k < n_up; k++) {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&up[k], cudaStreamNonBlocking));
+    CUDA_CHECK(cudaEventCreateWithFlags(&join[k], cudaEventDisableTiming));
+    CUDA_CHECK(cudaStreamWaitEvent(up[k], fork, 0));
+  }
+  for (size_t k = 0; d.uploads_done < q.uploads.size(); d.uploads_done++, k++) {
+    const Query::Upload& u = q.uploads[d.uploads_done];
+    CUDA_CHECK(cudaMemcpyAsync(d.arena + u.arena_off, u.src ? u.src : q.segs[u.seg].data + u.file_off, u.len, cudaMemcpyHostToDevice, up[k % n_up]));
+  }
+  for (int k = 0; k < n_up; k++) {
+    CUDA_CHECK(cudaEventRecord(join[k], up[k]));
+    CUDA_CHECK(cudaStreamWaitEvent(d.st, join[k], 0));
+    cudaEventDestroy(join[k]);   // (deferred by the runtime until the event has completed)
+    cudaStreamDestroy(up[k]);    // (likewise: the stream's work drains first)
+  }
+  cudaEventDestroy(fork);
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -14,7 +14,8 @@ void pinned_free(void* p);
 bool device_is_resident(const Query& q);   // lk_query_prepare has completed
 void device_layout(Query& q);              // plan_query's on_layout hook: segment cache / private arena placement + async H2D of what is not resident yet
 void device_begin_upload(Query& q);        // async H2D of the uploads listed so far
-void segment_load(SegmentInput& s);        // file -> pinned host memory owned by the query
+void segment_load(SegmentInput& s);        // whole file -> pinned host memory owned by the query
+void segment_open(SegmentInput& s);        // footer only (parsed from the file's tail); the touched chunks follow in device_layout
 void device_upload(Query& q);              // ... plus the index pools; waits for all of it
 void device_mark_group_tables_stale(Query& q);
 void device_execute(Query& q);             // clear table + fused scan kernel (async)

@@ -189,13 +189,30 @@ int FileMeta::leaf_index(const std::string& name) const {
   return -1;
 }
 
+static FileMeta parse_footer_thrift(const uint8_t* begin, const uint8_t* end);
+
 FileMeta parse_footer(const uint8_t* data, size_t len) {
   LK_CHECK(len >= 12 && memcmp(data, "PAR1", 4) == 0 && memcmp(data + len - 4, "PAR1", 4) == 0, LK_ERR_IO,
            "not a Parquet file (bad magic)");
   uint32_t flen;
   memcpy(&flen, data + len - 8, 4);
   LK_CHECK((size_t)flen + 12 <= len, LK_ERR_IO, "parquet: bad footer length");
-  TReader r(data + len - 8 - flen, data + len - 8);
+  return parse_footer_thrift(data + len - 8 - flen, data + len - 8);
+}
+
+bool parse_footer_tail(const uint8_t* tail, size_t tail_len, size_t file_len, FileMeta* out, size_t* need) {
+  LK_CHECK(file_len >= 12 && tail_len >= 8 && tail_len <= file_len && memcmp(tail + tail_len - 4, "PAR1", 4) == 0, LK_ERR_IO,
+           "not a Parquet file (bad magic)");
+  uint32_t flen;
+  memcpy(&flen, tail + tail_len - 8, 4);
+  LK_CHECK((size_t)flen + 12 <= file_len, LK_ERR_IO, "parquet: bad footer length");
+  if ((size_t)flen + 8 > tail_len) { *need = (size_t)flen + 8; return false; }
+  *out = parse_footer_thrift(tail + tail_len - 8 - flen, tail + tail_len - 8);
+  return true;
+}
+
+static FileMeta parse_footer_thrift(const uint8_t* begin, const uint8_t* end) {
+  TReader r(begin, end);
   FileMeta fm;
   std::vector<SchemaElem> schema;
   int fid, t, last = 0;

@@ -48,6 +48,9 @@ struct FileMeta {
 
 // Parses the footer of a Parquet file held in memory.  Throws lk::Error(LK_ERR_IO) if it is not Parquet.
 FileMeta parse_footer(const uint8_t* data, size_t len);
+// The same from the LAST `tail_len` bytes of a file of `file_len` bytes (a file that is read sparsely: footer first, then the
+// touched column chunks).  Returns false when the tail is too short to hold the footer: *need = bytes of tail required.
+bool parse_footer_tail(const uint8_t* tail, size_t tail_len, size_t file_len, FileMeta* out, size_t* need);
 
 struct PageInfo {
   uint32_t first_row = 0, num_rows = 0;  // chunk-level row range

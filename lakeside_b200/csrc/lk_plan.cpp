@@ -184,7 +184,8 @@ void plan_query(Query& q) {
 
   // ---- footers: DESCRIBE SELECT * FROM read_parquet([...], union_by_name=True) (Commons.scala:213-221) ----
   parallel_for((int)q.segs.size(), opt.host_threads, [&](int i) {
-    if (!q.segs[i].meta_from_cache) q.segs[i].meta = parse_footer(q.segs[i].data, q.segs[i].len);  // else: the segment cache remembered it
+    // (files bring their footer along: from the segment cache, or parsed from their tail when they were added)
+    if (!q.segs[i].meta_from_cache && !q.segs[i].sparse) q.segs[i].meta = parse_footer(q.segs[i].data, q.segs[i].len);
   });
   auto exists = [&](const std::string& name) {
     for (auto& s : q.segs)
@@ -340,9 +341,14 @@ void plan_query(Query& q) {
     }
   }
   trace.mark("arena layout");
-  // the device layer places the chunks (segment cache, private arena) and starts the copies; without one: all private
+  for (auto& sl : q.slots)
+    if (q.segs[sl.seg].data) sl.host = q.segs[sl.seg].data + sl.file_off;
+  // the device layer places the chunks (segment cache, private arena), reads what sparse files still owe and starts the
+  // copies; without one: all private
   if (q.on_layout) q.on_layout();
   else layout_private_arena(q, std::vector<uint8_t>());
+  std::vector<int> slot_of(q.rgs.size() * (size_t)np, -1);
+  for (size_t k = 0; k < q.slots.size(); k++) slot_of[(size_t)q.slots[k].rgi * np + q.slots[k].pcol] = (int)k;
   parallel_for((int)q.rgs.size(), opt.host_threads, [&](int i) {
     RowGroupPlan& rp = q.rgs[i];
     const SegmentInput& seg = q.segs[rp.seg];
@@ -351,7 +357,12 @@ void plan_query(Query& q) {
       if (li < 0) continue;  // union_by_name: the column is NULL for this file
       if (rp.from_cache[p]) continue;  // index (and bytes) came with the cached column
       const PCol& pc = q.pcols[p];
-      rp.chunks[p] = index_chunk(seg.data, seg.len, seg.meta.leaves[li], seg.meta.row_groups[rp.rg].columns[li],
+      // the chunk's bytes in host memory, addressed by FILE offset like everything index_chunk reads (only offsets inside
+      // the chunk are touched, so a view that holds just this chunk serves as well as the whole file)
+      const ChunkSlot& sl = q.slots[slot_of[(size_t)i * np + p]];
+      LK_CHECK(sl.host != nullptr, LK_ERR_IO, "segment '" + seg.name + "': column chunk bytes were not read");
+      const uint8_t* file_view = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(sl.host) - (uintptr_t)sl.file_off);
+      rp.chunks[p] = index_chunk(file_view, seg.len, seg.meta.leaves[li], seg.meta.row_groups[rp.rg].columns[li],
                                  seg.meta.row_groups[rp.rg].num_rows, pc.string_typed, !q.device_index);
       if (pc.string_typed)
         for (auto& pg : rp.chunks[p].pages)

@@ -79,12 +79,17 @@ struct SegmentInput {
   uint64_t id_mtime_ns = 0, id_ino = 0;
   std::shared_ptr<CachedSegment> cached;
   bool meta_from_cache = false;
+  // a file is read sparsely: its footer when it is added, then -- once the plan knows them -- only the byte ranges of the
+  // touched column chunks that no cached block holds (one pinned block, the ranges back to back); `data` stays null
+  bool sparse = false;
+  size_t sparse_bytes = 0;
 };
 
 // one touched column chunk: where its bytes are in the file and how much room it needs in device memory
 struct ChunkSlot {
   int rgi = -1, pcol = -1, seg = -1, leaf = -1;  // row-group slot (Query::rgs), touched column, segment, leaf index in the file
   uint64_t file_off = 0, len = 0, reserve = 0;
+  const uint8_t* host = nullptr;  // the chunk's first byte in host memory (inside the whole file, or inside a sparse read)
 };
 
 // one physical column touched by the query

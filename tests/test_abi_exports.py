@@ -42,6 +42,39 @@ def test_no_cpu_fallback_without_device():
     assert e.value.code == _lib.LK_ERR_CUDA
 
 
+def test_segment_cache_bookkeeping_needs_no_device():
+    # capacity / statistics of the HBM-resident segment cache are host-side bookkeeping: configurable before any GPU is touched
+    from lakeside_b200 import api
+
+    st = api.cache_stats()
+    try:
+        api.cache_configure(123456)
+        assert api.cache_stats()["capacity_bytes"] == 123456
+        api.cache_configure(0)
+        api.cache_clear()
+        s0 = api.cache_stats()
+        assert s0["capacity_bytes"] == 0 and s0["resident_bytes"] == 0 and s0["segments"] == 0
+        with pytest.raises(api.LakesideError):
+            api.cache_configure(-1)
+    finally:
+        api.cache_configure(st["capacity_bytes"])
+
+
+def test_file_segments_without_a_device_fail_loudly(tmp_path):
+    import torch
+
+    from lakeside_b200 import _lib, api
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    f = tmp_path / "x.parquet"
+    f.write_bytes(b"PAR1" + b"\0" * 32 + b"PAR1")
+    with pytest.raises(api.LakesideError) as e:
+        api.eval_glob('{"baseExpr": {"dataset": "logs", "filter": {"k": "a", "v": ["b"], "op": "eq"}, "chart": {"aggregation": "sum"}}, '
+                      '"segmentRequests": [{"stepInMillis": 1, "startTs": 0, "endTs": 1}]}', [str(f)])
+    assert e.value.code == _lib.LK_ERR_CUDA
+
+
 def test_product_package_never_imports_the_oracle():
     pkg = os.path.join(ROOT, "lakeside_b200")
     for dp, _, files in os.walk(pkg):

@@ -63,7 +63,7 @@ int lk_device_count(void); /* 0 when no CUDA device is visible; never fails */
  * Segments handed over as caller buffers (lk_query_add_segment_buffer) have no identity and are never cached.
  * stats: [0] capacity bytes, [1] resident bytes, [2] segments, [3] column hits, [4] column misses, [5] evicted segments. */
 int lk_cache_stats(int64_t* stats /*[6]*/);
-int lk_cache_configure(int64_t capacity_bytes);
+int lk_cache_configure(int64_t capacity_bytes); /* -1: the default */
 void lk_cache_clear(void);
 
 /* Pinned host memory for segment bytes handed to lk_query_add_segment_buffer (fast H2D). */

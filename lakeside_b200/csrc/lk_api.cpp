@@ -97,8 +97,9 @@ int lk_cache_stats(int64_t* out) {
 }
 int lk_cache_configure(int64_t capacity_bytes) {
   return guard([&] {
-    LK_CHECK(capacity_bytes >= 0, LK_ERR_INVALID, "capacity_bytes must be >= 0");
+    LK_CHECK(capacity_bytes >= -1, LK_ERR_INVALID, "capacity_bytes must be >= 0, or -1 for the default (a third of the device's memory)");
     global_options().segment_cache_bytes = capacity_bytes;
+    if (capacity_bytes < 0) capacity_bytes = device_default_cache_bytes();  // 0 before lk_init: device_init resolves the default then
     segment_cache().set_capacity((size_t)capacity_bytes);
   });
 }

@@ -34,6 +34,7 @@ void device_resolve(Query& q);
 static std::mutex g_mu;
 static bool g_inited = false;
 static int g_num_sms = 148;
+static int64_t g_default_cache_bytes = 0;
 static cudaStream_t g_cache_stream = nullptr;
 
 int device_count() {
@@ -65,7 +66,8 @@ void device_init() {
   PoolAlloc::release = pinned_free;
   // HBM-resident segment cache (lk_cache.h): a third of the device's memory unless lk_init said otherwise
   int64_t cache_bytes = global_options().segment_cache_bytes;
-  if (cache_bytes < 0) cache_bytes = (int64_t)(prop.totalGlobalMem / 3);
+  g_default_cache_bytes = (int64_t)(prop.totalGlobalMem / 3);
+  if (cache_bytes < 0) cache_bytes = g_default_cache_bytes;
   segment_cache().set_capacity((size_t)cache_bytes);
   CUDA_CHECK(cudaStreamCreateWithFlags(&g_cache_stream, cudaStreamNonBlocking));
   g_inited = true;
@@ -81,6 +83,7 @@ void cache_free_device(void* p) {
 }
 
 int num_sms() { return g_num_sms; }
+int64_t device_default_cache_bytes() { return g_default_cache_bytes; }
 
 // pinned host memory, cached by power-of-two size class
 struct PinnedPool {

@@ -8,6 +8,7 @@ int device_count();
 void device_init();
 void device_shutdown();
 int num_sms();
+int64_t device_default_cache_bytes();  // a third of the device's memory; 0 before device_init
 void* pinned_alloc(size_t bytes);
 void pinned_free(void* p);
 

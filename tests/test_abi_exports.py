@@ -55,9 +55,9 @@ def test_segment_cache_bookkeeping_needs_no_device():
         s0 = api.cache_stats()
         assert s0["capacity_bytes"] == 0 and s0["resident_bytes"] == 0 and s0["segments"] == 0
         with pytest.raises(api.LakesideError):
-            api.cache_configure(-1)
+            api.cache_configure(-2)
     finally:
-        api.cache_configure(st["capacity_bytes"])
+        api.cache_configure(st["capacity_bytes"] if st["capacity_bytes"] > 0 else -1)  # (-1: the default, resolved by lk_init)
 
 
 def test_file_segments_without_a_device_fail_loudly(tmp_path):

@@ -731,6 +731,9 @@ struct lk_merge {
   uint32_t* m_stream = nullptr;
   unsigned long long* m_key = nullptr;
   cudaEvent_t ev_mid = nullptr;
+  // steady state of the run path (verdict known): the two clears and nine small-to-large kernels of a run are one CUDA graph --
+  // the ordering kernels take 4-10 us each, about as long as the gaps between separately launched dependent kernels
+  cudaGraphExec_t graph = nullptr;
 };
 
 namespace lk {
@@ -844,11 +847,9 @@ static void merge_run_elems(lk_merge* m) {
   CUDA_CHECK(cudaGetLastError());
 }
 
-void merge_run(lk_merge* m) {
-  CUDA_CHECK(cudaSetDevice(global_options().device));
-  CUDA_CHECK(cudaEventRecord(m->ev[2], m->st));
+static void merge_enqueue_runs(lk_merge* m, bool first_half, bool second_half, bool record_mid) {
   const int rev = m->reverse ? 1 : 0;
-  if (m->total > 0 && m->mode != 2) {
+  if (first_half) {
     // run detection and the verdict (R, D, cells) -- see mrun_* above
     CUDA_CHECK(cudaMemsetAsync(m->r_ctl, 0, sizeof(MrunCtl), m->st));
     CUDA_CHECK(cudaMemsetAsync(m->r_hset, 0xff, (size_t)MRUN_HSET * 8, m->st));
@@ -860,6 +861,46 @@ void merge_run(lk_merge* m) {
     const size_t dsmem = (m->mode == 0 || m->known_distinct > 1024) ? (size_t)MRUN_DMAX * 8 : 1024 * 8;
     mrun_distinct_kernel<<<1, 256, dsmem, m->st>>>(m->r_ctl, m->r_dlist, m->r_dsorted, m->K, m->cell_cap);
     CUDA_CHECK(cudaGetLastError());
+  }
+  if (second_half) {
+    const int wide = num_sms() * 4;
+    mrun_matrix_kernel<<<wide, 256, 0, m->st>>>(m->r_ctl, m->r_key, m->r_start, m->r_stream, m->r_dsorted, m->K, m->r_mat);
+    mrun_cells_sum_kernel<<<m->cell_parts, 256, 0, m->st>>>(m->r_ctl, m->K, m->r_mat, m->r_parts);
+    mrun_cells_scan_kernel<<<1, 1024, 0, m->st>>>(m->r_ctl, m->K, m->r_parts);
+    mrun_cells_emit_kernel<<<m->cell_parts, 256, 0, m->st>>>(m->r_ctl, m->K, m->total, m->r_mat, m->r_start, m->r_stream, m->r_key, m->r_parts, m->m_dst,
+                                                             m->m_src, m->m_stream, m->m_key);
+    if (record_mid) CUDA_CHECK(cudaEventRecord(m->ev_mid, m->st));
+    mrun_copy_kernel<<<m->ntiles, MG_BLOCK, 0, m->st>>>(m->r_ctl, m->d_gid, m->d_val, m->total, rev, m->m_dst, m->m_src, m->m_stream, m->m_key, m->o_ts,
+                                                        m->o_gid, m->o_val, m->o_src);
+    CUDA_CHECK(cudaGetLastError());
+  }
+}
+
+void merge_run(lk_merge* m) {
+  CUDA_CHECK(cudaSetDevice(global_options().device));
+  CUDA_CHECK(cudaEventRecord(m->ev[2], m->st));
+  static const bool no_graph = getenv("LK_MERGE_NO_GRAPH") != nullptr;  // tuning aid
+  if (m->total > 0 && m->mode == 1 && !no_graph) {
+    // verdict known (the job's inputs never change): the whole run is one graph launch
+    if (!m->graph) {
+      cudaGraph_t g = nullptr;
+      CUDA_CHECK(cudaStreamBeginCapture(m->st, cudaStreamCaptureModeThreadLocal));
+      try {
+        merge_enqueue_runs(m, true, true, false);
+      } catch (...) { cudaStreamEndCapture(m->st, &g); if (g) cudaGraphDestroy(g); throw; }
+      CUDA_CHECK(cudaStreamEndCapture(m->st, &g));
+      cudaError_t e = cudaGraphInstantiate(&m->graph, g, 0);
+      cudaGraphDestroy(g);
+      CUDA_CHECK(e);
+    }
+    CUDA_CHECK(cudaEventRecord(m->ev_mid, m->st));  // (no split inside a graph launch: [2] reads 0)
+    CUDA_CHECK(cudaGraphLaunch(m->graph, m->st));
+    CUDA_CHECK(cudaEventRecord(m->ev[3], m->st));
+    m->ran = true;
+    return;
+  }
+  if (m->total > 0 && m->mode != 2) {
+    merge_enqueue_runs(m, true, false, false);
     if (m->mode == 0) {  // first run of this job: one read-back decides which kernels follow (the inputs never change)
       MrunCtl h;
       CUDA_CHECK(cudaMemcpyAsync(&h, m->r_ctl, sizeof h, cudaMemcpyDeviceToHost, m->st));
@@ -868,18 +909,8 @@ void merge_run(lk_merge* m) {
       m->known_distinct = h.n_distinct;
     }
   }
-  if (m->total > 0 && m->mode == 1) {
-    const int wide = num_sms() * 4;
-    mrun_matrix_kernel<<<wide, 256, 0, m->st>>>(m->r_ctl, m->r_key, m->r_start, m->r_stream, m->r_dsorted, m->K, m->r_mat);
-    mrun_cells_sum_kernel<<<m->cell_parts, 256, 0, m->st>>>(m->r_ctl, m->K, m->r_mat, m->r_parts);
-    mrun_cells_scan_kernel<<<1, 1024, 0, m->st>>>(m->r_ctl, m->K, m->r_parts);
-    mrun_cells_emit_kernel<<<m->cell_parts, 256, 0, m->st>>>(m->r_ctl, m->K, m->total, m->r_mat, m->r_start, m->r_stream, m->r_key, m->r_parts, m->m_dst,
-                                                             m->m_src, m->m_stream, m->m_key);
-    CUDA_CHECK(cudaEventRecord(m->ev_mid, m->st));
-    mrun_copy_kernel<<<m->ntiles, MG_BLOCK, 0, m->st>>>(m->r_ctl, m->d_gid, m->d_val, m->total, rev, m->m_dst, m->m_src, m->m_stream, m->m_key, m->o_ts,
-                                                        m->o_gid, m->o_val, m->o_src);
-    CUDA_CHECK(cudaGetLastError());
-  } else if (m->total > 0) {
+  if (m->total > 0 && m->mode == 1) merge_enqueue_runs(m, false, true, true);
+  else if (m->total > 0) {
     CUDA_CHECK(cudaEventRecord(m->ev_mid, m->st));
     merge_run_elems(m);
   }
@@ -975,6 +1006,7 @@ void merge_destroy(lk_merge* m) {
   }
   for (auto& e : m->ev) if (e) cudaEventDestroy(e);
   if (m->ev_mid) cudaEventDestroy(m->ev_mid);
+  if (m->graph) cudaGraphExecDestroy(m->graph);
   delete m;
 }
 

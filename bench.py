@@ -462,12 +462,12 @@ def run_c5(args, reference=False):
         "metric": metric, "value": n / (k_ms / 1e3), "unit": "elements/s", "n_gpus": 1, "steps": args.steps, "warmup": nw,
         "ms_per_step": k_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": desc, "l2": "671 MB of streams + output: larger than the 126 MB L2"},
-        "roofline": {"bound": "hbm", "kernel": "lk merge (split + merge-path tile kernels)", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "lk merge by runs (mrun_flags .. mrun_copy: run detection, D x K rank matrix, coalesced run copy; one CUDA graph per run)", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_launch": 40 * n, "kernel_ms": k_ms,
                      "note": "algorithmic bytes = 2 x 20 B per element (SURVEY §8d)"},
         "cpu_baseline": cpu, "parity": {"ok": ok, "checks": {"merged (timestamp, source) order == stable sort by (timestamp, source descending)": ok}},
         "e2e": {"value": n / min(e2e_t), "unit": "elements/s", "h2d_bytes_per_step": 20 * n, "d2h_bytes_per_step": 24 * n, "ms_per_step": min(e2e_t) * 1e3},
-        "gpu_launches": args.steps * 3, "clocks": clocks}))
+        "gpu_launches": args.steps * 9, "clocks": clocks}))  # mrun_flags, scan, fill, distinct, matrix, cells_sum, cells_scan, cells_emit, copy
 
 
 # ----------------------------------------------------------------------------------------------------------------------

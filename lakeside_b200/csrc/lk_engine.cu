@@ -106,6 +106,9 @@ void* pinned_alloc(size_t bytes) {
       }
   }
   void* p = nullptr;
+  // (worker threads of the planner and of the sparse segment reads come here too: a fresh thread's current device is 0, and an
+  // allocation there would create a context on GPU 0 from every rank of a multi-GPU box)
+  cudaSetDevice(global_options().device);
   cudaError_t e = cudaHostAlloc(&p, cap, cudaHostAllocDefault);
   if (e != cudaSuccess) { cudaGetLastError(); fail(e == cudaErrorMemoryAllocation ? LK_ERR_NOMEM : LK_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e)); }
   std::lock_guard<std::mutex> lk(g_pinned.mu);

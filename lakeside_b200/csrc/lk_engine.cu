@@ -77,6 +77,7 @@ void device_init() {
 // (queries drop theirs after synchronising their stream)
 void cache_free_device(void* p) {
   if (!p) return;
+  cudaSetDevice(global_options().device);  // (the last reference may go away on any thread)
   if (g_cache_stream) cudaFreeAsync(p, g_cache_stream);
   else cudaFree(p);
   cudaGetLastError();
@@ -248,6 +249,7 @@ Query::~Query() {
   const auto t_destroy0 = std::chrono::steady_clock::now();
   if (dev) {
     Device& d = *dev;
+    cudaSetDevice(global_options().device);  // (a query may be destroyed on another thread than the one that ran it)
     if (d.st2) cudaStreamSynchronize(d.st2);
     if (d.st) cudaStreamSynchronize(d.st);
     auto fr = [&](void* p) { if (p) cudaFreeAsync(p, d.st); };

@@ -9,6 +9,8 @@
 #include <chrono>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
+#include <string_view>
 
 #include "lk_query.h"
 
@@ -762,12 +764,15 @@ void plan_query(Query& q) {
   q.local_dicts.assign(q.key_pcols.size(), {});
   for (size_t k = 0; k < q.key_pcols.size(); k++) {
     std::vector<std::string>& d = q.local_dicts[k];
+    // the same few dozen strings come back from every row group: dedupe first (hash set of views into the chunk indexes),
+    // sort only the distinct ones (100 segments x 4 key columns: 14 k strings, 144 distinct)
+    std::unordered_set<std::string_view> seen;
     for (auto& rp : q.rgs) {
       const ChunkIndex& ci = rp.chunks[q.key_pcols[k]];
-      d.insert(d.end(), ci.dict_strings.begin(), ci.dict_strings.end());
+      for (auto& s : ci.dict_strings)
+        if (seen.insert(std::string_view(s)).second) d.emplace_back(s);
     }
     std::sort(d.begin(), d.end());
-    d.erase(std::unique(d.begin(), d.end()), d.end());
   }
   q.key_dicts = q.local_dicts;
   trace.mark("local dictionaries");
